@@ -1,0 +1,15 @@
+"""numcl_b200 -- Python host mirror of numcl's einsum / broadcast / reduce API over the B200 backend.
+
+The product is numcl_b200/libnumcl_cuda.so (C ABI in include/numcl_cuda.h, kernels in csrc/).
+These modules mirror the reference's operator interface for the hot path -- same names, argument
+meaning and error behaviour -- so the parity tests read like numcl's own tests.  No CPU fallback.
+"""
+from ._lib import (NumclCudaError, NumclShapeError, NumclUnsupportedError, lib, load, shutdown)  # noqa: F401
+from .array import (NArray, arange, asarray, empty, full, ones, random_array, zeros)  # noqa: F401
+from .einsum import einsum  # noqa: F401
+from .einsum_spec import EinsumSpecError, einsum_normalize_subscripts  # noqa: F401
+from .linalg import diag, eye, inner, kron, matmul, outer, transpose, vdot  # noqa: F401
+from .numeric import (add, broadcast, clip, div, map_array, map_array_into, maximum, minimum, mul,  # noqa: F401
+                      one_minus, one_plus, sub)
+from .reduce import amax, amin, avg, mean, prod, reduce_array, stdev, var, variance  # noqa: F401
+from .reduce import sum  # noqa: F401,A004

@@ -1,0 +1,160 @@
+"""ctypes binding of libnumcl_cuda.so (include/numcl_cuda.h).
+
+This is the Python twin of the CFFI stubs in lisp/numcl-cuda-ffi.lisp.  There is no CPU fallback:
+if the shared library is missing or no B200 is visible, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libnumcl_cuda.so")
+
+MAX_RANK, MAX_INDEX, MAX_OPERANDS, MAX_EXPR, MAX_OPTS = 8, 16, 8, 48, 8
+
+OK, ERR_INVALID, ERR_SHAPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
+OUT_ACCUMULATE, OUT_FRESH = 0, 1
+
+OPS = dict(ADD=0, SUB=1, MUL=2, DIV=3, MAX=4, MIN=5, EQ=6, NE=7, LE=8, GE=9, LT=10, GT=11,
+           LOGAND=12, LOGIOR=13, LOGXOR=14,
+           NEG=32, ABS=33, SQUARE=34, SQRT=35, LOGNOT=36, IDENTITY=37, EXP=38, LOG=39, SIN=40, COS=41,
+           TAN=42, TANH=43, SIGNUM=44,
+           X_INPUT=64, X_OUTPUT=65, X_CONST_INT=66, X_CONST_F32=67, X_CONST_F64=68)
+
+# every symbol include/numcl_cuda.h declares (tests/test_abi.py checks the .so exports them all)
+EXPORTS = [
+    "ncl_init", "ncl_shutdown", "ncl_last_error", "ncl_version", "ncl_device_count", "ncl_set_stream",
+    "ncl_get_stream", "ncl_sync", "ncl_launch_count", "ncl_last_kernel", "ncl_force_generic",
+    "ncl_alloc", "ncl_free", "ncl_buf_ptr", "ncl_buf_bytes", "ncl_wrap", "ncl_h2d", "ncl_d2h",
+    "ncl_host_alloc_pinned", "ncl_host_free", "ncl_storage_bytes", "ncl_fill", "ncl_fill_random",
+    "ncl_einsum", "ncl_broadcast", "ncl_fold", "ncl_map", "ncl_reduce", "ncl_convert",
+    "ncl_comm_unique_id", "ncl_comm_init", "ncl_comm_destroy", "ncl_allreduce", "ncl_reduce_all_sharded",
+]
+
+
+class ExprNode(C.Structure):
+    _fields_ = [("op", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("pad", C.c_int32),
+                ("ival", C.c_int64), ("fval", C.c_double)]
+
+
+class Expr(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pad", C.c_int32), ("node", ExprNode * MAX_EXPR)]
+
+
+class IterOpt(C.Structure):
+    _fields_ = [("key", C.c_int32), ("has_start", C.c_int32), ("has_end", C.c_int32), ("pad", C.c_int32),
+                ("start", C.c_int64), ("end", C.c_int64), ("step", C.c_int64)]
+
+
+class EinsumDesc(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("n_out", C.c_int32), ("n_iter", C.c_int32),
+                ("iter", C.c_int32 * MAX_INDEX),
+                ("in_rank", C.c_int32 * MAX_OPERANDS),
+                ("in_spec", (C.c_int32 * MAX_RANK) * MAX_OPERANDS),
+                ("out_rank", C.c_int32 * MAX_OPERANDS),
+                ("out_spec", (C.c_int32 * MAX_RANK) * MAX_OPERANDS),
+                ("in_nopt", C.c_int32 * MAX_OPERANDS),
+                ("out_nopt", C.c_int32 * MAX_OPERANDS),
+                ("in_opt", (IterOpt * MAX_OPTS) * MAX_OPERANDS),
+                ("out_opt", (IterOpt * MAX_OPTS) * MAX_OPERANDS),
+                ("transform", Expr * MAX_OPERANDS)]
+
+
+class Tensor(C.Structure):
+    _fields_ = [("buf", C.c_void_p), ("host", C.c_void_p), ("dtype", C.c_int32), ("rank", C.c_int32),
+                ("dims", C.c_int64 * MAX_RANK), ("elem_offset", C.c_int64)]
+
+
+class NumclCudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"numcl-cuda error {code}: {msg}")
+        self.code = code
+
+
+class NumclShapeError(NumclCudaError, AssertionError):
+    """The reference signals these as failed `assert`s before the loop nest runs."""
+
+
+class NumclUnsupportedError(NumclCudaError, NotImplementedError):
+    pass
+
+
+_lib = None
+_inited = False
+
+
+def load():
+    """dlopen the library (no GPU needed); raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(f"{SO_PATH} is missing: run `python -m numcl_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(SO_PATH, mode=C.RTLD_GLOBAL)
+    L.ncl_last_error.restype = C.c_char_p
+    L.ncl_version.restype = C.c_char_p
+    L.ncl_last_kernel.restype = C.c_char_p
+    L.ncl_launch_count.restype = C.c_int64
+    L.ncl_get_stream.restype = C.c_void_p
+    L.ncl_set_stream.argtypes = [C.c_void_p]
+    L.ncl_alloc.restype = C.c_void_p
+    L.ncl_alloc.argtypes = [C.c_size_t, C.c_int]
+    L.ncl_free.argtypes = [C.c_void_p]
+    L.ncl_buf_ptr.restype = C.c_void_p
+    L.ncl_buf_ptr.argtypes = [C.c_void_p]
+    L.ncl_buf_bytes.restype = C.c_size_t
+    L.ncl_buf_bytes.argtypes = [C.c_void_p]
+    L.ncl_wrap.restype = C.c_void_p
+    L.ncl_wrap.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    L.ncl_h2d.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    L.ncl_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    L.ncl_host_alloc_pinned.restype = C.c_void_p
+    L.ncl_host_alloc_pinned.argtypes = [C.c_size_t]
+    L.ncl_host_free.argtypes = [C.c_void_p]
+    L.ncl_storage_bytes.restype = C.c_size_t
+    L.ncl_storage_bytes.argtypes = [C.c_int, C.c_int64]
+    L.ncl_fill.argtypes = [C.POINTER(Tensor), C.c_int, C.c_int64, C.c_double]
+    L.ncl_fill_random.argtypes = [C.POINTER(Tensor), C.c_uint64, C.c_int, C.c_double, C.c_double]
+    L.ncl_einsum.argtypes = [C.POINTER(EinsumDesc), C.POINTER(Tensor), C.c_int, C.POINTER(Tensor), C.c_int, C.c_uint]
+    L.ncl_broadcast.argtypes = [C.c_int, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor)]
+    L.ncl_fold.argtypes = [C.c_int, C.c_int, C.POINTER(Tensor), C.c_int, C.POINTER(Tensor)]
+    L.ncl_map.argtypes = [C.POINTER(Expr), C.POINTER(Tensor), C.c_int, C.POINTER(Tensor)]
+    L.ncl_reduce.argtypes = [C.c_int, C.POINTER(Tensor), C.POINTER(C.c_int), C.c_int, C.POINTER(Tensor), C.c_uint]
+    L.ncl_convert.argtypes = [C.POINTER(Tensor), C.POINTER(Tensor)]
+    L.ncl_comm_unique_id.argtypes = [C.c_void_p]
+    L.ncl_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ncl_allreduce.argtypes = [C.c_int, C.POINTER(Tensor)]
+    L.ncl_reduce_all_sharded.argtypes = [C.c_int, C.POINTER(Tensor), C.POINTER(Tensor)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc == OK:
+        return
+    msg = load().ncl_last_error().decode(errors="replace")
+    if rc == ERR_SHAPE:
+        raise NumclShapeError(rc, msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NumclUnsupportedError(rc, msg)
+    raise NumclCudaError(rc, msg)
+
+
+def lib():
+    """The initialised library bound to this process's GPU (LOCAL_RANK, default 0)."""
+    global _inited
+    L = load()
+    if not _inited:
+        dev = int(os.environ.get("NUMCL_CUDA_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        devs = (C.c_int * 1)(dev)
+        check(L.ncl_init(1, devs))
+        _inited = True
+    return L
+
+
+def shutdown():
+    global _inited
+    if _lib is not None and _inited:
+        _lib.ncl_shutdown()
+        _inited = False

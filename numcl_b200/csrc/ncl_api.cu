@@ -1,0 +1,502 @@
+// ncl_api.cu -- the C ABI (include/numcl_cuda.h): context, buffers, and the lowering of every
+// entry point to the Nest the reference's loop generators would have emitted.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+#include "ncl_internal.h"
+
+static Context g_ctx;
+static std::recursive_mutex g_mu;
+static thread_local char g_err[1024] = "";
+Context& ctx() { return g_ctx; }
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return NCL_OK;
+  return set_error(NCL_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+static int grow(void** p, size_t* have, size_t want) {
+  if (*have >= want) return NCL_OK;
+  if (*p) { NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); NCL_CUDA(cudaFree(*p)); *p = nullptr; *have = 0; }
+  size_t sz = want + want / 4 + (1u << 20);
+  NCL_CUDA(cudaMalloc(p, sz)); *have = sz; return NCL_OK;
+}
+int ensure_scratch(size_t bytes) { return grow(&g_ctx.scratch, &g_ctx.scratch_bytes, bytes); }
+int ensure_scratch2(size_t bytes) { return grow(&g_ctx.scratch2, &g_ctx.scratch2_bytes, bytes); }
+
+#define LOCK std::lock_guard<std::recursive_mutex> lock__(g_mu)
+#define NEED_INIT if (!g_ctx.inited) return set_error(NCL_ERR_STATE, "ncl_init has not been called")
+
+extern "C" {
+
+const char* ncl_last_error(void) { return g_err; }
+const char* ncl_version(void) { return "numcl-cuda 0.1 (sm_100a)"; }
+
+int ncl_init(int ndev, const int* devs) {
+  LOCK;
+  if (g_ctx.inited) return NCL_OK;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return set_error(NCL_ERR_CUDA, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
+  if (ndev <= 0) ndev = 1;
+  if (ndev > 16) return set_error(NCL_ERR_INVALID, "ndev > 16");
+  g_ctx.ndev = ndev;
+  for (int i = 0; i < ndev; i++) g_ctx.devs[i] = devs ? devs[i] : i;
+  NCL_CUDA(cudaSetDevice(g_ctx.devs[0]));
+  cudaDeviceProp prop; NCL_CUDA(cudaGetDeviceProperties(&prop, g_ctx.devs[0]));
+  if (prop.major != 10) return set_error(NCL_ERR_STATE, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  g_ctx.sm_count = prop.multiProcessorCount;
+  NCL_CUDA(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
+  g_ctx.stream = g_ctx.own_stream;
+  NCL_CUDA(cudaMalloc((void**)&g_ctx.ticket, 64 * sizeof(unsigned int)));
+  NCL_CUDA(cudaMemset(g_ctx.ticket, 0, 64 * sizeof(unsigned int)));
+  long long consts[8] = {0, 1, 0, 0, 0, 0, 0, 0};
+  NCL_CUDA(cudaMalloc(&g_ctx.consts, sizeof consts));
+  NCL_CUDA(cudaMemcpy(g_ctx.consts, consts, sizeof consts, cudaMemcpyHostToDevice));
+  g_ctx.launches = 0; g_ctx.last_kernel = ""; g_ctx.inited = true;
+  return NCL_OK;
+}
+
+void ncl_shutdown(void) {
+  LOCK;
+  if (!g_ctx.inited) return;
+  cudaStreamSynchronize(g_ctx.stream);
+  if (g_ctx.scratch) cudaFree(g_ctx.scratch);
+  if (g_ctx.scratch2) cudaFree(g_ctx.scratch2);
+  if (g_ctx.ticket) cudaFree(g_ctx.ticket);
+  if (g_ctx.consts) cudaFree(g_ctx.consts);
+  if (g_ctx.pinned) cudaFreeHost(g_ctx.pinned);
+  if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
+  g_ctx = Context();
+}
+
+int ncl_device_count(void) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) return 0; return c; }
+int ncl_set_stream(void* s) { LOCK; NEED_INIT; g_ctx.stream = s ? (cudaStream_t)s : g_ctx.own_stream; return NCL_OK; }
+void* ncl_get_stream(void) { return (void*)g_ctx.stream; }
+int ncl_sync(void) { NEED_INIT; NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); return NCL_OK; }
+int64_t ncl_launch_count(void) { return g_ctx.launches; }
+const char* ncl_last_kernel(void) { return g_ctx.last_kernel; }
+int ncl_force_generic(int on) { g_ctx.force_generic = on != 0; return NCL_OK; }
+
+// ---- buffers ----------------------------------------------------------------------------------
+ncl_buf* ncl_alloc(size_t bytes, int dev_slot) {
+  LOCK;
+  if (!g_ctx.inited) { set_error(NCL_ERR_STATE, "ncl_init has not been called"); return nullptr; }
+  if (dev_slot < 0 || dev_slot >= g_ctx.ndev) { set_error(NCL_ERR_INVALID, "bad device slot %d", dev_slot); return nullptr; }
+  void* p = nullptr;
+  size_t sz = bytes ? ((bytes + 255) & ~(size_t)255) : 256;
+  cudaError_t e = cudaMalloc(&p, sz);
+  if (e != cudaSuccess) { set_error(NCL_ERR_NOMEM, "cudaMalloc(%zu): %s", sz, cudaGetErrorString(e)); return nullptr; }
+  ncl_buf* b = new ncl_buf{p, sz, dev_slot, true};
+  return b;
+}
+int ncl_free(ncl_buf* b) {
+  LOCK;
+  if (!b) return NCL_OK;
+  if (b->owned && b->ptr) { cudaStreamSynchronize(g_ctx.stream); cudaFree(b->ptr); }
+  delete b; return NCL_OK;
+}
+void* ncl_buf_ptr(const ncl_buf* b) { return b ? b->ptr : nullptr; }
+size_t ncl_buf_bytes(const ncl_buf* b) { return b ? b->bytes : 0; }
+ncl_buf* ncl_wrap(void* p, size_t bytes, int dev_slot) { return new ncl_buf{p, bytes, dev_slot, false}; }
+int ncl_h2d(ncl_buf* dst, size_t off, const void* host, size_t bytes) {
+  NEED_INIT;
+  if (!dst || off + bytes > dst->bytes) return set_error(NCL_ERR_INVALID, "ncl_h2d out of range");
+  NCL_CUDA(cudaMemcpyAsync((char*)dst->ptr + off, host, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+  return NCL_OK;
+}
+int ncl_d2h(void* host, const ncl_buf* src, size_t off, size_t bytes) {
+  NEED_INIT;
+  if (!src || off + bytes > src->bytes) return set_error(NCL_ERR_INVALID, "ncl_d2h out of range");
+  NCL_CUDA(cudaMemcpyAsync(host, (const char*)src->ptr + off, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+  NCL_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  return NCL_OK;
+}
+void* ncl_host_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_error(NCL_ERR_NOMEM, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+  return p;
+}
+int ncl_host_free(void* p) { if (p) cudaFreeHost(p); return NCL_OK; }
+size_t ncl_storage_bytes(int dtype, int64_t n) {
+  if (dtype < 0 || dtype >= NCL_DTYPE_COUNT) return 0;
+  int64_t padded = 8 * ((n + 7) / 8); if (padded == 0) padded = 8;
+  return (size_t)((padded * g_dt[dtype].slot_bits + 7) / 8);
+}
+
+}  // extern "C"
+
+// ---- tensors -> operands, with staging of host-resident tensors ---------------------------------
+static int64_t total_elems(const ncl_tensor* t) { int64_t n = 1; for (int i = 0; i < t->rank; i++) n *= t->dims[i]; return n; }
+
+static int check_tensor(const ncl_tensor* t, const char* what) {
+  if (!t) return set_error(NCL_ERR_INVALID, "%s is NULL", what);
+  if (t->dtype < 0 || t->dtype >= NCL_DTYPE_COUNT) return set_error(NCL_ERR_INVALID, "%s: bad dtype %d", what, t->dtype);
+  if (t->rank < 0 || t->rank > NCL_MAX_RANK) return set_error(NCL_ERR_INVALID, "%s: bad rank %d", what, t->rank);
+  for (int i = 0; i < t->rank; i++) if (t->dims[i] < 0) return set_error(NCL_ERR_INVALID, "%s: negative dimension", what);
+  if ((t->buf == nullptr) == (t->host == nullptr)) return set_error(NCL_ERR_INVALID, "%s: exactly one of buf / host must be set", what);
+  if (t->elem_offset < 0) return set_error(NCL_ERR_INVALID, "%s: negative offset", what);
+  return NCL_OK;
+}
+
+// Host-resident tensors are staged through a device arena that lives for the call.
+struct Stager {
+  struct Item { const ncl_tensor* t; char* dev; size_t bytes; bool is_out; };
+  std::vector<Item> items; size_t used = 0;
+  static size_t need(const ncl_tensor* t) { return (ncl_storage_bytes(t->dtype, t->elem_offset + total_elems(t)) + 255) & ~(size_t)255; }
+  int plan(const ncl_tensor* ts, int n, bool is_out) {
+    for (int i = 0; i < n; i++) if (ts[i].host) { items.push_back({&ts[i], nullptr, need(&ts[i]), is_out}); used += items.back().bytes; }
+    return NCL_OK;
+  }
+  int upload(bool outputs_too) {
+    if (!used) return NCL_OK;
+    NCL_TRY(ensure_scratch2(used));
+    size_t off = 0;
+    for (auto& it : items) {
+      it.dev = (char*)g_ctx.scratch2 + off; off += it.bytes;
+      size_t live = ncl_storage_bytes(it.t->dtype, it.t->elem_offset + total_elems(it.t));
+      if (!it.is_out || outputs_too)
+        NCL_CUDA(cudaMemcpyAsync(it.dev, it.t->host, live, cudaMemcpyHostToDevice, g_ctx.stream));
+    }
+    return NCL_OK;
+  }
+  char* dev_of(const ncl_tensor* t) { for (auto& it : items) if (it.t == t) return it.dev; return nullptr; }
+  int download() {
+    bool any = false;
+    for (auto& it : items) if (it.is_out) {
+      size_t live = ncl_storage_bytes(it.t->dtype, it.t->elem_offset + total_elems(it.t));
+      NCL_CUDA(cudaMemcpyAsync(it.t->host, it.dev, live, cudaMemcpyDeviceToHost, g_ctx.stream)); any = true;
+    }
+    if (any) NCL_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return NCL_OK;
+  }
+};
+
+static void operand_from(const ncl_tensor* t, Stager& st, Operand* o) {
+  memset(o, 0, sizeof *o);
+  o->dtype = t->dtype; o->offset = t->elem_offset;
+  if (t->buf) { o->base = (char*)t->buf->ptr; o->n_storage = (int64_t)((t->buf->bytes * 8) / g_dt[t->dtype].slot_bits); }
+  else { o->base = st.dev_of(t); o->n_storage = (int64_t)((Stager::need(t) * 8) / g_dt[t->dtype].slot_bits); }
+}
+static void rowmajor_strides(const ncl_tensor* t, int64_t* s) { int64_t acc = 1; for (int i = t->rank - 1; i >= 0; i--) { s[i] = acc; acc *= t->dims[i]; } }
+
+// ---- einsum: shape-resolver + plan-broadcast + nest construction -----------------------------------
+static int64_t normalize_index(int64_t index, int64_t dim) {            // src/3einsum.lisp:274-278
+  if (index < 0) { if (dim == 0) return 0; int64_t m = index % dim; if (m < 0) m += dim; return m; }
+  return index < dim ? index : dim;
+}
+static int64_t ceil_div(int64_t a, int64_t b) { int64_t q = a / b, r = a % b; if (r != 0 && ((r > 0) == (b > 0))) q++; return q; }
+static const ncl_iter_opt* find_opt(const ncl_iter_opt* o, int n, int key) { for (int i = 0; i < n; i++) if (o[i].key == key) return &o[i]; return nullptr; }
+
+#define QMAX 64
+struct Resolver {
+  int64_t q[QMAX]; bool set[QMAX];
+  int M = 0; bool bc = false;
+  int64_t plan_dim[NCL_MAX_OPERANDS + 1][NCL_MAX_RANK], plan_step[NCL_MAX_OPERANDS + 1][NCL_MAX_RANK];
+  int unify(int idx, int64_t w) {
+    if (idx < 0 || idx >= QMAX) return set_error(NCL_ERR_INVALID, "index number %d out of range", idx);
+    if (set[idx] && q[idx] != w) return set_error(NCL_ERR_SHAPE, "index %d is used with widths %lld and %lld", idx, (long long)q[idx], (long long)w);
+    q[idx] = w; set[idx] = true; return NCL_OK;
+  }
+};
+static int range_width(const ncl_tensor* t, int axis, const ncl_iter_opt* o, int64_t* w) {   // :280-285
+  int64_t D = t->dims[axis];
+  int64_t start = (o && o->has_start) ? o->start : 0, end = (o && o->has_end) ? o->end : D, step = o ? o->step : 1;
+  if (step == 0) return set_error(NCL_ERR_INVALID, ":step 0");
+  *w = ceil_div(normalize_index(end, D) - normalize_index(start, D), step);
+  if (*w < 0) *w = 0;
+  return NCL_OK;
+}
+// one array through shape-resolver (src/3einsum.lisp:287-338); block = dims of the `-` block
+static int resolve_array(Resolver& R, const ncl_tensor* t, const int32_t* spec, int rank, const ncl_iter_opt* opts, int nopt,
+                         const char* what, int which, int* has_block, int* block_rank, int64_t* block) {
+  int bpos = -1;
+  for (int k = 0; k < rank; k++) {
+    if (spec[k] == -1) { if (bpos >= 0) return set_error(NCL_ERR_INVALID, "%s %d: more than one `-` in a spec", what, which); bpos = k; }
+    else if (spec[k] < 0) return set_error(NCL_ERR_INVALID, "%s %d: bad index %d", what, which, spec[k]);
+  }
+  *has_block = bpos >= 0;
+  if (bpos < 0) {
+    if (t->rank != rank) return set_error(NCL_ERR_SHAPE, "%s %d has rank %d but its spec has %d indices", what, which, t->rank, rank);
+    for (int i = 0; i < rank; i++) { int64_t w; NCL_TRY(range_width(t, i, find_opt(opts, nopt, spec[i]), &w)); NCL_TRY(R.unify(spec[i], w)); }
+    return NCL_OK;
+  }
+  // The reference sizes the strides of axes that precede `-` from the plan's first step only
+  // (%dimension-step-size, common-lisp.lisp:60-66), which addresses garbage unless `-` leads.
+  if (bpos != 0) return set_error(NCL_ERR_UNSUPPORTED, "%s %d: `-` must be the leading axis of a spec (reference quirk, see DESIGN.md)", what, which);
+  int after = rank - 1;
+  if (t->rank < after) return set_error(NCL_ERR_SHAPE, "%s %d has too few axes for its spec", what, which);
+  for (int i = 0; i < after; i++) {
+    int axis = t->rank - 1 - i; int idx = spec[rank - 1 - i];
+    int64_t w; NCL_TRY(range_width(t, axis, find_opt(opts, nopt, idx), &w)); NCL_TRY(R.unify(idx, w));
+  }
+  *block_rank = t->rank - after;
+  for (int k = 0; k < *block_rank; k++) block[k] = t->dims[k];
+  return NCL_OK;
+}
+
+static int build_einsum_nest(const ncl_einsum_desc* d, const ncl_tensor* in, ncl_tensor* out, unsigned flags,
+                             Stager& st, Nest* nest) {
+  if (d->n_in < 0 || d->n_in > NCL_MAX_OPERANDS || d->n_out < 1 || d->n_out > NCL_MAX_OPERANDS) return set_error(NCL_ERR_INVALID, "bad operand counts");
+  if (d->n_iter < 0 || d->n_iter > NCL_MAX_INDEX) return set_error(NCL_ERR_INVALID, "bad n_iter");
+  Resolver R; memset(R.set, 0, sizeof R.set); memset(R.q, 0, sizeof R.q);
+  int has_block[2 * NCL_MAX_OPERANDS] = {0}, brank[2 * NCL_MAX_OPERANDS] = {0};
+  int64_t block[2 * NCL_MAX_OPERANDS][NCL_MAX_RANK];
+  int nb = 0;
+  for (int i = 0; i < d->n_in; i++) {
+    if (d->in_rank[i] < 0 || d->in_rank[i] > NCL_MAX_RANK) return set_error(NCL_ERR_INVALID, "bad spec rank");
+    NCL_TRY(resolve_array(R, &in[i], d->in_spec[i], d->in_rank[i], d->in_opt[i], d->in_nopt[i], "input", i, &has_block[i], &brank[i], block[i]));
+    if (has_block[i]) nb++;
+  }
+  if (nb) {
+    // plan-broadcast (src/3einsum.lisp:378-425); the generated code indexes the plan rows by array
+    // position (common-lisp.lisp:219-223), which is only right with one output and `-` on every input
+    if (nb != d->n_in || d->n_out != 1) return set_error(NCL_ERR_UNSUPPORTED, "`-` needs every input to carry it and exactly one output (reference quirk)");
+    R.bc = true; R.M = 0;
+    for (int i = 0; i < d->n_in; i++) if (brank[i] > R.M) R.M = brank[i];
+    for (int r = 0; r <= d->n_in; r++) for (int j = 0; j < NCL_MAX_RANK; j++) { R.plan_dim[r][j] = 1; R.plan_step[r][j] = 1; }
+    for (int i = 0; i < d->n_in; i++) for (int k = 0; k < brank[i]; k++) R.plan_dim[i + 1][R.M - brank[i] + k] = block[i][k];
+    for (int i = 0; i < d->n_in; i++) for (int j = 0; j < R.M; j++) if (R.plan_dim[i + 1][j] > R.plan_dim[0][j]) R.plan_dim[0][j] = R.plan_dim[i + 1][j];
+    for (int i = 0; i < d->n_in; i++) for (int j = 0; j < R.M; j++)
+      if (!(R.plan_dim[i + 1][j] == 1 || R.plan_dim[i + 1][j] == R.plan_dim[0][j])) return set_error(NCL_ERR_SHAPE, "broadcast blocks are incompatible on axis %d", j);
+    for (int r = 0; r <= d->n_in; r++) for (int j = R.M - 2; j >= 0; j--) R.plan_step[r][j] = R.plan_dim[r][j + 1] * R.plan_step[r][j + 1];
+  }
+  for (int o = 0; o < d->n_out; o++) {
+    if (d->out_rank[o] < 0 || d->out_rank[o] > NCL_MAX_RANK) return set_error(NCL_ERR_INVALID, "bad spec rank");
+    for (int k = 0; k < d->out_rank[o]; k++) { int idx = d->out_spec[o][k]; if (idx >= 0 && (idx >= QMAX || !R.set[idx])) return set_error(NCL_ERR_INVALID, "output index %d is not bound by any input", idx); }
+    int hb, br; int64_t bl[NCL_MAX_RANK];
+    NCL_TRY(resolve_array(R, &out[o], d->out_spec[o], d->out_rank[o], d->out_opt[o], d->out_nopt[o], "output", o, &hb, &br, bl));
+    has_block[NCL_MAX_OPERANDS + o] = hb;
+    if (hb) {                                                   // %output-result-shapes-match-p :431-437
+      if (!R.bc || br != R.M) return set_error(NCL_ERR_SHAPE, "The output shapes do not match the broadcast plan!");
+      for (int k = 0; k < br; k++) if (bl[k] != R.plan_dim[0][k]) return set_error(NCL_ERR_SHAPE, "The output shapes do not match the broadcast plan!");
+    }
+  }
+  // loops
+  nest->nloops = 0; nest->n_in = d->n_in; nest->n_out = d->n_out; nest->fresh = (flags & NCL_OUT_FRESH) != 0;
+  for (int i = 0; i < d->n_in; i++) operand_from(&in[i], st, &nest->in[i]);
+  for (int o = 0; o < d->n_out; o++) operand_from(&out[o], st, &nest->out[o]);
+  auto later_product = [&](const int32_t* spec, int rank, int ax) { int64_t ss = 1; for (int r2 = ax + 1; r2 < rank; r2++) ss *= R.q[spec[r2]]; return ss; };
+  for (int it = 0; it < d->n_iter; it++) {
+    int idx = d->iter[it];
+    if (idx >= 0) {
+      if (idx >= QMAX || !R.set[idx]) return set_error(NCL_ERR_INVALID, "iter index %d is unbound", idx);
+      if (nest->nloops >= NCL_MAX_LOOPS) return set_error(NCL_ERR_UNSUPPORTED, "too many loops");
+      int L = nest->nloops++;
+      nest->extent[L] = R.q[idx];
+      auto one = [&](Operand& op, const int32_t* spec, int rank, const ncl_iter_opt* opts, int nopt) {
+        int64_t stride = 0; bool first = true;
+        for (int ax = 0; ax < rank; ax++) {
+          if (spec[ax] != idx) continue;
+          const ncl_iter_opt* o = find_opt(opts, nopt, ax);              // (assoc a-axis a-opts): by AXIS POSITION, common-lisp.lisp:129
+          int64_t start = (o && o->has_start) ? o->start : 0, step = o ? o->step : 1;
+          int64_t ss = later_product(spec, rank, ax);                    // Π of the later ?dims, :132-134
+          stride += step * ss;                                            // repeated index: strides add up, :137-143
+          if (first) { op.offset += start * ss; first = false; }
+        }
+        op.stride[L] = stride;
+      };
+      for (int o = 0; o < d->n_out; o++) one(nest->out[o], d->out_spec[o], d->out_rank[o], d->out_opt[o], d->out_nopt[o]);
+      for (int i = 0; i < d->n_in; i++) one(nest->in[i], d->in_spec[i], d->in_rank[i], d->in_opt[i], d->in_nopt[i]);
+    } else if (idx == -1) {
+      if (!R.bc) return set_error(NCL_ERR_INVALID, "iter-specs has `-` but no input does");
+      for (int j = 0; j < R.M; j++) {                                     // %einsum-broadcast: rec over the plan axes, :176-224
+        if (nest->nloops >= NCL_MAX_LOOPS) return set_error(NCL_ERR_UNSUPPORTED, "too many loops");
+        int L = nest->nloops++;
+        nest->extent[L] = R.plan_dim[0][j];
+        for (int o = 0; o < d->n_out; o++)
+          nest->out[o].stride[L] = has_block[NCL_MAX_OPERANDS + o] ? R.plan_step[0][j] * later_product(d->out_spec[o], d->out_rank[o], 0) : 0;
+        for (int i = 0; i < d->n_in; i++)
+          nest->in[i].stride[L] = (has_block[i] && R.plan_dim[i + 1][j] != 1) ? R.plan_step[i + 1][j] * later_product(d->in_spec[i], d->in_rank[i], 0) : 0;
+      }
+    } else return set_error(NCL_ERR_INVALID, "bad iter entry %d", idx);
+  }
+  // transforms
+  int in_dt[NCL_MAX_OPERANDS], out_dt[NCL_MAX_OPERANDS];
+  for (int i = 0; i < d->n_in; i++) in_dt[i] = in[i].dtype;
+  for (int o = 0; o < d->n_out; o++) out_dt[o] = out[o].dtype;
+  for (int o = 0; o < d->n_out; o++) NCL_TRY(type_expr(&d->transform[o], in_dt, d->n_in, out_dt, d->n_out, o, &nest->transform[o]));
+  return NCL_OK;
+}
+
+// ---- small expression builders ------------------------------------------------------------------------
+static void x_leaf(ncl_expr* e, int op, int a) { ncl_expr_node& n = e->node[e->n++]; memset(&n, 0, sizeof n); n.op = op; n.a = a; }
+static void x_const_i(ncl_expr* e, int64_t v) { ncl_expr_node& n = e->node[e->n++]; memset(&n, 0, sizeof n); n.op = NCL_X_CONST_INT; n.ival = v; }
+static void x_op(ncl_expr* e, int op, int a, int b) { ncl_expr_node& n = e->node[e->n++]; memset(&n, 0, sizeof n); n.op = op; n.a = a; n.b = b; }
+
+static int broadcast_nest(const ncl_tensor* args, int n_args, ncl_tensor* r, Stager& st, Nest* nest) {
+  // broadcast-p / broadcast-result-shape, src/4numeric.lisp:174-199: right-aligned, dims equal or 1
+  int rr = r->rank;
+  for (int a = 0; a < n_args; a++) if (args[a].rank > rr) return set_error(NCL_ERR_SHAPE, "result rank %d is smaller than an argument's rank %d", rr, args[a].rank);
+  nest->nloops = rr; nest->n_in = n_args; nest->n_out = 1; nest->fresh = true;
+  operand_from(r, st, &nest->out[0]);
+  int64_t rs[NCL_MAX_RANK]; rowmajor_strides(r, rs);
+  for (int k = 0; k < rr; k++) { nest->extent[k] = r->dims[k]; nest->out[0].stride[k] = rs[k]; }
+  for (int a = 0; a < n_args; a++) {
+    operand_from(&args[a], st, &nest->in[a]);
+    int64_t as[NCL_MAX_RANK]; rowmajor_strides(&args[a], as);
+    for (int k = 0; k < rr; k++) {
+      int ai = args[a].rank - rr + k;
+      int64_t da = ai >= 0 ? args[a].dims[ai] : 1;
+      if (!(da == r->dims[k] || da == 1))
+        return set_error(NCL_ERR_SHAPE, "Given arrays have incompatible shape for broadcasting: axis %d has %lld vs result %lld", k, (long long)da, (long long)r->dims[k]);
+      nest->in[a].stride[k] = (ai >= 0 && da != 1) ? as[ai] : 0;
+    }
+  }
+  for (int k = 0; k < rr; k++) {                                 // result dim must be the max of the arguments'
+    int64_t mx = 1; for (int a = 0; a < n_args; a++) { int ai = args[a].rank - rr + k; if (ai >= 0 && args[a].dims[ai] > mx) mx = args[a].dims[ai]; }
+    bool any_zero = false; for (int a = 0; a < n_args; a++) { int ai = args[a].rank - rr + k; if (ai >= 0 && args[a].dims[ai] == 0) any_zero = true; }
+    if (!any_zero && r->dims[k] != mx) return set_error(NCL_ERR_SHAPE, "result axis %d is %lld, expected %lld", k, (long long)r->dims[k], (long long)mx);
+  }
+  return NCL_OK;
+}
+
+template <class F> static int with_staging(const ncl_tensor* in, int n_in, ncl_tensor* out, int n_out, bool upload_outputs, F body) {
+  Stager st;
+  st.plan(in, n_in, false); st.plan(out, n_out, true);
+  NCL_TRY(st.upload(upload_outputs));
+  NCL_TRY(body(st));
+  return st.download();
+}
+
+extern "C" {
+
+int ncl_einsum(const ncl_einsum_desc* desc, const ncl_tensor* in, int n_in, ncl_tensor* out, int n_out, unsigned flags) {
+  LOCK; NEED_INIT;
+  if (!desc) return set_error(NCL_ERR_INVALID, "desc is NULL");
+  if (n_in != desc->n_in || n_out != desc->n_out) return set_error(NCL_ERR_INVALID, "einsum: %d/%d arrays for %d/%d specs", n_in, n_out, desc->n_in, desc->n_out);
+  for (int i = 0; i < n_in; i++) NCL_TRY(check_tensor(&in[i], "input"));
+  for (int o = 0; o < n_out; o++) NCL_TRY(check_tensor(&out[o], "output"));
+  return with_staging(in, n_in, out, n_out, !(flags & NCL_OUT_FRESH), [&](Stager& st) {
+    Nest* nest = new Nest;
+    int rc = build_einsum_nest(desc, in, out, flags, st, nest);
+    if (rc == NCL_OK) rc = run_nest(*nest);
+    delete nest; return rc;
+  });
+}
+
+int ncl_fold(int op, int use_identity, const ncl_tensor* args, int n, ncl_tensor* r) {
+  LOCK; NEED_INIT;
+  if (n < 1 || n > NCL_MAX_OPERANDS) return set_error(NCL_ERR_INVALID, "ncl_fold: %d arguments", n);
+  if (op < 0 || op >= NCL_OP_BINARY_END) return set_error(NCL_ERR_INVALID, "ncl_fold: op %d is not binary", op);
+  if (n == 1 && !use_identity) return set_error(NCL_ERR_INVALID, "ncl_fold: one argument needs the identity");
+  for (int i = 0; i < n; i++) NCL_TRY(check_tensor(&args[i], "argument"));
+  NCL_TRY(check_tensor(r, "result"));
+  return with_staging(args, n, r, 1, false, [&](Stager& st) {
+    Nest* nest = new Nest;
+    int rc = broadcast_nest(args, n, r, st, nest);
+    if (rc == NCL_OK) {
+      ncl_expr e; e.n = 0;
+      int acc;
+      if (use_identity) {                                        // (reduce ... :initial-value ident), src/4numeric.lisp:528-542
+        int64_t ident = (op == NCL_OP_MUL || op == NCL_OP_DIV) ? 1 : 0;
+        x_const_i(&e, ident); x_leaf(&e, NCL_X_INPUT, 1); x_op(&e, op, 0, 1); acc = 2;
+      } else { x_leaf(&e, NCL_X_INPUT, 1); acc = 0; }
+      for (int i = 1; i < n; i++) { x_leaf(&e, NCL_X_INPUT, i + 1); x_op(&e, op, acc, e.n - 1); acc = e.n - 1; }
+      int in_dt[NCL_MAX_OPERANDS]; for (int i = 0; i < n; i++) in_dt[i] = args[i].dtype;
+      int out_dt = r->dtype;
+      rc = type_expr(&e, in_dt, n, &out_dt, 1, 0, &nest->transform[0]);
+    }
+    if (rc == NCL_OK) rc = run_nest(*nest);
+    delete nest; return rc;
+  });
+}
+
+int ncl_broadcast(int op, const ncl_tensor* x, const ncl_tensor* y, ncl_tensor* r) {
+  if (!x || !y) return set_error(NCL_ERR_INVALID, "NULL argument");
+  ncl_tensor args[2] = {*x, *y};
+  return ncl_fold(op, 0, args, 2, r);
+}
+
+int ncl_map(const ncl_expr* fn, const ncl_tensor* args, int n, ncl_tensor* r) {
+  LOCK; NEED_INIT;
+  if (!fn || n < 1 || n > NCL_MAX_OPERANDS) return set_error(NCL_ERR_INVALID, "ncl_map: bad arguments");
+  for (int i = 0; i < n; i++) NCL_TRY(check_tensor(&args[i], "argument"));
+  NCL_TRY(check_tensor(r, "result"));
+  for (int i = 0; i < n; i++) {                                  // (assert (equal (shape sequence) result-shape)), :41-44
+    if (args[i].rank != r->rank) return set_error(NCL_ERR_SHAPE, "map-array: shapes differ");
+    for (int k = 0; k < r->rank; k++) if (args[i].dims[k] != r->dims[k]) return set_error(NCL_ERR_SHAPE, "map-array: shapes differ");
+  }
+  return with_staging(args, n, r, 1, false, [&](Stager& st) {
+    Nest* nest = new Nest;
+    int rc = broadcast_nest(args, n, r, st, nest);
+    int in_dt[NCL_MAX_OPERANDS]; for (int i = 0; i < n; i++) in_dt[i] = args[i].dtype;
+    int out_dt = r->dtype;
+    if (rc == NCL_OK) rc = type_expr(fn, in_dt, n, &out_dt, 1, 0, &nest->transform[0]);
+    if (rc == NCL_OK && expr_reads_output(nest->transform[0])) rc = set_error(NCL_ERR_INVALID, "map function may not read @");
+    if (rc == NCL_OK) rc = run_nest(*nest);
+    delete nest; return rc;
+  });
+}
+
+int ncl_convert(const ncl_tensor* a, ncl_tensor* r) {
+  ncl_expr e; e.n = 0; x_leaf(&e, NCL_X_INPUT, 1);
+  return ncl_map(&e, a, 1, r);
+}
+
+int ncl_reduce(int op, const ncl_tensor* a, const int* axes, int n_axes, ncl_tensor* r, unsigned flags) {
+  LOCK; NEED_INIT;
+  NCL_TRY(check_tensor(a, "array")); NCL_TRY(check_tensor(r, "result"));
+  if (!(op == NCL_OP_ADD || op == NCL_OP_MUL || op == NCL_OP_MAX || op == NCL_OP_MIN))
+    return set_error(NCL_ERR_UNSUPPORTED, "reduce-array function must be one of + * max min on the CUDA backend");
+  bool summed[NCL_MAX_RANK] = {false};
+  if (n_axes == 0) for (int k = 0; k < a->rank; k++) summed[k] = true;            // axes nil -> all, src/5reduce.lisp:48-55
+  for (int k = 0; k < n_axes; k++) { if (axes[k] < 0 || axes[k] >= a->rank) return set_error(NCL_ERR_INVALID, "bad axis %d", axes[k]); summed[axes[k]] = true; }
+  int rk = 0;
+  for (int ax = 0; ax < a->rank; ax++) if (!summed[ax]) { if (rk >= r->rank || r->dims[rk] != a->dims[ax]) return set_error(NCL_ERR_SHAPE, "reduce: result shape mismatch"); rk++; }
+  if (rk != r->rank) return set_error(NCL_ERR_SHAPE, "reduce: result rank %d, expected %d", r->rank, rk);
+  bool fresh = (flags & NCL_OUT_FRESH) != 0;
+  return with_staging(a, 1, r, 1, !fresh, [&](Stager& st) {
+    Nest* nest = new Nest;
+    nest->nloops = a->rank; nest->n_in = 1; nest->n_out = 1; nest->fresh = fresh;
+    operand_from(a, st, &nest->in[0]); operand_from(r, st, &nest->out[0]);
+    int64_t as[NCL_MAX_RANK], rs[NCL_MAX_RANK]; rowmajor_strides(a, as); rowmajor_strides(r, rs);
+    int k = 0;
+    for (int ax = 0; ax < a->rank; ax++) {                       // loops nest in axis order 0..rank-1, :82-87
+      nest->extent[ax] = a->dims[ax]; nest->in[0].stride[ax] = as[ax];
+      nest->out[0].stride[ax] = summed[ax] ? 0 : rs[k++];
+    }
+    if (fresh) {                                                  // identities of sum / prod / amax / amin, :103-126 + 1constants.lisp
+      nest->has_identity = true;
+      const DtInfo& d = g_dt[r->dtype];
+      if (op == NCL_OP_ADD) { nest->ident_i = 0; nest->ident_f = 0.0; }
+      else if (op == NCL_OP_MUL) { nest->ident_i = 1; nest->ident_f = 1.0; }
+      else {
+        bool mx = op == NCL_OP_MAX;
+        if (d.cls == CLS_F) nest->ident_f = mx ? -3.4028234663852886e38 : 3.4028234663852886e38;
+        else if (d.cls == CLS_D) nest->ident_f = mx ? -1.7976931348623157e308 : 1.7976931348623157e308;
+        else {
+          int64_t lo, hi;
+          if (d.is_signed) { lo = d.value_bits >= 64 ? INT64_MIN : -((int64_t)1 << (d.value_bits - 1)); hi = d.value_bits >= 64 ? INT64_MAX : ((int64_t)1 << (d.value_bits - 1)) - 1; }
+          else { lo = 0; hi = d.value_bits >= 63 ? INT64_MAX : ((int64_t)1 << d.value_bits) - 1; }
+          nest->ident_i = mx ? lo : hi;
+        }
+      }
+    }
+    ncl_expr e; e.n = 0; x_leaf(&e, NCL_X_OUTPUT, 1); x_leaf(&e, NCL_X_INPUT, 1); x_op(&e, op, 0, 1);   // (funcall fn r a)
+    int in_dt = a->dtype, out_dt = r->dtype;
+    int rc = type_expr(&e, &in_dt, 1, &out_dt, 1, 0, &nest->transform[0]);
+    if (rc == NCL_OK) rc = run_nest(*nest);
+    delete nest; return rc;
+  });
+}
+
+int ncl_fill(ncl_tensor* t, int value_is_float, int64_t ival, double fval) {
+  LOCK; NEED_INIT; NCL_TRY(check_tensor(t, "tensor"));
+  if (!t->buf) return set_error(NCL_ERR_UNSUPPORTED, "ncl_fill works on device-resident tensors");
+  return fill_const(t->buf->ptr, t->dtype, t->elem_offset, total_elems(t), value_is_float != 0, ival, fval);
+}
+int ncl_fill_random(ncl_tensor* t, uint64_t seed, int dist, double lo, double hi) {
+  LOCK; NEED_INIT; NCL_TRY(check_tensor(t, "tensor"));
+  if (!t->buf) return set_error(NCL_ERR_UNSUPPORTED, "ncl_fill_random works on device-resident tensors");
+  return fill_random(t->buf->ptr, t->dtype, t->elem_offset, total_elems(t), seed, dist, lo, hi);
+}
+
+}  // extern "C"

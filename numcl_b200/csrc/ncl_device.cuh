@@ -1,0 +1,216 @@
+// ncl_device.cuh -- device-side building blocks shared by all kernel families.
+//
+// Semantics are Common Lisp's as SBCL x86-64 compiles them:
+//   * float + - * / are IEEE round-to-nearest-even, each op rounded separately: the __f*_rn /
+//     __d*_rn intrinsics are never contracted into FMA, and the library is built without
+//     --use_fast_math / -ftz so denormals survive;
+//   * integer ops are exact in 64-bit two's complement and wrapped only by the final %coerce
+//     (src/1type.lisp:673-694), which commutes with + - * (mod 2^w);
+//   * (max a b) = (if (>= a b) a b), (min a b) = (if (<= a b) a b).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ncl_internal.h"
+
+// ---- load / store kinds: what the host canonicalises an ncl_dtype to ---------------------------
+enum LoadKind { LK_U8 = 0, LK_S8, LK_U16, LK_S16, LK_U32, LK_S32, LK_W64, LK_T64, LK_F32, LK_F64,
+                LK_P1, LK_P2, LK_P4 };
+enum StoreKind { SK_8 = 0, SK_16, SK_32, SK_64, SK_F32, SK_F64, SK_P1, SK_P2, SK_P4 };
+
+struct StoreSpec { int kind; int shift; unsigned long long mask; };   // int: slot = (v & mask) << shift
+
+__host__ __device__ inline int lk_bits(int lk) {
+  switch (lk) { case LK_U8: case LK_S8: return 8; case LK_U16: case LK_S16: return 16;
+    case LK_U32: case LK_S32: case LK_F32: return 32; case LK_W64: case LK_T64: case LK_F64: return 64;
+    case LK_P1: return 1; case LK_P2: return 2; default: return 4; }
+}
+__host__ __device__ inline int sk_bits(int sk) {
+  switch (sk) { case SK_8: return 8; case SK_16: return 16; case SK_32: case SK_F32: return 32;
+    case SK_64: case SK_F64: return 64; case SK_P1: return 1; case SK_P2: return 2; default: return 4; }
+}
+inline int dtype_load_kind(int dt) {
+  switch (dt) {
+    case NCL_BIT: return LK_P1; case NCL_UB2: return LK_P2; case NCL_UB4: return LK_P4;
+    case NCL_UB7: case NCL_UB8: return LK_U8; case NCL_UB15: case NCL_UB16: return LK_U16;
+    case NCL_UB31: case NCL_UB32: return LK_U32; case NCL_UB62: case NCL_FIXNUM: return LK_T64;
+    case NCL_UB63: case NCL_UB64: case NCL_SB64: return LK_W64;   // ub64 >= 2^63 reads as negative: documented limit
+    case NCL_SB8: return LK_S8; case NCL_SB16: return LK_S16; case NCL_SB32: return LK_S32;
+    case NCL_F32: return LK_F32; default: return LK_F64;
+  }
+}
+inline StoreSpec dtype_store_spec(int dt) {
+  const DtInfo& d = g_dt[dt];
+  StoreSpec s; s.shift = d.tagged ? 1 : 0;
+  s.mask = (d.is_signed || d.value_bits >= 64) ? ~0ull : ((1ull << d.value_bits) - 1);
+  if (d.cls == CLS_F) s.kind = SK_F32; else if (d.cls == CLS_D) s.kind = SK_F64;
+  else switch (d.slot_bits) { case 1: s.kind = SK_P1; break; case 2: s.kind = SK_P2; break; case 4: s.kind = SK_P4; break;
+    case 8: s.kind = SK_8; break; case 16: s.kind = SK_16; break; case 32: s.kind = SK_32; break; default: s.kind = SK_64; }
+  return s;
+}
+
+// ---- class value types -----------------------------------------------------------------------------
+template <int C> struct ClsT;
+template <> struct ClsT<CLS_I> { typedef long long T; };
+template <> struct ClsT<CLS_F> { typedef float T; };
+template <> struct ClsT<CLS_D> { typedef double T; };
+
+template <class T> __device__ __forceinline__ T from_i64(long long v);
+template <> __device__ __forceinline__ long long from_i64<long long>(long long v) { return v; }
+template <> __device__ __forceinline__ float from_i64<float>(long long v) { return __ll2float_rn(v); }
+template <> __device__ __forceinline__ double from_i64<double>(long long v) { return __ll2double_rn(v); }
+template <class T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ long long from_f32<long long>(float v) { return (long long)v; }   // unreachable by typing
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ double from_f32<double>(float v) { return (double)v; }
+template <class T> __device__ __forceinline__ T from_f64(double v);
+template <> __device__ __forceinline__ long long from_f64<long long>(double v) { return (long long)v; }   // unreachable
+template <> __device__ __forceinline__ float from_f64<float>(double v) { return __double2float_rn(v); }   // unreachable
+template <> __device__ __forceinline__ double from_f64<double>(double v) { return v; }
+
+// scalar element load of any kind, converted to class type T (the int->float conversion is the
+// contagion CL performs before a mixed op: round-to-nearest)
+template <class T>
+__device__ __forceinline__ T load_scalar(const char* base, long long idx, int lk) {
+  switch (lk) {
+    case LK_U8:  return from_i64<T>(((const unsigned char*)base)[idx]);
+    case LK_S8:  return from_i64<T>(((const signed char*)base)[idx]);
+    case LK_U16: return from_i64<T>(((const unsigned short*)base)[idx]);
+    case LK_S16: return from_i64<T>(((const short*)base)[idx]);
+    case LK_U32: return from_i64<T>(((const unsigned int*)base)[idx]);
+    case LK_S32: return from_i64<T>(((const int*)base)[idx]);
+    case LK_W64: return from_i64<T>(((const long long*)base)[idx]);
+    case LK_T64: return from_i64<T>(((const long long*)base)[idx] >> 1);
+    case LK_F32: return from_f32<T>(((const float*)base)[idx]);
+    case LK_F64: return from_f64<T>(((const double*)base)[idx]);
+    case LK_P1:  return from_i64<T>((((const unsigned char*)base)[idx >> 3] >> (idx & 7)) & 1);
+    case LK_P2:  return from_i64<T>((((const unsigned char*)base)[idx >> 2] >> ((idx & 3) * 2)) & 3);
+    default:     return from_i64<T>((((const unsigned char*)base)[idx >> 1] >> ((idx & 1) * 4)) & 15);
+  }
+}
+
+// %coerce of a class value into an integer slot (src/1type.lisp:673-694): (round x) half-even, then wrap.
+__device__ __forceinline__ long long round_to_i64(long long v) { return v; }
+__device__ __forceinline__ long long round_to_i64(float v) { return __float2ll_rn(v); }
+__device__ __forceinline__ long long round_to_i64(double v) { return __double2ll_rn(v); }
+__device__ __forceinline__ float to_f32(long long v) { return __ll2float_rn(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(double v) { return __double2float_rn(v); }
+__device__ __forceinline__ double to_f64(long long v) { return __ll2double_rn(v); }
+__device__ __forceinline__ double to_f64(float v) { return (double)v; }
+__device__ __forceinline__ double to_f64(double v) { return v; }
+
+// scalar store; sub-byte slots are updated with word atomics so neighbouring threads may own
+// neighbouring fields of the same word.
+template <class T>
+__device__ __forceinline__ void store_scalar(char* base, long long idx, StoreSpec s, T v) {
+  if (s.kind == SK_F32) { ((float*)base)[idx] = to_f32(v); return; }
+  if (s.kind == SK_F64) { ((double*)base)[idx] = to_f64(v); return; }
+  unsigned long long w = (((unsigned long long)round_to_i64(v)) & s.mask) << s.shift;
+  switch (s.kind) {
+    case SK_8:  ((unsigned char*)base)[idx] = (unsigned char)w; break;
+    case SK_16: ((unsigned short*)base)[idx] = (unsigned short)w; break;
+    case SK_32: ((unsigned int*)base)[idx] = (unsigned int)w; break;
+    case SK_64: ((unsigned long long*)base)[idx] = w; break;
+    default: {
+      int bits = (s.kind == SK_P1) ? 1 : (s.kind == SK_P2) ? 2 : 4;
+      long long bitpos = idx * bits;
+      unsigned int* word = (unsigned int*)base + (bitpos >> 5);
+      int sh = (int)(bitpos & 31);
+      unsigned int m = ((1u << bits) - 1u) << sh;
+      atomicAnd(word, ~m);
+      atomicOr(word, ((unsigned int)w << sh) & m);
+    }
+  }
+}
+
+// ---- correctly rounded (coerce (/ n d) 'single-float) for integers n, d ----------------------------
+// CL produces the exact ratio and rounds once.  Fast path: both exactly representable in double;
+// quotient rounded toward zero, made odd when inexact (sticky), then one RN to 24 bits.
+__device__ inline float ratio_to_f32(long long n, long long d) {
+  if (d == 0) return (n > 0) ? __int_as_float(0x7f800000) : (n < 0 ? __int_as_float(0xff800000) : __int_as_float(0x7fc00000));
+  const long long lim = 1ll << 53;
+  if (n > -lim && n < lim && d > -lim && d < lim) {
+    double dn = (double)n, dd = (double)d;
+    double q = __ddiv_rz(dn, dd);
+    double r = __fma_rn(q, dd, -dn);                 // exact residual: q*d - n
+    if (r != 0.0) q = __longlong_as_double(__double_as_longlong(q) | 1ll);
+    return __double2float_rn(q);
+  }
+  // slow path: binary long division for 26 quotient bits + sticky
+  bool neg = (n < 0) != (d < 0);
+  unsigned long long un = n < 0 ? (unsigned long long)(-(n + 1)) + 1ull : (unsigned long long)n;
+  unsigned long long ud = d < 0 ? (unsigned long long)(-(d + 1)) + 1ull : (unsigned long long)d;
+  if (un == 0) return 0.0f;
+  int bn = 64 - __clzll(un), bd = 64 - __clzll(ud);
+  int s = 26 + bd - bn;                              // quotient of (un << s) / ud has 26 or 27 bits
+  // compute floor(un * 2^s / ud) by restoring division on the bits of un followed by s zero bits
+  unsigned long long rem = 0, q = 0;
+  int total = bn + (s > 0 ? s : 0);
+  for (int i = 0; i < total; i++) {
+    int bit = (i < bn) ? (int)((un >> (bn - 1 - i)) & 1ull) : 0;
+    bool carry = (rem >> 63) != 0;                   // rem < ud <= 2^64-1; doubling may overflow
+    rem = (rem << 1) | (unsigned long long)bit;
+    q <<= 1;
+    if (carry || rem >= ud) { rem -= ud; q |= 1ull; }
+  }
+  int exp2 = -(s > 0 ? s : 0);
+  if (s < 0) {                                        // drop -s low quotient bits into sticky
+    unsigned long long low = q & ((1ull << (-s)) - 1ull);
+    q >>= (-s); if (low) rem = 1; exp2 = -s;
+  }
+  if (rem) q |= 1ull;
+  float f = __ull2float_rn(q);
+  f = ldexpf(f, exp2);
+  return neg ? -f : f;
+}
+
+// ---- scalar functions of the whitelist, per class ------------------------------------------------------
+template <class T> struct Ops;
+template <> struct Ops<long long> {
+  typedef long long T; typedef unsigned long long U;
+  static __device__ __forceinline__ T add(T a, T b) { return (T)((U)a + (U)b); }
+  static __device__ __forceinline__ T sub(T a, T b) { return (T)((U)a - (U)b); }
+  static __device__ __forceinline__ T mul(T a, T b) { return (T)((U)a * (U)b); }
+  static __device__ __forceinline__ T mx(T a, T b) { return a >= b ? a : b; }
+  static __device__ __forceinline__ T mn(T a, T b) { return a <= b ? a : b; }
+  static __device__ __forceinline__ T neg(T a) { return (T)(0ull - (U)a); }
+  static __device__ __forceinline__ T abs_(T a) { return a < 0 ? neg(a) : a; }
+  static __device__ __forceinline__ T zero() { return 0; }
+};
+template <> struct Ops<float> {
+  typedef float T;
+  static __device__ __forceinline__ T add(T a, T b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ T sub(T a, T b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ T mul(T a, T b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ T div(T a, T b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ T mx(T a, T b) { return a >= b ? a : b; }
+  static __device__ __forceinline__ T mn(T a, T b) { return a <= b ? a : b; }
+  static __device__ __forceinline__ T neg(T a) { return -a; }
+  static __device__ __forceinline__ T abs_(T a) { return fabsf(a); }
+  static __device__ __forceinline__ T zero() { return 0.0f; }
+};
+template <> struct Ops<double> {
+  typedef double T;
+  static __device__ __forceinline__ T add(T a, T b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ T sub(T a, T b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ T mul(T a, T b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ T div(T a, T b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ T mx(T a, T b) { return a >= b ? a : b; }
+  static __device__ __forceinline__ T mn(T a, T b) { return a <= b ? a : b; }
+  static __device__ __forceinline__ T neg(T a) { return -a; }
+  static __device__ __forceinline__ T abs_(T a) { return fabs(a); }
+  static __device__ __forceinline__ T zero() { return 0.0; }
+};
+
+// counter-based generator shared bit for bit with oracle/numcl_oracle.c (nco_fill_random)
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// warp / block reductions
+template <class T, class F> __device__ __forceinline__ T warp_reduce(T v, F f) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = f(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

@@ -1,0 +1,98 @@
+// ncl_internal.h -- host-side internals of libnumcl_cuda.so (not part of the ABI).
+//
+// Every public entry point lowers its arguments to ONE intermediate form, the Nest: the loop
+// nest the reference's generators would have emitted (loops outer->inner with extents, one
+// element-stride per array per loop, which loops are contracted for each output, and a
+// statically typed TRANSFORM expression).  The planner (ncl_plan.cu) then picks a kernel family:
+//   K1/K2/K6 elementwise (k_elementwise.cu), K3 reductions (k_reduce.cu), K5 permutation
+//   (k_transpose.cu), K4 contractions (k_gemm_*.cu), or the reference-ordered generic nest kernel
+//   (k_generic.cu) for everything else on the whitelist.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/numcl_cuda.h"
+
+#define NCL_MAX_LOOPS 24          // einsum indices + expanded broadcast-block axes
+#define NCL_MAX_ARR   9           // arrays in one nest: outputs + inputs
+
+// ---- value classes: the three machine representations a Lisp real takes inside a kernel -------
+enum NclCls { CLS_I = 0, CLS_F = 1, CLS_D = 2, CLS_R = 3 /* ratio: int/int before %coerce */ };
+
+struct DtInfo { int slot_bits, value_bits, is_signed, tagged, cls; const char* name; };
+extern const DtInfo g_dt[NCL_DTYPE_COUNT];
+
+// ---- statically typed expression ----------------------------------------------------------------
+struct XNode { int op, a, b, cls; int64_t ival; double fval; };
+struct Expr {
+  int n = 0;
+  XNode node[NCL_MAX_EXPR];
+};
+
+struct Operand {
+  char*   base = nullptr;          // device pointer to the base vector
+  int     dtype = 0;
+  int64_t offset = 0;              // element offset of the nest origin
+  int64_t stride[NCL_MAX_LOOPS];   // elements, per loop
+  int64_t n_storage = 0;           // elements addressable in the base vector (bounds check)
+};
+
+struct Nest {
+  int nloops = 0;
+  int64_t extent[NCL_MAX_LOOPS];
+  int n_in = 0, n_out = 0;
+  Operand in[NCL_MAX_OPERANDS];
+  Operand out[NCL_MAX_OPERANDS];
+  Expr transform[NCL_MAX_OPERANDS];     // one per output, typed
+  bool fresh = false;                   // outputs are not read: they start from zero / identity
+  // for reductions through ncl_reduce with fresh=true the accumulator starts from this identity
+  bool has_identity = false; int64_t ident_i = 0; double ident_f = 0;
+};
+
+// ---- context ------------------------------------------------------------------------------------
+struct ncl_buf { void* ptr; size_t bytes; int dev_slot; bool owned; };
+
+struct Context {
+  bool inited = false;
+  int ndev = 0; int devs[16];
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  const char* last_kernel = "";
+  bool force_generic = false;
+  // scratch: reduction partials, GEMM operand splits, host staging
+  void* scratch = nullptr; size_t scratch_bytes = 0;
+  void* scratch2 = nullptr; size_t scratch2_bytes = 0;
+  unsigned int* ticket = nullptr;       // zero-initialised counters for last-block reductions
+  void* consts = nullptr;               // [sb64 0][sb64 1]
+  void* pinned = nullptr; size_t pinned_bytes = 0;
+};
+Context& ctx();
+int  set_error(int code, const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+#define NCL_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+#define NCL_TRY(call) do { int r__ = (call); if (r__ != NCL_OK) return r__; } while (0)
+int  ensure_scratch(size_t bytes);       // ctx().scratch  >= bytes
+int  ensure_scratch2(size_t bytes);
+inline void note_launch(const char* name, int n = 1) { ctx().launches += n; ctx().last_kernel = name; }
+
+// ---- expression helpers (ncl_plan.cu) -------------------------------------------------------------
+int  type_expr(const ncl_expr* src, const int* in_dtype, int n_in, const int* out_dtype, int n_out,
+               int self_out, Expr* dst);
+bool expr_reads_output(const Expr& e);
+
+// ---- kernel families; each returns NCL_OK, an error, or NCL_ERR_UNSUPPORTED to fall through ------
+int launch_generic(const Nest& n);                        // k_generic.cu
+int try_elementwise(const Nest& n);                       // k_elementwise.cu
+int try_reduce(const Nest& n);                            // k_reduce.cu
+int try_transpose(const Nest& n);                         // k_transpose.cu
+int try_gemm(const Nest& n);                              // k_gemm.cu (dispatch to f64/tf32/simt)
+int run_nest(Nest& n);                                    // ncl_plan.cu: canonicalise + dispatch
+
+int fill_const(void* base, int dtype, int64_t offset, int64_t n, bool is_float, int64_t iv, double fv);   // k_fill.cu
+int fill_random(void* base, int dtype, int64_t offset, int64_t n, uint64_t seed, int dist, double lo, double hi);
+
+// full reduce of a contiguous array into a float64/int64 partial on the device (k_reduce.cu):
+// used by ncl_reduce_all_sharded before the all-reduce.
+int reduce_all_to_partial(int op, const Operand& a, int64_t n, void* partial8);
+int finalize_partial(int op, const void* partial8, int cls, Operand& r, bool fresh);

@@ -1,0 +1,106 @@
+// ncl_plan.cu -- static typing of TRANSFORM expressions and kernel-family dispatch.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "ncl_internal.h"
+
+const DtInfo g_dt[NCL_DTYPE_COUNT] = {
+  {1, 1, 0, 0, CLS_I, "bit"},   {2, 2, 0, 0, CLS_I, "ub2"},   {4, 4, 0, 0, CLS_I, "ub4"},
+  {8, 7, 0, 0, CLS_I, "ub7"},   {8, 8, 0, 0, CLS_I, "ub8"},   {16, 15, 0, 0, CLS_I, "ub15"},
+  {16, 16, 0, 0, CLS_I, "ub16"}, {32, 31, 0, 0, CLS_I, "ub31"}, {32, 32, 0, 0, CLS_I, "ub32"},
+  {64, 62, 0, 1, CLS_I, "ub62"}, {64, 63, 0, 0, CLS_I, "ub63"}, {64, 64, 0, 0, CLS_I, "ub64"},
+  {8, 8, 1, 0, CLS_I, "sb8"},   {16, 16, 1, 0, CLS_I, "sb16"}, {32, 32, 1, 0, CLS_I, "sb32"},
+  {64, 63, 1, 1, CLS_I, "fixnum"}, {64, 64, 1, 0, CLS_I, "sb64"},
+  {32, 0, 1, 0, CLS_F, "f32"},  {64, 0, 1, 0, CLS_D, "f64"},
+};
+
+// ---- expression typing: Common Lisp contagion, decided once on the host ----------------------------
+static int contagion(int a, int b) {
+  if (a == CLS_D || b == CLS_D) return CLS_D;
+  if (a == CLS_F || b == CLS_F) return CLS_F;
+  if (a == CLS_R || b == CLS_R) return CLS_R;
+  return CLS_I;
+}
+
+int type_expr(const ncl_expr* src, const int* in_dtype, int n_in, const int* out_dtype, int n_out,
+              int self_out, Expr* dst) {
+  if (src->n <= 0 || src->n > NCL_MAX_EXPR) return set_error(NCL_ERR_INVALID, "transform has %d nodes", src->n);
+  dst->n = src->n;
+  for (int k = 0; k < src->n; k++) {
+    const ncl_expr_node& s = src->node[k]; XNode& x = dst->node[k];
+    x.op = s.op; x.a = s.a; x.b = s.b; x.ival = s.ival; x.fval = s.fval; x.cls = CLS_I;
+    switch (s.op) {
+      case NCL_X_INPUT:
+        if (s.a < 1 || s.a > n_in) return set_error(NCL_ERR_INVALID, "transform refers to $%d but there are %d inputs", s.a, n_in);
+        x.cls = g_dt[in_dtype[s.a - 1]].cls; break;
+      case NCL_X_OUTPUT:
+        if (s.a < 1 || s.a > n_out) return set_error(NCL_ERR_INVALID, "transform refers to @%d but there are %d outputs", s.a, n_out);
+        x.cls = g_dt[out_dtype[s.a - 1]].cls; break;
+      case NCL_X_CONST_INT: x.cls = CLS_I; break;
+      case NCL_X_CONST_F32: x.cls = CLS_F; break;
+      case NCL_X_CONST_F64: x.cls = CLS_D; break;
+      default: {
+        if (s.a < 0 || s.a >= k) return set_error(NCL_ERR_INVALID, "transform node %d: bad child", k);
+        int ca = dst->node[s.a].cls;
+        if (s.op >= 0 && s.op < NCL_OP_BINARY_END) {
+          if (s.b < 0 || s.b >= k) return set_error(NCL_ERR_INVALID, "transform node %d: bad child", k);
+          int cb = dst->node[s.b].cls;
+          int cc = contagion(ca, cb);
+          if (cc == CLS_R) return set_error(NCL_ERR_UNSUPPORTED, "arithmetic on an unreduced integer ratio is outside the CUDA whitelist");
+          if (s.op >= NCL_OP_LOGAND) { if (ca != CLS_I || cb != CLS_I) return set_error(NCL_ERR_INVALID, "bitwise function on non-integers"); x.cls = CLS_I; }
+          else if (s.op >= NCL_OP_EQ) x.cls = CLS_I;
+          else if (s.op == NCL_OP_DIV && cc == CLS_I) x.cls = CLS_R;
+          else x.cls = cc;
+        } else {
+          switch (s.op) {
+            case NCL_OP_NEG: case NCL_OP_ABS: case NCL_OP_SQUARE: case NCL_OP_SIGNUM: case NCL_OP_IDENTITY:
+              if (ca == CLS_R && s.op != NCL_OP_IDENTITY) return set_error(NCL_ERR_UNSUPPORTED, "function of an integer ratio");
+              x.cls = ca; break;
+            case NCL_OP_LOGNOT:
+              if (ca != CLS_I) return set_error(NCL_ERR_INVALID, "lognot of a non-integer"); x.cls = CLS_I; break;
+            case NCL_OP_SQRT: case NCL_OP_EXP: case NCL_OP_LOG: case NCL_OP_SIN: case NCL_OP_COS: case NCL_OP_TAN: case NCL_OP_TANH:
+              x.cls = (ca == CLS_D) ? CLS_D : CLS_F; break;      // float substitution: rational -> single-float
+            default:
+              return set_error(NCL_ERR_UNSUPPORTED, "function code %d is not on the CUDA whitelist", s.op);
+          }
+        }
+      }
+    }
+  }
+  (void)self_out;
+  return NCL_OK;
+}
+
+bool expr_reads_output(const Expr& e) {
+  for (int k = 0; k < e.n; k++) if (e.node[k].op == NCL_X_OUTPUT) return true;
+  return false;
+}
+
+// ---- dispatch -------------------------------------------------------------------------------------
+static int check_bounds(const Operand& a, const Nest& n, const char* what, int idx) {
+  long long lo = a.offset, hi = a.offset;
+  for (int l = 0; l < n.nloops; l++) {
+    if (n.extent[l] <= 0) return NCL_OK;       // empty nest touches nothing
+    long long span = (n.extent[l] - 1) * a.stride[l];
+    if (span > 0) hi += span; else lo += span;
+  }
+  if (lo < 0 || hi >= a.n_storage)
+    return set_error(NCL_ERR_SHAPE, "%s %d would be addressed at elements %lld..%lld of a %lld-element base vector",
+                     what, idx, lo, hi, (long long)a.n_storage);
+  return NCL_OK;
+}
+
+int run_nest(Nest& n) {
+  for (int i = 0; i < n.n_in; i++) NCL_TRY(check_bounds(n.in[i], n, "input", i));
+  for (int o = 0; o < n.n_out; o++) NCL_TRY(check_bounds(n.out[o], n, "output", o));
+  bool empty = false;
+  for (int l = 0; l < n.nloops; l++) if (n.extent[l] == 0) empty = true;
+  if (!ctx().force_generic && !empty) {
+    int rc;
+    if ((rc = try_gemm(n)) != NCL_ERR_UNSUPPORTED) return rc;
+    if ((rc = try_reduce(n)) != NCL_ERR_UNSUPPORTED) return rc;
+    if ((rc = try_transpose(n)) != NCL_ERR_UNSUPPORTED) return rc;
+    if ((rc = try_elementwise(n)) != NCL_ERR_UNSUPPORTED) return rc;
+  }
+  return launch_generic(n);
+}
