@@ -1,0 +1,171 @@
+// k_elementwise.cu -- host side of K1/K2/K6: expression pattern -> functor, nest -> EwParams.
+// The kernel template and its documentation live in k_elementwise.cuh; the instantiations are
+// split by value class over k_ew_*.cu.
+#include "k_elementwise.cuh"
+
+// ---- host: expression pattern -> functor, nest -> EwParams ---------------------------------------------------
+
+
+struct Slot { int kind; int idx; };   // kind 0: input idx (0-based); 1: the output (read); 2: const 0; 3: const 1
+struct Match { int shape; int n; Slot s[3]; };
+
+static bool leaf_slot(const Expr& e, int k, int self_out, Slot* s) {
+  const XNode& x = e.node[k];
+  if (x.op == NCL_X_INPUT) { s->kind = 0; s->idx = x.a - 1; return true; }
+  if (x.op == NCL_X_OUTPUT && x.a == self_out + 1) { s->kind = 1; s->idx = 0; return true; }
+  if (x.op == NCL_X_CONST_INT && (x.ival == 0 || x.ival == 1)) { s->kind = 2 + (int)x.ival; s->idx = 0; return true; }
+  return false;
+}
+static bool is_const(const Expr& e, int k, long long v) { return e.node[k].op == NCL_X_CONST_INT && e.node[k].ival == v; }
+static bool is_self_out(const Expr& e, int k, int self_out) { return e.node[k].op == NCL_X_OUTPUT && e.node[k].a == self_out + 1; }
+
+static int bin_shape(int op) {
+  switch (op) { case NCL_OP_ADD: return S_ADD; case NCL_OP_SUB: return S_SUB; case NCL_OP_MUL: return S_MUL; case NCL_OP_DIV: return S_DIV;
+    case NCL_OP_MAX: return S_MAX; case NCL_OP_MIN: return S_MIN; case NCL_OP_EQ: return S_EQ; case NCL_OP_NE: return S_NE;
+    case NCL_OP_LE: return S_LE; case NCL_OP_GE: return S_GE; case NCL_OP_LT: return S_LT; case NCL_OP_GT: return S_GT;
+    case NCL_OP_LOGAND: return S_AND; case NCL_OP_LOGIOR: return S_IOR; case NCL_OP_LOGXOR: return S_XOR; default: return S_NONE; }
+}
+static int un_shape(int op) {
+  switch (op) { case NCL_OP_NEG: return S_NEG; case NCL_OP_ABS: return S_ABS; case NCL_OP_SQUARE: return S_SQUARE; case NCL_OP_LOGNOT: return S_NOT;
+    case NCL_OP_IDENTITY: return S_COPY; case NCL_OP_SQRT: return S_SQRT; case NCL_OP_EXP: return S_EXP; case NCL_OP_LOG: return S_LOG;
+    case NCL_OP_SIN: return S_SIN; case NCL_OP_COS: return S_COS; case NCL_OP_TAN: return S_TAN; case NCL_OP_TANH: return S_TANH; default: return S_NONE; }
+}
+
+static bool match_expr(const Expr& e, int self_out, bool fresh, Match* m) {
+  int r = e.n - 1; const XNode& root = e.node[r];
+  m->n = 0; m->shape = S_NONE;
+  if (root.op == NCL_X_INPUT) { m->shape = S_COPY; m->n = 1; return leaf_slot(e, r, self_out, &m->s[0]); }
+  if (root.op >= 0 && root.op < NCL_OP_BINARY_END) {
+    const XNode& A = e.node[root.a]; const XNode& B = e.node[root.b];
+    // (+ (+ 0 $a) $b) / (* (* 1 $a) $b): identity-seeded folds of numcl:+ and numcl:*
+    if ((root.op == NCL_OP_ADD || root.op == NCL_OP_MUL) && A.op == root.op && is_const(e, A.a, root.op == NCL_OP_ADD ? 0 : 1)
+        && e.node[A.b].op == NCL_X_INPUT && B.op == NCL_X_INPUT) {
+      m->shape = root.op == NCL_OP_ADD ? S_ADD0 : S_MUL; m->n = 2;
+      return leaf_slot(e, A.b, self_out, &m->s[0]) && leaf_slot(e, root.b, self_out, &m->s[1]);
+    }
+    // default transform (+ @1 (* $a $b)) / (+ @1 $a)
+    if (root.op == NCL_OP_ADD && is_self_out(e, root.a, self_out)) {
+      if (B.op == NCL_OP_MUL && e.node[B.a].op == NCL_X_INPUT && e.node[B.b].op == NCL_X_INPUT) {
+        if (fresh) { m->shape = S_MUL0; m->n = 2; return leaf_slot(e, B.a, self_out, &m->s[0]) && leaf_slot(e, B.b, self_out, &m->s[1]); }
+        m->shape = S_ADDMUL; m->n = 3;
+        return leaf_slot(e, root.a, self_out, &m->s[0]) && leaf_slot(e, B.a, self_out, &m->s[1]) && leaf_slot(e, B.b, self_out, &m->s[2]);
+      }
+      if (B.op == NCL_X_INPUT && fresh) { m->shape = S_ADD0U; m->n = 1; return leaf_slot(e, root.b, self_out, &m->s[0]); }
+    }
+    Slot a, b;
+    if (leaf_slot(e, root.a, self_out, &a) && leaf_slot(e, root.b, self_out, &b)) {
+      if ((a.kind == 1 || b.kind == 1) && fresh) return false;      // reads a fresh output: let the generic path define it
+      m->shape = bin_shape(root.op); m->n = 2; m->s[0] = a; m->s[1] = b; return m->shape != S_NONE;
+    }
+    return false;
+  }
+  if (root.op >= NCL_OP_NEG && root.op <= NCL_OP_SIGNUM) {
+    Slot a; if (!leaf_slot(e, root.a, self_out, &a) || a.kind != 0) return false;
+    m->shape = un_shape(root.op); m->n = 1; m->s[0] = a; return m->shape != S_NONE;
+  }
+  return false;
+}
+
+int try_elementwise(const Nest& n) {
+  if (n.n_out != 1) return NCL_ERR_UNSUPPORTED;
+  const Operand& out = n.out[0];
+  for (int l = 0; l < n.nloops; l++) if (n.extent[l] > 1 && out.stride[l] == 0) return NCL_ERR_UNSUPPORTED;   // contracted loop
+  Match m;
+  if (!match_expr(n.transform[0], 0, n.fresh, &m)) return NCL_ERR_UNSUPPORTED;
+  Context& c = ctx();
+  // operands
+  Operand ops[3]; int ocls[3];
+  for (int k = 0; k < m.n; k++) {
+    const Slot& s = m.s[k];
+    if (s.kind == 0) { if (s.idx < 0 || s.idx >= n.n_in) return NCL_ERR_UNSUPPORTED; ops[k] = n.in[s.idx]; }
+    else if (s.kind == 1) ops[k] = out;
+    else { memset(&ops[k], 0, sizeof(Operand)); ops[k].base = (char*)c.consts; ops[k].dtype = NCL_SB64; ops[k].offset = s.kind - 2; ops[k].n_storage = 8; }
+    ocls[k] = g_dt[ops[k].dtype].cls;
+  }
+  int cc = CLS_I;
+  for (int k = 0; k < m.n; k++) if (ocls[k] > cc) cc = ocls[k];
+  if ((m.shape == S_ADDMUL || m.shape == S_MUL0) && m.n >= 2) {
+    // a*b must be computed in the operands' own class before it meets the accumulator
+    int pc = ocls[m.n - 1] > ocls[m.n - 2] ? ocls[m.n - 1] : ocls[m.n - 2];
+    if (pc != cc && !(ocls[m.n - 1] == ocls[m.n - 2])) return NCL_ERR_UNSUPPORTED;
+    if (ocls[m.n - 1] != cc || ocls[m.n - 2] != cc) return NCL_ERR_UNSUPPORTED;
+  }
+  int out_cls = g_dt[out.dtype].cls;
+  int shape = m.shape;
+  bool is_cmp = shape >= S_EQ && shape <= S_GT;
+  if (shape == S_DIV && cc == CLS_I) { shape = S_IDIV; if (out_cls != CLS_F) return NCL_ERR_UNSUPPORTED; }
+  else if (is_cmp) { if (out_cls != CLS_I) return NCL_ERR_UNSUPPORTED; }
+  else if (out_cls != cc) return NCL_ERR_UNSUPPORTED;                    // float->int rounding stores etc.: generic path
+  if ((shape >= S_SQRT && shape <= S_TANH) && cc == CLS_I) return NCL_ERR_UNSUPPORTED;   // typed F by the host: inputs convert first
+
+  // ---- collapse the nest: drop unit loops, sort by output stride, merge ----
+  struct D { long long ext; long long st[4]; };
+  D d[NCL_MAX_LOOPS]; int nd = 0;
+  for (int l = 0; l < n.nloops; l++) {
+    if (n.extent[l] == 1) continue;
+    d[nd].ext = n.extent[l]; d[nd].st[0] = out.stride[l];
+    for (int k = 0; k < 3; k++) d[nd].st[1 + k] = k < m.n ? ops[k].stride[l] : 0;
+    nd++;
+  }
+  for (int i = 1; i < nd; i++) { D t = d[i]; int j = i - 1; while (j >= 0 && llabs(d[j].st[0]) < llabs(t.st[0])) { d[j + 1] = d[j]; j--; } d[j + 1] = t; }
+  for (int i = nd - 1; i > 0; i--) {             // merge d[i-1] (outer) with d[i] (inner)
+    bool ok = true;
+    for (int k = 0; k < 4; k++) if (d[i - 1].st[k] != d[i].st[k] * d[i].ext) ok = false;
+    if (ok) { d[i - 1].ext *= d[i].ext; for (int k = 0; k < 4; k++) d[i - 1].st[k] = d[i].st[k]; for (int j = i; j + 1 < nd; j++) d[j] = d[j + 1]; nd--; }
+  }
+  if (nd == 0) { d[0].ext = 1; for (int k = 0; k < 4; k++) d[0].st[k] = 0; d[0].st[0] = 1; nd = 1; }
+  if (nd > EW_MAXD) return NCL_ERR_UNSUPPORTED;
+  if (d[nd - 1].st[0] != 1) return NCL_ERR_UNSUPPORTED;
+  for (int i = 0; i < nd; i++) if (d[i].ext > 0xffffffffLL) return NCL_ERR_UNSUPPORTED;
+
+  StoreSpec sk = dtype_store_spec(out.dtype);
+  int out_bits = g_dt[out.dtype].slot_bits;
+  int E = out_bits >= 8 ? 128 / out_bits : 32;
+  if (out_bits < 8 && out_bits != 1) return NCL_ERR_UNSUPPORTED;           // ub2/ub4 outputs: generic path
+  // vector eligibility: inner extent divisible, every vectorised operand 16B-aligned at every row start
+  const D& in0 = d[nd - 1];
+  auto aligned = [&](int e) {
+    if (in0.ext % e) return false;
+    auto chk = [&](const Operand& o, int slot, int k) {
+      int sb = g_dt[o.dtype].slot_bits;
+      if (sb < 8 && slot != 0) return false;            // packed inputs are read element-wise (E = 1)
+      long long bytes = (long long)e * sb / 8; long long a = bytes >= 16 ? 16 : bytes;
+      if (a <= 1) return true;
+      if (((uintptr_t)o.base + (o.offset * sb) / 8) % a) return false;
+      if ((o.offset * sb) % 8) return false;
+      for (int i = 0; i < nd - 1; i++) if (((d[i].st[k] * sb) / 8) % a || (d[i].st[k] * sb) % 8) return false;
+      (void)slot; return true;
+    };
+    if (!chk(out, 0, 0)) return false;
+    for (int k = 0; k < m.n; k++) { if (in0.st[1 + k] == 1) { if (!chk(ops[k], 1 + k, 1 + k)) return false; } else if (in0.st[1 + k] != 0) return false; }
+    return true;
+  };
+  if (E > 1 && !aligned(E)) { if (out_bits < 8) return NCL_ERR_UNSUPPORTED; E = 1; }
+
+  EwKernel kfn = nullptr;
+  if (shape == S_IDIV) kfn = ew_pick_idiv(E);
+  else if (is_cmp) { if (E != 32) return NCL_ERR_UNSUPPORTED; kfn = ew_pick_cmp(shape, cc); }
+  else if (cc == CLS_F) kfn = ew_pick_f32(shape, E);
+  else if (cc == CLS_D) kfn = ew_pick_f64(shape, E);
+  else kfn = ew_pick_int(shape, E);
+  if (!kfn) return NCL_ERR_UNSUPPORTED;
+
+  EwParams p; memset(&p, 0, sizeof p);
+  p.nd = nd; p.n_in = m.n; p.sk = sk;
+  for (int i = 0; i < nd; i++) {                      // reverse: params dim 0 is the innermost
+    const D& s = d[nd - 1 - i];
+    p.ext[i] = (unsigned)(i == 0 ? s.ext / E : s.ext);
+    for (int k = 0; k < 4; k++) p.st[k][i] = s.st[k];
+  }
+  p.base[0] = out.base; p.off[0] = out.offset;
+  for (int k = 0; k < m.n; k++) { p.base[1 + k] = ops[k].base; p.off[1 + k] = ops[k].offset; p.lk[k] = dtype_load_kind(ops[k].dtype); }
+  unsigned long long nch = 1; for (int i = 0; i < nd; i++) nch *= p.ext[i];
+  p.nchunks = nch;
+  if (nch == 0) return NCL_OK;
+  int U = E == 32 ? 1 : 4;
+  unsigned long long blocks = (nch + (unsigned long long)EW_THREADS * U - 1) / ((unsigned long long)EW_THREADS * U);
+  if (blocks > 0x7fffffffull) return NCL_ERR_UNSUPPORTED;
+  kfn<<<(unsigned)blocks, EW_THREADS, 0, c.stream>>>(p);
+  note_launch(E == 1 ? "bcast_scalar" : "bcast_vec");
+  return cuda_fail(cudaGetLastError(), "ew_kernel");
+}

@@ -1,0 +1,165 @@
+// k_elementwise.cu -- K1/K2/K6: broadcast elementwise and same-shape map kernels.
+//
+// Replaces the inner loops of broadcast-core (src/4numeric.lisp:228-293), map-array-into
+// (:78-113) and einsum nests without a contracted index (common-lisp.lisp:108-224, e.g.
+// `(- - -> (+ $1 $2) -> -)`, `(i j -> ij)`, `(i -> (f $1) -> i)`).
+//
+// HBM-bound: no reuse, so no shared memory.  Layout of the work:
+//   * the nest is collapsed on the host to <= 6 dims with the output's contiguous dim innermost;
+//   * one thread handles a CHUNK of E consecutive output elements = 16 bytes of output
+//     (E = 16 / sizeof(out slot); E = 32 when the output is a packed bit array), so stores are
+//     full 128-bit vectors and every warp store instruction writes 512 contiguous bytes;
+//   * inputs whose innermost stride is 1 are read with the matching vector load, inputs whose
+//     innermost stride is 0 (numpy broadcasting: `b` of (numcl:+ a b), scalars) are read once and
+//     splat -- stride-0 indexing, not a materialised copy;
+//   * each thread issues U independent chunks' loads before any math for memory-level
+//     parallelism; grid = chunks / (256*U).
+// Arithmetic follows ncl_device.cuh (IEEE rn, no FMA contraction, CL max/min, exact integers).
+#pragma once
+#include "ncl_device.cuh"
+
+#define EW_MAXD 6
+#define EW_THREADS 256
+
+struct EwParams {
+  int nd, n_in;
+  unsigned ext[EW_MAXD];               // ext[0] counts chunks, ext[d>0] elements
+  long long st[4][EW_MAXD];            // [0] = output, [1..3] = inputs; elements
+  char* base[4]; long long off[4];
+  int lk[3]; StoreSpec sk;
+  unsigned long long nchunks;
+};
+
+enum Shape { S_NONE = 0, S_ADD, S_SUB, S_MUL, S_DIV, S_MAX, S_MIN, S_ADD0, S_MUL0, S_IDIV, S_EQ, S_NE, S_LE, S_GE, S_LT, S_GT,
+             S_AND, S_IOR, S_XOR, S_COPY, S_ADD0U, S_NEG, S_ABS, S_SQUARE, S_NOT, S_SQRT, S_EXP, S_LOG, S_SIN, S_COS, S_TAN, S_TANH,
+             S_ADDMUL };
+
+// ---- functors ------------------------------------------------------------------------------------------------
+template <class T> struct FnAdd { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return Ops<T>::add(a, b); } };
+template <class T> struct FnSub { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return Ops<T>::sub(a, b); } };
+template <class T> struct FnMul { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return Ops<T>::mul(a, b); } };
+template <class T> struct FnDiv { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return Ops<T>::div(a, b); } };
+template <class T> struct FnMax { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return Ops<T>::mx(a, b); } };
+template <class T> struct FnMin { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return Ops<T>::mn(a, b); } };
+// (+ (+ 0 a) b): the identity-seeded fold of numcl:+ (src/4numeric.lisp:528); 0.0 + -0.0 = +0.0
+template <class T> struct FnAdd0 { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return Ops<T>::add(Ops<T>::add(Ops<T>::zero(), a), b); } };
+// (+ 0 (* a b)): default transform into a fresh output
+template <class T> struct FnMul0 { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return Ops<T>::add(Ops<T>::zero(), Ops<T>::mul(a, b)); } };
+struct FnIDiv { typedef float R; static __device__ __forceinline__ float f(long long a, long long b) { return ratio_to_f32(a, b); } };
+template <class T> struct FnEq { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a == b; } };
+template <class T> struct FnNe { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a != b; } };
+template <class T> struct FnLe { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a <= b; } };
+template <class T> struct FnGe { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a >= b; } };
+template <class T> struct FnLt { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a < b; } };
+template <class T> struct FnGt { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a > b; } };
+struct FnAnd { typedef long long R; static __device__ __forceinline__ long long f(long long a, long long b) { return a & b; } };
+struct FnIor { typedef long long R; static __device__ __forceinline__ long long f(long long a, long long b) { return a | b; } };
+struct FnXor { typedef long long R; static __device__ __forceinline__ long long f(long long a, long long b) { return a ^ b; } };
+// unary
+template <class T> struct FnCopy { typedef T R; static __device__ __forceinline__ T f(T a) { return a; } };
+template <class T> struct FnAdd0U { typedef T R; static __device__ __forceinline__ T f(T a) { return Ops<T>::add(Ops<T>::zero(), a); } };
+template <class T> struct FnNeg { typedef T R; static __device__ __forceinline__ T f(T a) { return Ops<T>::neg(a); } };
+template <class T> struct FnAbs { typedef T R; static __device__ __forceinline__ T f(T a) { return Ops<T>::abs_(a); } };
+template <class T> struct FnSquare { typedef T R; static __device__ __forceinline__ T f(T a) { return Ops<T>::mul(a, a); } };
+struct FnNot { typedef long long R; static __device__ __forceinline__ long long f(long long a) { return ~a; } };
+template <class T> struct FnSqrt;
+template <> struct FnSqrt<float> { typedef float R; static __device__ __forceinline__ float f(float a) { return __fsqrt_rn(a); } };
+template <> struct FnSqrt<double> { typedef double R; static __device__ __forceinline__ double f(double a) { return __dsqrt_rn(a); } };
+#define LIBM_FN(NAME, FF, DF) template <class T> struct NAME; \
+  template <> struct NAME<float> { typedef float R; static __device__ __forceinline__ float f(float a) { return FF(a); } }; \
+  template <> struct NAME<double> { typedef double R; static __device__ __forceinline__ double f(double a) { return DF(a); } };
+LIBM_FN(FnExp, expf, exp) LIBM_FN(FnLog, logf, log) LIBM_FN(FnSin, sinf, sin) LIBM_FN(FnCos, cosf, cos)
+LIBM_FN(FnTan, tanf, tan) LIBM_FN(FnTanh, tanhf, tanh)
+// ternary: a + b*c, each op rounded on its own (the einsum leaf with a live accumulator)
+template <class T> struct FnAddMul { typedef T R; static __device__ __forceinline__ T f(T a, T b, T c) { return Ops<T>::add(a, Ops<T>::mul(b, c)); } };
+
+// ---- the kernel -------------------------------------------------------------------------------------------------
+template <class TI, class F, int NIN, int E, int U>
+__global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ EwParams p) {
+  typedef typename F::R TO;
+  const unsigned long long tile = (unsigned long long)blockIdx.x * (EW_THREADS * U);
+  long long offs[U][4]; bool valid[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    unsigned long long q = tile + (unsigned long long)u * EW_THREADS + threadIdx.x;
+    valid[u] = q < p.nchunks;
+    unsigned long long q0, r;
+    if (p.nchunks <= 0xffffffffull) { unsigned int qq = (unsigned int)q; q0 = qq % p.ext[0]; r = qq / p.ext[0]; }
+    else { q0 = q % p.ext[0]; r = q / p.ext[0]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) offs[u][k] = p.off[k] + (long long)q0 * E * p.st[k][0];
+    for (int d = 1; d < p.nd; d++) {
+      unsigned long long c;
+      if (p.nchunks <= 0xffffffffull) { unsigned int rr = (unsigned int)r; c = rr % p.ext[d]; r = rr / p.ext[d]; }
+      else { c = r % p.ext[d]; r = r / p.ext[d]; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) offs[u][k] += (long long)c * p.st[k][d];
+    }
+  }
+  TI x[U][NIN][E];
+#pragma unroll
+  for (int u = 0; u < U; u++)
+    if (valid[u]) {
+#pragma unroll
+      for (int k = 0; k < NIN; k++) load_elems<TI, E>(p.base[1 + k], offs[u][1 + k], p.lk[k], p.st[1 + k][0] != 0, x[u][k]);
+    }
+#pragma unroll
+  for (int u = 0; u < U; u++)
+    if (valid[u]) {
+      TO y[E];
+#pragma unroll
+      for (int i = 0; i < E; i++) {
+        if constexpr (NIN == 1) y[i] = F::f(x[u][0][i]);
+        else if constexpr (NIN == 2) y[i] = F::f(x[u][0][i], x[u][1][i]);
+        else y[i] = F::f(x[u][0][i], x[u][1][i], x[u][2][i]);
+      }
+      store_elems<TO, E>(p.base[0], offs[u][0], p.sk, y);
+    }
+}
+
+typedef void (*EwKernel)(const EwParams);
+template <class TI, class F, int NIN, int E> static EwKernel kern() { return (EwKernel)ew_kernel<TI, F, NIN, E, (E == 1 ? 4 : (E == 32 ? 1 : 4))>; }
+template <int E> static int ufactor() { return E == 1 ? 4 : (E == 32 ? 1 : 4); }
+
+template <class T, int E> static EwKernel pick_arith(int shape) {     // T-class in, T-class out
+  switch (shape) {
+    case S_ADD: return kern<T, FnAdd<T>, 2, E>(); case S_SUB: return kern<T, FnSub<T>, 2, E>(); case S_MUL: return kern<T, FnMul<T>, 2, E>();
+    case S_MAX: return kern<T, FnMax<T>, 2, E>(); case S_MIN: return kern<T, FnMin<T>, 2, E>(); case S_ADD0: return kern<T, FnAdd0<T>, 2, E>();
+    case S_MUL0: return kern<T, FnMul0<T>, 2, E>(); case S_COPY: return kern<T, FnCopy<T>, 1, E>(); case S_ADD0U: return kern<T, FnAdd0U<T>, 1, E>();
+    case S_NEG: return kern<T, FnNeg<T>, 1, E>(); case S_ABS: return kern<T, FnAbs<T>, 1, E>(); case S_SQUARE: return kern<T, FnSquare<T>, 1, E>();
+    case S_ADDMUL: return kern<T, FnAddMul<T>, 3, E>();
+    default: return nullptr;
+  }
+}
+template <class T, int E> static EwKernel pick_float(int shape) {
+  if (EwKernel k = pick_arith<T, E>(shape)) return k;
+  switch (shape) {
+    case S_DIV: return kern<T, FnDiv<T>, 2, E>(); case S_SQRT: return kern<T, FnSqrt<T>, 1, E>(); case S_EXP: return kern<T, FnExp<T>, 1, E>();
+    case S_LOG: return kern<T, FnLog<T>, 1, E>(); case S_SIN: return kern<T, FnSin<T>, 1, E>(); case S_COS: return kern<T, FnCos<T>, 1, E>();
+    case S_TAN: return kern<T, FnTan<T>, 1, E>(); case S_TANH: return kern<T, FnTanh<T>, 1, E>();
+    default: return nullptr;
+  }
+}
+template <int E> static EwKernel pick_int(int shape) {
+  if (EwKernel k = pick_arith<long long, E>(shape)) return k;
+  switch (shape) {
+    case S_AND: return kern<long long, FnAnd, 2, E>(); case S_IOR: return kern<long long, FnIor, 2, E>(); case S_XOR: return kern<long long, FnXor, 2, E>();
+    case S_NOT: return kern<long long, FnNot, 1, E>();
+    default: return nullptr;
+  }
+}
+template <class T, int E> static EwKernel pick_cmp(int shape) {
+  switch (shape) {
+    case S_EQ: return kern<T, FnEq<T>, 2, E>(); case S_NE: return kern<T, FnNe<T>, 2, E>(); case S_LE: return kern<T, FnLe<T>, 2, E>();
+    case S_GE: return kern<T, FnGe<T>, 2, E>(); case S_LT: return kern<T, FnLt<T>, 2, E>(); case S_GT: return kern<T, FnGt<T>, 2, E>();
+    default: return nullptr;
+  }
+}
+
+
+// one translation unit per value class keeps the build parallel
+EwKernel ew_pick_f32(int shape, int E);
+EwKernel ew_pick_f64(int shape, int E);
+EwKernel ew_pick_int(int shape, int E);
+EwKernel ew_pick_cmp(int shape, int cls);
+EwKernel ew_pick_idiv(int E);

@@ -1,0 +1,102 @@
+// k_transpose.cu -- K5: N-D axis permutation, the einsum nests with no contracted index whose input
+// and output are contiguous along DIFFERENT loops: `transpose` (src/4linear-algebra2.lisp:38-45),
+// `(ij -> ji)`, `(abcd -> dbca)` (config C5b).
+//
+// HBM-bound copy.  A direct kernel would be coalesced on one side only, so the (input-contiguous,
+// output-contiguous) plane is tiled through shared memory: a 256-thread block reads a TILE x TILE
+// tile along the input's contiguous loop (each warp instruction covers 256 contiguous bytes for
+// 8-byte elements), parks it in a padded tile (row pitch TILE+1: conflict-free for both phases) and
+// writes it out along the output's contiguous loop.  All remaining loops are batch coordinates
+// decoded from the block index.  Elements pass through the value class, so element-type
+// changing copies (ub8 -> fixnum: an integer einsum output is always fixnum, 3einsum.lisp:517-518)
+// and the `0 + x` of the default transform into a fresh output (-0.0 -> +0.0) cost nothing extra.
+#include "ncl_device.cuh"
+
+#define TR_MAXB 6
+
+struct TrParams {
+  const char* in; char* out; long long in_off, out_off; int lk; StoreSpec sk;
+  long long ni, no;                 // extents of the input-contiguous loop (i) and output-contiguous loop (o)
+  long long in_so, out_si;          // input stride along o, output stride along i (elements)
+  int nb; long long bext[TR_MAXB], bin[TR_MAXB], bout[TR_MAXB];
+  long long tiles_i, tiles_o;
+  int add_zero;                     // default transform into a fresh output: x + 0
+};
+
+template <class T, int TILE>
+__global__ void __launch_bounds__(256) transpose_kernel(const __grid_constant__ TrParams p) {
+  __shared__ T tile[TILE][TILE + 1];
+  long long b = blockIdx.x;
+  long long ti = b % p.tiles_i; b /= p.tiles_i;
+  long long to = b % p.tiles_o; b /= p.tiles_o;
+  long long ibase = p.in_off, obase = p.out_off;
+  for (int k = p.nb - 1; k >= 0; k--) { long long c = b % p.bext[k]; b /= p.bext[k]; ibase += c * p.bin[k]; obase += c * p.bout[k]; }
+  const int tx = threadIdx.x % TILE, ty = threadIdx.x / TILE;
+  constexpr int ROWS = 256 / TILE;
+  long long i0 = ti * TILE, o0 = to * TILE;
+  // load: rows of the tile run along o, threads along i (input-contiguous)
+#pragma unroll
+  for (int r = 0; r < TILE; r += ROWS) {
+    long long o = o0 + r + ty, i = i0 + tx;
+    if (o < p.no && i < p.ni) tile[r + ty][tx] = load_scalar<T>(p.in, ibase + o * p.in_so + i, p.lk);
+  }
+  __syncthreads();
+  // store: rows run along i, threads along o (output-contiguous)
+#pragma unroll
+  for (int r = 0; r < TILE; r += ROWS) {
+    long long i = i0 + r + ty, o = o0 + tx;
+    if (i < p.ni && o < p.no) {
+      T v = tile[tx][r + ty];
+      if (p.add_zero) v = Ops<T>::add(Ops<T>::zero(), v);
+      store_scalar<T>(p.out, obase + i * p.out_si + o, p.sk, v);
+    }
+  }
+}
+
+int try_transpose(const Nest& n) {
+  if (n.n_out != 1 || n.n_in != 1) return NCL_ERR_UNSUPPORTED;
+  const Operand& in = n.in[0]; const Operand& out = n.out[0];
+  const Expr& e = n.transform[0];
+  int add_zero = 0;
+  const XNode& root = e.node[e.n - 1];
+  if (root.op == NCL_X_INPUT) add_zero = 0;
+  else if (e.n == 3 && root.op == NCL_OP_ADD && e.node[root.a].op == NCL_X_OUTPUT && e.node[root.b].op == NCL_X_INPUT && n.fresh) add_zero = 1;
+  else return NCL_ERR_UNSUPPORTED;
+  int icls = g_dt[in.dtype].cls, ocls = g_dt[out.dtype].cls;
+  if (icls != ocls) return NCL_ERR_UNSUPPORTED;
+  if (g_dt[in.dtype].slot_bits < 8 || g_dt[out.dtype].slot_bits < 8) return NCL_ERR_UNSUPPORTED;
+  int li = -1, lo = -1;
+  for (int l = 0; l < n.nloops; l++) {
+    if (n.extent[l] == 1) continue;
+    if (out.stride[l] == 0 || in.stride[l] == 0) return NCL_ERR_UNSUPPORTED;   // contraction or broadcast
+    if (in.stride[l] == 1 && li < 0) li = l;
+    if (out.stride[l] == 1 && lo < 0) lo = l;
+  }
+  if (li < 0 || lo < 0 || li == lo) return NCL_ERR_UNSUPPORTED;
+  TrParams p; memset(&p, 0, sizeof p);
+  p.in = in.base; p.out = out.base; p.in_off = in.offset; p.out_off = out.offset;
+  p.lk = dtype_load_kind(in.dtype); p.sk = dtype_store_spec(out.dtype); p.add_zero = add_zero;
+  p.ni = n.extent[li]; p.no = n.extent[lo]; p.in_so = in.stride[lo]; p.out_si = out.stride[li];
+  // batch loops, merged where both sides allow
+  struct B { long long ext, sin, sout; } bd[NCL_MAX_LOOPS]; int nb = 0;
+  for (int l = 0; l < n.nloops; l++) { if (l == li || l == lo || n.extent[l] == 1) continue; bd[nb++] = {n.extent[l], in.stride[l], out.stride[l]}; }
+  for (int i = 1; i < nb; i++) { B t = bd[i]; int j = i - 1; while (j >= 0 && bd[j].sout < t.sout) { bd[j + 1] = bd[j]; j--; } bd[j + 1] = t; }
+  for (int i = nb - 1; i > 0; i--)
+    if (bd[i - 1].sin == bd[i].sin * bd[i].ext && bd[i - 1].sout == bd[i].sout * bd[i].ext) {
+      bd[i - 1].ext *= bd[i].ext; bd[i - 1].sin = bd[i].sin; bd[i - 1].sout = bd[i].sout;
+      for (int j = i; j + 1 < nb; j++) bd[j] = bd[j + 1]; nb--;
+    }
+  if (nb > TR_MAXB) return NCL_ERR_UNSUPPORTED;
+  p.nb = nb; long long batch = 1;
+  for (int i = 0; i < nb; i++) { p.bext[i] = bd[i].ext; p.bin[i] = bd[i].sin; p.bout[i] = bd[i].sout; batch *= bd[i].ext; }
+  int tile = (icls == CLS_F) ? 64 : 32;
+  p.tiles_i = (p.ni + tile - 1) / tile; p.tiles_o = (p.no + tile - 1) / tile;
+  long long blocks = p.tiles_i * p.tiles_o * batch;
+  if (blocks > 0x7fffffffLL || blocks <= 0) return NCL_ERR_UNSUPPORTED;
+  Context& c = ctx();
+  if (icls == CLS_F) transpose_kernel<float, 64><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+  else if (icls == CLS_D) transpose_kernel<double, 32><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+  else transpose_kernel<long long, 32><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+  note_launch("transpose_tile");
+  return cuda_fail(cudaGetLastError(), "transpose_kernel");
+}

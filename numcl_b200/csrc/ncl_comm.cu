@@ -1,0 +1,148 @@
+// ncl_comm.cu -- multi-GPU: combining per-GPU reduction partials over NVLink.
+//
+// The reference has no collectives.  The path shards naturally along the outer axis (one process
+// per GPU, each holding a row slab), so the only exchange step is the all-reduce of reduction
+// partials: one float64/int64 element for a full reduce, the kept-axis vector for a reduction over
+// the sharded axis.  NCCL is bound lazily with dlopen so that the library has no link-time
+// dependency and shares the NCCL instance a host process (e.g. torch) may already have loaded.
+#include <dlfcn.h>
+#include <string.h>
+#include "ncl_device.cuh"
+
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+typedef int (*fn_get_uid)(nccl_uid*);
+typedef int (*fn_init_rank)(nccl_comm*, int, nccl_uid, int);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
+typedef int (*fn_destroy)(nccl_comm);
+typedef const char* (*fn_errstr)(int);
+
+static struct {
+  void* h; fn_get_uid get_uid; fn_init_rank init_rank; fn_allreduce allreduce; fn_destroy destroy; fn_errstr errstr;
+  nccl_comm comm; int rank, world; void* partial;   // 8-byte device slot for the sharded full reduce
+} g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.h) return NCL_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !g_nccl.h; i++) g_nccl.h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl.h) return set_error(NCL_ERR_STATE, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.get_uid = (fn_get_uid)dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.init_rank = (fn_init_rank)dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.destroy = (fn_destroy)dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.errstr = (fn_errstr)dlsym(g_nccl.h, "ncclGetErrorString");
+  if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.destroy)
+    return set_error(NCL_ERR_STATE, "libnccl.so.2 lacks the expected symbols");
+  return NCL_OK;
+}
+static int nccl_fail(int rc, const char* what) {
+  if (rc == 0) return NCL_OK;
+  return set_error(NCL_ERR_CUDA, "%s: %s", what, g_nccl.errstr ? g_nccl.errstr(rc) : "NCCL error");
+}
+
+// r <- fn(init, partial) with one rounding into r's element type
+template <class W>
+__global__ void finalize_kernel(const W* partial, char* out, long long off, StoreSpec sk, int out_lk, int fresh, int op, long long ident_i, double ident_f) {
+  W s = *partial;
+  W init;
+  if (fresh) init = std::is_integral<W>::value ? (W)ident_i : (W)ident_f;
+  else init = load_scalar<W>(out, off, out_lk);
+  W r = op == NCL_OP_ADD ? Ops<W>::add(init, s) : op == NCL_OP_MUL ? Ops<W>::mul(init, s) : op == NCL_OP_MAX ? Ops<W>::mx(init, s) : Ops<W>::mn(init, s);
+  store_scalar<W>(out, off, sk, r);
+}
+
+int finalize_partial(int op, const void* partial8, int cls, Operand& r, bool fresh) {
+  Context& c = ctx();
+  StoreSpec sk = dtype_store_spec(r.dtype); int lk = dtype_load_kind(r.dtype);
+  long long ident_i = op == NCL_OP_MUL ? 1 : 0; double ident_f = op == NCL_OP_MUL ? 1.0 : 0.0;
+  const DtInfo& d = g_dt[r.dtype];
+  if (op == NCL_OP_MAX || op == NCL_OP_MIN) {
+    bool mx = op == NCL_OP_MAX;
+    if (d.cls == CLS_F) ident_f = mx ? -3.4028234663852886e38 : 3.4028234663852886e38;
+    else if (d.cls == CLS_D) ident_f = mx ? -1.7976931348623157e308 : 1.7976931348623157e308;
+    else ident_i = mx ? (d.is_signed ? -(1ll << (d.value_bits >= 64 ? 62 : d.value_bits - 1)) : 0)
+                      : (d.is_signed ? (1ll << (d.value_bits >= 64 ? 62 : d.value_bits - 1)) - 1 : (d.value_bits >= 63 ? INT64_MAX : (1ll << d.value_bits) - 1));
+  }
+  if (cls == CLS_I) finalize_kernel<long long><<<1, 1, 0, c.stream>>>((const long long*)partial8, r.base, r.offset, sk, lk, fresh, op, ident_i, ident_f);
+  else finalize_kernel<double><<<1, 1, 0, c.stream>>>((const double*)partial8, r.base, r.offset, sk, lk, fresh, op, ident_i, ident_f);
+  note_launch("reduce_finalize");
+  return cuda_fail(cudaGetLastError(), "finalize_kernel");
+}
+
+extern "C" {
+
+int ncl_comm_unique_id(void* id128) {
+  NCL_TRY(nccl_load());
+  nccl_uid u; NCL_TRY(nccl_fail(g_nccl.get_uid(&u), "ncclGetUniqueId"));
+  memcpy(id128, &u, sizeof u); return NCL_OK;
+}
+int ncl_comm_init(const void* id128, int rank, int world) {
+  if (!ctx().inited) return set_error(NCL_ERR_STATE, "ncl_init has not been called");
+  NCL_TRY(nccl_load());
+  if (g_nccl.comm) return NCL_OK;
+  nccl_uid u; memcpy(&u, id128, sizeof u);
+  NCL_TRY(nccl_fail(g_nccl.init_rank(&g_nccl.comm, world, u, rank), "ncclCommInitRank"));
+  g_nccl.rank = rank; g_nccl.world = world;
+  NCL_CUDA(cudaMalloc(&g_nccl.partial, 64));
+  return NCL_OK;
+}
+int ncl_comm_destroy(void) {
+  if (g_nccl.comm) { cudaStreamSynchronize(ctx().stream); g_nccl.destroy(g_nccl.comm); g_nccl.comm = nullptr; }
+  if (g_nccl.partial) { cudaFree(g_nccl.partial); g_nccl.partial = nullptr; }
+  return NCL_OK;
+}
+
+static int nccl_dtype(int dt, int op, int* out) {
+  switch (dt) {
+    case NCL_F32: *out = 7; return NCL_OK;
+    case NCL_F64: *out = 8; return NCL_OK;
+    case NCL_SB64: case NCL_UB63: *out = 4; return NCL_OK;
+    case NCL_UB64: *out = 5; return NCL_OK;
+    case NCL_FIXNUM: case NCL_UB62:      // tagged words: (a<<1)+(b<<1) = (a+b)<<1, order preserved for max/min
+      if (op == NCL_OP_MUL) return set_error(NCL_ERR_UNSUPPORTED, "all-reduce product of tagged fixnums");
+      *out = 4; return NCL_OK;
+    case NCL_SB32: *out = 2; return NCL_OK;
+    case NCL_UB31: case NCL_UB32: *out = 3; return NCL_OK;
+    case NCL_SB8: *out = 0; return NCL_OK;
+    case NCL_UB7: case NCL_UB8: *out = 1; return NCL_OK;
+    default: return set_error(NCL_ERR_UNSUPPORTED, "all-reduce of element type %s", g_dt[dt].name);
+  }
+}
+static int nccl_op(int op, int* out) {
+  switch (op) { case NCL_OP_ADD: *out = 0; return NCL_OK; case NCL_OP_MUL: *out = 1; return NCL_OK;
+    case NCL_OP_MAX: *out = 2; return NCL_OK; case NCL_OP_MIN: *out = 3; return NCL_OK;
+    default: return set_error(NCL_ERR_UNSUPPORTED, "all-reduce op %d", op); }
+}
+
+int ncl_allreduce(int op, ncl_tensor* t) {
+  if (!g_nccl.comm) return set_error(NCL_ERR_STATE, "ncl_comm_init has not been called");
+  if (!t || !t->buf) return set_error(NCL_ERR_INVALID, "ncl_allreduce needs a device-resident tensor");
+  int ndt, nop; NCL_TRY(nccl_dtype(t->dtype, op, &ndt)); NCL_TRY(nccl_op(op, &nop));
+  int64_t n = 1; for (int i = 0; i < t->rank; i++) n *= t->dims[i];
+  char* p = (char*)t->buf->ptr + (t->elem_offset * g_dt[t->dtype].slot_bits) / 8;
+  return nccl_fail(g_nccl.allreduce(p, p, (size_t)n, ndt, nop, g_nccl.comm, ctx().stream), "ncclAllReduce");
+}
+
+int ncl_reduce_all_sharded(int op, const ncl_tensor* a, ncl_tensor* r) {
+  if (!ctx().inited) return set_error(NCL_ERR_STATE, "ncl_init has not been called");
+  if (!a || !r || !a->buf || !r->buf) return set_error(NCL_ERR_INVALID, "ncl_reduce_all_sharded needs device-resident tensors");
+  if (r->rank != 0) return set_error(NCL_ERR_SHAPE, "result of a full reduce is a rank-0 array");
+  if (g_dt[a->dtype].cls != g_dt[r->dtype].cls) return set_error(NCL_ERR_UNSUPPORTED, "element classes differ");
+  int nop; NCL_TRY(nccl_op(op, &nop));
+  Operand ao; memset(&ao, 0, sizeof ao); ao.base = (char*)a->buf->ptr; ao.dtype = a->dtype; ao.offset = a->elem_offset;
+  int64_t n = 1; for (int i = 0; i < a->rank; i++) n *= a->dims[i];
+  void* slot = g_nccl.partial;
+  bool own_slot = false;
+  if (!slot) { NCL_CUDA(cudaMalloc(&slot, 64)); own_slot = true; }       // single process: no communicator needed
+  int cls = g_dt[a->dtype].cls;
+  NCL_TRY(reduce_all_to_partial(op, ao, n, slot));
+  if (g_nccl.comm && g_nccl.world > 1)
+    NCL_TRY(nccl_fail(g_nccl.allreduce(slot, slot, 1, cls == CLS_I ? 4 : 8, nop, g_nccl.comm, ctx().stream), "ncclAllReduce"));
+  Operand ro; memset(&ro, 0, sizeof ro); ro.base = (char*)r->buf->ptr; ro.dtype = r->dtype; ro.offset = r->elem_offset;
+  int rc = finalize_partial(op, slot, cls, ro, true);
+  if (own_slot) { cudaStreamSynchronize(ctx().stream); cudaFree(slot); }
+  return rc;
+}
+
+}  // extern "C"

@@ -202,6 +202,129 @@ template <> struct Ops<double> {
   static __device__ __forceinline__ T zero() { return 0.0; }
 };
 
+#include <type_traits>
+// ---- vector chunk I/O ----------------------------------------------------------------------------------
+template <int NBYTES> struct Chunk { unsigned int w[(NBYTES + 3) / 4]; };
+
+template <int NBYTES> __device__ __forceinline__ void ld_chunk(Chunk<NBYTES>& c, const char* p) {
+  if constexpr (NBYTES >= 16) {
+#pragma unroll
+    for (int i = 0; i < NBYTES / 16; i++) {
+      uint4 v = __ldg((const uint4*)p + i);
+      c.w[4 * i] = v.x; c.w[4 * i + 1] = v.y; c.w[4 * i + 2] = v.z; c.w[4 * i + 3] = v.w;
+    }
+  } else if constexpr (NBYTES == 8) { uint2 v = __ldg((const uint2*)p); c.w[0] = v.x; c.w[1] = v.y; }
+  else if constexpr (NBYTES == 4) c.w[0] = __ldg((const unsigned int*)p);
+  else if constexpr (NBYTES == 2) c.w[0] = __ldg((const unsigned short*)p);
+  else c.w[0] = __ldg((const unsigned char*)p);
+}
+template <int NBYTES> __device__ __forceinline__ void st_chunk(const Chunk<NBYTES>& c, char* p) {
+  if constexpr (NBYTES >= 16) {
+#pragma unroll
+    for (int i = 0; i < NBYTES / 16; i++) ((uint4*)p)[i] = make_uint4(c.w[4 * i], c.w[4 * i + 1], c.w[4 * i + 2], c.w[4 * i + 3]);
+  } else if constexpr (NBYTES == 8) *(uint2*)p = make_uint2(c.w[0], c.w[1]);
+  else if constexpr (NBYTES == 4) *(unsigned int*)p = c.w[0];
+  else if constexpr (NBYTES == 2) *(unsigned short*)p = (unsigned short)c.w[0];
+  else *(unsigned char*)p = (unsigned char)c.w[0];
+}
+// element i of a chunk of BITS-wide slots
+template <int BITS, int NBYTES> __device__ __forceinline__ unsigned long long chunk_get(const Chunk<NBYTES>& c, int i) {
+  if constexpr (BITS == 64) return ((unsigned long long)c.w[2 * i + 1] << 32) | c.w[2 * i];
+  else if constexpr (BITS == 32) return c.w[i];
+  else if constexpr (BITS == 16) return (c.w[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+  else return (c.w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+}
+template <int BITS, int NBYTES> __device__ __forceinline__ void chunk_put(Chunk<NBYTES>& c, int i, unsigned long long v) {
+  if constexpr (BITS == 64) { c.w[2 * i] = (unsigned int)v; c.w[2 * i + 1] = (unsigned int)(v >> 32); }
+  else if constexpr (BITS == 32) c.w[i] = (unsigned int)v;
+  else if constexpr (BITS == 16) { if ((i & 1) == 0) c.w[i >> 1] = (unsigned int)(v & 0xffffu); else c.w[i >> 1] |= (unsigned int)(v & 0xffffu) << 16; }
+  else { if ((i & 3) == 0) c.w[i >> 2] = (unsigned int)(v & 0xffu); else c.w[i >> 2] |= (unsigned int)(v & 0xffu) << ((i & 3) * 8); }
+}
+
+template <class T, int E, int BITS, bool SIGNED, bool TAGGED>
+__device__ __forceinline__ void load_int_chunk(const char* base, long long idx, T (&v)[E]) {
+  Chunk<E * BITS / 8> c; ld_chunk(c, base + idx * (BITS / 8));
+#pragma unroll
+  for (int i = 0; i < E; i++) {
+    unsigned long long u = chunk_get<BITS>(c, i);
+    long long s;
+    if constexpr (BITS == 64) s = TAGGED ? ((long long)u >> 1) : (long long)u;
+    else if constexpr (SIGNED) s = (long long)((long long)(u << (64 - BITS)) >> (64 - BITS));
+    else s = (long long)u;
+    v[i] = from_i64<T>(s);
+  }
+}
+
+// E consecutive elements starting at element idx (innermost stride 1), or one element splat (stride 0)
+template <class T, int E>
+__device__ __forceinline__ void load_elems(const char* base, long long idx, int lk, bool contiguous, T (&v)[E]) {
+  if (!contiguous || E == 1) {
+    T s = load_scalar<T>(base, idx, lk);
+#pragma unroll
+    for (int i = 0; i < E; i++) v[i] = s;
+    return;
+  }
+  if constexpr (E > 1) {
+    switch (lk) {
+      case LK_U8:  load_int_chunk<T, E, 8, false, false>(base, idx, v); break;
+      case LK_S8:  load_int_chunk<T, E, 8, true, false>(base, idx, v); break;
+      case LK_U16: load_int_chunk<T, E, 16, false, false>(base, idx, v); break;
+      case LK_S16: load_int_chunk<T, E, 16, true, false>(base, idx, v); break;
+      case LK_U32: load_int_chunk<T, E, 32, false, false>(base, idx, v); break;
+      case LK_S32: load_int_chunk<T, E, 32, true, false>(base, idx, v); break;
+      case LK_W64: load_int_chunk<T, E, 64, true, false>(base, idx, v); break;
+      case LK_T64: load_int_chunk<T, E, 64, true, true>(base, idx, v); break;
+      case LK_F32: { Chunk<E * 4> c; ld_chunk(c, base + idx * 4);
+#pragma unroll
+        for (int i = 0; i < E; i++) v[i] = from_f32<T>(__uint_as_float(c.w[i])); break; }
+      default: { Chunk<E * 8> c; ld_chunk(c, base + idx * 8);       // LK_F64 (sub-byte kinds never reach the fast path)
+#pragma unroll
+        for (int i = 0; i < E; i++) v[i] = from_f64<T>(__longlong_as_double((long long)chunk_get<64>(c, i))); break; }
+    }
+  }
+}
+
+template <class TO, int E>
+__device__ __forceinline__ void store_elems(char* base, long long idx, const StoreSpec& sk, const TO (&v)[E]) {
+  if constexpr (E == 1) { store_scalar<TO>(base, idx, sk, v[0]); return; }
+  else if constexpr (sizeof(TO) == 4 && !std::is_integral<TO>::value) {               // float -> f32 slots
+    Chunk<E * 4> c;
+#pragma unroll
+    for (int i = 0; i < E; i++) c.w[i] = __float_as_uint(v[i]);
+    st_chunk(c, base + idx * 4);
+  } else if constexpr (!std::is_integral<TO>::value) {                                  // double -> f64 slots
+    Chunk<E * 8> c;
+#pragma unroll
+    for (int i = 0; i < E; i++) chunk_put<64>(c, i, (unsigned long long)__double_as_longlong(v[i]));
+    st_chunk(c, base + idx * 8);
+  } else {                                                                              // integers: %coerce wrap, then slot
+    if constexpr (E == 32) {                                                            // packed bits: one word
+      unsigned int w = 0;
+#pragma unroll
+      for (int i = 0; i < 32; i++) w |= ((unsigned int)v[i] & 1u) << i;
+      *(unsigned int*)(base + (idx >> 3)) = w;
+    } else {
+      if constexpr (E == 16) { Chunk<16> c;
+#pragma unroll
+        for (int i = 0; i < E; i++) chunk_put<8>(c, i, (((unsigned long long)v[i]) & sk.mask) << sk.shift);
+        st_chunk(c, base + idx); }
+      else if constexpr (E == 8) { Chunk<16> c;
+#pragma unroll
+        for (int i = 0; i < E; i++) chunk_put<16>(c, i, (((unsigned long long)v[i]) & sk.mask) << sk.shift);
+        st_chunk(c, base + idx * 2); }
+      else if constexpr (E == 4) { Chunk<16> c;
+#pragma unroll
+        for (int i = 0; i < E; i++) chunk_put<32>(c, i, (((unsigned long long)v[i]) & sk.mask) << sk.shift);
+        st_chunk(c, base + idx * 4); }
+      else { Chunk<16> c;
+#pragma unroll
+        for (int i = 0; i < E; i++) chunk_put<64>(c, i, (((unsigned long long)v[i]) & sk.mask) << sk.shift);
+        st_chunk(c, base + idx * 8); }
+    }
+  }
+}
+
+
 // counter-based generator shared bit for bit with oracle/numcl_oracle.c (nco_fill_random)
 __host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
   x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;

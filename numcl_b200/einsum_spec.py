@@ -108,7 +108,9 @@ class EinsumSpecs:
             if isinstance(f, Sym):
                 return f.lower()
             if isinstance(f, Double):
-                return repr(float(f)) + "d0"
+                return "%.17gd0" % float(f)
+            if isinstance(f, float):
+                return "%.9g" % f
             return repr(f)
 
         def opts(o):
