@@ -116,7 +116,10 @@ int try_elementwise(const Nest& n) {
   if (nd == 0) { d[0].ext = 1; for (int k = 0; k < 4; k++) d[0].st[k] = 0; d[0].st[0] = 1; nd = 1; }
   if (nd > EW_MAXD) return NCL_ERR_UNSUPPORTED;
   if (d[nd - 1].st[0] != 1) return NCL_ERR_UNSUPPORTED;
-  for (int i = 0; i < nd; i++) if (d[i].ext > 0xffffffffLL) return NCL_ERR_UNSUPPORTED;
+  for (int i = 0; i < nd; i++) {
+    if (d[i].ext >= 0x7fffffffLL) return NCL_ERR_UNSUPPORTED;
+    for (int k = 0; k < 4; k++) if (llabs(d[i].st[k]) >= 0x7fffffffLL) return NCL_ERR_UNSUPPORTED;
+  }
 
   StoreSpec sk = dtype_store_spec(out.dtype);
   int out_bits = g_dt[out.dtype].slot_bits;
@@ -155,12 +158,18 @@ int try_elementwise(const Nest& n) {
   for (int i = 0; i < nd; i++) {                      // reverse: params dim 0 is the innermost
     const D& s = d[nd - 1 - i];
     p.ext[i] = (unsigned)(i == 0 ? s.ext / E : s.ext);
-    for (int k = 0; k < 4; k++) p.st[k][i] = s.st[k];
+    if (p.ext[i] <= 1) { p.mul[i] = 0; p.shr[i] = 0; }
+    else {                                            // q / ext = umulhi(q, ceil(2^(31+s)/ext)) >> (s-1), s = ceil(log2 ext), q < 2^31
+      unsigned s2 = 0; while ((1ull << s2) < p.ext[i]) s2++;
+      p.mul[i] = (unsigned)(((1ull << (31 + s2)) + p.ext[i] - 1) / p.ext[i]); p.shr[i] = s2 - 1;
+    }
+    for (int k = 0; k < 4; k++) p.st[k][i] = (int)s.st[k];
   }
   p.base[0] = out.base; p.off[0] = out.offset;
   for (int k = 0; k < m.n; k++) { p.base[1 + k] = ops[k].base; p.off[1 + k] = ops[k].offset; p.lk[k] = dtype_load_kind(ops[k].dtype); }
   unsigned long long nch = 1; for (int i = 0; i < nd; i++) nch *= p.ext[i];
-  p.nchunks = nch;
+  if (nch >= 0x7fffffffull) return NCL_ERR_UNSUPPORTED;        // > 2^31 chunks: generic path
+  p.nchunks = (unsigned)nch;
   if (nch == 0) return NCL_OK;
   int U = E == 32 ? 1 : 4;
   unsigned long long blocks = (nch + (unsigned long long)EW_THREADS * U - 1) / ((unsigned long long)EW_THREADS * U);

@@ -24,11 +24,13 @@
 struct EwParams {
   int nd, n_in;
   unsigned ext[EW_MAXD];               // ext[0] counts chunks, ext[d>0] elements
-  long long st[4][EW_MAXD];            // [0] = output, [1..3] = inputs; elements
+  unsigned mul[EW_MAXD], shr[EW_MAXD]; // q / ext[d] = umulhi(q, mul) >> shr for q < 2^31 (mul == 0: ext is 1)
+  int st[4][EW_MAXD];                  // [0] = output, [1..3] = inputs; elements (|stride| < 2^31)
   char* base[4]; long long off[4];
   int lk[3]; StoreSpec sk;
-  unsigned long long nchunks;
+  unsigned nchunks;                    // < 2^31
 };
+__device__ __forceinline__ unsigned ew_div(unsigned q, unsigned mul, unsigned shr) { return mul ? (__umulhi(q, mul) >> shr) : q; }
 
 enum Shape { S_NONE = 0, S_ADD, S_SUB, S_MUL, S_DIV, S_MAX, S_MIN, S_ADD0, S_MUL0, S_IDIV, S_EQ, S_NE, S_LE, S_GE, S_LT, S_GT,
              S_AND, S_IOR, S_XOR, S_COPY, S_ADD0U, S_NEG, S_ABS, S_SQUARE, S_NOT, S_SQRT, S_EXP, S_LOG, S_SIN, S_COS, S_TAN, S_TANH,
@@ -77,21 +79,19 @@ template <class T> struct FnAddMul { typedef T R; static __device__ __forceinlin
 template <class TI, class F, int NIN, int E, int U>
 __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ EwParams p) {
   typedef typename F::R TO;
-  const unsigned long long tile = (unsigned long long)blockIdx.x * (EW_THREADS * U);
+  const unsigned tile = blockIdx.x * (EW_THREADS * U);
   long long offs[U][4]; bool valid[U];
 #pragma unroll
   for (int u = 0; u < U; u++) {
-    unsigned long long q = tile + (unsigned long long)u * EW_THREADS + threadIdx.x;
+    unsigned q = tile + u * EW_THREADS + threadIdx.x;
     valid[u] = q < p.nchunks;
-    unsigned long long q0, r;
-    if (p.nchunks <= 0xffffffffull) { unsigned int qq = (unsigned int)q; q0 = qq % p.ext[0]; r = qq / p.ext[0]; }
-    else { q0 = q % p.ext[0]; r = q / p.ext[0]; }
+    unsigned r = ew_div(q, p.mul[0], p.shr[0]);
+    int q0 = (int)(q - r * p.ext[0]);
 #pragma unroll
-    for (int k = 0; k < 4; k++) offs[u][k] = p.off[k] + (long long)q0 * E * p.st[k][0];
+    for (int k = 0; k < 4; k++) offs[u][k] = p.off[k] + (long long)(q0 * E) * p.st[k][0];
     for (int d = 1; d < p.nd; d++) {
-      unsigned long long c;
-      if (p.nchunks <= 0xffffffffull) { unsigned int rr = (unsigned int)r; c = rr % p.ext[d]; r = rr / p.ext[d]; }
-      else { c = r % p.ext[d]; r = r / p.ext[d]; }
+      unsigned r2 = ew_div(r, p.mul[d], p.shr[d]);
+      int c = (int)(r - r2 * p.ext[d]); r = r2;
 #pragma unroll
       for (int k = 0; k < 4; k++) offs[u][k] += (long long)c * p.st[k][d];
     }

@@ -1,3 +1,68 @@
-// k_gemm.cu -- K4 dispatch (contractions).  Kernel families land in k_gemm_*.cu.
-#include "ncl_internal.h"
-int try_gemm(const Nest&) { return NCL_ERR_UNSUPPORTED; }
+// k_gemm.cu -- K4 dispatch: recognise a dense contraction in a nest and route it.
+//
+// A nest is a (batched) GEMM when it has two inputs, one output, the default transform
+// (+ @1 (* $1 $2)) (src/3einsum.lisp:176-178) and every loop falls into exactly one class by which
+// arrays it moves:  batch (A, B, C) | M (A, C) | N (B, C) | K (A, B).  Each class must merge into
+// one strided dimension, with K contiguous in A, N contiguous in B and C (row-major operands, the
+// layout of `matmul` and `(bij bjk -> bik)`).  Anything else stays on the generic nest kernel.
+//   double-float            -> DMMA          (k_gemm_f64.cu)
+//   single-float, large     -> 3xTF32 tcgen05 (k_gemm_tf32.cu)
+//   single-float skinny/odd, all integer types -> FMA / IMAD tiles (k_gemm_simt.cu)
+#include "k_gemm.cuh"
+
+struct GDim { long long ext, sa, sb, sc; };
+
+static bool merge_group(GDim* d, int& n) {
+  // sort by |sc| (or |sa| for K, whose sc is 0) descending, then merge neighbours
+  auto key = [](const GDim& x) { return x.sc != 0 ? llabs(x.sc) : llabs(x.sa); };
+  for (int i = 1; i < n; i++) { GDim t = d[i]; int j = i - 1; while (j >= 0 && key(d[j]) < key(t)) { d[j + 1] = d[j]; j--; } d[j + 1] = t; }
+  for (int i = n - 1; i > 0; i--) {
+    if (d[i - 1].sa == d[i].sa * d[i].ext && d[i - 1].sb == d[i].sb * d[i].ext && d[i - 1].sc == d[i].sc * d[i].ext) {
+      d[i - 1].ext *= d[i].ext; d[i - 1].sa = d[i].sa; d[i - 1].sb = d[i].sb; d[i - 1].sc = d[i].sc;
+      for (int j = i; j + 1 < n; j++) d[j] = d[j + 1]; n--;
+    }
+  }
+  return n <= 1;
+}
+
+int try_gemm(const Nest& n) {
+  if (n.n_in != 2 || n.n_out != 1) return NCL_ERR_UNSUPPORTED;
+  const Expr& e = n.transform[0];
+  if (e.n != 5) return NCL_ERR_UNSUPPORTED;
+  const XNode& root = e.node[4];
+  if (root.op != NCL_OP_ADD || e.node[root.a].op != NCL_X_OUTPUT || e.node[root.b].op != NCL_OP_MUL) return NCL_ERR_UNSUPPORTED;
+  const XNode& mul = e.node[root.b];
+  if (e.node[mul.a].op != NCL_X_INPUT || e.node[mul.b].op != NCL_X_INPUT || e.node[mul.a].a == e.node[mul.b].a) return NCL_ERR_UNSUPPORTED;
+  const Operand& A = n.in[e.node[mul.a].a - 1]; const Operand& B = n.in[e.node[mul.b].a - 1]; const Operand& C = n.out[0];
+  int ca = g_dt[A.dtype].cls, cb = g_dt[B.dtype].cls, cc = g_dt[C.dtype].cls;
+  if (ca != cb || ca != cc) return NCL_ERR_UNSUPPORTED;               // mixed classes: the generic kernel has exact contagion
+  if (g_dt[A.dtype].slot_bits < 8 || g_dt[B.dtype].slot_bits < 8 || g_dt[C.dtype].slot_bits < 8) return NCL_ERR_UNSUPPORTED;
+  GDim gb[NCL_MAX_LOOPS], gm[NCL_MAX_LOOPS], gn[NCL_MAX_LOOPS], gk[NCL_MAX_LOOPS]; int nb = 0, nm = 0, nn = 0, nk = 0;
+  for (int l = 0; l < n.nloops; l++) {
+    if (n.extent[l] == 1) continue;
+    GDim d = {n.extent[l], A.stride[l], B.stride[l], C.stride[l]};
+    bool a = d.sa != 0, b = d.sb != 0, c = d.sc != 0;
+    if (a && b && c) gb[nb++] = d; else if (a && !b && c) gm[nm++] = d; else if (!a && b && c) gn[nn++] = d; else if (a && b && !c) gk[nk++] = d;
+    else return NCL_ERR_UNSUPPORTED;
+  }
+  if (nk == 0) return NCL_ERR_UNSUPPORTED;                              // no contraction: elementwise / outer product
+  if (!merge_group(gb, nb) || !merge_group(gm, nm) || !merge_group(gn, nn) || !merge_group(gk, nk)) return NCL_ERR_UNSUPPORTED;
+  GemmParams p; memset(&p, 0, sizeof p);
+  p.M = nm ? (int)gm[0].ext : 1; p.N = nn ? (int)gn[0].ext : 1; p.K = (int)gk[0].ext; p.batch = nb ? (int)gb[0].ext : 1;
+  if ((nm && gm[0].ext > 0x7fffffffLL) || (nn && gn[0].ext > 0x7fffffffLL) || gk[0].ext > 0x7fffffffLL || (nb && gb[0].ext > 0x7fffffffLL)) return NCL_ERR_UNSUPPORTED;
+  if (gk[0].sa != 1) return NCL_ERR_UNSUPPORTED;                        // A must be k-contiguous
+  if (nn && (gn[0].sb != 1 || gn[0].sc != 1)) return NCL_ERR_UNSUPPORTED; // B and C n-contiguous
+  p.lda = nm ? gm[0].sa : 0; p.ldb = gk[0].sb; p.ldc = nm ? gm[0].sc : 0;
+  p.sA = nb ? gb[0].sa : 0; p.sB = nb ? gb[0].sb : 0; p.sC = nb ? gb[0].sc : 0;
+  if (p.lda < 0 || p.ldb < 0 || p.ldc < 0 || p.sA < 0 || p.sB < 0 || p.sC < 0) return NCL_ERR_UNSUPPORTED;
+  p.A = A.base + (A.offset * g_dt[A.dtype].slot_bits) / 8; p.B = B.base + (B.offset * g_dt[B.dtype].slot_bits) / 8;
+  p.C = C.base + (C.offset * g_dt[C.dtype].slot_bits) / 8;
+  p.accumulate = n.fresh ? 0 : 1;
+  p.lkA = dtype_load_kind(A.dtype); p.lkB = dtype_load_kind(B.dtype); p.lkC = dtype_load_kind(C.dtype); p.skC = dtype_store_spec(C.dtype);
+  int rc = NCL_ERR_UNSUPPORTED;
+  long long work = (long long)p.M * p.N;
+  if (ca == CLS_D && A.dtype == NCL_F64 && p.M >= 32 && p.N >= 32) rc = gemm_f64_dmma(p);
+  else if (ca == CLS_F && work >= 128 * 128 && p.K >= 32) rc = gemm_f32_tf32x3(p);
+  if (rc != NCL_ERR_UNSUPPORTED) return rc;
+  return gemm_simt(p, ca);
+}

@@ -296,6 +296,13 @@ static int fill_common(RedParams& p, const Nest& n, int op) {
   (void)op; return NCL_OK;
 }
 
+// one resident wave: sm_count x (blocks of 256 threads that fit one SM for this kernel)
+static long long persistent_blocks(const void* kfn) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+  return (long long)ctx().sm_count * per_sm;
+}
+
 static bool aligned16(const Operand& o, long long elem_off) {
   int sb = g_dt[o.dtype].slot_bits;
   return (((uintptr_t)o.base + (elem_off * sb) / 8) % 16) == 0;
@@ -334,11 +341,12 @@ int try_reduce(const Nest& n) {
     p.vec = (R % Evec == 0) && aligned16(in, in.offset);
     int E = p.vec ? Evec : 1;
     long long work = p.vec ? R / E : R;
+    RedKernel kfn = kernel_for(cls, E, op, KALL);
     long long blocks = (work + 256 * 4 - 1) / (256 * 4);
-    long long cap = (long long)c.sm_count * 8; if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
+    long long cap = persistent_blocks((const void*)kfn); if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
     NCL_TRY(ensure_scratch((size_t)blocks * 8));
     p.block_partials = c.scratch; p.ticket = c.ticket; p.nblocks = (int)blocks;
-    kernel_for(cls, E, op, KALL)<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+    kfn<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
     note_launch("reduce_all");
     return cuda_fail(cudaGetLastError(), "reduce_all_kernel");
   }
@@ -405,10 +413,11 @@ int reduce_all_to_partial(int op, const Operand& a, int64_t count, void* partial
   p.vec = (count % Evec == 0) && aligned16(a, a.offset);
   int E = p.vec ? Evec : 1;
   long long work = p.vec ? count / E : count;
-  long long blocks = (work + 1023) / 1024; long long cap = (long long)c.sm_count * 8; if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
+  RedKernel kfn = kernel_for(cls, E, rop, KALL);
+  long long blocks = (work + 1023) / 1024; long long cap = persistent_blocks((const void*)kfn); if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
   NCL_TRY(ensure_scratch((size_t)blocks * 8));
   p.block_partials = c.scratch; p.ticket = c.ticket; p.nblocks = (int)blocks; p.raw_partial = partial8; p.fresh = 1;
-  kernel_for(cls, E, rop, KALL)<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+  kfn<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
   note_launch("reduce_all");
   return cuda_fail(cudaGetLastError(), "reduce_all_kernel");
 }
