@@ -167,13 +167,20 @@ int try_elementwise(const Nest& n) {
   }
   p.base[0] = out.base; p.off[0] = out.offset;
   for (int k = 0; k < m.n; k++) { p.base[1 + k] = ops[k].base; p.off[1 + k] = ops[k].offset; p.lk[k] = dtype_load_kind(ops[k].dtype); }
-  unsigned long long nch = 1; for (int i = 0; i < nd; i++) nch *= p.ext[i];
-  if (nch >= 0x7fffffffull) return NCL_ERR_UNSUPPORTED;        // > 2^31 chunks: generic path
-  p.nchunks = (unsigned)nch;
-  if (nch == 0) return NCL_OK;
   int U = E == 32 ? 1 : 4;
-  unsigned long long blocks = (nch + (unsigned long long)EW_THREADS * U - 1) / ((unsigned long long)EW_THREADS * U);
-  if (blocks > 0x7fffffffull) return NCL_ERR_UNSUPPORTED;
+  unsigned long long rows = 1; for (int i = 1; i < nd; i++) rows *= p.ext[i];
+  unsigned segs = (p.ext[0] + 32 * U - 1) / (32 * U);
+  unsigned long long nitems = rows * segs;
+  if (nitems >= 0x7fffffffull || (unsigned long long)p.ext[0] * E >= 0x7fffffffull) return NCL_ERR_UNSUPPORTED;   // beyond 2^31: generic path
+  if (nitems == 0) return NCL_OK;
+  p.segs_per_row = segs; p.nitems = (unsigned)nitems;
+  if (segs <= 1) { p.seg_mul = 0; p.seg_shr = 0; }
+  else { unsigned s2 = 0; while ((1ull << s2) < segs) s2++; p.seg_mul = (unsigned)(((1ull << (31 + s2)) + segs - 1) / segs); p.seg_shr = s2 - 1; }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfn, EW_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  unsigned long long blocks = (nitems + EW_THREADS / 32 - 1) / (EW_THREADS / 32);
+  unsigned long long cap = (unsigned long long)c.sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
   kfn<<<(unsigned)blocks, EW_THREADS, 0, c.stream>>>(p);
   note_launch(E == 1 ? "bcast_scalar" : "bcast_vec");
   return cuda_fail(cudaGetLastError(), "ew_kernel");

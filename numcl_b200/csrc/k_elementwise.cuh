@@ -28,7 +28,8 @@ struct EwParams {
   int st[4][EW_MAXD];                  // [0] = output, [1..3] = inputs; elements (|stride| < 2^31)
   char* base[4]; long long off[4];
   int lk[3]; StoreSpec sk;
-  unsigned nchunks;                    // < 2^31
+  unsigned segs_per_row, seg_mul, seg_shr;   // a row of ext[0] chunks is cut into warp segments of 32*U chunks
+  unsigned nitems;                     // rows * segs_per_row, < 2^31
 };
 __device__ __forceinline__ unsigned ew_div(unsigned q, unsigned mul, unsigned shr) { return mul ? (__umulhi(q, mul) >> shr) : q; }
 
@@ -76,45 +77,56 @@ LIBM_FN(FnTan, tanf, tan) LIBM_FN(FnTanh, tanhf, tanh)
 template <class T> struct FnAddMul { typedef T R; static __device__ __forceinline__ T f(T a, T b, T c) { return Ops<T>::add(a, Ops<T>::mul(b, c)); } };
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
+// Persistent: one resident wave of CTAs; every WARP repeatedly takes a work item = one segment of
+// 32*U chunks of one innermost row.  The (row, segment) -> offsets decode is warp-uniform and paid
+// once per item; lane l then handles chunks l, l+32, ... of the segment, so each load / store
+// instruction of the warp covers 32 consecutive chunks (512 contiguous bytes for 16-byte chunks).
 template <class TI, class F, int NIN, int E, int U>
 __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ EwParams p) {
   typedef typename F::R TO;
-  const unsigned tile = blockIdx.x * (EW_THREADS * U);
-  long long offs[U][4]; bool valid[U];
+  const int lane = threadIdx.x & 31;
+  const unsigned nwarps = gridDim.x * (EW_THREADS / 32);
+  for (unsigned item = blockIdx.x * (EW_THREADS / 32) + (threadIdx.x >> 5); item < p.nitems; item += nwarps) {
+    unsigned row = ew_div(item, p.seg_mul, p.seg_shr);
+    unsigned seg = item - row * p.segs_per_row;
+    long long rowoff[4];
 #pragma unroll
-  for (int u = 0; u < U; u++) {
-    unsigned q = tile + u * EW_THREADS + threadIdx.x;
-    valid[u] = q < p.nchunks;
-    unsigned r = ew_div(q, p.mul[0], p.shr[0]);
-    int q0 = (int)(q - r * p.ext[0]);
+    for (int k = 0; k < 4; k++) rowoff[k] = p.off[k];
+    {
+      unsigned r = row;
+      for (int d = 1; d < p.nd; d++) {
+        unsigned r2 = ew_div(r, p.mul[d], p.shr[d]);
+        int c = (int)(r - r2 * p.ext[d]); r = r2;
 #pragma unroll
-    for (int k = 0; k < 4; k++) offs[u][k] = p.off[k] + (long long)(q0 * E) * p.st[k][0];
-    for (int d = 1; d < p.nd; d++) {
-      unsigned r2 = ew_div(r, p.mul[d], p.shr[d]);
-      int c = (int)(r - r2 * p.ext[d]); r = r2;
+        for (int k = 0; k < 4; k++) rowoff[k] += (long long)c * p.st[k][d];
+      }
+    }
+    const unsigned q0 = seg * (32 * U) + lane;
+    TI x[U][NIN][E];
 #pragma unroll
-      for (int k = 0; k < 4; k++) offs[u][k] += (long long)c * p.st[k][d];
+    for (int u = 0; u < U; u++) {
+      unsigned q = q0 + u * 32;
+      if (q < p.ext[0]) {
+#pragma unroll
+        for (int k = 0; k < NIN; k++)
+          load_elems<TI, E>(p.base[1 + k], rowoff[1 + k] + (long long)(int)(q * E) * p.st[1 + k][0], p.lk[k], p.st[1 + k][0] != 0, x[u][k]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      unsigned q = q0 + u * 32;
+      if (q < p.ext[0]) {
+        TO y[E];
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+          if constexpr (NIN == 1) y[i] = F::f(x[u][0][i]);
+          else if constexpr (NIN == 2) y[i] = F::f(x[u][0][i], x[u][1][i]);
+          else y[i] = F::f(x[u][0][i], x[u][1][i], x[u][2][i]);
+        }
+        store_elems<TO, E>(p.base[0], rowoff[0] + (long long)(int)(q * E), p.sk, y);
+      }
     }
   }
-  TI x[U][NIN][E];
-#pragma unroll
-  for (int u = 0; u < U; u++)
-    if (valid[u]) {
-#pragma unroll
-      for (int k = 0; k < NIN; k++) load_elems<TI, E>(p.base[1 + k], offs[u][1 + k], p.lk[k], p.st[1 + k][0] != 0, x[u][k]);
-    }
-#pragma unroll
-  for (int u = 0; u < U; u++)
-    if (valid[u]) {
-      TO y[E];
-#pragma unroll
-      for (int i = 0; i < E; i++) {
-        if constexpr (NIN == 1) y[i] = F::f(x[u][0][i]);
-        else if constexpr (NIN == 2) y[i] = F::f(x[u][0][i], x[u][1][i]);
-        else y[i] = F::f(x[u][0][i], x[u][1][i], x[u][2][i]);
-      }
-      store_elems<TO, E>(p.base[0], offs[u][0], p.sk, y);
-    }
 }
 
 typedef void (*EwKernel)(const EwParams);

@@ -1,3 +1,300 @@
-// k_gemm_tf32.cu -- placeholder until the tcgen05 3xTF32 kernel lands (next commit)
+// k_gemm_tf32.cu -- K4, single-float: `(ij jk -> ik)` / `(bij bjk -> bik)` as 3xTF32 on the
+// 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands fetched by the
+// TMA bulk-copy engine).
+//
+// Why 3xTF32: one TF32 MMA keeps 10 mantissa bits (~5e-4 relative), far outside the 1e-5 bar.
+// Each operand is split  x = hi + lo  with hi = rna_tf32(x), lo = rna_tf32(x - hi)  and
+//   A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi          (lo*lo ~ 2^-22 relative, dropped)
+// accumulated in fp32 in TMEM: ~5e-7 relative, about as good as the reference's own sequential
+// single-float accumulation.
+//
+// Two kernels:
+//  1. pack (HBM-bound pre-pass): splits A and B and writes them as PACKED TILES, byte-for-byte
+//     the shared-memory image tcgen05 wants -- K-major, 128-byte rows of 32 k-values, 8-row
+//     swizzle atoms (16-byte chunk c of row r stored at chunk c ^ (r & 7): UMMA SWIZZLE_128B) --
+//     with hi and lo tiles adjacent.  B is transposed on the way so both operands are K-major.
+//     A pipeline stage is then two plain contiguous blobs, fetched with two cp.async.bulk
+//     (SASS UBLKCP) instructions: no tensor maps, no address math in the hot loop.
+//  2. gemm: one CTA per 128 x 256 output tile, 10 warps, warp-specialised:
+//       warp 0      TMA producer  (one lane): empty[s] -> expect_tx -> 2 bulk copies -> full[s]
+//       warp 1      MMA issuer    (one lane): full[s] -> 4 k-steps x 3 tcgen05.mma -> commit -> empty[s]
+//       warps 2..9  epilogue: tmem_full[b] -> tcgen05.ld 32 lanes x 32 columns -> running fp32 sum -> global
+//     K is consumed in chunks of 256 that alternate between two TMEM accumulators (see the kernel).
 #include "k_gemm.cuh"
-int gemm_f32_tf32x3(const GemmParams&) { return NCL_ERR_UNSUPPORTED; }
+
+#define TF_BM 128
+#define TF_BN 256
+#define TF_BK 32
+#define TF_STAGES 2
+#define TF_A_TILE (TF_BM * TF_BK * 4)            // 16 KB
+#define TF_B_TILE (TF_BN * TF_BK * 4)            // 32 KB
+#define TF_STAGE_BYTES (2 * TF_A_TILE + 2 * TF_B_TILE)     // hi+lo of both: 96 KB
+#define TF_SMEM (TF_STAGES * TF_STAGE_BYTES + 2048)
+
+// ---- pack ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  unsigned h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  float r = __fsub_rn(x, hi);
+  if (!isfinite(hi)) r = 0.0f;                       // inf/nan stay in hi; inf - inf must not poison lo
+  unsigned l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+  lo = __uint_as_float(l);
+}
+__device__ __forceinline__ int swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+// A (M x K, k contiguous) -> tiles [b][mt][kt]{hi 16KB, lo 16KB}
+__global__ void __launch_bounds__(256) pack_a_kernel(const float* __restrict__ A, char* __restrict__ out, int M, int K, long long lda, long long sA,
+                                                     int MT, int KT) {
+  // one block per (kt, mt, b): 128 rows x 8 chunks = 1024 chunks, 4 per thread
+  const int kt = blockIdx.x, mt = blockIdx.y, b = blockIdx.z;
+  char* tile = out + (((long long)b * MT + mt) * KT + kt) * (2LL * TF_A_TILE);
+  const float* Ab = A + (long long)b * sA;
+  const bool vec = ((lda & 3) == 0) && ((sA & 3) == 0) && (((uintptr_t)A & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int idx = threadIdx.x + i * 256;
+    int row = idx >> 3, c = idx & 7;
+    int m = mt * TF_BM + row, k = kt * TF_BK + c * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < M) {
+      const float* src = Ab + (long long)m * lda + k;
+      if (vec && k + 3 < K) { float4 t = __ldg((const float4*)src); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+      else { for (int j = 0; j < 4; j++) if (k + j < K) v[j] = __ldg(src + j); }
+    }
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) split_tf32(v[j], h[j], l[j]);
+    int o = swz(row, c);
+    *(float4*)(tile + o) = make_float4(h[0], h[1], h[2], h[3]);
+    *(float4*)(tile + TF_A_TILE + o) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// B (K x N, n contiguous) -> transposed tiles [b][nt][kt]{hi 32KB, lo 32KB}, rows = n, 32 k-values per row
+__global__ void __launch_bounds__(256) pack_b_kernel(const float* __restrict__ B, char* __restrict__ out, int K, int N, long long ldb, long long sB,
+                                                     int NT, int KT) {
+  // one block per (kt, 64-column slab of n, b)
+  __shared__ float t[TF_BK][65];
+  const int kt = blockIdx.x, ns = blockIdx.y, b = blockIdx.z;
+  const int n_base = ns * 64;
+  const int nt = n_base / TF_BN, row_base = n_base % TF_BN;
+  char* tile = out + (((long long)b * NT + nt) * KT + kt) * (2LL * TF_B_TILE);
+  const float* Bb = B + (long long)b * sB;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 columns x 4 rows per pass
+#pragma unroll
+  for (int r = 0; r < TF_BK; r += 4) {
+    int k = kt * TF_BK + r + ty, n = n_base + tx;
+    t[r + ty][tx] = (k < K && n < N) ? __ldg(Bb + (long long)k * ldb + n) : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    int idx = threadIdx.x + i * 256;                            // 64 rows x 8 chunks
+    int rn = idx >> 3, c = idx & 7;
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) split_tf32(t[c * 4 + j][rn], h[j], l[j]);
+    int o = swz(row_base + rn, c);
+    *(float4*)(tile + o) = make_float4(h[0], h[1], h[2], h[3]);
+    *(float4*)(tile + TF_B_TILE + o) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("numcl-cuda: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// K-major SWIZZLE_128B operand tile at `addr` (1024B aligned + k-step offset): SBO = 1024 B between 8-row atoms
+__device__ __forceinline__ unsigned long long umma_desc(unsigned addr) {
+  return (unsigned long long)((addr >> 4) & 0x3fffu) | ((unsigned long long)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+#define TF_CHUNK_KB 8            // k-blocks (of 32) accumulated inside TMEM before the sum leaves the tensor core
+#define TF_THREADS 320           // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+
+// The tensor core ADDS into the TMEM accumulator with truncation (measured on B200: relative error
+// 7e-9 * K, always toward zero -- tools/tf32_error.py), which at K = 8192 would be 6e-5, outside the
+// 1e-5 bar.  So K is cut into chunks of TF_CHUNK_KB*32 = 256: each chunk is accumulated in TMEM
+// from zero (<= 1.8e-6), then the eight epilogue warps pull it out with tcgen05.ld and add it to a
+// running round-to-nearest fp32 sum held in registers (128 per thread).  Two TMEM accumulators
+// (2 x 256 columns) alternate so that draining chunk c overlaps the MMAs of chunk c+1.
+__global__ void __launch_bounds__(TF_THREADS, 1) gemm_tf32x3_kernel(const char* __restrict__ Ap, const char* __restrict__ Bp, float* __restrict__ C,
+                                                             int M, int N, int KT, long long ldc, long long sC, int MT, int NT, int accumulate) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * TF_STAGES + 4];
+  __shared__ unsigned tmem_slot;
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tm, tn; raster(blockIdx.x, MT, NT, 8, tm, tn);
+  const int b = blockIdx.y;
+  const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TF_STAGES]);
+  const unsigned tfull0 = smem_u32(&bars[2 * TF_STAGES]), tempty0 = smem_u32(&bars[2 * TF_STAGES + 2]);
+  const int NC = (KT + TF_CHUNK_KB - 1) / TF_CHUNK_KB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TF_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int t = 0; t < 2; t++) { mbar_init(tfull0 + 8 * t, 1); mbar_init(tempty0 + 8 * t, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                    // TMEM: 2 x 256 columns = two 128 x 256 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const char* a_src = Ap + (((long long)b * MT + tm) * KT) * (2LL * TF_A_TILE);
+      const char* b_src = Bp + (((long long)b * NT + tn) * KT) * (2LL * TF_B_TILE);
+      for (int kt = 0; kt < KT; kt++) {
+        int s = kt % TF_STAGES; unsigned ph = (kt / TF_STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        mbar_expect_tx(full0 + 8 * s, TF_STAGE_BYTES);
+        unsigned dst = smem_u32(smem + s * TF_STAGE_BYTES);
+        bulk_g2s(dst, a_src + (long long)kt * (2 * TF_A_TILE), 2 * TF_A_TILE, full0 + 8 * s);
+        bulk_g2s(dst + 2 * TF_A_TILE, b_src + (long long)kt * (2 * TF_B_TILE), 2 * TF_B_TILE, full0 + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TF_BN >> 3) << 17) | ((unsigned)(TF_BM >> 4) << 24);
+      int kt = 0;
+      for (int c = 0; c < NC; c++) {
+        const int buf = c & 1; const unsigned use = (unsigned)(c >> 1);
+        mbar_wait(tempty0 + 8 * buf, (use & 1) ^ 1);          // the epilogue has drained this accumulator
+        tc_fence_after();
+        const unsigned d_tmem = tmem_base + (unsigned)(buf * TF_BN);
+        const int kend = (kt + TF_CHUNK_KB < KT) ? kt + TF_CHUNK_KB : KT;
+        for (int first = 1; kt < kend; kt++) {
+          int s = kt % TF_STAGES; unsigned ph = (kt / TF_STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          unsigned a_hi = smem_u32(smem + s * TF_STAGE_BYTES), a_lo = a_hi + TF_A_TILE;
+          unsigned b_hi = a_hi + 2 * TF_A_TILE, b_lo = b_hi + TF_B_TILE;
+#pragma unroll
+          for (int ks = 0; ks < TF_BK / 8; ks++) {     // one MMA covers K = 8 tf32 = 32 bytes of every row
+            unsigned off = ks * 32;
+            tc_mma_tf32(d_tmem, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, first ? 0u : 1u);   // small terms first
+            first = 0;
+            tc_mma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
+            tc_mma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, 1u);
+          }
+          tc_commit(empty0 + 8 * s);                    // stage reusable once these MMAs have read it
+        }
+        tc_commit(tfull0 + 8 * buf);                    // chunk complete in TMEM
+      }
+    }
+  } else {
+    // epilogue warps 2..9: TMEM lane quarter q = warp % 4, column half h; thread owns 128 outputs of one row
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    float acc[128];
+#pragma unroll
+    for (int j = 0; j < 128; j++) acc[j] = 0.0f;
+    for (int c = 0; c < NC; c++) {
+      const int buf = c & 1; const unsigned use = (unsigned)(c >> 1);
+      mbar_wait(tfull0 + 8 * buf, use & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        unsigned r[32];
+        unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(buf * TF_BN + h * 128 + cc * 32);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[cc * 32 + j] = __fadd_rn(acc[cc * 32 + j], __uint_as_float(r[j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+    }
+    const int m = tm * TF_BM + q * 32 + lane;
+    const int nbase = tn * TF_BN + h * 128;
+    if (m < M) {
+      float* crow = C + (long long)b * sC + (long long)m * ldc + nbase;
+      const bool vec = ((ldc & 3) == 0) && ((sC & 3) == 0) && (((uintptr_t)C & 15) == 0);
+      if (vec && nbase + 127 < N) {
+#pragma unroll
+        for (int j = 0; j < 128; j += 4) {
+          float4 o = accumulate ? *(const float4*)(crow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 v = make_float4(__fadd_rn(o.x, acc[j]), __fadd_rn(o.y, acc[j + 1]), __fadd_rn(o.z, acc[j + 2]), __fadd_rn(o.w, acc[j + 3]));
+          *(float4*)(crow + j) = v;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 128; j++) if (nbase + j < N) {
+          float o = accumulate ? crow[j] : 0.0f;
+          crow[j] = __fadd_rn(o, acc[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+int gemm_f32_tf32x3(const GemmParams& p) {
+  Context& c = ctx();
+  if (p.lkA != LK_F32 || p.lkB != LK_F32 || p.lkC != LK_F32) return NCL_ERR_UNSUPPORTED;
+  if (((uintptr_t)p.C & 3) || ((uintptr_t)p.A & 3) || ((uintptr_t)p.B & 3)) return NCL_ERR_UNSUPPORTED;
+  int MT = (p.M + TF_BM - 1) / TF_BM, NT = (p.N + TF_BN - 1) / TF_BN, KT = (p.K + TF_BK - 1) / TF_BK;
+  if ((long long)MT * NT > 0x7fffffffLL || p.batch > 65535 || MT > 65535) return NCL_ERR_UNSUPPORTED;
+  size_t a_bytes = (size_t)p.batch * MT * KT * 2 * TF_A_TILE, b_bytes = (size_t)p.batch * NT * KT * 2 * TF_B_TILE;
+  NCL_TRY(ensure_scratch(a_bytes + b_bytes + 2048));
+  char* Ap = (char*)(((uintptr_t)c.scratch + 1023) & ~(uintptr_t)1023);
+  char* Bp = Ap + a_bytes;
+  static bool attr_set = false;
+  if (!attr_set) { NCL_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM)); attr_set = true; }
+  pack_a_kernel<<<dim3(KT, MT, p.batch), 256, 0, c.stream>>>((const float*)p.A, Ap, p.M, p.K, p.lda, p.sA, MT, KT);
+  int nslabs = NT * (TF_BN / 64);
+  pack_b_kernel<<<dim3(KT, nslabs, p.batch), 256, 0, c.stream>>>((const float*)p.B, Bp, p.K, p.N, p.ldb, p.sB, NT, KT);
+  NCL_TRY(cuda_fail(cudaGetLastError(), "pack kernels"));
+  gemm_tf32x3_kernel<<<dim3((unsigned)(MT * NT), (unsigned)p.batch), TF_THREADS, TF_SMEM, c.stream>>>(Ap, Bp, (float*)p.C, p.M, p.N, KT, p.ldc, p.sC, MT, NT, p.accumulate);
+  note_launch("gemm_tf32x3_tcgen05", 3);
+  return cuda_fail(cudaGetLastError(), "gemm_tf32x3_kernel");
+}

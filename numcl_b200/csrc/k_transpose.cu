@@ -3,9 +3,9 @@
 // `(ij -> ji)`, `(abcd -> dbca)` (config C5b).
 //
 // HBM-bound copy.  A direct kernel would be coalesced on one side only, so the (input-contiguous,
-// output-contiguous) plane is tiled through shared memory: a 256-thread block reads a TILE x TILE
-// tile along the input's contiguous loop (each warp instruction covers 256 contiguous bytes for
-// 8-byte elements), parks it in a padded tile (row pitch TILE+1: conflict-free for both phases) and
+// output-contiguous) plane is tiled through shared memory: a 256-thread block reads a 64 x 64
+// tile along the input's contiguous loop (512-byte runs for 8-byte elements, 16 independent loads
+// per thread), parks it in a padded tile (row pitch 65: conflict-free for both phases) and
 // writes it out along the output's contiguous loop.  All remaining loops are batch coordinates
 // decoded from the block index.  Elements pass through the value class, so element-type
 // changing copies (ub8 -> fixnum: an integer einsum output is always fixnum, 3einsum.lisp:517-518)
@@ -89,14 +89,14 @@ int try_transpose(const Nest& n) {
   if (nb > TR_MAXB) return NCL_ERR_UNSUPPORTED;
   p.nb = nb; long long batch = 1;
   for (int i = 0; i < nb; i++) { p.bext[i] = bd[i].ext; p.bin[i] = bd[i].sin; p.bout[i] = bd[i].sout; batch *= bd[i].ext; }
-  int tile = (icls == CLS_F) ? 64 : 32;
+  int tile = 64;
   p.tiles_i = (p.ni + tile - 1) / tile; p.tiles_o = (p.no + tile - 1) / tile;
   long long blocks = p.tiles_i * p.tiles_o * batch;
   if (blocks > 0x7fffffffLL || blocks <= 0) return NCL_ERR_UNSUPPORTED;
   Context& c = ctx();
   if (icls == CLS_F) transpose_kernel<float, 64><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
-  else if (icls == CLS_D) transpose_kernel<double, 32><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
-  else transpose_kernel<long long, 32><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+  else if (icls == CLS_D) transpose_kernel<double, 64><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+  else transpose_kernel<long long, 64><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
   note_launch("transpose_tile");
   return cuda_fail(cudaGetLastError(), "transpose_kernel");
 }

@@ -81,6 +81,17 @@ def main():
     tout = (nc._lib.Tensor * 1)(tq)
     med, best = timed(lambda: L.ncl_einsum(C.byref(desc), tin, 1, tout, 1, 1), flush=flush)
     out["C5b_transpose"] = dict(us=med * 1e6, best_us=best * 1e6, gbs=268435456 / med / 1e9, frac=268435456 / med / 1e9 / PEAK, kernel=L.ncl_last_kernel().decode())
+    # contractions
+    from numcl_b200.einsum import _memoized
+    for name, dt, spec, sa, sb, sc, flops in [("C3_f64", "f64", "ij jk -> ik", (8192, 8192), (8192, 8192), (8192, 8192), 2 * 8192 ** 3),
+                                               ("C3_f32", "f32", "ij jk -> ik", (4096, 4096), (4096, 4096), (4096, 4096), 2 * 4096 ** 3),
+                                               ("C4_f32", "f32", "bij bjk -> bik", (256, 512, 512), (256, 512, 512), (256, 512, 512), 2 * 256 * 512 ** 3)]:
+        _, d = _memoized(spec)
+        A = nc.random_array(sa, dt, 7, 0, -1.0, 1.0); B = nc.random_array(sb, dt, 8, 0, -1.0, 1.0); Cc = nc.empty(sc, dt)
+        tin = (nc._lib.Tensor * 2)(A.tensor(), B.tensor()); tout = (nc._lib.Tensor * 1)(Cc.tensor())
+        med, best = timed(lambda: L.ncl_einsum(C.byref(d), tin, 2, tout, 1, 1), iters=3, warm=1)
+        out[name] = dict(ms=med * 1e3, tflops=flops / med / 1e12, kernel=L.ncl_last_kernel().decode())
+        del A, B, Cc
     # denominators for the contractions: cuBLAS f64 and tf32 GEMM peaks
     for name, dt, tf32 in [("f64", torch.float64, False), ("tf32", torch.float32, True), ("f32", torch.float32, False)]:
         torch.backends.cuda.matmul.allow_tf32 = tf32
