@@ -77,6 +77,60 @@ LIBM_FN(FnTan, tanf, tan) LIBM_FN(FnTanh, tanhf, tanh)
 template <class T> struct FnAddMul { typedef T R; static __device__ __forceinline__ T f(T a, T b, T c) { return Ops<T>::add(a, Ops<T>::mul(b, c)); } };
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
+// All U chunks of one operand for one work item.  The element-kind switch is taken ONCE per operand
+// per item (it is warp-uniform); inside a case the U loads are unrolled with constant offsets.  An
+// operand that is broadcast along the innermost loop (stride 0) is read once and splat.
+template <class T, int E, int U, int BITS, bool SIGNED, bool TAGGED>
+__device__ __forceinline__ void load_op_int(const char* p, unsigned q0, unsigned ext0, T (&x)[U][E]) {
+#pragma unroll
+  for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) load_int_chunk<T, E, BITS, SIGNED, TAGGED>(p + (size_t)u * 32 * E * (BITS / 8), 0, x[u]);
+}
+template <class T, int E, int U>
+__device__ __forceinline__ void load_operand(const char* base, long long elem0, int st0, int lk, unsigned q0, unsigned ext0, T (&x)[U][E]) {
+  if (st0 == 0) {
+    T s = load_scalar<T>(base, elem0, lk);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int i = 0; i < E; i++) x[u][i] = s;
+    return;
+  }
+  if constexpr (E == 1) {
+#pragma unroll
+    for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) x[u][0] = load_scalar<T>(base, elem0 + (long long)(q0 + u * 32) * st0, lk);
+  } else {
+    const long long e0 = elem0 + (long long)q0 * E;          // st0 == 1 on the vector path
+    switch (lk) {
+      case LK_U8:  load_op_int<T, E, U, 8, false, false>(base + e0, q0, ext0, x); break;
+      case LK_S8:  load_op_int<T, E, U, 8, true, false>(base + e0, q0, ext0, x); break;
+      case LK_U16: load_op_int<T, E, U, 16, false, false>(base + e0 * 2, q0, ext0, x); break;
+      case LK_S16: load_op_int<T, E, U, 16, true, false>(base + e0 * 2, q0, ext0, x); break;
+      case LK_U32: load_op_int<T, E, U, 32, false, false>(base + e0 * 4, q0, ext0, x); break;
+      case LK_S32: load_op_int<T, E, U, 32, true, false>(base + e0 * 4, q0, ext0, x); break;
+      case LK_W64: load_op_int<T, E, U, 64, true, false>(base + e0 * 8, q0, ext0, x); break;
+      case LK_T64: load_op_int<T, E, U, 64, true, true>(base + e0 * 8, q0, ext0, x); break;
+      case LK_F32: {
+        const char* p = base + e0 * 4;
+#pragma unroll
+        for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) {
+          Chunk<E * 4> c; ld_chunk(c, p + (size_t)u * 32 * E * 4);
+#pragma unroll
+          for (int i = 0; i < E; i++) x[u][i] = from_f32<T>(__uint_as_float(c.w[i]));
+        }
+        break; }
+      default: {
+        const char* p = base + e0 * 8;
+#pragma unroll
+        for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) {
+          Chunk<E * 8> c; ld_chunk(c, p + (size_t)u * 32 * E * 8);
+#pragma unroll
+          for (int i = 0; i < E; i++) x[u][i] = from_f64<T>(__longlong_as_double((long long)chunk_get<64>(c, i)));
+        }
+        break; }
+    }
+  }
+}
+
 // Persistent: one resident wave of CTAs; every WARP repeatedly takes a work item = one segment of
 // 32*U chunks of one innermost row.  The (row, segment) -> offsets decode is warp-uniform and paid
 // once per item; lane l then handles chunks l, l+32, ... of the segment, so each load / store
@@ -102,16 +156,9 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
       }
     }
     const unsigned q0 = seg * (32 * U) + lane;
-    TI x[U][NIN][E];
+    TI x[NIN][U][E];
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      unsigned q = q0 + u * 32;
-      if (q < p.ext[0]) {
-#pragma unroll
-        for (int k = 0; k < NIN; k++)
-          load_elems<TI, E>(p.base[1 + k], rowoff[1 + k] + (long long)(int)(q * E) * p.st[1 + k][0], p.lk[k], p.st[1 + k][0] != 0, x[u][k]);
-      }
-    }
+    for (int k = 0; k < NIN; k++) load_operand<TI, E, U>(p.base[1 + k], rowoff[1 + k], p.st[1 + k][0], p.lk[k], q0, p.ext[0], x[k]);
 #pragma unroll
     for (int u = 0; u < U; u++) {
       unsigned q = q0 + u * 32;
@@ -119,9 +166,9 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
         TO y[E];
 #pragma unroll
         for (int i = 0; i < E; i++) {
-          if constexpr (NIN == 1) y[i] = F::f(x[u][0][i]);
-          else if constexpr (NIN == 2) y[i] = F::f(x[u][0][i], x[u][1][i]);
-          else y[i] = F::f(x[u][0][i], x[u][1][i], x[u][2][i]);
+          if constexpr (NIN == 1) y[i] = F::f(x[0][u][i]);
+          else if constexpr (NIN == 2) y[i] = F::f(x[0][u][i], x[1][u][i]);
+          else y[i] = F::f(x[0][u][i], x[1][u][i], x[2][u][i]);
         }
         store_elems<TO, E>(p.base[0], rowoff[0] + (long long)(int)(q * E), p.sk, y);
       }
@@ -130,7 +177,8 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
 }
 
 typedef void (*EwKernel)(const EwParams);
-template <class TI, class F, int NIN, int E> static EwKernel kern() { return (EwKernel)ew_kernel<TI, F, NIN, E, (E == 1 ? 4 : (E == 32 ? 1 : 4))>; }
+template <int E> constexpr int ew_u() { return E == 32 ? 1 : (E == 2 ? 8 : 4); }
+template <class TI, class F, int NIN, int E> static EwKernel kern() { return (EwKernel)ew_kernel<TI, F, NIN, E, ew_u<E>()>; }
 template <int E> static int ufactor() { return E == 1 ? 4 : (E == 32 ? 1 : 4); }
 
 template <class T, int E> static EwKernel pick_arith(int shape) {     // T-class in, T-class out

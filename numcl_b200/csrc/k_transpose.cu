@@ -53,6 +53,51 @@ __global__ void __launch_bounds__(256) transpose_kernel(const __grid_constant__ 
   }
 }
 
+// Fast path: same element type on both sides (or an integer type, for which `0 + x` is the identity):
+// the elements move as raw W-byte words, no element-kind dispatch in the loops.
+// FZ = 1 / 2: single / double floats through the default transform into a fresh output: x + 0.0.
+template <class WT, int TILE, int FZ>
+__global__ void __launch_bounds__(256) transpose_raw_kernel(const __grid_constant__ TrParams p) {
+  __shared__ WT tile[TILE][TILE + 1];
+  long long b = blockIdx.x;
+  long long ti = b % p.tiles_i; b /= p.tiles_i;
+  long long to = b % p.tiles_o; b /= p.tiles_o;
+  long long ibase = p.in_off, obase = p.out_off;
+  for (int k = p.nb - 1; k >= 0; k--) { long long c = b % p.bext[k]; b /= p.bext[k]; ibase += c * p.bin[k]; obase += c * p.bout[k]; }
+  const int tx = threadIdx.x % TILE, ty = threadIdx.x / TILE;
+  constexpr int ROWS = 256 / TILE;
+  const long long i0 = ti * TILE, o0 = to * TILE;
+  const WT* src = (const WT*)p.in + ibase + (o0 + ty) * p.in_so + i0 + tx;
+  WT* dst = (WT*)p.out + obase + (i0 + ty) * p.out_si + o0 + tx;
+  const bool full = (i0 + TILE <= p.ni) && (o0 + TILE <= p.no);
+  if (full) {
+    WT v[TILE / ROWS];
+#pragma unroll
+    for (int r = 0; r < TILE / ROWS; r++) v[r] = __ldg(src + (long long)(r * ROWS) * p.in_so);
+#pragma unroll
+    for (int r = 0; r < TILE / ROWS; r++) tile[r * ROWS + ty][tx] = v[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < TILE / ROWS; r++) {
+      WT w = tile[tx][r * ROWS + ty];
+      if constexpr (FZ == 1) w = (WT)__float_as_uint(__fadd_rn(0.0f, __uint_as_float((unsigned)w)));
+      if constexpr (FZ == 2) w = (WT)__double_as_longlong(__dadd_rn(0.0, __longlong_as_double((long long)w)));
+      dst[(long long)(r * ROWS) * p.out_si] = w;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < TILE; r += ROWS) if (o0 + r + ty < p.no && i0 + tx < p.ni) tile[r + ty][tx] = __ldg(src + (long long)r * p.in_so);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < TILE; r += ROWS) if (i0 + r + ty < p.ni && o0 + tx < p.no) {
+      WT w = tile[tx][r + ty];
+      if constexpr (FZ == 1) w = (WT)__float_as_uint(__fadd_rn(0.0f, __uint_as_float((unsigned)w)));
+      if constexpr (FZ == 2) w = (WT)__double_as_longlong(__dadd_rn(0.0, __longlong_as_double((long long)w)));
+      dst[(long long)r * p.out_si] = w;
+    }
+  }
+}
+
 int try_transpose(const Nest& n) {
   if (n.n_out != 1 || n.n_in != 1) return NCL_ERR_UNSUPPORTED;
   const Operand& in = n.in[0]; const Operand& out = n.out[0];
@@ -89,14 +134,33 @@ int try_transpose(const Nest& n) {
   if (nb > TR_MAXB) return NCL_ERR_UNSUPPORTED;
   p.nb = nb; long long batch = 1;
   for (int i = 0; i < nb; i++) { p.bext[i] = bd[i].ext; p.bin[i] = bd[i].sin; p.bout[i] = bd[i].sout; batch *= bd[i].ext; }
+  Context& c = ctx();
+  // raw-word fast path: identical storage on both sides
+  bool raw = in.dtype == out.dtype || (icls == CLS_I && g_dt[in.dtype].slot_bits == g_dt[out.dtype].slot_bits &&
+             g_dt[in.dtype].tagged == g_dt[out.dtype].tagged && g_dt[out.dtype].value_bits >= g_dt[in.dtype].value_bits &&
+             g_dt[in.dtype].is_signed == g_dt[out.dtype].is_signed);
+  int wbytes = g_dt[in.dtype].slot_bits / 8;
+  if (raw) {
+    int tile = wbytes >= 4 ? 32 : 64;
+    p.tiles_i = (p.ni + tile - 1) / tile; p.tiles_o = (p.no + tile - 1) / tile;
+    long long blocks = p.tiles_i * p.tiles_o * batch;
+    if (blocks > 0x7fffffffLL || blocks <= 0) return NCL_ERR_UNSUPPORTED;
+    int fz = (add_zero && icls == CLS_F) ? 1 : (add_zero && icls == CLS_D) ? 2 : 0;
+    unsigned g = (unsigned)blocks;
+    if (wbytes == 8) { if (fz == 2) transpose_raw_kernel<unsigned long long, 32, 2><<<g, 256, 0, c.stream>>>(p); else transpose_raw_kernel<unsigned long long, 32, 0><<<g, 256, 0, c.stream>>>(p); }
+    else if (wbytes == 4) { if (fz == 1) transpose_raw_kernel<unsigned int, 32, 1><<<g, 256, 0, c.stream>>>(p); else transpose_raw_kernel<unsigned int, 32, 0><<<g, 256, 0, c.stream>>>(p); }
+    else if (wbytes == 2) transpose_raw_kernel<unsigned short, 64, 0><<<g, 256, 0, c.stream>>>(p);
+    else transpose_raw_kernel<unsigned char, 64, 0><<<g, 256, 0, c.stream>>>(p);
+    note_launch("transpose_tile");
+    return cuda_fail(cudaGetLastError(), "transpose_raw_kernel");
+  }
   int tile = 64;
   p.tiles_i = (p.ni + tile - 1) / tile; p.tiles_o = (p.no + tile - 1) / tile;
   long long blocks = p.tiles_i * p.tiles_o * batch;
   if (blocks > 0x7fffffffLL || blocks <= 0) return NCL_ERR_UNSUPPORTED;
-  Context& c = ctx();
   if (icls == CLS_F) transpose_kernel<float, 64><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
   else if (icls == CLS_D) transpose_kernel<double, 64><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
   else transpose_kernel<long long, 64><<<(unsigned)blocks, 256, 0, c.stream>>>(p);
-  note_launch("transpose_tile");
+  note_launch("transpose_convert");
   return cuda_fail(cudaGetLastError(), "transpose_kernel");
 }
