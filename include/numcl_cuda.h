@@ -246,6 +246,11 @@ int ncl_allreduce(int op, ncl_tensor* t);
 /* Full reduce of a row-sharded array: local two-phase reduce to a float64/int64 partial,
  * all-reduce of that one element, one final rounding into r (rank-0 tensor, every rank). */
 int ncl_reduce_all_sharded(int op, const ncl_tensor* a_local, ncl_tensor* r);
+/* Same, but the all-reduce and the final rounding are issued on the library's communication
+ * stream and overlap with later work on the compute stream; ncl_comm_join() (or ncl_sync / any
+ * d2h) orders the compute stream after them. */
+int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a_local, ncl_tensor* r);
+int ncl_comm_join(void);
 
 #ifdef __cplusplus
 }

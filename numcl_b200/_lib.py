@@ -30,6 +30,7 @@ EXPORTS = [
     "ncl_host_alloc_pinned", "ncl_host_free", "ncl_storage_bytes", "ncl_fill", "ncl_fill_random",
     "ncl_einsum", "ncl_broadcast", "ncl_fold", "ncl_map", "ncl_reduce", "ncl_convert",
     "ncl_comm_unique_id", "ncl_comm_init", "ncl_comm_destroy", "ncl_allreduce", "ncl_reduce_all_sharded",
+    "ncl_reduce_all_sharded_async", "ncl_comm_join",
 ]
 
 
@@ -126,6 +127,7 @@ def load():
     L.ncl_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ncl_allreduce.argtypes = [C.c_int, C.POINTER(Tensor)]
     L.ncl_reduce_all_sharded.argtypes = [C.c_int, C.POINTER(Tensor), C.POINTER(Tensor)]
+    L.ncl_reduce_all_sharded_async.argtypes = [C.c_int, C.POINTER(Tensor), C.POINTER(Tensor)]
     _lib = L
     return L
 

@@ -80,7 +80,7 @@ void ncl_shutdown(void) {
 int ncl_device_count(void) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) return 0; return c; }
 int ncl_set_stream(void* s) { LOCK; NEED_INIT; g_ctx.stream = s ? (cudaStream_t)s : g_ctx.own_stream; return NCL_OK; }
 void* ncl_get_stream(void) { return (void*)g_ctx.stream; }
-int ncl_sync(void) { NEED_INIT; NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); return NCL_OK; }
+int ncl_sync(void) { NEED_INIT; ncl_comm_join(); NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); return NCL_OK; }
 int64_t ncl_launch_count(void) { return g_ctx.launches; }
 const char* ncl_last_kernel(void) { return g_ctx.last_kernel; }
 int ncl_force_generic(int on) { g_ctx.force_generic = on != 0; return NCL_OK; }
@@ -115,6 +115,7 @@ int ncl_h2d(ncl_buf* dst, size_t off, const void* host, size_t bytes) {
 int ncl_d2h(void* host, const ncl_buf* src, size_t off, size_t bytes) {
   NEED_INIT;
   if (!src || off + bytes > src->bytes) return set_error(NCL_ERR_INVALID, "ncl_d2h out of range");
+  ncl_comm_join();
   NCL_CUDA(cudaMemcpyAsync(host, (const char*)src->ptr + off, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
   NCL_CUDA(cudaStreamSynchronize(g_ctx.stream));
   return NCL_OK;

@@ -20,6 +20,7 @@ typedef const char* (*fn_errstr)(int);
 static struct {
   void* h; fn_get_uid get_uid; fn_init_rank init_rank; fn_allreduce allreduce; fn_destroy destroy; fn_errstr errstr;
   nccl_comm comm; int rank, world; void* partial;   // 8-byte device slot for the sharded full reduce
+  cudaStream_t comm_stream; cudaEvent_t ev_partial, ev_done; bool pending;
 } g_nccl;
 
 static int nccl_load() {
@@ -52,8 +53,9 @@ __global__ void finalize_kernel(const W* partial, char* out, long long off, Stor
   store_scalar<W>(out, off, sk, r);
 }
 
-int finalize_partial(int op, const void* partial8, int cls, Operand& r, bool fresh) {
-  Context& c = ctx();
+static int finalize_partial_on(cudaStream_t stream, int op, const void* partial8, int cls, Operand& r, bool fresh);
+int finalize_partial(int op, const void* partial8, int cls, Operand& r, bool fresh) { return finalize_partial_on(ctx().stream, op, partial8, cls, r, fresh); }
+static int finalize_partial_on(cudaStream_t stream, int op, const void* partial8, int cls, Operand& r, bool fresh) {
   StoreSpec sk = dtype_store_spec(r.dtype); int lk = dtype_load_kind(r.dtype);
   long long ident_i = op == NCL_OP_MUL ? 1 : 0; double ident_f = op == NCL_OP_MUL ? 1.0 : 0.0;
   const DtInfo& d = g_dt[r.dtype];
@@ -64,8 +66,8 @@ int finalize_partial(int op, const void* partial8, int cls, Operand& r, bool fre
     else ident_i = mx ? (d.is_signed ? -(1ll << (d.value_bits >= 64 ? 62 : d.value_bits - 1)) : 0)
                       : (d.is_signed ? (1ll << (d.value_bits >= 64 ? 62 : d.value_bits - 1)) - 1 : (d.value_bits >= 63 ? INT64_MAX : (1ll << d.value_bits) - 1));
   }
-  if (cls == CLS_I) finalize_kernel<long long><<<1, 1, 0, c.stream>>>((const long long*)partial8, r.base, r.offset, sk, lk, fresh, op, ident_i, ident_f);
-  else finalize_kernel<double><<<1, 1, 0, c.stream>>>((const double*)partial8, r.base, r.offset, sk, lk, fresh, op, ident_i, ident_f);
+  if (cls == CLS_I) finalize_kernel<long long><<<1, 1, 0, stream>>>((const long long*)partial8, r.base, r.offset, sk, lk, fresh, op, ident_i, ident_f);
+  else finalize_kernel<double><<<1, 1, 0, stream>>>((const double*)partial8, r.base, r.offset, sk, lk, fresh, op, ident_i, ident_f);
   note_launch("reduce_finalize");
   return cuda_fail(cudaGetLastError(), "finalize_kernel");
 }
@@ -85,10 +87,17 @@ int ncl_comm_init(const void* id128, int rank, int world) {
   NCL_TRY(nccl_fail(g_nccl.init_rank(&g_nccl.comm, world, u, rank), "ncclCommInitRank"));
   g_nccl.rank = rank; g_nccl.world = world;
   NCL_CUDA(cudaMalloc(&g_nccl.partial, 64));
+  NCL_CUDA(cudaStreamCreateWithFlags(&g_nccl.comm_stream, cudaStreamNonBlocking));
+  NCL_CUDA(cudaEventCreateWithFlags(&g_nccl.ev_partial, cudaEventDisableTiming));
+  NCL_CUDA(cudaEventCreateWithFlags(&g_nccl.ev_done, cudaEventDisableTiming));
   return NCL_OK;
 }
 int ncl_comm_destroy(void) {
-  if (g_nccl.comm) { cudaStreamSynchronize(ctx().stream); g_nccl.destroy(g_nccl.comm); g_nccl.comm = nullptr; }
+  if (g_nccl.comm) {
+    cudaStreamSynchronize(ctx().stream); cudaStreamSynchronize(g_nccl.comm_stream);
+    g_nccl.destroy(g_nccl.comm); g_nccl.comm = nullptr;
+    cudaStreamDestroy(g_nccl.comm_stream); cudaEventDestroy(g_nccl.ev_partial); cudaEventDestroy(g_nccl.ev_done); g_nccl.pending = false;
+  }
   if (g_nccl.partial) { cudaFree(g_nccl.partial); g_nccl.partial = nullptr; }
   return NCL_OK;
 }
@@ -124,7 +133,11 @@ int ncl_allreduce(int op, ncl_tensor* t) {
   return nccl_fail(g_nccl.allreduce(p, p, (size_t)n, ndt, nop, g_nccl.comm, ctx().stream), "ncclAllReduce");
 }
 
-int ncl_reduce_all_sharded(int op, const ncl_tensor* a, ncl_tensor* r) {
+// The collective and the final rounding run on the library's communication stream so that the
+// ~30 us latency of a one-element all-reduce hides behind whatever the caller launches next on the
+// compute stream (e.g. the axis-1 reduction of the same slab).  ncl_comm_join() orders the compute
+// stream after it.
+int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a, ncl_tensor* r) {
   if (!ctx().inited) return set_error(NCL_ERR_STATE, "ncl_init has not been called");
   if (!a || !r || !a->buf || !r->buf) return set_error(NCL_ERR_INVALID, "ncl_reduce_all_sharded needs device-resident tensors");
   if (r->rank != 0) return set_error(NCL_ERR_SHAPE, "result of a full reduce is a rank-0 array");
@@ -132,17 +145,32 @@ int ncl_reduce_all_sharded(int op, const ncl_tensor* a, ncl_tensor* r) {
   int nop; NCL_TRY(nccl_op(op, &nop));
   Operand ao; memset(&ao, 0, sizeof ao); ao.base = (char*)a->buf->ptr; ao.dtype = a->dtype; ao.offset = a->elem_offset;
   int64_t n = 1; for (int i = 0; i < a->rank; i++) n *= a->dims[i];
-  void* slot = g_nccl.partial;
-  bool own_slot = false;
-  if (!slot) { NCL_CUDA(cudaMalloc(&slot, 64)); own_slot = true; }       // single process: no communicator needed
   int cls = g_dt[a->dtype].cls;
-  NCL_TRY(reduce_all_to_partial(op, ao, n, slot));
-  if (g_nccl.comm && g_nccl.world > 1)
-    NCL_TRY(nccl_fail(g_nccl.allreduce(slot, slot, 1, cls == CLS_I ? 4 : 8, nop, g_nccl.comm, ctx().stream), "ncclAllReduce"));
   Operand ro; memset(&ro, 0, sizeof ro); ro.base = (char*)r->buf->ptr; ro.dtype = r->dtype; ro.offset = r->elem_offset;
-  int rc = finalize_partial(op, slot, cls, ro, true);
-  if (own_slot) { cudaStreamSynchronize(ctx().stream); cudaFree(slot); }
-  return rc;
+  if (!(g_nccl.comm && g_nccl.world > 1)) {                              // single process: no exchange
+    void* slot = nullptr; NCL_CUDA(cudaMalloc(&slot, 64));
+    int rc = reduce_all_to_partial(op, ao, n, slot);
+    if (rc == NCL_OK) rc = finalize_partial(op, slot, cls, ro, true);
+    cudaStreamSynchronize(ctx().stream); cudaFree(slot);
+    return rc;
+  }
+  if (g_nccl.pending) NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done, 0));   // the slot is single-buffered
+  NCL_TRY(reduce_all_to_partial(op, ao, n, g_nccl.partial));
+  NCL_CUDA(cudaEventRecord(g_nccl.ev_partial, ctx().stream));
+  NCL_CUDA(cudaStreamWaitEvent(g_nccl.comm_stream, g_nccl.ev_partial, 0));
+  NCL_TRY(nccl_fail(g_nccl.allreduce(g_nccl.partial, g_nccl.partial, 1, cls == CLS_I ? 4 : 8, nop, g_nccl.comm, g_nccl.comm_stream), "ncclAllReduce"));
+  NCL_TRY(finalize_partial_on(g_nccl.comm_stream, op, g_nccl.partial, cls, ro, true));
+  NCL_CUDA(cudaEventRecord(g_nccl.ev_done, g_nccl.comm_stream));
+  g_nccl.pending = true;
+  return NCL_OK;
+}
+int ncl_comm_join(void) {
+  if (g_nccl.pending) { NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done, 0)); g_nccl.pending = false; }
+  return NCL_OK;
+}
+int ncl_reduce_all_sharded(int op, const ncl_tensor* a, ncl_tensor* r) {
+  NCL_TRY(ncl_reduce_all_sharded_async(op, a, r));
+  return ncl_comm_join();
 }
 
 }  // extern "C"
