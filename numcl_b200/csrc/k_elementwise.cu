@@ -154,6 +154,32 @@ int try_elementwise(const Nest& n) {
   if (!kfn) return NCL_ERR_UNSUPPORTED;
 
   EwParams p; memset(&p, 0, sizeof p);
+  // Flat mode: two dims where every operand is either contiguous across both (same shape as the
+  // output), a row vector repeated over the outer dim (stride 0 there: numpy broadcasting), or a
+  // scalar.  The nest is then walked as ONE flat run of chunks; the row-vector operands are read at
+  // (chunk mod period).  This keeps warp segments full when rows are short (C5a: 256 elements).
+  if (nd == 2 && E > 1 && d[0].st[0] == d[1].ext && d[1].st[0] == 1 && d[1].ext * d[0].ext < 0x7fffffffLL) {
+    bool ok = true; unsigned period[3] = {0, 0, 0};
+    for (int k = 0; k < m.n && ok; k++) {
+      long long s_outer = d[0].st[1 + k], s_inner = d[1].st[1 + k];
+      if (s_inner == 1 && s_outer == d[1].ext) period[k] = 0;                 // flat
+      else if (s_inner == 1 && s_outer == 0) period[k] = (unsigned)(d[1].ext / E);   // row vector
+      else if (s_inner == 0 && s_outer == 0) period[k] = 0;                   // scalar
+      else ok = false;
+    }
+    if (ok) {
+      d[0].ext = d[0].ext * d[1].ext; d[0].st[0] = 1;
+      for (int k = 0; k < m.n; k++) d[0].st[1 + k] = d[1].st[1 + k];
+      nd = 1;
+      for (int k = 0; k < m.n; k++) if (period[k] >= 1) {
+        p.period[k] = period[k];
+        if (period[k] > 1) {
+          unsigned s2 = 0; while ((1ull << s2) < period[k]) s2++;
+          p.pmul[k] = (unsigned)(((1ull << (31 + s2)) + period[k] - 1) / period[k]); p.pshr[k] = s2 - 1;
+        }                                                                     // period 1: ew_div(q, 0, 0) = q, so q mod 1 = 0
+      }
+    }
+  }
   p.nd = nd; p.n_in = m.n; p.sk = sk;
   for (int i = 0; i < nd; i++) {                      // reverse: params dim 0 is the innermost
     const D& s = d[nd - 1 - i];

@@ -28,6 +28,7 @@ struct EwParams {
   int st[4][EW_MAXD];                  // [0] = output, [1..3] = inputs; elements (|stride| < 2^31)
   char* base[4]; long long off[4];
   int lk[3]; StoreSpec sk;
+  unsigned period[3], pmul[3], pshr[3]; // flat mode: input k repeats every period[k] chunks (0 = not periodic)
   unsigned segs_per_row, seg_mul, seg_shr;   // a row of ext[0] chunks is cut into warp segments of 32*U chunks
   unsigned nitems;                     // rows * segs_per_row, < 2^31
 };
@@ -85,6 +86,16 @@ __device__ __forceinline__ void load_op_int(const char* p, unsigned q0, unsigned
 #pragma unroll
   for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) load_int_chunk<T, E, BITS, SIGNED, TAGGED>(p + (size_t)u * 32 * E * (BITS / 8), 0, x[u]);
 }
+// periodic operand (numpy row-vector broadcast in flat mode): chunk q reads chunk q mod period
+template <class T, int E, int U>
+__device__ __forceinline__ void load_operand_periodic(const char* base, long long elem0, int lk, unsigned q0, unsigned ext0,
+                                                      unsigned period, unsigned pmul, unsigned pshr, T (&x)[U][E]) {
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    unsigned q = q0 + u * 32;
+    if (q < ext0) { unsigned qm = q - ew_div(q, pmul, pshr) * period; load_elems<T, E>(base, elem0 + (long long)qm * E, lk, true, x[u]); }
+  }
+}
 template <class T, int E, int U>
 __device__ __forceinline__ void load_operand(const char* base, long long elem0, int st0, int lk, unsigned q0, unsigned ext0, T (&x)[U][E]) {
   if (st0 == 0) {
@@ -131,15 +142,56 @@ __device__ __forceinline__ void load_operand(const char* base, long long elem0, 
   }
 }
 
+// all U chunks of the output for one item: the store-kind switch is taken once, offsets are constants
+template <class TO, int E, int U, int BITS>
+__device__ __forceinline__ void store_op_int(char* p, unsigned q0, unsigned ext0, const StoreSpec& sk, const TO (&y)[U][E]) {
+#pragma unroll
+  for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) {
+    Chunk<E * BITS / 8> c;
+#pragma unroll
+    for (int i = 0; i < E; i++) chunk_put<BITS>(c, i, (((unsigned long long)y[u][i]) & sk.mask) << sk.shift);
+    st_chunk(c, p + (size_t)u * 32 * E * (BITS / 8));
+  }
+}
+template <class TO, int E, int U>
+__device__ __forceinline__ void store_operand(char* base, long long elem0, unsigned q0, unsigned ext0, const StoreSpec& sk, const TO (&y)[U][E]) {
+  if constexpr (E == 1 || E == 32) {
+#pragma unroll
+    for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) store_elems<TO, E>(base, elem0 + (long long)(q0 + u * 32) * E, sk, y[u]);
+  } else if constexpr (!std::is_integral<TO>::value) {
+#pragma unroll
+    for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) store_elems<TO, E>(base, elem0 + (long long)(q0 + u * 32) * E, sk, y[u]);
+  } else {
+    const long long e0 = elem0 + (long long)q0 * E;
+    switch (sk.kind) {
+      case SK_8:  store_op_int<TO, E, U, 8>(base + e0, q0, ext0, sk, y); break;
+      case SK_16: store_op_int<TO, E, U, 16>(base + e0 * 2, q0, ext0, sk, y); break;
+      case SK_32: store_op_int<TO, E, U, 32>(base + e0 * 4, q0, ext0, sk, y); break;
+      default:    store_op_int<TO, E, U, 64>(base + e0 * 8, q0, ext0, sk, y); break;
+    }
+  }
+}
+
 // Persistent: one resident wave of CTAs; every WARP repeatedly takes a work item = one segment of
 // 32*U chunks of one innermost row.  The (row, segment) -> offsets decode is warp-uniform and paid
 // once per item; lane l then handles chunks l, l+32, ... of the segment, so each load / store
 // instruction of the warp covers 32 consecutive chunks (512 contiguous bytes for 16-byte chunks).
+// Flat mode (nd == 1 with periodic operands): a row-vector operand whose period divides the segment
+// gives every lane the SAME elements in every item, so it is loaded once, before the loop.
 template <class TI, class F, int NIN, int E, int U>
 __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ EwParams p) {
   typedef typename F::R TO;
   const int lane = threadIdx.x & 31;
   const unsigned nwarps = gridDim.x * (EW_THREADS / 32);
+  constexpr unsigned SEG = 32 * U;
+  TI x[NIN][U][E];
+  bool hoisted[NIN], stepped[NIN];
+#pragma unroll
+  for (int k = 0; k < NIN; k++) {
+    hoisted[k] = p.period[k] != 0 && (SEG % p.period[k]) == 0;        // item-invariant
+    stepped[k] = p.period[k] != 0 && !hoisted[k] && (p.period[k] % SEG) == 0;   // no wrap inside an item
+    if (hoisted[k]) load_operand_periodic<TI, E, U>(p.base[1 + k], p.off[1 + k], p.lk[k], (unsigned)lane, 0xffffffffu, p.period[k], p.pmul[k], p.pshr[k], x[k]);
+  }
   for (unsigned item = blockIdx.x * (EW_THREADS / 32) + (threadIdx.x >> 5); item < p.nitems; item += nwarps) {
     unsigned row = ew_div(item, p.seg_mul, p.seg_shr);
     unsigned seg = item - row * p.segs_per_row;
@@ -155,24 +207,27 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
         for (int k = 0; k < 4; k++) rowoff[k] += (long long)c * p.st[k][d];
       }
     }
-    const unsigned q0 = seg * (32 * U) + lane;
-    TI x[NIN][U][E];
+    const unsigned q0 = seg * SEG + lane;
 #pragma unroll
-    for (int k = 0; k < NIN; k++) load_operand<TI, E, U>(p.base[1 + k], rowoff[1 + k], p.st[1 + k][0], p.lk[k], q0, p.ext[0], x[k]);
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      unsigned q = q0 + u * 32;
-      if (q < p.ext[0]) {
-        TO y[E];
-#pragma unroll
-        for (int i = 0; i < E; i++) {
-          if constexpr (NIN == 1) y[i] = F::f(x[0][u][i]);
-          else if constexpr (NIN == 2) y[i] = F::f(x[0][u][i], x[1][u][i]);
-          else y[i] = F::f(x[0][u][i], x[1][u][i], x[2][u][i]);
-        }
-        store_elems<TO, E>(p.base[0], rowoff[0] + (long long)(int)(q * E), p.sk, y);
-      }
+    for (int k = 0; k < NIN; k++) {
+      if (hoisted[k]) continue;
+      if (stepped[k]) {
+        unsigned s0 = seg * SEG;
+        unsigned base_chunk = s0 - ew_div(s0, p.pmul[k], p.pshr[k]) * p.period[k];
+        load_operand<TI, E, U>(p.base[1 + k], rowoff[1 + k] + ((long long)base_chunk - (long long)s0) * E, 1, p.lk[k], q0, p.ext[0], x[k]);
+      } else if (p.period[k]) load_operand_periodic<TI, E, U>(p.base[1 + k], rowoff[1 + k], p.lk[k], q0, p.ext[0], p.period[k], p.pmul[k], p.pshr[k], x[k]);
+      else load_operand<TI, E, U>(p.base[1 + k], rowoff[1 + k], p.st[1 + k][0], p.lk[k], q0, p.ext[0], x[k]);
     }
+    TO y[U][E];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int i = 0; i < E; i++) {
+        if constexpr (NIN == 1) y[u][i] = F::f(x[0][u][i]);
+        else if constexpr (NIN == 2) y[u][i] = F::f(x[0][u][i], x[1][u][i]);
+        else y[u][i] = F::f(x[0][u][i], x[1][u][i], x[2][u][i]);
+      }
+    store_operand<TO, E, U>(p.base[0], rowoff[0], q0, p.ext[0], p.sk, y);
   }
 }
 

@@ -15,7 +15,7 @@
 //     with hi and lo tiles adjacent.  B is transposed on the way so both operands are K-major.
 //     A pipeline stage is then two plain contiguous blobs, fetched with two cp.async.bulk
 //     (SASS UBLKCP) instructions: no tensor maps, no address math in the hot loop.
-//  2. gemm: one CTA per 128 x 256 output tile, 10 warps, warp-specialised:
+//  2. gemm: persistent, one CTA per SM looping over 128 x 256 output tiles, 10 warps, warp-specialised:
 //       warp 0      TMA producer  (one lane): empty[s] -> expect_tx -> 2 bulk copies -> full[s]
 //       warp 1      MMA issuer    (one lane): full[s] -> 4 k-steps x 3 tcgen05.mma -> commit -> empty[s]
 //       warps 2..9  epilogue: tmem_full[b] -> tcgen05.ld 32 lanes x 32 columns -> running fp32 sum -> global
@@ -150,17 +150,20 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarri
 // running round-to-nearest fp32 sum held in registers (128 per thread).  Two TMEM accumulators
 // (2 x 256 columns) alternate so that draining chunk c overlaps the MMAs of chunk c+1.
 __global__ void __launch_bounds__(TF_THREADS, 1) gemm_tf32x3_kernel(const char* __restrict__ Ap, const char* __restrict__ Bp, float* __restrict__ C,
-                                                             int M, int N, int KT, long long ldc, long long sC, int MT, int NT, int accumulate) {
+                                                             int M, int N, int KT, long long ldc, long long sC, int MT, int NT, int batch, int accumulate) {
+  // PERSISTENT: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The smem ring
+  // and the two TMEM accumulators keep rolling across tile boundaries, so the MMAs of the next tile
+  // run while the epilogue warps are still storing the previous one.
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bars[2 * TF_STAGES + 4];
   __shared__ unsigned tmem_slot;
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int tm, tn; raster(blockIdx.x, MT, NT, 8, tm, tn);
-  const int b = blockIdx.y;
   const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TF_STAGES]);
   const unsigned tfull0 = smem_u32(&bars[2 * TF_STAGES]), tempty0 = smem_u32(&bars[2 * TF_STAGES + 2]);
   const int NC = (KT + TF_CHUNK_KB - 1) / TF_CHUNK_KB;
+  const int tiles_per_batch = MT * NT;
+  const int total_tiles = tiles_per_batch * batch;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TF_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -178,94 +181,105 @@ __global__ void __launch_bounds__(TF_THREADS, 1) gemm_tf32x3_kernel(const char* 
 
   if (warp == 0) {
     if (lane == 0) {
-      const char* a_src = Ap + (((long long)b * MT + tm) * KT) * (2LL * TF_A_TILE);
-      const char* b_src = Bp + (((long long)b * NT + tn) * KT) * (2LL * TF_B_TILE);
-      for (int kt = 0; kt < KT; kt++) {
-        int s = kt % TF_STAGES; unsigned ph = (kt / TF_STAGES) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        mbar_expect_tx(full0 + 8 * s, TF_STAGE_BYTES);
-        unsigned dst = smem_u32(smem + s * TF_STAGE_BYTES);
-        bulk_g2s(dst, a_src + (long long)kt * (2 * TF_A_TILE), 2 * TF_A_TILE, full0 + 8 * s);
-        bulk_g2s(dst + 2 * TF_A_TILE, b_src + (long long)kt * (2 * TF_B_TILE), 2 * TF_B_TILE, full0 + 8 * s);
+      unsigned it = 0;                                // k-blocks issued so far (all tiles)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int b = t / tiles_per_batch, tm, tn; raster(t - b * tiles_per_batch, MT, NT, 8, tm, tn);
+        const char* a_src = Ap + (((long long)b * MT + tm) * KT) * (2LL * TF_A_TILE);
+        const char* b_src = Bp + (((long long)b * NT + tn) * KT) * (2LL * TF_B_TILE);
+        for (int kt = 0; kt < KT; kt++, it++) {
+          int s = it % TF_STAGES; unsigned ph = (it / TF_STAGES) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, TF_STAGE_BYTES);
+          unsigned dst = smem_u32(smem + s * TF_STAGE_BYTES);
+          bulk_g2s(dst, a_src + (long long)kt * (2 * TF_A_TILE), 2 * TF_A_TILE, full0 + 8 * s);
+          bulk_g2s(dst + 2 * TF_A_TILE, b_src + (long long)kt * (2 * TF_B_TILE), 2 * TF_B_TILE, full0 + 8 * s);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
       const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TF_BN >> 3) << 17) | ((unsigned)(TF_BM >> 4) << 24);
-      int kt = 0;
-      for (int c = 0; c < NC; c++) {
-        const int buf = c & 1; const unsigned use = (unsigned)(c >> 1);
-        mbar_wait(tempty0 + 8 * buf, (use & 1) ^ 1);          // the epilogue has drained this accumulator
-        tc_fence_after();
-        const unsigned d_tmem = tmem_base + (unsigned)(buf * TF_BN);
-        const int kend = (kt + TF_CHUNK_KB < KT) ? kt + TF_CHUNK_KB : KT;
-        for (int first = 1; kt < kend; kt++) {
-          int s = kt % TF_STAGES; unsigned ph = (kt / TF_STAGES) & 1;
-          mbar_wait(full0 + 8 * s, ph);
+      unsigned it = 0, g = 0;                         // k-blocks / chunks consumed so far (all tiles)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int kt = 0;
+        for (int c = 0; c < NC; c++, g++) {
+          const int buf = g & 1; const unsigned use = g >> 1;
+          mbar_wait(tempty0 + 8 * buf, (use & 1) ^ 1);          // the epilogue has drained this accumulator
           tc_fence_after();
-          unsigned a_hi = smem_u32(smem + s * TF_STAGE_BYTES), a_lo = a_hi + TF_A_TILE;
-          unsigned b_hi = a_hi + 2 * TF_A_TILE, b_lo = b_hi + TF_B_TILE;
+          const unsigned d_tmem = tmem_base + (unsigned)(buf * TF_BN);
+          const int kend = (kt + TF_CHUNK_KB < KT) ? kt + TF_CHUNK_KB : KT;
+          for (int first = 1; kt < kend; kt++, it++) {
+            int s = it % TF_STAGES; unsigned ph = (it / TF_STAGES) & 1;
+            mbar_wait(full0 + 8 * s, ph);
+            tc_fence_after();
+            unsigned a_hi = smem_u32(smem + s * TF_STAGE_BYTES), a_lo = a_hi + TF_A_TILE;
+            unsigned b_hi = a_hi + 2 * TF_A_TILE, b_lo = b_hi + TF_B_TILE;
 #pragma unroll
-          for (int ks = 0; ks < TF_BK / 8; ks++) {     // one MMA covers K = 8 tf32 = 32 bytes of every row
-            unsigned off = ks * 32;
-            tc_mma_tf32(d_tmem, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, first ? 0u : 1u);   // small terms first
-            first = 0;
-            tc_mma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
-            tc_mma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, 1u);
+            for (int ks = 0; ks < TF_BK / 8; ks++) {     // one MMA covers K = 8 tf32 = 32 bytes of every row
+              unsigned off = ks * 32;
+              tc_mma_tf32(d_tmem, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, first ? 0u : 1u);   // small terms first
+              first = 0;
+              tc_mma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
+              tc_mma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, 1u);
+            }
+            tc_commit(empty0 + 8 * s);                    // stage reusable once these MMAs have read it
           }
-          tc_commit(empty0 + 8 * s);                    // stage reusable once these MMAs have read it
+          tc_commit(tfull0 + 8 * buf);                    // chunk complete in TMEM
         }
-        tc_commit(tfull0 + 8 * buf);                    // chunk complete in TMEM
       }
     }
   } else {
     // epilogue warps 2..9: TMEM lane quarter q = warp % 4, column half h; thread owns 128 outputs of one row
     const int q = warp & 3, h = (warp - 2) >> 2;
-    float acc[128];
+    const bool vec = ((ldc & 3) == 0) && ((sC & 3) == 0) && (((uintptr_t)C & 15) == 0);
+    unsigned g = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int b = t / tiles_per_batch, tm, tn; raster(t - b * tiles_per_batch, MT, NT, 8, tm, tn);
+      float acc[128];
 #pragma unroll
-    for (int j = 0; j < 128; j++) acc[j] = 0.0f;
-    for (int c = 0; c < NC; c++) {
-      const int buf = c & 1; const unsigned use = (unsigned)(c >> 1);
-      mbar_wait(tfull0 + 8 * buf, use & 1);
-      tc_fence_after();
+      for (int j = 0; j < 128; j++) acc[j] = 0.0f;
+      for (int c = 0; c < NC; c++, g++) {
+        const int buf = g & 1; const unsigned use = g >> 1;
+        mbar_wait(tfull0 + 8 * buf, use & 1);
+        tc_fence_after();
 #pragma unroll
-      for (int cc = 0; cc < 4; cc++) {
-        unsigned r[32];
-        unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(buf * TF_BN + h * 128 + cc * 32);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                     : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int cc = 0; cc < 4; cc++) {
+          unsigned r[32];
+          unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(buf * TF_BN + h * 128 + cc * 32);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                       : "r"(taddr) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; j++) acc[cc * 32 + j] = __fadd_rn(acc[cc * 32 + j], __uint_as_float(r[j]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
-    }
-    const int m = tm * TF_BM + q * 32 + lane;
-    const int nbase = tn * TF_BN + h * 128;
-    if (m < M) {
-      float* crow = C + (long long)b * sC + (long long)m * ldc + nbase;
-      const bool vec = ((ldc & 3) == 0) && ((sC & 3) == 0) && (((uintptr_t)C & 15) == 0);
-      if (vec && nbase + 127 < N) {
-#pragma unroll
-        for (int j = 0; j < 128; j += 4) {
-          float4 o = accumulate ? *(const float4*)(crow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 v = make_float4(__fadd_rn(o.x, acc[j]), __fadd_rn(o.y, acc[j + 1]), __fadd_rn(o.z, acc[j + 2]), __fadd_rn(o.w, acc[j + 3]));
-          *(float4*)(crow + j) = v;
+          for (int j = 0; j < 32; j++) acc[cc * 32 + j] = __fadd_rn(acc[cc * 32 + j], __uint_as_float(r[j]));
         }
-      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      }
+      const int m = tm * TF_BM + q * 32 + lane;
+      const int nbase = tn * TF_BN + h * 128;
+      if (m < M) {
+        float* crow = C + (long long)b * sC + (long long)m * ldc + nbase;
+        if (vec && nbase + 127 < N) {
 #pragma unroll
-        for (int j = 0; j < 128; j++) if (nbase + j < N) {
-          float o = accumulate ? crow[j] : 0.0f;
-          crow[j] = __fadd_rn(o, acc[j]);
+          for (int j = 0; j < 128; j += 4) {
+            float4 o = accumulate ? *(const float4*)(crow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 v = make_float4(__fadd_rn(o.x, acc[j]), __fadd_rn(o.y, acc[j + 1]), __fadd_rn(o.z, acc[j + 2]), __fadd_rn(o.w, acc[j + 3]));
+            *(float4*)(crow + j) = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 128; j++) if (nbase + j < N) {
+            float o = accumulate ? crow[j] : 0.0f;
+            crow[j] = __fadd_rn(o, acc[j]);
+          }
         }
       }
     }
@@ -294,7 +308,10 @@ int gemm_f32_tf32x3(const GemmParams& p) {
   int nslabs = NT * (TF_BN / 64);
   pack_b_kernel<<<dim3(KT, nslabs, p.batch), 256, 0, c.stream>>>((const float*)p.B, Bp, p.K, p.N, p.ldb, p.sB, NT, KT);
   NCL_TRY(cuda_fail(cudaGetLastError(), "pack kernels"));
-  gemm_tf32x3_kernel<<<dim3((unsigned)(MT * NT), (unsigned)p.batch), TF_THREADS, TF_SMEM, c.stream>>>(Ap, Bp, (float*)p.C, p.M, p.N, KT, p.ldc, p.sC, MT, NT, p.accumulate);
+  long long total_tiles = (long long)MT * NT * p.batch;
+  if (total_tiles > 0x7fffffffLL) return NCL_ERR_UNSUPPORTED;
+  unsigned grid = (unsigned)(total_tiles < c.sm_count ? total_tiles : c.sm_count);
+  gemm_tf32x3_kernel<<<grid, TF_THREADS, TF_SMEM, c.stream>>>(Ap, Bp, (float*)p.C, p.M, p.N, KT, p.ldc, p.sC, MT, NT, p.batch, p.accumulate);
   note_launch("gemm_tf32x3_tcgen05", 3);
   return cuda_fail(cudaGetLastError(), "gemm_tf32x3_kernel");
 }
