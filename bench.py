@@ -72,6 +72,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 break
+            time.sleep(0.0005)        # yield the GIL: the launch loop of this rank must not be starved
 
     def start(self):
         if self.nv:
@@ -272,6 +273,10 @@ def run_ours(args):
     ta, trows, ttot = a.tensor(), rows.tensor(), total.tensor()
     ax1 = (C.c_int * 1)(1)
 
+    sync_a = nc.zeros((8,), type="f32")
+    sync_r = nc.empty((), type="f32")
+    tsync_a, tsync_r = sync_a.tensor(), sync_r.tensor()
+
     def step(ev=None):
         # N > 1: the full sum goes first so that its one-element all-reduce (communication stream)
         # hides behind the axis-1 kernel, which needs no exchange; ncl_comm_join closes the step.
@@ -302,20 +307,37 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    # per-kernel events on every 4th step only: with N ranks in lock-step the host side of a step must
+    # stay far below the 0.34 ms of device work, or the slowest rank's launch loop sets the pace
+    ev_steps = [i for i in range(args.steps) if i % 4 == 0]
+    evmap = {i: [torch.cuda.Event(enable_timing=True) for _ in range(4)] for i in ev_steps}
+    evs = list(evmap.values())
     l0 = L.ncl_launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        # device-side alignment: ranks leave the host barrier up to milliseconds apart; a one-element
+        # all-reduce enqueued BEFORE the start event makes every GPU begin its timed region together,
+        # so the max-over-ranks time does not charge the first rank for the last rank's late start
+        _lib.check(L.ncl_reduce_all_sharded(_lib.OPS["ADD"], C.byref(tsync_a), C.byref(tsync_r)))
     t_start.record(stream)
+    h0 = time.perf_counter()
     for i in range(args.steps):
-        step(evs[i])
+        step(evmap.get(i))
+    host_enqueue = time.perf_counter() - h0
     t_end.record(stream)
     barrier()
     launches = L.ncl_launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     elapsed = t_start.elapsed_time(t_end) * 1e-3
-    t_row = sum(e[0].elapsed_time(e[3]) for e in evs) * 1e-3 / args.steps
-    t_all = sum(e[1].elapsed_time(e[2]) for e in evs) * 1e-3 / args.steps
+    t_row = sum(e[0].elapsed_time(e[3]) for e in evs) * 1e-3 / len(evs)
+    t_all = sum(e[1].elapsed_time(e[2]) for e in evs) * 1e-3 / len(evs)
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([elapsed, t_row, t_all, host_enqueue / args.steps], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(x[0].item() / args.steps * 1e3, 4) for x in allr], "row_us": [round(x[1].item() * 1e6, 1) for x in allr],
+                    "full_us": [round(x[2].item() * 1e6, 1) for x in allr], "host_enqueue_us": [round(x[3].item() * 1e6, 1) for x in allr]}
         tt = torch.tensor([elapsed, t_row, t_all], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed, t_row, t_all = tt.tolist()
@@ -388,8 +410,11 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": N_ROWS * N_COLS * 4 * 1, "d2h_bytes_per_step": N_ROWS * 4 + 4,
                 "steps": e2e_steps, "api": "ncl_h2d + ncl_reduce x2 + ncl_d2h (pinned host slab)"},
         "gpu_launches": int(launches),
+        "host_enqueue_us_per_step": host_enqueue / args.steps * 1e6,
         "clocks": clocks,
     }
+    if per_rank:
+        line["per_rank"] = per_rank
     if cpu:
         line["cpu_baseline"] = cpu
     if others:

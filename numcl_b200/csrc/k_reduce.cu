@@ -46,6 +46,10 @@ struct RedParams {
   // all
   void* block_partials; unsigned int* ticket; int nblocks;
   void* raw_partial;                               // when set: write the f64/i64 partial here and skip the final store
+  // fused all-reduce over NVLink peer memory (sharded full reduce): every rank's mailbox is mapped
+  // into every other rank; the LAST block of this kernel pushes the local partial into all peers'
+  // mailboxes, waits for theirs, folds them in rank order and stores the final value itself.
+  unsigned long long* const* peers; int rank, world; unsigned long long seq;
 };
 
 template <class T> __device__ __forceinline__ T ident_of(const RedParams& p) {
@@ -167,6 +171,45 @@ __global__ void __launch_bounds__(256) reduce_all_kernel(const __grid_constant__
   W s = (OP == R_ADD) ? (W)0 : (OP == R_MUL) ? (W)1 : ((volatile W*)partials)[0];
   for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) s = Red<W, OP>::f(s, ((volatile W*)partials)[i]);
   s = block_combine<W, OP, 256>(s);
+  if (p.world > 1) {
+    // ---- compute + collective in ONE kernel: P2P stores / loads on NVLink-mapped mailboxes -------
+    // mailbox layout per rank: [parity 2][source rank world]{value bits, sequence}; the parity slot of
+    // call n cannot be overwritten by call n+2 before every rank has consumed call n (each rank only
+    // reaches n+2 after receiving everybody's n+1, which is sent after n was read).
+    __shared__ unsigned long long xch[64];
+    if (threadIdx.x == 0) { *p.ticket = 0; xch[63] = (unsigned long long)(std::is_integral<T>::value ? (long long)s : __double_as_longlong((double)s)); }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < p.world) {
+      const size_t slot = (((size_t)(p.seq & 1) * p.world) + p.rank) * 2;
+      volatile unsigned long long* remote = p.peers[t] + slot;
+      remote[0] = xch[63];
+      __threadfence_system();
+      remote[1] = p.seq;                                                   // publish
+      volatile unsigned long long* mine = p.peers[p.rank] + (((size_t)(p.seq & 1) * p.world) + t) * 2;
+      long long t0 = clock64();
+      unsigned long long seen;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine + 1) : "memory");
+        if (seen != p.seq && clock64() - t0 > 20000000000LL) { printf("numcl-cuda: peer %d did not arrive (rank %d)\n", t, p.rank); __trap(); }
+      } while (seen != p.seq);
+      xch[t] = mine[0];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      W tot;
+      if constexpr (std::is_integral<T>::value) tot = (W)(long long)xch[0]; else tot = (W)__longlong_as_double((long long)xch[0]);
+      for (int r = 1; r < p.world; r++) {
+        W v; if constexpr (std::is_integral<T>::value) v = (W)(long long)xch[r]; else v = (W)__longlong_as_double((long long)xch[r]);
+        tot = Red<W, OP>::f(tot, v);                                       // rank order: every rank gets the same bits
+      }
+      W init = p.fresh ? (W)ident_of<T>(p) : (W)load_scalar<T>(p.out, p.out_off, p.out_lk);
+      W r = Red<W, OP>::f(init, tot);
+      if constexpr (std::is_integral<T>::value) store_scalar<long long>(p.out, p.out_off, p.sk, r);
+      else store_scalar<double>(p.out, p.out_off, p.sk, r);
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     *p.ticket = 0;                                   // re-arm for the next launch on this stream
     if (p.raw_partial) { *(W*)p.raw_partial = s; return; }
@@ -398,6 +441,39 @@ int try_reduce(const Nest& n) {
     NCL_TRY(cuda_fail(cudaGetLastError(), "reduce_col_finish_kernel"));
   }
   return NCL_OK;
+}
+
+// sharded full reduce with the exchange fused into the kernel (peer mailboxes over NVLink)
+int reduce_all_p2p(int op, const Operand& a, int64_t count, const Operand& r, unsigned long long* const* peers, int rank, int world,
+                   unsigned long long seq) {
+  Context& c = ctx();
+  int cls = g_dt[a.dtype].cls; int sb = g_dt[a.dtype].slot_bits;
+  if (sb < 8 || world > 63) return NCL_ERR_UNSUPPORTED;
+  int rop = op == NCL_OP_ADD ? R_ADD : op == NCL_OP_MUL ? R_MUL : op == NCL_OP_MAX ? R_MAX : op == NCL_OP_MIN ? R_MIN : -1;
+  if (rop < 0) return NCL_ERR_UNSUPPORTED;
+  RedParams p; memset(&p, 0, sizeof p);
+  p.in = a.base; p.in_off = a.offset; p.lk = dtype_load_kind(a.dtype); p.cols = count;
+  p.out = r.base; p.out_off = r.offset; p.sk = dtype_store_spec(r.dtype); p.out_lk = dtype_load_kind(r.dtype);
+  p.fresh = 1; p.ident_i = rop == R_MUL ? 1 : 0; p.ident_f = rop == R_MUL ? 1.0 : 0.0;
+  if (rop == R_MAX || rop == R_MIN) {
+    const DtInfo& d = g_dt[r.dtype]; bool mx = rop == R_MAX;
+    if (d.cls == CLS_F) p.ident_f = mx ? -3.4028234663852886e38 : 3.4028234663852886e38;
+    else if (d.cls == CLS_D) p.ident_f = mx ? -1.7976931348623157e308 : 1.7976931348623157e308;
+    else if (d.is_signed) p.ident_i = mx ? (d.value_bits >= 64 ? INT64_MIN : -(1ll << (d.value_bits - 1))) : (d.value_bits >= 64 ? INT64_MAX : (1ll << (d.value_bits - 1)) - 1);
+    else p.ident_i = mx ? 0 : (d.value_bits >= 63 ? INT64_MAX : (1ll << d.value_bits) - 1);
+  }
+  int Evec = 128 / sb;
+  p.vec = (count % Evec == 0) && aligned16(a, a.offset);
+  int E = p.vec ? Evec : 1;
+  long long work = p.vec ? count / E : count;
+  RedKernel kfn = kernel_for(cls, E, rop, KALL);
+  long long blocks = (work + 1023) / 1024; long long cap = persistent_blocks((const void*)kfn); if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
+  NCL_TRY(ensure_scratch((size_t)blocks * 8));
+  p.block_partials = c.scratch; p.ticket = c.ticket; p.nblocks = (int)blocks;
+  p.peers = peers; p.rank = rank; p.world = world; p.seq = seq;
+  kfn<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+  note_launch("reduce_all_p2p");
+  return cuda_fail(cudaGetLastError(), "reduce_all_kernel (p2p)");
 }
 
 // local phase of a sharded full reduce: contiguous a -> one float64 / int64 partial on the device

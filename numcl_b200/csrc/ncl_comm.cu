@@ -15,10 +15,13 @@ typedef int (*fn_get_uid)(nccl_uid*);
 typedef int (*fn_init_rank)(nccl_comm*, int, nccl_uid, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
 typedef int (*fn_destroy)(nccl_comm);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
 
 static struct {
-  void* h; fn_get_uid get_uid; fn_init_rank init_rank; fn_allreduce allreduce; fn_destroy destroy; fn_errstr errstr;
+  void* h; fn_get_uid get_uid; fn_init_rank init_rank; fn_allreduce allreduce; fn_destroy destroy; fn_errstr errstr; fn_allgather allgather;
+  // peer mailboxes for the fused one-element all-reduce (NVLink P2P, CUDA IPC)
+  unsigned long long* mbox; unsigned long long** peers_host; unsigned long long** peers_dev; bool p2p; unsigned long long seq;
   nccl_comm comm; int rank, world; void* partial;   // 8-byte device slot for the sharded full reduce
   cudaStream_t comm_stream; cudaEvent_t ev_partial, ev_done; bool pending;
 } g_nccl;
@@ -33,6 +36,7 @@ static int nccl_load() {
   g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.h, "ncclAllReduce");
   g_nccl.destroy = (fn_destroy)dlsym(g_nccl.h, "ncclCommDestroy");
   g_nccl.errstr = (fn_errstr)dlsym(g_nccl.h, "ncclGetErrorString");
+  g_nccl.allgather = (fn_allgather)dlsym(g_nccl.h, "ncclAllGather");
   if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.destroy)
     return set_error(NCL_ERR_STATE, "libnccl.so.2 lacks the expected symbols");
   return NCL_OK;
@@ -72,6 +76,48 @@ static int finalize_partial_on(cudaStream_t stream, int op, const void* partial8
   return cuda_fail(cudaGetLastError(), "finalize_kernel");
 }
 
+// Map every rank's mailbox into this process (CUDA IPC over NVLink).  The 64-byte IPC handles travel
+// through one ncclAllGather; any failure simply leaves p2p off.
+static void setup_p2p() {
+  g_nccl.p2p = false;
+  if (!g_nccl.allgather || g_nccl.world < 2 || g_nccl.world > 63 || getenv("NUMCL_CUDA_NO_P2P")) return;
+  const int W = g_nccl.world; cudaStream_t st = ctx().stream;
+  size_t mbytes = (size_t)2 * W * 16;
+  if (cudaMalloc((void**)&g_nccl.mbox, mbytes) != cudaSuccess) return;
+  cudaMemset(g_nccl.mbox, 0, mbytes);
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, g_nccl.mbox) != cudaSuccess) { cudaGetLastError(); return; }
+  char* dev_handles = nullptr;
+  if (cudaMalloc((void**)&dev_handles, (size_t)W * sizeof mine) != cudaSuccess) return;
+  cudaMemcpy(dev_handles + (size_t)g_nccl.rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice);
+  cudaDeviceSynchronize();
+  if (g_nccl.allgather(dev_handles + (size_t)g_nccl.rank * sizeof mine, dev_handles, sizeof mine, 0 /* ncclChar */, g_nccl.comm, st) != 0) { cudaFree(dev_handles); return; }
+  if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(dev_handles); return; }
+  cudaIpcMemHandle_t* all = new cudaIpcMemHandle_t[W];
+  cudaMemcpy(all, dev_handles, (size_t)W * sizeof mine, cudaMemcpyDeviceToHost);
+  cudaFree(dev_handles);
+  g_nccl.peers_host = new unsigned long long*[W];
+  bool ok = true;
+  for (int r = 0; r < W && ok; r++) {
+    if (r == g_nccl.rank) { g_nccl.peers_host[r] = g_nccl.mbox; continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    g_nccl.peers_host[r] = (unsigned long long*)p;
+  }
+  delete[] all;
+  if (!ok) return;
+  if (cudaMalloc((void**)&g_nccl.peers_dev, (size_t)W * sizeof(void*)) != cudaSuccess) return;
+  cudaMemcpy(g_nccl.peers_dev, g_nccl.peers_host, (size_t)W * sizeof(void*), cudaMemcpyHostToDevice);
+  // nobody may push before every rank has zeroed and mapped its mailbox: one more (tiny) collective as a barrier
+  int* flag = nullptr;
+  if (cudaMalloc((void**)&flag, 64) != cudaSuccess) return;
+  cudaMemset(flag, 0, 64);
+  bool synced = g_nccl.allreduce(flag, flag, 1, 2 /* ncclInt32 */, 0 /* sum */, g_nccl.comm, st) == 0 && cudaStreamSynchronize(st) == cudaSuccess;
+  cudaFree(flag);
+  if (!synced) return;
+  g_nccl.seq = 0; g_nccl.p2p = true;
+}
+
 extern "C" {
 
 int ncl_comm_unique_id(void* id128) {
@@ -87,9 +133,13 @@ int ncl_comm_init(const void* id128, int rank, int world) {
   NCL_TRY(nccl_fail(g_nccl.init_rank(&g_nccl.comm, world, u, rank), "ncclCommInitRank"));
   g_nccl.rank = rank; g_nccl.world = world;
   NCL_CUDA(cudaMalloc(&g_nccl.partial, 64));
-  NCL_CUDA(cudaStreamCreateWithFlags(&g_nccl.comm_stream, cudaStreamNonBlocking));
+  // highest priority: the collective's single CTA must be scheduled ahead of the thousands of pending
+  // blocks of whatever compute kernel it is meant to overlap
+  int prio_lo = 0, prio_hi = 0; NCL_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  NCL_CUDA(cudaStreamCreateWithPriority(&g_nccl.comm_stream, cudaStreamNonBlocking, prio_hi));
   NCL_CUDA(cudaEventCreateWithFlags(&g_nccl.ev_partial, cudaEventDisableTiming));
   NCL_CUDA(cudaEventCreateWithFlags(&g_nccl.ev_done, cudaEventDisableTiming));
+  setup_p2p();                                          // best effort: without it the NCCL path is used
   return NCL_OK;
 }
 int ncl_comm_destroy(void) {
@@ -153,6 +203,13 @@ int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a, ncl_tensor* r) {
     if (rc == NCL_OK) rc = finalize_partial(op, slot, cls, ro, true);
     cudaStreamSynchronize(ctx().stream); cudaFree(slot);
     return rc;
+  }
+  if (g_nccl.p2p) {
+    // ONE kernel: local reduce, then its last block exchanges partials with the peers over NVLink-mapped
+    // mailboxes and writes the final value.  No NCCL call, no second launch.
+    int rc = reduce_all_p2p(op, ao, n, ro, g_nccl.peers_dev, g_nccl.rank, g_nccl.world, ++g_nccl.seq);
+    if (rc != NCL_ERR_UNSUPPORTED) return rc;
+    --g_nccl.seq;
   }
   if (g_nccl.pending) NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done, 0));   // the slot is single-buffered
   NCL_TRY(reduce_all_to_partial(op, ao, n, g_nccl.partial));

@@ -96,3 +96,5 @@ int fill_random(void* base, int dtype, int64_t offset, int64_t n, uint64_t seed,
 // used by ncl_reduce_all_sharded before the all-reduce.
 int reduce_all_to_partial(int op, const Operand& a, int64_t n, void* partial8);
 int finalize_partial(int op, const void* partial8, int cls, Operand& r, bool fresh);
+int reduce_all_p2p(int op, const Operand& a, int64_t n, const Operand& r, unsigned long long* const* peers, int rank, int world,
+                   unsigned long long seq);
