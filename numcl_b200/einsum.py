@@ -253,9 +253,12 @@ def einsum(subscripts, *args):
         raise TypeError(f"einsum: {len(args)} arrays for {n_in} inputs and up to {n_out} outputs")
     ins = list(args[:n_in])
     outs = list(args[n_in:]) + [None] * (n_in + n_out - len(args))
-    for a in ins:
+    for a in list(ins) + [o for o in outs if o is not None]:
         if not isinstance(a, NArray):
             raise TypeError("einsum inputs must be NArray")
+        # einsum-lambda keeps only the base vector (src/3einsum.lisp:485-487): a displaced view would
+        # silently be read from element 0.  Fenced rather than reproduced.
+        assert a.offset == 0, "einsum on a displaced view: the reference drops the displacement offset"
     _, _, shapes = resolve_shapes(specs, [a.shape for a in ins], [o.shape if o is not None else None for o in outs])
     fresh = all(o is None for o in outs)
     if not fresh and any(o is None for o in outs):

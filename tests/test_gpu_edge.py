@@ -1,0 +1,135 @@
+"""Edge cases the reference's tests touch or imply: empty and rank-0 arrays, ragged / odd shapes that
+leave the vector paths, displaced views, multi-axis reductions, aliasing, host-resident operands."""
+import numpy as np
+import pytest
+
+import refsem
+from test_gpu_parity import SEED, assert_bit_exact, rand, to_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def test_empty_arrays(nc, oracle):
+    # a size-0 axis against a size-1 axis: the reference's result shape is (mapcar #'max ...) = 1 and its
+    # loop writes nothing (4numeric.lisp:187-199,263-273) -- an array of uninitialised memory.  Fenced.
+    with pytest.raises(AssertionError):
+        nc.add(nc.zeros((0, 5), type="f32"), nc.ones((5,), type="f32"))
+    e = nc.add(nc.zeros((0, 5), type="f32"), nc.zeros((0, 5), type="f32"))
+    assert e.shape == (0, 5) and e.numpy().size == 0
+    z = nc.asarray(np.zeros((3, 0), dtype=np.float32), type="f32")
+    assert nc.sum(z, axes=1).numpy().tolist() == [0.0, 0.0, 0.0]          # (full kept-shape 0.0), nothing to add
+    assert nc.sum(z) == 0.0
+    assert nc.amax(z, axes=1).numpy().tolist() == [np.float32(-3.4028234663852886e38)] * 3
+    A = nc.asarray(np.zeros((4, 0), dtype=np.float64), type="f64")
+    B = nc.asarray(np.zeros((0, 6), dtype=np.float64), type="f64")
+    assert np.array_equal(nc.matmul(A, B).numpy(), np.zeros((4, 6)))        # zeros output, zero contraction steps
+    t = nc.einsum("ij -> ji", nc.asarray(np.zeros((0, 7), dtype=np.int64), type="fixnum"))
+    assert t.shape == (7, 0)
+
+
+def test_rank0_arrays_and_scalars(nc, oracle):
+    x = nc.full((), 3.5, type="f32")
+    y = nc.full((), 2, type="ub2")
+    r = nc.mul(x, y)
+    assert r.shape == () and r.item() == 7.0
+    assert nc.add(2, 3) == 5                                  # scalars only: plain CL arithmetic (4numeric.lisp:205-206)
+    assert nc.einsum("i i ->", nc.asarray(np.arange(5), type="fixnum"), nc.asarray(np.arange(5), type="fixnum")) == 30
+
+
+@pytest.mark.parametrize("shape_a,shape_b", [((3, 5, 7), (7,)), ((3, 5, 7), (5, 1)), ((1, 9), (9, 1)), ((2, 3, 1, 5), (4, 1)), ((6, 1, 11), (1, 13, 1)),
+                                              ((1023,), (1023,)), ((17, 1001), (1001,)), ((5, 3, 2, 2, 3, 2), (3, 2))])
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum", "ub8", "sb16"])
+def test_ragged_broadcast_shapes_bit_exact(nc, oracle, shape_a, shape_b, dt):
+    lo, hi = (-3.0, 3.0) if dt in ("f32", "f64") else (0, 100)
+    a = rand(oracle, shape_a, dt, SEED, 2 if dt in ("f32", "f64") else 0, lo, hi)
+    b = rand(oracle, shape_b, dt, SEED + 1, 0, lo, hi)
+    for op, f in (("+", nc.add), ("*", nc.mul), ("max", nc.maximum), ("-", nc.sub)):
+        assert_bit_exact(f(to_gpu(nc, a), to_gpu(nc, b)), refsem.arith(oracle, op, [a, b]))
+
+
+def test_displaced_views_in_broadcast_and_reduce(nc, oracle):
+    """broadcast and reduce-array honour the displacement offset (array-displacement's second value,
+    4numeric.lisp:225-227); einsum does not (3einsum.lisp:485-487), so the host mirror refuses it."""
+    base = rand(oracle, (40,), "f32", SEED, 1, -8, 8)
+    v = base.values()
+    g = to_gpu(nc, base)
+    view = nc.NArray((5, 4), "f32", _storage=g._buf, offset=7)
+    view._base = g
+    oview = oracle.OArr((5, 4), "f32", storage=base.storage, offset=7)
+    assert np.array_equal(view.numpy(), v[7:27].reshape(5, 4))
+    b = rand(oracle, (4,), "f32", SEED + 1, 1, -8, 8)
+    assert_bit_exact(nc.add(view, to_gpu(nc, b)), refsem.arith(oracle, "+", [oview, b]))
+    assert_bit_exact(nc.sum(view, axes=1), refsem.reduce_array(oracle, "+", oview, (1,)))
+    assert nc.sum(view) == float(v[7:27].sum())
+    with pytest.raises(AssertionError):
+        nc.einsum("ij -> ji", view)
+
+
+@pytest.mark.parametrize("shape,axes", [((4, 5, 6, 7), (1, 3)), ((4, 5, 6, 7), (0, 2)), ((4, 5, 6, 7), (0, 1, 2)), ((4, 5, 6, 7), (1, 2, 3)),
+                                        ((3, 1, 5), (1,)), ((2, 3, 4, 5, 6), (0, 2, 4)), ((129, 33), (0,)), ((1, 4096), (1,)), ((4099,), None)])
+@pytest.mark.parametrize("dt", ["f64", "sb32", "f32"])
+def test_multi_axis_reductions_bit_exact(nc, oracle, shape, axes, dt):
+    a = rand(oracle, shape, dt, SEED, 1, -8, 8)
+    for fn, f in (("+", nc.sum), ("max", nc.amax), ("min", nc.amin), ("*", nc.prod)):
+        src = a if fn != "*" else rand(oracle, shape, dt, SEED, 1, 1, 2)          # products stay exact
+        want = refsem.reduce_array(oracle, fn, src, axes)
+        got = f(to_gpu(nc, src), axes=axes)
+        if want.shape == ():
+            assert got == want.values().reshape(-1)[0]
+        else:
+            assert_bit_exact(got, want)
+
+
+def test_map_array_forms_and_aliasing(nc, oracle):
+    a = rand(oracle, (33, 7), "f32", SEED, 2, -2.0, 2.0)
+    b = rand(oracle, (33, 7), "f32", SEED + 1, 0, -2.0, 2.0)
+    c = rand(oracle, (33, 7), "ub8", SEED + 2, 0, 0, 9)
+    form = "(max (* $1 $2) (+ $3 0.5))"
+    assert_bit_exact(nc.map_array(form, to_gpu(nc, a), to_gpu(nc, b), to_gpu(nc, c)), oracle.map_array(form, [a, b, c], "f32"))
+    # in place: (map-array-into a 'cl:+ a b)
+    ga = to_gpu(nc, a)
+    nc.map_array_into(ga, "cl:+", ga, to_gpu(nc, b))
+    assert_bit_exact(ga, oracle.map_array("(+ $1 $2)", [a, b], "f32"))
+    with pytest.raises(AssertionError):
+        nc.map_array("cl:+", to_gpu(nc, a), nc.zeros((7, 33), type="f32"))
+
+
+def test_float_into_integer_output_rounds_half_even(nc, oracle):
+    """%coerce: (round x) then wrap (1type.lisp:673-694)"""
+    v = np.array([0.5, 1.5, 2.5, -0.5, -1.5, 127.5, 128.5, 300.7, -129.5], dtype=np.float32)
+    a = oracle.OArr.from_values(v, "f32")
+    for dt in ("sb8", "ub8", "fixnum", "ub4"):
+        r = nc.NArray(v.shape, dt)
+        nc.map_array_into(r, "identity", to_gpu(nc, a))
+        assert_bit_exact(r, oracle.map_array("(identity $1)", [a], dt))
+
+
+def test_host_resident_operands_match_device(nc, oracle):
+    A, B = rand(oracle, (200, 96), "f32", SEED, 1, -4, 4), rand(oracle, (96, 136), "f32", SEED + 1, 1, -4, 4)
+    dev = nc.matmul(to_gpu(nc, A), to_gpu(nc, B))
+    host = nc.matmul(to_gpu(nc, A).to("host"), to_gpu(nc, B).to("host"))
+    assert host.where == "host" and np.array_equal(host.numpy(), dev.numpy())
+    x = rand(oracle, (300, 77), "f64", SEED, 1, -8, 8)
+    assert np.array_equal(nc.sum(to_gpu(nc, x).to("host"), axes=0).numpy(), nc.sum(to_gpu(nc, x), axes=0).numpy())
+
+
+def test_int_division_correctly_rounded(nc, oracle):
+    """(/ int int) is an exact ratio in CL, rounded ONCE into single-float"""
+    n = rand(oracle, (4096,), "fixnum", SEED, 0, -(2 ** 40), 2 ** 40)
+    d = rand(oracle, (4096,), "fixnum", SEED + 1, 0, 1, 2 ** 30)
+    assert_bit_exact(nc.div(to_gpu(nc, n), to_gpu(nc, d)), refsem.arith(oracle, "/", [n, d]))
+    big_n = rand(oracle, (512,), "fixnum", SEED + 2, 0, 2 ** 58, 2 ** 61)       # beyond 2^53: the long-division path
+    big_d = rand(oracle, (512,), "fixnum", SEED + 3, 0, 3, 2 ** 57)
+    assert_bit_exact(nc.div(to_gpu(nc, big_n), to_gpu(nc, big_d)), refsem.arith(oracle, "/", [big_n, big_d]))
+
+
+def test_errors_mirror_reference_assertions(nc):
+    a = nc.zeros((3, 4), type="f32")
+    with pytest.raises(AssertionError):
+        nc.einsum("ij jk -> ik", a, nc.zeros((5, 6), type="f32"))          # (assert (= ...)) in shape-resolver
+    with pytest.raises(nc.EinsumSpecError):
+        nc.einsum("i0 -> i", a)
+    with pytest.raises(TypeError):
+        nc.einsum("ij jk -> ik", a)
+    with pytest.raises(nc.NumclUnsupportedError):
+        nc.reduce_array("logior", nc.asarray(np.arange(4), type="fixnum"))
