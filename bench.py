@@ -126,7 +126,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------
-def time_other_configs(nc, L, torch, stream, peak):
+def time_other_configs(nc, L, torch, stream, peak, contractions=True):
     """C1, C3, C4, C5 of BASELINE.json, device resident, rotating buffer sets so that no operand of
     the next launch is still in L2 (126 MB)."""
     from numcl_b200 import _lib
@@ -213,6 +213,8 @@ def time_other_configs(nc, L, torch, stream, peak):
             best = min(best, e0.elapsed_time(e1) * 1e-3)
         torch.backends.cuda.matmul.allow_tf32 = False
         return 2 * n ** 3 / best / 1e12
+    if not contractions:
+        return out
     try:
         _, mm = _memoized("ij jk -> ik")
         _, bmm = _memoized("bij bjk -> bik")
@@ -390,7 +392,7 @@ def run_ours(args):
         want = O.fast_sum_axis1_f32(ah).astype(np.float64)
         cpu["parity_rel_err_axis1_vs_port"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
         if not args.skip_others:
-            others = time_other_configs(nc, L, torch, stream, peak)
+            others = time_other_configs(nc, L, torch, stream, peak, contractions=not args.no_contractions)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -432,6 +434,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-others", action="store_true")
+    ap.add_argument("--no-contractions", action="store_true", help="skip C3/C4 in `others` (bring-up)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -193,7 +193,7 @@ int try_elementwise(const Nest& n) {
   }
   p.base[0] = out.base; p.off[0] = out.offset;
   for (int k = 0; k < m.n; k++) { p.base[1 + k] = ops[k].base; p.off[1 + k] = ops[k].offset; p.lk[k] = dtype_load_kind(ops[k].dtype); }
-  int U = E == 32 ? 1 : (E == 2 ? 8 : 4);
+  int U = E == 32 ? 1 : 4;
   unsigned long long rows = 1; for (int i = 1; i < nd; i++) rows *= p.ext[i];
   unsigned segs = (p.ext[0] + 32 * U - 1) / (32 * U);
   unsigned long long nitems = rows * segs;

@@ -218,6 +218,21 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
       } else if (p.period[k]) load_operand_periodic<TI, E, U>(p.base[1 + k], rowoff[1 + k], p.lk[k], q0, p.ext[0], p.period[k], p.pmul[k], p.pshr[k], x[k]);
       else load_operand<TI, E, U>(p.base[1 + k], rowoff[1 + k], p.st[1 + k][0], p.lk[k], q0, p.ext[0], x[k]);
     }
+    if (p.nd == 1) {
+      // flat mode: pull the streaming operands of this warp's NEXT item into L2 now, so that its loads
+      // pay L2 latency instead of DRAM latency (one prefetch instruction per 512-byte warp row)
+      const unsigned nq0 = q0 + nwarps * SEG;
+#pragma unroll
+      for (int k = 0; k < NIN; k++) {
+        if (p.period[k] == 0 && p.st[1 + k][0] == 1) {
+          const int bytes = lk_bits(p.lk[k]) >> 3;
+          const char* a = p.base[1 + k] + (p.off[1 + k] + (long long)nq0 * E) * bytes;
+#pragma unroll
+          for (int u = 0; u < U; u++)
+            if (nq0 + u * 32 < p.ext[0]) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + (size_t)u * 32 * E * bytes));
+        }
+      }
+    }
     TO y[U][E];
 #pragma unroll
     for (int u = 0; u < U; u++)
@@ -232,7 +247,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
 }
 
 typedef void (*EwKernel)(const EwParams);
-template <int E> constexpr int ew_u() { return E == 32 ? 1 : (E == 2 ? 8 : 4); }
+template <int E> constexpr int ew_u() { return E == 32 ? 1 : 4; }
 template <class TI, class F, int NIN, int E> static EwKernel kern() { return (EwKernel)ew_kernel<TI, F, NIN, E, ew_u<E>()>; }
 template <int E> static int ufactor() { return E == 1 ? 4 : (E == 32 ? 1 : 4); }
 

@@ -241,8 +241,10 @@ int launch_generic(const Nest& n) {
     }
     for (int i = 1; i < nk; i++) { int k = kept[i], j = i - 1; while (j >= 0 && out.stride[kept[j]] < out.stride[k]) { kept[j + 1] = kept[j]; j--; } kept[j + 1] = k; }
     p.n_kept = nk; p.n_con = nc; p.n_arr = 1 + n.n_in; p.total = 1;
+    // an empty KEPT loop means there is no output element; an empty CONTRACTED loop still leaves the
+    // accumulator's start value (zeros / the identity) to be stored
     bool empty = false;
-    for (int l = 0; l < n.nloops; l++) if (n.extent[l] == 0) empty = true;
+    for (int l = 0; l < n.nloops; l++) if (n.extent[l] == 0 && out.stride[l] != 0) empty = true;
     for (int i = 0; i < nk; i++) { p.ext[i] = n.extent[kept[i]]; p.total *= p.ext[i]; }
     for (int i = 0; i < nc; i++) p.ext[nk + i] = n.extent[con[i]];
     auto fill_arr = [&](int slot, const Operand& a) {

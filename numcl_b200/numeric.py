@@ -95,8 +95,10 @@ def _fold(fn: str, args, use_identity: bool):
     shape = ()
     for k, t in enumerate(chain[1:]):
         acc = ti.type_of_dtype(ti.upgrade(ti.infer_type(fn, acc, t)))
-    for a in args:
-        shape = broadcast_result_shape(shape, a.shape if isinstance(a, NArray) else ())
+    shapes = [a.shape if isinstance(a, NArray) else () for a in args]
+    shape = shapes[0]
+    for sh in shapes[1:]:
+        shape = broadcast_result_shape(shape, sh)
     arrs = [_as_array(a, like) for a in args]
     r = empty(shape, type=ti.upgrade(acc), where=like.where)
     ts = (_lib.Tensor * len(arrs))(*[a.tensor() for a in arrs])
