@@ -5,10 +5,10 @@ These modules mirror the reference's operator interface for the hot path -- same
 meaning and error behaviour -- so the parity tests read like numcl's own tests.  No CPU fallback.
 """
 from ._lib import (NumclCudaError, NumclShapeError, NumclUnsupportedError, lib, load, shutdown)  # noqa: F401
-from .array import (NArray, arange, asarray, empty, full, ones, random_array, zeros)  # noqa: F401
+from .array import (NArray, arange, asarray, astype, copy, empty, full, ones, random_array, zeros)  # noqa: F401
 from .einsum import einsum  # noqa: F401
 from .einsum_spec import EinsumSpecError, einsum_normalize_subscripts  # noqa: F401
-from .linalg import diag, eye, inner, kron, matmul, outer, transpose, vdot  # noqa: F401
+from .linalg import diag, eye, inner, kron, matmul, matmul_star, matrix_chain_order, outer, transpose, vdot  # noqa: F401
 from .numeric import (add, broadcast, clip, div, map_array, map_array_into, maximum, minimum, mul,  # noqa: F401
                       one_minus, one_plus, sub)
 from .reduce import amax, amin, avg, mean, prod, reduce_array, stdev, var, variance  # noqa: F401

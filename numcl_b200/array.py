@@ -211,3 +211,17 @@ def random_array(shape, type, seed, dist=0, lo=0.0, hi=1.0) -> NArray:
     t = a.tensor()
     _lib.check(_lib.lib().ncl_fill_random(C.byref(t), C.c_uint64(seed), dist, float(lo), float(hi)))
     return a
+
+
+def astype(array: NArray, type) -> NArray:
+    """(astype array type), src/3copy.lisp:38-43: every element through %coerce into `type`
+    (ncl_convert: a conversion kernel instead of the host map-into)."""
+    r = NArray(array.shape, type, where=array.where)
+    ta, tr = array.tensor(), r.tensor()
+    _lib.check(_lib.lib().ncl_convert(C.byref(ta), C.byref(tr)))
+    return r
+
+
+def copy(array: NArray) -> NArray:
+    """(copy array), src/3copy.lisp:27-36: a fresh zero-offset array with the same contents."""
+    return astype(array, array.dtype)

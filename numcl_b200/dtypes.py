@@ -91,10 +91,12 @@ def wrap(values: np.ndarray, dt) -> np.ndarray:
     w = dt.value_bits
     if w >= 64:
         return v
-    if dt.signed:
-        half = np.int64(1) << np.int64(w - 1)
-        return ((v + half) & ((np.int64(1) << np.int64(w)) - 1)) - half
-    return v & ((np.int64(1) << np.int64(w)) - 1)
+    u = v.view(np.uint64) if v.ndim else np.uint64(int(v) & 0xFFFFFFFFFFFFFFFF)
+    mask = np.uint64((1 << w) - 1)
+    if dt.signed:                                   # two's complement wrap in unsigned arithmetic (no overflow warnings)
+        half = np.uint64(1 << (w - 1))
+        return (((u + half) & mask) - half).astype(np.int64) if isinstance(u, np.ndarray) else np.int64(int(((u + half) & mask)) - int(half))
+    return (u & mask).astype(np.int64) if isinstance(u, np.ndarray) else np.int64(int(u & mask))
 
 
 def pack(values: np.ndarray, dt) -> np.ndarray:

@@ -49,3 +49,40 @@ def eye(n, type="bit", where="device"):
     import numpy as np
     from .array import asarray
     return asarray(np.eye(n, dtype=np.int64), type=type, where=where)
+
+
+def matrix_chain_order(dims):
+    """matrix-chain-order, src/4linear-algebra3.lisp:179-215: the classic O(n^3) DP over
+    single-float costs; index[i][j] = split point of the product of matrices i..j."""
+    import numpy as np
+    n = len(dims) - 1
+    d = [np.float32(x) for x in dims]
+    cost = [[np.float32(0.0)] * n for _ in range(n)]
+    index = [[0] * n for _ in range(n)]
+    for length in range(2, n + 1):
+        for i in range(0, n - length + 1):
+            j = i + length - 1
+            cost[i][j] = np.float32(3.4028235e38)
+            for k in range(i, j):
+                c = np.float32(cost[i][k] + cost[k + 1][j] + d[i] * d[k + 1] * d[j + 1])
+                if c < cost[i][j]:
+                    cost[i][j] = c
+                    index[i][j] = k
+    return index
+
+
+def matmul_star(*args):
+    """matmul*, src/4linear-algebra3.lisp:152-177: multiply a chain of matrices in the order that
+    minimises the intermediate sizes; every product is an einsum '(ij jk -> ik) on the backend."""
+    n = len(args)
+    if n == 1:
+        return args[0]
+    dims = [args[0].shape[0]] + [a.shape[1] for a in args]
+    order = matrix_chain_order(dims)
+
+    def rec(i, j):
+        if i == j:
+            return args[i]
+        k = order[i][j]
+        return matmul(rec(i, k), rec(k + 1, j))
+    return rec(0, n - 1)

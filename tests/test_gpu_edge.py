@@ -133,3 +133,17 @@ def test_errors_mirror_reference_assertions(nc):
         nc.einsum("ij jk -> ik", a)
     with pytest.raises(nc.NumclUnsupportedError):
         nc.reduce_array("logior", nc.asarray(np.arange(4), type="fixnum"))
+
+
+def test_matmul_star_copy_astype(nc, oracle):
+    mats = [rand(oracle, s, "fixnum", SEED + k, 0, 0, 5) for k, s in enumerate([(10, 30), (30, 5), (5, 60), (60, 4)])]
+    want = mats[0].values()
+    for m in mats[1:]:
+        want = want @ m.values()
+    got = nc.matmul_star(*[to_gpu(nc, m) for m in mats])
+    assert np.array_equal(got.numpy(), want)
+    a = rand(oracle, (50, 7), "f32", SEED, 0, -300.0, 300.0)
+    g = to_gpu(nc, a)
+    assert_bit_exact(nc.copy(g), a)
+    for dt in ("fixnum", "sb8", "f64", "ub8"):
+        assert_bit_exact(nc.astype(g, dt), oracle.map_array("(identity $1)", [a], dt))

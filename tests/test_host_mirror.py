@@ -160,3 +160,26 @@ def test_build_desc_roundtrip():
     d = build_desc(einsum_normalize_subscripts("i -> (cl:+ @1 $1) -> -> ((i :start 5 :end 9 :step 2))"))
     assert (d.n_in, d.n_out, d.n_iter, d.iter[0]) == (1, 1, 1, 0)
     assert d.in_nopt[0] == 1 and (d.in_opt[0][0].key, d.in_opt[0][0].start, d.in_opt[0][0].end, d.in_opt[0][0].step) == (0, 5, 9, 2)
+
+
+def test_matrix_chain_order_is_optimal():
+    """matmul*'s DP (src/4linear-algebra3.lisp:179-215) against brute force on small chains"""
+    import itertools
+    from numcl_b200.linalg import matrix_chain_order
+
+    def cost_of(order, dims, i, j):
+        if i == j:
+            return 0
+        k = order[i][j]
+        return cost_of(order, dims, i, k) + cost_of(order, dims, k + 1, j) + dims[i] * dims[k + 1] * dims[j + 1]
+
+    def brute(dims, i, j):
+        if i == j:
+            return 0
+        return min(brute(dims, i, k) + brute(dims, k + 1, j) + dims[i] * dims[k + 1] * dims[j + 1] for k in range(i, j))
+    rng = np.random.default_rng(3)
+    for n in (2, 3, 4, 5, 6):
+        for _ in range(5):
+            dims = [int(x) for x in rng.integers(1, 40, size=n + 1)]
+            order = matrix_chain_order(dims)
+            assert cost_of(order, dims, 0, n - 1) == brute(dims, 0, n - 1)
