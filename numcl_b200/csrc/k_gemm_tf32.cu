@@ -292,10 +292,295 @@ __global__ void __launch_bounds__(TF_THREADS, 1) gemm_tf32x3_kernel(const char* 
   }
 }
 
+
+// ===== fused variant: the hi/lo split happens INSIDE the GEMM kernel ================================================
+//
+// For small matrices (C4: 256 x 512^3) the pack pre-pass and the doubled operand stream cost more HBM
+// time than the MMAs take (DESIGN.md "C4").  Here the raw fp32 operands are read once by CONVERTER
+// warps straight from global memory (L2 serves the re-reads of a batch), split in registers and
+// stored to shared memory as the four swizzled tf32 tiles the tensor core wants:
+//   warps 0..3    convert A   128 x 32 block  -> A_hi, A_lo   K-major  SWIZZLE_128B (as in the pack kernel)
+//   warps 4..11   convert B    32 x 256 block -> B_hi, B_lo   MN-major: B is n-contiguous in memory and
+//                 tcgen05 takes it as is (instruction-descriptor bit 16), so no transpose.  The only
+//                 MN-major layout 32-bit operands have is SWIZZLE_128B_BASE32B (descriptor layout type 1):
+//                 atom = 4 k-rows x 128 B (32 n), 32-byte units of a row XORed with (k & 3), i.e. byte
+//                 address bits [5,7) ^= bits [7,9).  Stage layout [n-atom (8)][32 k-rows x 128 B]:
+//                 LBO (next n-atom) = 4096 B, SBO (next 4-row group) = 512 B; a K = 8 MMA spans two groups.
+//   warp 12       MMA issuer (one lane), as above
+//   warps 13..16  epilogue (one per TMEM lane quarter).  K is still cut into chunks of 256 (TMEM truncation, see above) but the
+//                 running sum lives in C itself: chunk 0 stores, later chunks add to what this thread
+//                 stored (same thread, same addresses, L1/L2 hits) -- no 128-register accumulator, so
+//                 17 warps fit in the register file.  Used for K <= TF_FUSED_MAX_K only.
+// (Tried and dropped: an 18th warp prefetching the raw rows into L2 with cp.async.bulk.prefetch -- 2.5x slower.)
+// Every converter thread keeps the NEXT k-block's 8 x 16 B in registers while it converts the current
+// one, so global latency overlaps conversion + the wait for a free stage.
+// Shapes: M % 128 == 0, N % 256 == 0, K % 32 == 0, 16-byte aligned rows; anything else takes the packed path.
+#define TFF_CONV_WARPS 12
+#define TFF_MMA_WARP 12
+#define TFF_EPI_WARP0 13
+#define TFF_EPI_WARPS 4
+#define TFF_THREADS ((TFF_EPI_WARP0 + TFF_EPI_WARPS) * 32)     // 544: 17 warps, at most 5 per SM sub-partition -> 96 registers each
+#define TF_FUSED_MAX_K 1024
+#define TFF_STG_PITCH 36                          // floats per staged row (32 + 4: 16-byte aligned, bank-conflict free)
+#define TFF_STG_BYTES (32 * TFF_STG_PITCH * 4)
+#define TFF_SMEM (TF_SMEM + TFF_EPI_WARPS * TFF_STG_BYTES)
+
+// MN-major SWIZZLE_128B_BASE32B operand (layout type 1): LBO = 4096 B to the next 32-column atom, SBO = 512 B
+// to the next group of 4 k-rows
+__device__ __forceinline__ unsigned long long umma_desc_mn(unsigned addr) {
+  return (unsigned long long)((addr >> 4) & 0x3fffu) | ((unsigned long long)(4096u >> 4) << 16) |
+         ((unsigned long long)(512u >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// hi = rna_tf32(x), lo = rna_tf32(x - hi) with integer rounding: ptxas expands cvt.rna.tf32 into a
+// guarded add/mask anyway; sharing one finiteness test between hi, lo and the inf/NaN rule of
+// split_tf32 brings the split from ~12 to 8 instructions per element (the converters are ALU-bound).
+__device__ __forceinline__ void split_fast(float x, unsigned& hi, unsigned& lo) {
+  const unsigned b = __float_as_uint(x);
+  const bool fin = fabsf(x) < __int_as_float(0x7f800000);
+  unsigned h = (b + 0x1000u) & 0xffffe000u;             // round to nearest, ties away, 10 mantissa bits kept
+  h = fin ? h : b;                                       // inf / NaN pass through untouched
+  const float r = __fsub_rn(x, __uint_as_float(h));      // exact
+  const unsigned l = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+  hi = h; lo = fin ? l : 0u;
+}
+__device__ __forceinline__ void split4(const float4& v, uint4& h, uint4& l) {
+  split_fast(v.x, h.x, l.x); split_fast(v.y, h.y, l.y); split_fast(v.z, h.z, l.z); split_fast(v.w, h.w, l.w);
+}
+__device__ __forceinline__ void sts128(unsigned addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(TFF_THREADS, 1) gemm_tf32x3_fused_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                                                            int KT, long long lda, long long ldb, long long ldc,
+                                                                            long long sA, long long sB, long long sC,
+                                                                            int MT, int NT, int batch, int accumulate) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * TF_STAGES + 4];
+  __shared__ unsigned tmem_slot;
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TF_STAGES]);
+  const unsigned tfull0 = smem_u32(&bars[2 * TF_STAGES]), tempty0 = smem_u32(&bars[2 * TF_STAGES + 2]);
+  const int NC = (KT + TF_CHUNK_KB - 1) / TF_CHUNK_KB;
+  const int tiles_per_batch = MT * NT;
+  const int total_tiles = tiles_per_batch * batch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TF_STAGES; s++) { mbar_init(full0 + 8 * s, TFF_CONV_WARPS); mbar_init(empty0 + 8 * s, 1); }
+    for (int t = 0; t < 2; t++) { mbar_init(tfull0 + 8 * t, 1); mbar_init(tempty0 + 8 * t, TFF_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TFF_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = tmem_slot;
+
+  if (warp < TFF_CONV_WARPS) {
+    // ---- converters -------------------------------------------------------------------------------------
+    const bool isA = warp < 4;
+    const int ct = isA ? (int)threadIdx.x : (int)threadIdx.x - 128;
+    // A thread: chunk i -> row (ct>>3) + 16 i, 16-byte column ct&7.   B thread: chunk i -> k (ct>>6) + 4 i, 16-byte column ct&63.
+    const int r0 = isA ? (ct >> 3) : (ct >> 6), c0 = isA ? (ct & 7) : (ct & 63);
+    const long long step = isA ? 16 * lda : 4 * ldb;                 // elements between this thread's chunks
+    const long long kstep = isA ? (long long)TF_BK : (long long)TF_BK * ldb;   // elements between k-blocks
+    // smem offset of this thread's hi chunk i inside a stage: (i odd ? off_odd : off_even) + (i >> 1) * pair_stride
+    unsigned off_even, off_odd, pair_stride;
+    if (isA) { off_even = (unsigned)swz(r0, c0); off_odd = off_even + 16 * 128; pair_stride = 32 * 128; }   // (row + 16 i) & 7 == row & 7
+    else {
+      // k = r0 + 4 i: k & 3 = r0 for every i, so the swizzled 16-byte column is fixed and the offset is linear in i
+      off_even = (unsigned)(2 * TF_A_TILE + (c0 >> 3) * 4096 + r0 * 128 + (((c0 & 7) ^ (r0 << 1)) << 4));
+      off_odd = off_even + 4 * 128;
+      pair_stride = 8 * 128;
+    }
+    const unsigned lo_off = isA ? TF_A_TILE : TF_B_TILE;
+    auto tile_ptr = [&](int t) -> const float* {
+      int b = t / tiles_per_batch, tm, tn; raster(t - b * tiles_per_batch, MT, NT, 8, tm, tn);
+      return isA ? A + (long long)b * sA + ((long long)tm * TF_BM + r0) * lda + c0 * 4
+                 : B + (long long)b * sB + (long long)r0 * ldb + (long long)tn * TF_BN + c0 * 4;
+    };
+    int t = blockIdx.x, kt = 0;
+    bool have = t < total_tiles;
+    const float* src = have ? tile_ptr(t) : nullptr;
+    float4 cur[8], nxt[8];
+    if (have) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) cur[i] = __ldg((const float4*)(src + i * step));
+    }
+    unsigned it = 0;
+    while (have) {
+      int nkt = kt + 1, ntile = t; bool nhave = true;
+      if (nkt == KT) { nkt = 0; ntile = t + gridDim.x; nhave = ntile < total_tiles; if (nhave) src = tile_ptr(ntile); }
+      if (nhave) {
+        const float* s2 = src + nkt * kstep;
+#pragma unroll
+        for (int i = 0; i < 8; i++) nxt[i] = __ldg((const float4*)(s2 + i * step));
+      }
+      const int s = it % TF_STAGES; const unsigned ph = (it / TF_STAGES) & 1;
+      mbar_wait(empty0 + 8 * s, ph ^ 1);
+      const unsigned st = smem_u32(smem) + s * TF_STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        uint4 h, l; split4(cur[i], h, l);
+        const unsigned d = st + ((i & 1) ? off_odd : off_even) + (i >> 1) * pair_stride;
+        sts128(d, h);
+        sts128(d + lo_off, l);
+      }
+      fence_proxy_async_smem();                       // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full0 + 8 * s);
+#pragma unroll
+      for (int i = 0; i < 8; i++) cur[i] = nxt[i];
+      t = ntile; kt = nkt; have = nhave; it++;
+    }
+  } else if (warp == TFF_MMA_WARP) {
+    if (lane == 0) {
+      // as the packed kernel, plus bit 16: B is MN-major
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((unsigned)(TF_BN >> 3) << 17) | ((unsigned)(TF_BM >> 4) << 24);
+      unsigned it = 0, g = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int kt = 0;
+        for (int c = 0; c < NC; c++, g++) {
+          const int buf = g & 1; const unsigned use = g >> 1;
+          mbar_wait(tempty0 + 8 * buf, (use & 1) ^ 1);
+          tc_fence_after();
+          const unsigned d_tmem = tmem_base + (unsigned)(buf * TF_BN);
+          const int kend = (kt + TF_CHUNK_KB < KT) ? kt + TF_CHUNK_KB : KT;
+          for (int first = 1; kt < kend; kt++, it++) {
+            int s = it % TF_STAGES; unsigned ph = (it / TF_STAGES) & 1;
+            mbar_wait(full0 + 8 * s, ph);
+            tc_fence_after();
+            unsigned a_hi = smem_u32(smem + s * TF_STAGE_BYTES), a_lo = a_hi + TF_A_TILE;
+            unsigned b_hi = a_hi + 2 * TF_A_TILE, b_lo = b_hi + TF_B_TILE;
+#pragma unroll
+            for (int ks = 0; ks < TF_BK / 8; ks++) {
+              unsigned aoff = ks * 32, boff = ks * 1024;           // A: 32 B along the row; B: the next 8 k-rows
+              tc_mma_tf32(d_tmem, umma_desc(a_lo + aoff), umma_desc_mn(b_hi + boff), idesc, first ? 0u : 1u);
+              first = 0;
+              tc_mma_tf32(d_tmem, umma_desc(a_hi + aoff), umma_desc_mn(b_lo + boff), idesc, 1u);
+              tc_mma_tf32(d_tmem, umma_desc(a_hi + aoff), umma_desc_mn(b_hi + boff), idesc, 1u);
+            }
+            tc_commit(empty0 + 8 * s);
+          }
+          tc_commit(tfull0 + 8 * buf);
+        }
+      }
+    }
+  } else {
+    // ---- epilogue: TMEM lane quarter q = warp % 4 (hardware rule), all 256 columns ----------------------------
+    // tcgen05.ld hands every lane one ROW (32 consecutive columns); stored like that a warp instruction
+    // would touch 32 different 128-byte lines.  Each 32 x 32 slab is therefore turned through a private
+    // 4.5 KB staging buffer (pitch 36 floats: conflict-free both ways) so that one instruction moves
+    // 4 complete 128-byte row segments of C.
+    const int q = warp & 3;
+    const unsigned stg = smem_u32(smem) + TF_STAGES * TF_STAGE_BYTES + (warp - TFF_EPI_WARP0) * TFF_STG_BYTES;
+    const unsigned stg_w = stg + lane * (TFF_STG_PITCH * 4);                       // this lane's row when writing
+    const int rr = lane >> 3, c4 = lane & 7;                                       // when reading: rows rr + 4 p, 16-byte column c4
+    const unsigned stg_r = stg + rr * (TFF_STG_PITCH * 4) + c4 * 16;
+    unsigned g = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int b = t / tiles_per_batch, tm, tn; raster(t - b * tiles_per_batch, MT, NT, 8, tm, tn);
+      float* cbase = C + (long long)b * sC + ((long long)tm * TF_BM + q * 32 + rr) * ldc + (long long)tn * TF_BN + c4 * 4;
+      for (int c = 0; c < NC; c++, g++) {
+        const int buf = g & 1; const unsigned use = g >> 1;
+        const bool add = (c > 0) || accumulate;
+        mbar_wait(tfull0 + 8 * buf, use & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < TF_BN / 32; cc++) {
+          unsigned r[32];
+          unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(buf * TF_BN + cc * 32);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                       : "r"(taddr) : "memory");
+          float* dst = cbase + cc * 32;
+          float4 old[8];
+          if (add) {                        // the running sum so far, fetched while the TMEM load is in flight
+#pragma unroll
+            for (int p = 0; p < 8; p++) old[p] = *(const float4*)(dst + (long long)(4 * p) * ldc);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (cc == TF_BN / 32 - 1) {                     // everything is out of TMEM: hand the accumulator back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) sts128(stg_w + j * 4, make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int p = 0; p < 8; p++) {
+            uint4 v = lds128(stg_r + p * (4 * TFF_STG_PITCH * 4));
+            float4 o = add ? old[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+            *(float4*)(dst + (long long)(4 * p) * ldc) = make_float4(__fadd_rn(o.x, __uint_as_float(v.x)), __fadd_rn(o.y, __uint_as_float(v.y)),
+                                                                       __fadd_rn(o.z, __uint_as_float(v.z)), __fadd_rn(o.w, __uint_as_float(v.w)));
+          }
+          __syncwarp();                                   // staging buffer is rewritten by the next slab
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TFF_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// NUMCL_TF32_MODE = auto | packed | fused  (debug/benchmark knob; `fused` still requires an eligible shape)
+static int tf32_mode() {
+  const char* e = getenv("NUMCL_TF32_MODE");
+  if (!e) return 0;
+  return !strcmp(e, "packed") ? 1 : !strcmp(e, "fused") ? 2 : 0;
+}
+
+static int gemm_f32_tf32x3_fused(const GemmParams& p) {
+  Context& c = ctx();
+  int MT = p.M / TF_BM, NT = p.N / TF_BN, KT = p.K / TF_BK;
+  long long total_tiles = (long long)MT * NT * p.batch;
+  if (total_tiles > 0x7fffffffLL) return NCL_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) { NCL_CUDA(cudaFuncSetAttribute(gemm_tf32x3_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TFF_SMEM)); attr_set = true; }
+  unsigned grid = (unsigned)(total_tiles < c.sm_count ? total_tiles : c.sm_count);
+  gemm_tf32x3_fused_kernel<<<grid, TFF_THREADS, TFF_SMEM, c.stream>>>((const float*)p.A, (const float*)p.B, (float*)p.C, KT, p.lda, p.ldb, p.ldc,
+                                                                       p.sA, p.sB, p.sC, MT, NT, p.batch, p.accumulate);
+  note_launch("gemm_tf32x3_fused_tcgen05", 1);
+  return cuda_fail(cudaGetLastError(), "gemm_tf32x3_fused_kernel");
+}
+
+static bool fused_eligible(const GemmParams& p) {
+  if (p.M % TF_BM || p.N % TF_BN || p.K % TF_BK || p.K > TF_FUSED_MAX_K) return false;
+  if ((p.lda & 3) || (p.ldb & 3) || (p.ldc & 3) || (p.sA & 3) || (p.sB & 3) || (p.sC & 3)) return false;
+  if (((uintptr_t)p.A & 15) || ((uintptr_t)p.B & 15) || ((uintptr_t)p.C & 15)) return false;
+  return true;
+}
+
 int gemm_f32_tf32x3(const GemmParams& p) {
   Context& c = ctx();
   if (p.lkA != LK_F32 || p.lkB != LK_F32 || p.lkC != LK_F32) return NCL_ERR_UNSUPPORTED;
   if (((uintptr_t)p.C & 3) || ((uintptr_t)p.A & 3) || ((uintptr_t)p.B & 3)) return NCL_ERR_UNSUPPORTED;
+  {
+    // the pack pre-pass costs 3x the operand bytes; per output tile that is worth it only when the
+    // operands are re-used by many tiles (large M and N).  Small matrices: split inside the kernel.
+    int mode = tf32_mode();
+    bool small = (long long)p.M * p.N <= 1024LL * 1024LL;    // measured crossover (tools/gemm_fused_check.py)
+    if (mode != 1 && fused_eligible(p) && (mode == 2 || small)) return gemm_f32_tf32x3_fused(p);
+  }
   int MT = (p.M + TF_BM - 1) / TF_BM, NT = (p.N + TF_BN - 1) / TF_BN, KT = (p.K + TF_BK - 1) / TF_BK;
   if ((long long)MT * NT > 0x7fffffffLL || p.batch > 65535 || MT > 65535) return NCL_ERR_UNSUPPORTED;
   size_t a_bytes = (size_t)p.batch * MT * KT * 2 * TF_A_TILE, b_bytes = (size_t)p.batch * NT * KT * 2 * TF_B_TILE;

@@ -351,7 +351,8 @@ def test_matmul_float_within_tolerance(nc, oracle, dt, tol, m, k, n):
     if dt == "f64" and m >= 32 and n >= 32 and k % 2 == 0 and n % 2 == 0:
         assert nc.lib().ncl_last_kernel() == b"gemm_f64_dmma"
     if dt == "f32" and m * n >= 128 * 128 and k >= 32:
-        assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_tcgen05"
+        fused = m % 128 == 0 and n % 256 == 0 and k % 32 == 0 and k <= 1024 and m * n <= 1024 * 1024
+        assert nc.lib().ncl_last_kernel() == (b"gemm_tf32x3_fused_tcgen05" if fused else b"gemm_tf32x3_tcgen05")
 
 
 def test_matmul_f64_interpreter_agrees_with_fast_loop(oracle):
@@ -369,6 +370,60 @@ def test_batched_einsum_within_tolerance(nc, oracle, dt, tol):
         ref = np.stack([oracle.fast_matmul(A.values()[i], B.values()[i]) for i in range(6)])
     got = nc.einsum("bij bjk -> bik", to_gpu(nc, A), to_gpu(nc, B))
     assert _frob(got.numpy(), ref) <= tol
+
+
+@pytest.mark.parametrize("b,m,k,n", [(1, 128, 32, 256), (3, 256, 96, 512), (2, 384, 544, 256), (5, 128, 1024, 768)])
+def test_batched_einsum_fused_split_kernel(nc, oracle, b, m, k, n):
+    """tile-aligned single-float shapes take the kernel that splits hi/lo in shared memory (one launch,
+    no pack pre-pass); same tolerance vs numcl's nest, and it must agree with the packed path's error level"""
+    A, B = rand(oracle, (b, m, k), "f32", SEED, 0, -1.0, 1.0), rand(oracle, (b, k, n), "f32", SEED + 1, 0, -1.0, 1.0)
+    ref = oracle.fast_bmm_f32(A.values(), B.values())
+    got = nc.einsum("bij bjk -> bik", to_gpu(nc, A), to_gpu(nc, B))
+    assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_fused_tcgen05"
+    assert _frob(got.numpy(), ref) <= 1e-5
+    truth = A.values().astype(np.float64) @ B.values().astype(np.float64)
+    assert _frob(got.numpy(), truth) <= 4e-6          # 3xTF32 + chunked accumulation: ~2e-6
+
+
+def test_fused_split_kernel_specials_and_accumulate(nc, oracle):
+    """inf / NaN operands stay non-finite (the split keeps them in the hi part; inf * lo-part may turn an
+    IEEE inf into NaN, as in every split-precision GEMM -- SBCL would trap there, SURVEY 8b "Errors"), NaN
+    stays NaN, and a caller-supplied result is accumulated into (src/3einsum.lisp:468)"""
+    rng = np.random.default_rng(5)
+    A = rng.uniform(-1, 1, (128, 64)).astype(np.float32); B = rng.uniform(-1, 1, (64, 256)).astype(np.float32)
+    A[3, 5] = np.inf; A[7, 9] = np.nan; B[11, 17] = -np.inf
+    A[9, 0] = np.float32(np.frombuffer(np.uint32(0x7fffffff).tobytes(), dtype=np.float32)[0])    # CUDA's canonical NaN
+    got = nc.matmul(nc.asarray(A, type="f32"), nc.asarray(B, type="f32")).numpy()
+    assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_fused_tcgen05"
+    with np.errstate(invalid="ignore", over="ignore"):
+        want = A.astype(np.float64) @ B.astype(np.float64)
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    assert np.all(np.isnan(got[np.isnan(want)]))
+    fin = np.isfinite(want)
+    assert np.allclose(got[fin], want[fin], rtol=0, atol=1e-4)
+    C0 = rng.uniform(-1, 1, (128, 256)).astype(np.float32)
+    A2 = rng.uniform(-1, 1, (128, 512)).astype(np.float32); B2 = rng.uniform(-1, 1, (512, 256)).astype(np.float32)
+    c = nc.asarray(C0, type="f32")
+    nc.matmul(nc.asarray(A2, type="f32"), nc.asarray(B2, type="f32"), c)
+    assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_fused_tcgen05"
+    assert _frob(c.numpy(), C0.astype(np.float64) + A2.astype(np.float64) @ B2.astype(np.float64)) <= 4e-6
+
+
+def test_batched_einsum_c4_full_size(nc, oracle):
+    """config C4 at full size (256 x 512^3): three batches checked against numcl's nest, all against linearity"""
+    bsz = 256
+    a = nc.random_array((bsz, 512, 512), "f32", SEED, 0, -1.0, 1.0)
+    b = nc.random_array((bsz, 512, 512), "f32", SEED + 1, 0, -1.0, 1.0)
+    r = nc.einsum("bij bjk -> bik", a, b)
+    assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_fused_tcgen05"
+    got = r.numpy()
+    A, B = a.numpy(), b.numpy()
+    for i in (0, 131, 255):
+        ref = oracle.fast_bmm_f32(A[i:i + 1], B[i:i + 1])
+        assert _frob(got[i:i + 1], ref) <= 1e-5
+    # row sums of every product: sum_k (sum_j A[b,i,j] B[b,j,k]) = A[b,i,:] . rowsum(B[b])
+    want = np.einsum("bij,bj->bi", A.astype(np.float64), B.astype(np.float64).sum(axis=2))
+    assert _frob(got.astype(np.float64).sum(axis=2), want) <= 1e-5
 
 
 @pytest.mark.parametrize("ta,tb", [("fixnum", "fixnum"), ("ub8", "ub8"), ("ub8", "fixnum"), ("sb16", "ub4")])
