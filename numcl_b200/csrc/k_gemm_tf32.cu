@@ -542,11 +542,258 @@ __global__ void __launch_bounds__(TFF_THREADS, 1) gemm_tf32x3_fused_kernel(const
   }
 }
 
+// ===== fused variant on CTA PAIRS (tcgen05 cta_group::2) ============================================================
+//
+// The single-CTA fused kernel is bound by the SM's shared-memory data path (per k-block: 48 KB LDG fill +
+// 96 KB converter stores + 144 KB tensor-core operand reads).  Two CTAs of a cluster (one TPC) share one
+// 256 x 256 output tile: UMMA M = 256, each CTA owns 128 rows of A and D and only HALF of B (128 of the
+// 256 columns); the tensor cores fetch the other half from the peer's shared memory.  Per CTA and k-block
+// that is 32 KB LDG + 64 KB stores + 96 KB operand reads, and a 64 KB stage, so three stages fit.
+//   warps 0..3  convert A (128 x 32), warps 4..7 convert this CTA's B half (32 x 128)
+//   warp 8      leader CTA only: issues tcgen05.mma.cta_group::2; commits are multicast to both CTAs
+//   warps 9..12 epilogue of this CTA's 128 rows (TMEM lanes) x 256 columns
+// full[] and tmem_empty[] live in the LEADER's shared memory; the peer's warps arrive on them remotely
+// (mapa + mbarrier.arrive.release.cluster).  Needs M % 256 == 0 on top of the fused kernel's conditions.
+#define F2_CONV_WARPS 8
+#define F2_MMA_WARP 8
+#define F2_EPI_WARP0 9
+#define F2_EPI_WARPS 4
+#define F2_THREADS ((F2_EPI_WARP0 + F2_EPI_WARPS) * 32)          // 416: 13 warps, <= 128 registers
+#define F2_CPT 8                                                  // 16-byte chunks per converter thread and k-block
+#define F2_STAGES 3
+#define F2_B_TILE (TF_BK * 128 * 4)                               // this CTA's half of B: 16 KB
+#define F2_STAGE_BYTES (2 * TF_A_TILE + 2 * F2_B_TILE)            // 64 KB
+#define F2_SMEM (F2_STAGES * F2_STAGE_BYTES + 2048 + F2_EPI_WARPS * TFF_STG_BYTES)
+
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(unsigned cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity) {
+  long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("numcl-cuda: cluster mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tc_commit2(unsigned bar) {          // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_tf32(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 1) gemm_tf32x3_fused2_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                                                            int KT, long long lda, long long ldb, long long ldc,
+                                                                            long long sA, long long sB, long long sC,
+                                                                            int MT2, int NT, int batch, int accumulate) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[3 * F2_STAGES + 4];
+  __shared__ unsigned tmem_slot;
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[F2_STAGES]);
+  const unsigned tfull0 = smem_u32(&bars[2 * F2_STAGES]), tempty0 = smem_u32(&bars[2 * F2_STAGES + 2]);
+  const unsigned pfull0 = smem_u32(&bars[2 * F2_STAGES + 4]);          // leader only: "the peer's half of stage s is converted"
+  const unsigned pfull0_leader = mapa_u32(pfull0, 0), tempty0_leader = mapa_u32(tempty0, 0);
+  const int NC = (KT + TF_CHUNK_KB - 1) / TF_CHUNK_KB;
+  const int tiles_per_batch = MT2 * NT;
+  const int total_tiles = tiles_per_batch * batch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < F2_STAGES; s++) { mbar_init(full0 + 8 * s, F2_CONV_WARPS); mbar_init(empty0 + 8 * s, 1); mbar_init(pfull0 + 8 * s, 1); }
+    for (int t = 0; t < 2; t++) { mbar_init(tfull0 + 8 * t, 1); mbar_init(tempty0 + 8 * t, 2 * F2_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == F2_MMA_WARP) {                          // one warp of EACH CTA: the pair's TMEM is allocated collectively
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                                  // barriers initialised and TMEM allocated in both CTAs
+  tc_fence_after();
+  const unsigned tmem_base = tmem_slot;
+
+  if (warp < F2_CONV_WARPS) {
+    // ---- converters -------------------------------------------------------------------------------------
+    const bool isA = warp < 4;
+    const int ct = isA ? (int)threadIdx.x : (int)threadIdx.x - 128;
+    // A thread: chunk i -> row (ct>>3) + 16 i, 16-byte column ct&7.   B thread: chunk i -> k (ct>>5) + 4 i, 16-byte column ct&31.
+    // Both swizzles depend on the row only through bits that i does not change, so the smem offset is linear in i.
+    const int r0 = isA ? (ct >> 3) : (ct >> 5), c0 = isA ? (ct & 7) : (ct & 31);
+    const long long step = isA ? 16 * lda : 4 * ldb;
+    const long long kstep = isA ? (long long)TF_BK : (long long)TF_BK * ldb;
+    const unsigned off0 = isA ? (unsigned)swz(r0, c0)
+                              : (unsigned)(2 * TF_A_TILE + (c0 >> 3) * 4096 + r0 * 128 + (((c0 & 7) ^ (r0 << 1)) << 4));
+    const unsigned istride = isA ? 16 * 128 : 4 * 128;
+    const unsigned lo_off = isA ? TF_A_TILE : F2_B_TILE;
+    auto tile_ptr = [&](int t) -> const float* {
+      int b = t / tiles_per_batch, tm, tn; raster(t - b * tiles_per_batch, MT2, NT, 8, tm, tn);
+      return isA ? A + (long long)b * sA + ((long long)(2 * tm + (int)rank) * TF_BM + r0) * lda + c0 * 4
+                 : B + (long long)b * sB + (long long)r0 * ldb + (long long)tn * TF_BN + (int)rank * 128 + c0 * 4;
+    };
+    // one k-block of look-ahead in registers; the three-stage ring absorbs the rest
+    int lt = pair, lkt = 0;                                   // load cursor
+    const float* lsrc = lt < total_tiles ? tile_ptr(lt) : nullptr;
+    auto load_next = [&](float4 (&dst)[F2_CPT]) {
+      if (lt >= total_tiles) return;
+      const float* s2 = lsrc + lkt * kstep;
+#pragma unroll
+      for (int i = 0; i < F2_CPT; i++) dst[i] = __ldg((const float4*)(s2 + i * step));
+      if (++lkt == KT) { lkt = 0; lt += npairs; if (lt < total_tiles) lsrc = tile_ptr(lt); }
+    };
+    float4 cur[F2_CPT], n1[F2_CPT];
+    load_next(cur);
+    long long nblocks = 0;
+    for (int t = pair; t < total_tiles; t += npairs) nblocks += KT;
+    for (unsigned it = 0; it < (unsigned)nblocks; it++) {
+      load_next(n1);
+      const int s = it % F2_STAGES; const unsigned ph = (it / F2_STAGES) & 1;
+      mbar_wait(empty0 + 8 * s, ph ^ 1);              // own CTA's copy: the multicast commit arrives on both
+      const unsigned st = smem_u32(smem) + s * F2_STAGE_BYTES + off0;
+#pragma unroll
+      for (int i = 0; i < F2_CPT; i++) {
+        uint4 h, l; split4(cur[i], h, l);
+        sts128(st + i * istride, h);
+        sts128(st + i * istride + lo_off, l);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full0 + 8 * s);      // local and cheap; the peer's forwarder relays it (see warp F2_MMA_WARP)
+#pragma unroll
+      for (int i = 0; i < F2_CPT; i++) cur[i] = n1[i];
+    }
+  } else if (warp == F2_MMA_WARP) {
+    if (rank == 1 && lane == 0) {
+      // Forwarder.  A cluster-scope release costs a full memory barrier (MEMBAR.ALL.GPU + ERRBAR: ~0.7 us,
+      // 36 % of the converters' time when every converter warp arrived remotely).  So the converters
+      // arrive on their own CTA's full[] and this otherwise idle thread relays ONE arrival per k-block
+      // to the leader, off the converters' critical path.
+      long long nblocks = 0;
+      for (int t = pair; t < total_tiles; t += npairs) nblocks += KT;
+      for (unsigned it = 0; it < (unsigned)nblocks; it++) {
+        const int s = it % F2_STAGES; const unsigned ph = (it / F2_STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        mbar_arrive_remote(pfull0_leader + 8 * s);
+      }
+    }
+    if (rank == 0 && lane == 0) {
+      // D f32, A/B tf32, B MN-major (bit 16), N = 256, M = 256 over the pair
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((unsigned)(256 >> 3) << 17) | ((unsigned)(256 >> 4) << 24);
+      unsigned it = 0, g = 0;
+      for (int t = pair; t < total_tiles; t += npairs) {
+        int kt = 0;
+        for (int c = 0; c < NC; c++, g++) {
+          const int buf = g & 1; const unsigned use = g >> 1;
+          mbar_wait_cluster(tempty0 + 8 * buf, (use & 1) ^ 1);
+          tc_fence_after();
+          const unsigned d_tmem = tmem_base + (unsigned)(buf * TF_BN);
+          const int kend = (kt + TF_CHUNK_KB < KT) ? kt + TF_CHUNK_KB : KT;
+          for (int first = 1; kt < kend; kt++, it++) {
+            int s = it % F2_STAGES; unsigned ph = (it / F2_STAGES) & 1;
+            mbar_wait(full0 + 8 * s, ph);                  // this CTA's converters
+            mbar_wait_cluster(pfull0 + 8 * s, ph);         // the peer's, relayed
+            tc_fence_after();
+            unsigned a_hi = smem_u32(smem) + s * F2_STAGE_BYTES, a_lo = a_hi + TF_A_TILE;
+            unsigned b_hi = a_hi + 2 * TF_A_TILE, b_lo = b_hi + F2_B_TILE;
+#pragma unroll
+            for (int ks = 0; ks < TF_BK / 8; ks++) {
+              unsigned aoff = ks * 32, boff = ks * 1024;
+              tc_mma2_tf32(d_tmem, umma_desc(a_lo + aoff), umma_desc_mn(b_hi + boff), idesc, first ? 0u : 1u);
+              first = 0;
+              tc_mma2_tf32(d_tmem, umma_desc(a_hi + aoff), umma_desc_mn(b_lo + boff), idesc, 1u);
+              tc_mma2_tf32(d_tmem, umma_desc(a_hi + aoff), umma_desc_mn(b_hi + boff), idesc, 1u);
+            }
+            tc_commit2(empty0 + 8 * s);
+          }
+          tc_commit2(tfull0 + 8 * buf);
+        }
+      }
+    }
+  } else {
+    // ---- epilogue: this CTA's 128 rows, TMEM lane quarter q = warp % 4, all 256 columns ------------------------
+    // (eight warps on 32 x 16 slabs were tried: slower, 0.56 vs 0.43 ms on C4)
+    const int q = warp & 3;
+    const unsigned stg = smem_u32(smem) + F2_STAGES * F2_STAGE_BYTES + (warp - F2_EPI_WARP0) * TFF_STG_BYTES;
+    const unsigned stg_w = stg + lane * (TFF_STG_PITCH * 4);
+    const int rr = lane >> 3, c4 = lane & 7;
+    const unsigned stg_r = stg + rr * (TFF_STG_PITCH * 4) + c4 * 16;
+    unsigned g = 0;
+    for (int t = pair; t < total_tiles; t += npairs) {
+      int b = t / tiles_per_batch, tm, tn; raster(t - b * tiles_per_batch, MT2, NT, 8, tm, tn);
+      float* cbase = C + (long long)b * sC + ((long long)(2 * tm + (int)rank) * TF_BM + q * 32 + rr) * ldc + (long long)tn * TF_BN + c4 * 4;
+      for (int c = 0; c < NC; c++, g++) {
+        const int buf = g & 1; const unsigned use = g >> 1;
+        const bool add = (c > 0) || accumulate;
+        mbar_wait(tfull0 + 8 * buf, use & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < TF_BN / 32; cc++) {
+          unsigned r[32];
+          unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(buf * TF_BN + cc * 32);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                       : "r"(taddr) : "memory");
+          float* dst = cbase + cc * 32;
+          float4 old[8];
+          if (add) {                                      // the running sum so far, requested while the TMEM load is in flight
+#pragma unroll
+            for (int p = 0; p < 8; p++) old[p] = *(const float4*)(dst + (long long)(4 * p) * ldc);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (cc == TF_BN / 32 - 1) {                     // everything is out of TMEM: hand the accumulator back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty0_leader + 8 * buf);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) sts128(stg_w + j * 4, make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int p = 0; p < 8; p++) {
+            uint4 v = lds128(stg_r + p * (4 * TFF_STG_PITCH * 4));
+            float4 o = add ? old[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+            *(float4*)(dst + (long long)(4 * p) * ldc) = make_float4(__fadd_rn(o.x, __uint_as_float(v.x)), __fadd_rn(o.y, __uint_as_float(v.y)),
+                                                                       __fadd_rn(o.z, __uint_as_float(v.z)), __fadd_rn(o.w, __uint_as_float(v.w)));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                                  // the peer's smem and TMEM stay alive until both CTAs are done
+  if (warp == F2_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // NUMCL_TF32_MODE = auto | packed | fused  (debug/benchmark knob; `fused` still requires an eligible shape)
 static int tf32_mode() {
   const char* e = getenv("NUMCL_TF32_MODE");
   if (!e) return 0;
-  return !strcmp(e, "packed") ? 1 : !strcmp(e, "fused") ? 2 : 0;
+  return !strcmp(e, "packed") ? 1 : !strcmp(e, "fused") ? 2 : !strcmp(e, "fused2") ? 3 : 0;
 }
 
 static int gemm_f32_tf32x3_fused(const GemmParams& p) {
@@ -561,6 +808,25 @@ static int gemm_f32_tf32x3_fused(const GemmParams& p) {
                                                                        p.sA, p.sB, p.sC, MT, NT, p.batch, p.accumulate);
   note_launch("gemm_tf32x3_fused_tcgen05", 1);
   return cuda_fail(cudaGetLastError(), "gemm_tf32x3_fused_kernel");
+}
+
+static int gemm_f32_tf32x3_fused2(const GemmParams& p) {
+  Context& c = ctx();
+  int MT2 = p.M / 256, NT = p.N / TF_BN, KT = p.K / TF_BK;
+  long long total_tiles = (long long)MT2 * NT * p.batch;
+  if (total_tiles > 0x7fffffffLL) return NCL_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) { NCL_CUDA(cudaFuncSetAttribute(gemm_tf32x3_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM)); attr_set = true; }
+  long long pairs = c.sm_count / 2;
+  if (total_tiles < pairs) pairs = total_tiles;
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(F2_THREADS); cfg.dynamicSmemBytes = F2_SMEM; cfg.stream = c.stream;
+  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  NCL_TRY(cuda_fail(cudaLaunchKernelEx(&cfg, gemm_tf32x3_fused2_kernel, (const float*)p.A, (const float*)p.B, (float*)p.C, KT, p.lda, p.ldb, p.ldc,
+                                       p.sA, p.sB, p.sC, MT2, NT, p.batch, p.accumulate), "gemm_tf32x3_fused2_kernel launch"));
+  note_launch("gemm_tf32x3_fused_2cta_tcgen05", 1);
+  return cuda_fail(cudaGetLastError(), "gemm_tf32x3_fused2_kernel");
 }
 
 static bool fused_eligible(const GemmParams& p) {
@@ -579,6 +845,7 @@ int gemm_f32_tf32x3(const GemmParams& p) {
     // operands are re-used by many tiles (large M and N).  Small matrices: split inside the kernel.
     int mode = tf32_mode();
     bool small = (long long)p.M * p.N <= 1024LL * 1024LL;    // measured crossover (tools/gemm_fused_check.py)
+    if (mode == 3 && fused_eligible(p) && p.M % 256 == 0) return gemm_f32_tf32x3_fused2(p);
     if (mode != 1 && fused_eligible(p) && (mode == 2 || small)) return gemm_f32_tf32x3_fused(p);
   }
   int MT = (p.M + TF_BM - 1) / TF_BM, NT = (p.N + TF_BN - 1) / TF_BN, KT = (p.K + TF_BK - 1) / TF_BK;

@@ -10,6 +10,8 @@ import torch
 sys.path.insert(0, ".")
 import numcl_b200 as nc  # noqa: E402
 
+MODES = os.environ.get("GEMM_MODES", "packed,fused").split(",")
+
 
 def run(mode, a, b, spec):
     os.environ["NUMCL_TF32_MODE"] = mode
@@ -26,14 +28,14 @@ def accuracy():
         B = rng.uniform(-1, 1, (bt, K, N)).astype(np.float32)
         ref = A.astype(np.float64) @ B.astype(np.float64)
         a, b = nc.asarray(A, type="f32"), nc.asarray(B, type="f32")
-        for mode in ("packed", "fused"):
+        for mode in MODES:
             r, k = run(mode, a, b, "bij bjk -> bik")
             got = r.numpy().astype(np.float64)
             rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
             bad = not (rel < 1e-5)
             ok &= not bad
             print(f"b={bt} M={M} N={N} K={K} mode={mode:6s} kernel={k:28s} rel_frob={rel:.3e} {'BAD' if bad else ''}", flush=True)
-            if bad and mode == "fused":
+            if bad and mode != "packed":
                 e = np.abs(got - ref)[0]
                 print("   max err", e.max(), "at", np.unravel_index(e.argmax(), e.shape), " err by 32-col block:",
                       np.array2string(e.reshape(M, N // 32, 32).max(axis=(0, 2)), precision=2),
@@ -41,7 +43,7 @@ def accuracy():
     # accumulate into a supplied output
     A = rng.uniform(-1, 1, (256, 512)).astype(np.float32); B = rng.uniform(-1, 1, (512, 256)).astype(np.float32)
     C0 = rng.uniform(-1, 1, (256, 256)).astype(np.float32)
-    os.environ["NUMCL_TF32_MODE"] = "fused"
+    os.environ["NUMCL_TF32_MODE"] = MODES[-1]
     c = nc.asarray(C0, type="f32")
     nc.einsum("ij jk -> ik", nc.asarray(A, type="f32"), nc.asarray(B, type="f32"), c)
     ref = C0.astype(np.float64) + A.astype(np.float64) @ B.astype(np.float64)
@@ -76,7 +78,7 @@ def timing():
         from numcl_b200.einsum import _memoized
         specs, desc = _memoized("bij bjk -> bik")
         tin = (nc._lib.Tensor * 2)(a.tensor(), b.tensor()); tout = (nc._lib.Tensor * 1)(r.tensor())
-        for mode in ("packed", "fused"):
+        for mode in MODES:
             os.environ["NUMCL_TF32_MODE"] = mode
             med, best = timed(lambda: L.ncl_einsum(C.byref(desc), tin, 2, tout, 1, 1))
             fl = 2.0 * bt * M * N * K
