@@ -647,15 +647,27 @@ __global__ void __launch_bounds__(F2_THREADS, 1) gemm_tf32x3_fused2_kernel(const
       return isA ? A + (long long)b * sA + ((long long)(2 * tm + (int)rank) * TF_BM + r0) * lda + c0 * 4
                  : B + (long long)b * sB + (long long)r0 * ldb + (long long)tn * TF_BN + (int)rank * 128 + c0 * 4;
     };
-    // one k-block of look-ahead in registers; the three-stage ring absorbs the rest
+    // One k-block of look-ahead in registers, and an L2 prefetch two k-blocks beyond that: about half of the
+    // loads are first touches that come from HBM (> 1.5 us under load, longer than one iteration), and there
+    // are no registers for a second look-ahead set.  One lane per 128-byte line issues the prefetch.
     int lt = pair, lkt = 0;                                   // load cursor
     const float* lsrc = lt < total_tiles ? tile_ptr(lt) : nullptr;
+    const float* nsrc = lt + npairs < total_tiles ? tile_ptr(lt + npairs) : nullptr;     // the tile after the cursor's
+    const bool pf_lane = (c0 & 7) == 0;
     auto load_next = [&](float4 (&dst)[F2_CPT]) {
       if (lt >= total_tiles) return;
       const float* s2 = lsrc + lkt * kstep;
 #pragma unroll
       for (int i = 0; i < F2_CPT; i++) dst[i] = __ldg((const float4*)(s2 + i * step));
-      if (++lkt == KT) { lkt = 0; lt += npairs; if (lt < total_tiles) lsrc = tile_ptr(lt); }
+      if (pf_lane) {
+        const int pk = lkt + 2;
+        const float* ps = pk < KT ? lsrc + pk * kstep : ((nsrc && pk - KT < KT) ? nsrc + (pk - KT) * kstep : nullptr);
+        if (ps) {
+#pragma unroll
+          for (int i = 0; i < F2_CPT; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + i * step));
+        }
+      }
+      if (++lkt == KT) { lkt = 0; lt += npairs; lsrc = nsrc; nsrc = lt + npairs < total_tiles ? tile_ptr(lt + npairs) : nullptr; }
     };
     float4 cur[F2_CPT], n1[F2_CPT];
     load_next(cur);
