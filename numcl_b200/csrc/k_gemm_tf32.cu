@@ -835,8 +835,9 @@ static int gemm_f32_tf32x3_fused2(const GemmParams& p) {
   cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(F2_THREADS); cfg.dynamicSmemBytes = F2_SMEM; cfg.stream = c.stream;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  NCL_TRY(cuda_fail(cudaLaunchKernelEx(&cfg, gemm_tf32x3_fused2_kernel, (const float*)p.A, (const float*)p.B, (float*)p.C, KT, p.lda, p.ldb, p.ldc,
-                                       p.sA, p.sB, p.sC, MT2, NT, p.batch, p.accumulate), "gemm_tf32x3_fused2_kernel launch"));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_fused2_kernel, (const float*)p.A, (const float*)p.B, (float*)p.C, KT, p.lda, p.ldb, p.ldc,
+                                     p.sA, p.sB, p.sC, MT2, NT, p.batch, p.accumulate);
+  if (e != cudaSuccess) { cudaGetLastError(); return NCL_ERR_UNSUPPORTED; }     // no CTA pairs on this device/partition: single-CTA kernel
   note_launch("gemm_tf32x3_fused_2cta_tcgen05", 1);
   return cuda_fail(cudaGetLastError(), "gemm_tf32x3_fused2_kernel");
 }
@@ -856,9 +857,16 @@ int gemm_f32_tf32x3(const GemmParams& p) {
     // the pack pre-pass costs 3x the operand bytes; per output tile that is worth it only when the
     // operands are re-used by many tiles (large M and N).  Small matrices: split inside the kernel.
     int mode = tf32_mode();
-    bool small = (long long)p.M * p.N <= 1024LL * 1024LL;    // measured crossover (tools/gemm_fused_check.py)
-    if (mode == 3 && fused_eligible(p) && p.M % 256 == 0) return gemm_f32_tf32x3_fused2(p);
-    if (mode != 1 && fused_eligible(p) && (mode == 2 || small)) return gemm_f32_tf32x3_fused(p);
+    const long long mn = (long long)p.M * p.N;
+    if (mode != 1 && fused_eligible(p)) {
+      // measured crossovers (tools/gemm_fused_check.py): CTA pairs win up to 2048^2 outputs per matrix, the
+      // single-CTA kernel up to 1024^2, the pack pre-pass beyond
+      if (p.M % 256 == 0 && (mode == 3 || (mode == 0 && mn <= 2048LL * 2048LL))) {
+        int rc = gemm_f32_tf32x3_fused2(p);
+        if (rc != NCL_ERR_UNSUPPORTED) return rc;
+      }
+      if (mode == 2 || mode == 3 || mn <= 1024LL * 1024LL) return gemm_f32_tf32x3_fused(p);
+    }
   }
   int MT = (p.M + TF_BM - 1) / TF_BM, NT = (p.N + TF_BN - 1) / TF_BN, KT = (p.K + TF_BK - 1) / TF_BK;
   if ((long long)MT * NT > 0x7fffffffLL || p.batch > 65535 || MT > 65535) return NCL_ERR_UNSUPPORTED;

@@ -339,6 +339,16 @@ def _frob(got, ref):
     return np.linalg.norm(got - ref) / np.linalg.norm(ref)
 
 
+def _tf32_kernel(m, n, k):
+    """which single-float GEMM kernel k_gemm_tf32.cu::gemm_f32_tf32x3 picks"""
+    eligible = m % 128 == 0 and n % 256 == 0 and k % 32 == 0 and k <= 1024
+    if eligible and m % 256 == 0 and m * n <= 2048 * 2048:
+        return b"gemm_tf32x3_fused_2cta_tcgen05"
+    if eligible and m * n <= 1024 * 1024:
+        return b"gemm_tf32x3_fused_tcgen05"
+    return b"gemm_tf32x3_tcgen05"
+
+
 @pytest.mark.parametrize("dt,tol", [("f64", 1e-12), ("f32", 1e-5)])
 @pytest.mark.parametrize("m,k,n", [(256, 192, 320), (130, 70, 50), (1024, 1024, 1024), (128, 4096, 128), (33, 2, 65)])
 def test_matmul_float_within_tolerance(nc, oracle, dt, tol, m, k, n):
@@ -351,8 +361,7 @@ def test_matmul_float_within_tolerance(nc, oracle, dt, tol, m, k, n):
     if dt == "f64" and m >= 32 and n >= 32 and k % 2 == 0 and n % 2 == 0:
         assert nc.lib().ncl_last_kernel() == b"gemm_f64_dmma"
     if dt == "f32" and m * n >= 128 * 128 and k >= 32:
-        fused = m % 128 == 0 and n % 256 == 0 and k % 32 == 0 and k <= 1024 and m * n <= 1024 * 1024
-        assert nc.lib().ncl_last_kernel() == (b"gemm_tf32x3_fused_tcgen05" if fused else b"gemm_tf32x3_tcgen05")
+        assert nc.lib().ncl_last_kernel() == _tf32_kernel(m, n, k)
 
 
 def test_matmul_f64_interpreter_agrees_with_fast_loop(oracle):
@@ -372,40 +381,42 @@ def test_batched_einsum_within_tolerance(nc, oracle, dt, tol):
     assert _frob(got.numpy(), ref) <= tol
 
 
-@pytest.mark.parametrize("b,m,k,n", [(1, 128, 32, 256), (3, 256, 96, 512), (2, 384, 544, 256), (5, 128, 1024, 768)])
+@pytest.mark.parametrize("b,m,k,n", [(1, 128, 32, 256), (3, 256, 96, 512), (2, 384, 544, 256), (5, 128, 1024, 768),
+                                     (1, 256, 32, 256), (7, 512, 288, 512), (150, 256, 64, 256), (2, 1024, 1024, 1024)])
 def test_batched_einsum_fused_split_kernel(nc, oracle, b, m, k, n):
-    """tile-aligned single-float shapes take the kernel that splits hi/lo in shared memory (one launch,
-    no pack pre-pass); same tolerance vs numcl's nest, and it must agree with the packed path's error level"""
+    """tile-aligned single-float shapes take the kernels that split hi/lo in shared memory (one launch, no
+    pack pre-pass; on CTA pairs when M % 256 == 0); same tolerance vs numcl's nest as the packed path"""
     A, B = rand(oracle, (b, m, k), "f32", SEED, 0, -1.0, 1.0), rand(oracle, (b, k, n), "f32", SEED + 1, 0, -1.0, 1.0)
     ref = oracle.fast_bmm_f32(A.values(), B.values())
     got = nc.einsum("bij bjk -> bik", to_gpu(nc, A), to_gpu(nc, B))
-    assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_fused_tcgen05"
+    assert nc.lib().ncl_last_kernel() == _tf32_kernel(m, n, k) != b"gemm_tf32x3_tcgen05"
     assert _frob(got.numpy(), ref) <= 1e-5
     truth = A.values().astype(np.float64) @ B.values().astype(np.float64)
     assert _frob(got.numpy(), truth) <= 4e-6          # 3xTF32 + chunked accumulation: ~2e-6
 
 
-def test_fused_split_kernel_specials_and_accumulate(nc, oracle):
+@pytest.mark.parametrize("m", [128, 256])
+def test_fused_split_kernel_specials_and_accumulate(nc, oracle, m):
     """inf / NaN operands stay non-finite (the split keeps them in the hi part; inf * lo-part may turn an
     IEEE inf into NaN, as in every split-precision GEMM -- SBCL would trap there, SURVEY 8b "Errors"), NaN
     stays NaN, and a caller-supplied result is accumulated into (src/3einsum.lisp:468)"""
     rng = np.random.default_rng(5)
-    A = rng.uniform(-1, 1, (128, 64)).astype(np.float32); B = rng.uniform(-1, 1, (64, 256)).astype(np.float32)
+    A = rng.uniform(-1, 1, (m, 64)).astype(np.float32); B = rng.uniform(-1, 1, (64, 256)).astype(np.float32)
     A[3, 5] = np.inf; A[7, 9] = np.nan; B[11, 17] = -np.inf
     A[9, 0] = np.float32(np.frombuffer(np.uint32(0x7fffffff).tobytes(), dtype=np.float32)[0])    # CUDA's canonical NaN
     got = nc.matmul(nc.asarray(A, type="f32"), nc.asarray(B, type="f32")).numpy()
-    assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_fused_tcgen05"
+    assert nc.lib().ncl_last_kernel() == _tf32_kernel(m, 256, 64)
     with np.errstate(invalid="ignore", over="ignore"):
         want = A.astype(np.float64) @ B.astype(np.float64)
     assert np.array_equal(np.isfinite(got), np.isfinite(want))
     assert np.all(np.isnan(got[np.isnan(want)]))
     fin = np.isfinite(want)
     assert np.allclose(got[fin], want[fin], rtol=0, atol=1e-4)
-    C0 = rng.uniform(-1, 1, (128, 256)).astype(np.float32)
-    A2 = rng.uniform(-1, 1, (128, 512)).astype(np.float32); B2 = rng.uniform(-1, 1, (512, 256)).astype(np.float32)
+    C0 = rng.uniform(-1, 1, (m, 256)).astype(np.float32)
+    A2 = rng.uniform(-1, 1, (m, 512)).astype(np.float32); B2 = rng.uniform(-1, 1, (512, 256)).astype(np.float32)
     c = nc.asarray(C0, type="f32")
     nc.matmul(nc.asarray(A2, type="f32"), nc.asarray(B2, type="f32"), c)
-    assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_fused_tcgen05"
+    assert nc.lib().ncl_last_kernel() == _tf32_kernel(m, 256, 512)
     assert _frob(c.numpy(), C0.astype(np.float64) + A2.astype(np.float64) @ B2.astype(np.float64)) <= 4e-6
 
 
@@ -415,7 +426,7 @@ def test_batched_einsum_c4_full_size(nc, oracle):
     a = nc.random_array((bsz, 512, 512), "f32", SEED, 0, -1.0, 1.0)
     b = nc.random_array((bsz, 512, 512), "f32", SEED + 1, 0, -1.0, 1.0)
     r = nc.einsum("bij bjk -> bik", a, b)
-    assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_fused_tcgen05"
+    assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_fused_2cta_tcgen05"
     got = r.numpy()
     A, B = a.numpy(), b.numpy()
     for i in (0, 131, 255):
