@@ -91,11 +91,53 @@ __global__ void fill_kernel(FillParams p) {
   }
 }
 
+// Constant fill of a byte-addressable type: the slot pattern is produced once per thread by the SAME store
+// routine the scalar kernel uses (bit-identical by construction), replicated to 16 bytes, and streamed
+// with 128-bit stores over the 16-byte aligned body; the unaligned head and tail are scalar.
+// (write-only streams want many CTAs: 32 per SM measured best, tools/micro/write_bw.cu)
+__global__ void __launch_bounds__(256) fill_const_vec_kernel(FillParams p) {
+  unsigned long long tmp[2] = {0ull, 0ull};
+  {
+    long long iv = p.iv; float f = (float)p.fv; double d = p.fv;
+    if (!p.is_float) { f = __ll2float_rn(iv); d = __ll2double_rn(iv); }
+    if (p.cls == CLS_F) fill_store_direct<float>((char*)tmp, 0, p.st, f);
+    else if (p.cls == CLS_D) fill_store_direct<double>((char*)tmp, 0, p.st, d);
+    else if (!p.is_float) fill_store_direct<long long>((char*)tmp, 0, p.st, iv);
+    else fill_store_direct<double>((char*)tmp, 0, p.st, p.fv);
+  }
+  const int sb = p.slot_bits >> 3;                                  // slot bytes: 1, 2, 4, 8
+  unsigned long long pat = tmp[0];
+  if (sb == 1) pat = (pat & 0xffull) * 0x0101010101010101ull;
+  else if (sb == 2) pat = (pat & 0xffffull) * 0x0001000100010001ull;
+  else if (sb == 4) pat = (pat & 0xffffffffull) * 0x0000000100000001ull;
+  char* start = p.base + p.offset * sb;
+  const long long nbytes = p.n * sb;
+  long long head = (16 - (long long)((uintptr_t)start & 15)) & 15;
+  if (head > nbytes) head = nbytes;
+  const long long body = (nbytes - head) >> 4;                      // 16-byte chunks
+  const long long tail0 = head + (body << 4);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  const uint4 v = make_uint4((unsigned)pat, (unsigned)(pat >> 32), (unsigned)pat, (unsigned)(pat >> 32));
+  uint4* b = (uint4*)(start + head);
+  for (long long i = tid; i < body; i += stride) b[i] = v;
+  // head and tail: at most 15 bytes each
+  for (long long o = tid * sb; o < head; o += stride * sb) memcpy(start + o, &pat, sb);
+  for (long long o = tail0 + tid * sb; o < nbytes; o += stride * sb) memcpy(start + o, &pat, sb);
+}
+
 static int launch_fill(FillParams& p) {
   Context& c = ctx();
   if (p.n <= 0) return NCL_OK;
   if (p.slot_bits < 8 && ((p.offset * p.slot_bits) % 32) != 0)
     return set_error(NCL_ERR_UNSUPPORTED, "fill of a packed array needs a 32-bit aligned element offset");
+  if (!p.random && p.slot_bits >= 8 && p.n * (p.slot_bits >> 3) >= 4096) {
+    long long chunks = (p.n * (p.slot_bits >> 3)) >> 4;
+    long long blocks = (chunks + 255) / 256, cap = (long long)c.sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    fill_const_vec_kernel<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+    note_launch("fill_vec");
+    return cuda_fail(cudaGetLastError(), "fill_const_vec_kernel");
+  }
   long long work = p.slot_bits >= 8 ? p.n : (p.n * p.slot_bits + 31) / 32;
   long long blocks = (work + 255) / 256;
   long long cap = (long long)c.sm_count * 16;

@@ -147,3 +147,27 @@ def test_matmul_star_copy_astype(nc, oracle):
     assert_bit_exact(nc.copy(g), a)
     for dt in ("fixnum", "sb8", "f64", "ub8"):
         assert_bit_exact(nc.astype(g, dt), oracle.map_array("(identity $1)", [a], dt))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt,value", [("ub8", 200), ("sb16", -1234), ("ub31", 123456789), ("fixnum", -(2 ** 40) - 3), ("sb64", 2 ** 62 + 5),
+                                      ("f32", 1.5), ("f64", -2.25)])
+@pytest.mark.parametrize("n,offset", [(4099, 0), (4099, 1), (100003, 3), (65536, 7), (513, 5)])
+def test_full_vectorised_fill_with_displacement(nc, dt, value, n, offset):
+    """(full shape value), src/2zeros.lisp:46-50, on a displaced array: the 128-bit body, the scalar head and
+    tail give the same slots as the scalar kernel, and nothing outside [offset, offset + n) is written"""
+    import ctypes as C
+    from numcl_b200 import _lib
+    from numcl_b200.array import NArray
+    a = NArray((n,), dt, offset=offset)
+    a.set_raw(np.full(a.nbytes, 0xAB, dtype=np.uint8))
+    t = a.tensor()
+    isf = isinstance(value, float)
+    _lib.check(_lib.lib().ncl_fill(C.byref(t), 1 if isf else 0, 0 if isf else int(value), float(value)))
+    got = a.numpy()
+    assert np.all(got == (np.float64(value) if isf else np.int64(value)))
+    raw = a.raw()
+    sb = a.dtype.slot_bits // 8
+    assert np.all(raw[: offset * sb] == 0xAB) and np.all(raw[(offset + n) * sb:] == 0xAB)
+    if n * sb >= 4096:
+        assert nc.lib().ncl_last_kernel() == b"fill_vec"
