@@ -801,6 +801,9 @@ __global__ void __launch_bounds__(F2_THREADS, 1) gemm_tf32x3_fused2_kernel(const
   }
 }
 
+// (The pack + GEMM path was also tried on CTA pairs -- half of the packed B tile per CTA, three 64 KB stages:
+// identical accuracy, no gain (8192^3: 4.66 vs 4.68 ms): that path is bound by the tensor pipe and the
+// power-capped clock, not by shared memory.  Not kept.)
 // NUMCL_TF32_MODE = auto | packed | fused  (debug/benchmark knob; `fused` still requires an eligible shape)
 static int tf32_mode() {
   const char* e = getenv("NUMCL_TF32_MODE");

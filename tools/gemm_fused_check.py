@@ -23,7 +23,7 @@ def accuracy():
     rng = np.random.default_rng(0)
     ok = True
     for (bt, M, N, K) in [(1, 128, 256, 32), (1, 128, 256, 64), (1, 128, 256, 256), (1, 128, 256, 512), (1, 256, 512, 512),
-                          (3, 512, 512, 512), (1, 384, 768, 1024), (2, 128, 512, 96)]:
+                          (3, 512, 512, 512), (1, 384, 768, 1024), (2, 128, 512, 96), (1, 300, 700, 2500), (2, 640, 256, 4096)]:
         A = rng.uniform(-1, 1, (bt, M, K)).astype(np.float32)
         B = rng.uniform(-1, 1, (bt, K, N)).astype(np.float32)
         ref = A.astype(np.float64) @ B.astype(np.float64)
@@ -71,7 +71,10 @@ def timed(fn, iters=20, warm=3):
 
 def timing():
     L = nc.lib()
-    for (bt, M, N, K) in [(256, 512, 512, 512), (64, 1024, 1024, 1024), (1024, 256, 256, 256), (4, 2048, 2048, 1024), (1, 4096, 4096, 1024)]:
+    shapes = [(256, 512, 512, 512), (64, 1024, 1024, 1024), (1024, 256, 256, 256), (4, 2048, 2048, 1024), (1, 4096, 4096, 1024)]
+    if "big" in sys.argv:
+        shapes = [(1, 4096, 4096, 4096), (1, 8192, 8192, 8192), (1, 4096, 4096, 1024), (3, 1000, 1500, 700)]
+    for (bt, M, N, K) in shapes:
         a = nc.random_array((bt, M, K), "f32", 1, 0, -1.0, 1.0)
         b = nc.random_array((bt, K, N), "f32", 2, 0, -1.0, 1.0)
         r = nc.empty((bt, M, N), "f32")
