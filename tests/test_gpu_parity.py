@@ -472,3 +472,35 @@ def test_matmul_c3_sampled_rows(nc, oracle):
     for r0 in (0, 1000, 2040):
         ref = oracle.fast_matmul(A.values(), B.values(), rows=(r0, min(r0 + 22, n)))
         assert _frob(got[r0:r0 + ref.shape[0]], ref) <= 1e-12
+
+
+def test_matmul_c3_f32_full_size_sampled_rows(nc, oracle):
+    """config C3 single-float at full size (8192^3, pack + 3xTF32 tcgen05 GEMM): 3 x 8 sampled rows in the
+    reference's own accumulation order, and the whole product against a linear property"""
+    n = 8192
+    a = nc.random_array((n, n), "f32", SEED, 0, -1.0, 1.0)
+    b = nc.random_array((n, n), "f32", SEED + 1, 0, -1.0, 1.0)
+    r = nc.matmul(a, b)
+    assert nc.lib().ncl_last_kernel() == b"gemm_tf32x3_tcgen05"
+    A, B, got = a.numpy(), b.numpy(), r.numpy()
+    for r0 in (0, 4099, 8184):
+        ref = oracle.fast_matmul(A, B, rows=(r0, r0 + 8))
+        assert _frob(got[r0:r0 + 8], ref) <= 1e-5
+    # C @ 1 = A @ (B @ 1): every row of the product is covered
+    want = A.astype(np.float64) @ B.astype(np.float64).sum(axis=1)
+    assert _frob(got.astype(np.float64).sum(axis=1), want) <= 1e-5
+
+
+def test_matmul_c3_f64_full_size_sampled_rows(nc, oracle):
+    """config C3 double-float at full size (8192^3, DMMA): sampled rows in the reference order (1e-12) + linearity"""
+    n = 8192
+    a = nc.random_array((n, n), "f64", SEED, 0, -1.0, 1.0)
+    b = nc.random_array((n, n), "f64", SEED + 1, 0, -1.0, 1.0)
+    r = nc.matmul(a, b)
+    assert nc.lib().ncl_last_kernel() == b"gemm_f64_dmma"
+    A, B, got = a.numpy(), b.numpy(), r.numpy()
+    for r0 in (0, 4099, 8188):
+        ref = oracle.fast_matmul(A, B, rows=(r0, r0 + 4))
+        assert _frob(got[r0:r0 + 4], ref) <= 1e-12
+    want = A @ B.sum(axis=1)
+    assert _frob(got.sum(axis=1), want) <= 1e-12
