@@ -205,7 +205,11 @@ int try_elementwise(const Nest& n) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfn, EW_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
   unsigned long long blocks = (nitems + EW_THREADS / 32 - 1) / (EW_THREADS / 32);
-  unsigned long long cap = (unsigned long long)c.sm_count * per_sm;
+  // Four waves instead of one when no operand is hoisted out of the item loop (measured on C1: 23.7 -> 22.5 us,
+  // better tail balance); a hoisted row vector is re-read per CTA, and there one resident wave is faster (C5a).
+  int over = 4;
+  for (int k = 0; k < m.n; k++) if (p.period[k] != 0 && ((32u * U) % p.period[k]) == 0) over = 1;
+  unsigned long long cap = (unsigned long long)c.sm_count * per_sm * over;
   if (blocks > cap) blocks = cap;
   kfn<<<(unsigned)blocks, EW_THREADS, 0, c.stream>>>(p);
   note_launch(E == 1 ? "bcast_scalar" : "bcast_vec");
