@@ -66,6 +66,9 @@ static bool match_expr(const Expr& e, int self_out, bool fresh, Match* m) {
   return false;
 }
 
+int ew_widen_launch(int a_lk, int op, const char* a, const char* b, char* out, unsigned nchunks, int bmode, unsigned period, int btag, int swap,
+                    unsigned long long mask, int shift);                 // k_ew_widen.cu
+
 int try_elementwise(const Nest& n) {
   if (n.n_out != 1) return NCL_ERR_UNSUPPORTED;
   const Operand& out = n.out[0];
@@ -177,6 +180,29 @@ int try_elementwise(const Nest& n) {
           unsigned s2 = 0; while ((1ull << s2) < period[k]) s2++;
           p.pmul[k] = (unsigned)(((1ull << (31 + s2)) + period[k] - 1) / period[k]); p.pshr[k] = s2 - 1;
         }                                                                     // period 1: ew_div(q, 0, 0) = q, so q mod 1 = 0
+      }
+    }
+  }
+  // ---- widening integer family (k_ew_widen.cu): narrow int array (op) 64-bit operand -> 64-bit result, flat ----
+  if (nd == 1 && E == 2 && cc == CLS_I && out_cls == CLS_I && m.n == 2 && !is_cmp && d[0].ext / 2 < 0x7fffffffLL) {
+    int wop = shape == S_ADD || shape == S_ADD0 ? 0 : shape == S_SUB ? 1 : shape == S_MUL || shape == S_MUL0 ? 2 : shape == S_MAX ? 3 : shape == S_MIN ? 4 : -1;
+    int lk0 = dtype_load_kind(ops[0].dtype), lk1 = dtype_load_kind(ops[1].dtype);
+    auto narrow = [&](int k, int lk) { return lk >= LK_U8 && lk <= LK_S32 && d[0].st[1 + k] == 1 && p.period[k] == 0; };
+    auto wide = [&](int lk) { return lk == LK_T64 || lk == LK_W64; };
+    int ia = narrow(0, lk0) && wide(lk1) ? 0 : (narrow(1, lk1) && wide(lk0) ? 1 : -1);
+    if (wop >= 0 && ia >= 0) {
+      const int ib = 1 - ia;
+      int bmode = -1;
+      if (p.period[ib] != 0) bmode = (128u % p.period[ib]) == 0 ? 1 : ((p.period[ib] % 128u) == 0 ? 2 : -1);
+      else if (d[0].st[1 + ib] == 1) bmode = 0;
+      else if (d[0].st[1 + ib] == 0) bmode = 3;
+      if (bmode >= 0) {
+        const int la = ia == 0 ? lk0 : lk1, lb = ia == 0 ? lk1 : lk0;
+        const char* ap = ops[ia].base + (ops[ia].offset * g_dt[ops[ia].dtype].slot_bits) / 8;
+        const char* bp = ops[ib].base + ops[ib].offset * 8;
+        char* op = out.base + out.offset * 8;
+        int rc = ew_widen_launch(la, wop, ap, bp, op, (unsigned)(d[0].ext / 2), bmode, p.period[ib], lb == LK_T64 ? 1 : 0, ia == 1 ? 1 : 0, sk.mask, sk.shift);
+        if (rc != NCL_ERR_UNSUPPORTED) return rc;
       }
     }
   }

@@ -115,9 +115,36 @@ def test_u8_times_fixnum_wraps_at_63_bits(nc, oracle):
     got = nc.mul(to_gpu(nc, x), to_gpu(nc, y))
     assert want.dtype == "fixnum"
     assert_bit_exact(got, want)
-    assert nc.lib().ncl_last_kernel() == b"bcast_vec"
+    assert nc.lib().ncl_last_kernel() == b"bcast_widen"
     fast = oracle.fast_mul2_u8_fix(x.values().astype(np.uint8), y.storage[: 256 * 8].view(np.int64))
     assert np.array_equal(got.raw()[: x.size * 8].view(np.int64), fast.reshape(-1))
+
+
+@pytest.mark.parametrize("op", ["+", "-", "*", "max", "min"])
+@pytest.mark.parametrize("narrow", ["ub8", "sb8", "ub15", "sb16", "ub31", "sb32"])
+@pytest.mark.parametrize("wide", ["fixnum", "sb64"])
+def test_widening_integer_family_bit_exact(nc, oracle, op, narrow, wide):
+    """k_ew_widen.cu: narrow integer array (op) 64-bit operand -> 64-bit result, in both operand orders and in all
+    four layouts of the 64-bit operand (row vector shorter / longer than a warp item, same shape, scalar), with a
+    ragged last item; bit-exact against numcl's broadcast, including the 63/64-bit wrap"""
+    from numcl_b200.dtypes import dtype
+    d = dtype(narrow)
+    f = {"+": nc.add, "-": nc.sub, "*": nc.mul, "max": nc.maximum, "min": nc.minimum}[op]
+    big = 2 ** 61 if op == "*" else 2 ** 40
+    for shape_x, shape_y in [((37, 64), (64,)), ((5, 512), (512,)), ((3, 7, 130), (3, 7, 130)), ((1000,), ())]:
+        x = rand(oracle, shape_x, narrow, SEED, 0, max(d.lo, -30000), min(d.hi, 30000))
+        if shape_y == ():
+            for s in (7, -3):
+                assert_bit_exact(f(to_gpu(nc, x), s), refsem.arith(oracle, op, [x, s]))
+                assert_bit_exact(f(s, to_gpu(nc, x)), refsem.arith(oracle, op, [s, x]))
+            continue
+        y = rand(oracle, shape_y, wide, SEED + 1, 0, -big, big)
+        for args in ([x, y], [y, x]):
+            want = refsem.arith(oracle, op, args)
+            got = f(*[to_gpu(nc, a) for a in args])
+            assert_bit_exact(got, want)
+            if want.dtype in ("fixnum", "sb64"):
+                assert nc.lib().ncl_last_kernel() == b"bcast_widen"
 
 
 @pytest.mark.parametrize("op", ["=/bit", "</bit", ">=/bit"])
