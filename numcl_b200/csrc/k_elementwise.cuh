@@ -12,8 +12,11 @@
 //   * inputs whose innermost stride is 1 are read with the matching vector load, inputs whose
 //     innermost stride is 0 (numpy broadcasting: `b` of (numcl:+ a b), scalars) are read once and
 //     splat -- stride-0 indexing, not a materialised copy;
-//   * each thread issues U independent chunks' loads before any math for memory-level
-//     parallelism; grid = chunks / (256*U).
+//   * each thread issues U independent chunks' loads before any math for memory-level parallelism;
+//     persistent warps walk work items of 32*U chunks (one resident wave of CTAs, or four waves when
+//     nothing is hoisted out of the item loop -- see try_elementwise);
+//   * the widening integer shape (narrow int array x 64-bit operand -> 64-bit) has its own
+//     kind-specialised family in k_ew_widen.cu.
 // Arithmetic follows ncl_device.cuh (IEEE rn, no FMA contraction, CL max/min, exact integers).
 #pragma once
 #include "ncl_device.cuh"
@@ -250,7 +253,6 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
 typedef void (*EwKernel)(const EwParams);
 template <int E> constexpr int ew_u() { return E == 32 ? 1 : 4; }
 template <class TI, class F, int NIN, int E> static EwKernel kern() { return (EwKernel)ew_kernel<TI, F, NIN, E, ew_u<E>()>; }
-template <int E> static int ufactor() { return E == 1 ? 4 : (E == 32 ? 1 : 4); }
 
 template <class T, int E> static EwKernel pick_arith(int shape) {     // T-class in, T-class out
   switch (shape) {
