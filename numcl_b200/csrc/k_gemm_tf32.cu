@@ -704,9 +704,15 @@ __global__ void __launch_bounds__(F2_THREADS, 1) gemm_tf32x3_fused2_kernel(const
         mbar_arrive_remote(pfull0_leader + 8 * s);
       }
     }
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
+      // The whole warp walks the loop (uniform control flow, so descriptor and barrier arithmetic can stay in
+      // uniform registers) and one lane issues.  Descriptors are the stage-0 descriptor plus a constant: with
+      // the loop under `if (lane == 0)` ptxas rebuilt every 64-bit descriptor in vector registers and moved
+      // it over with R2UR, ~20 instructions per MMA, and ncu showed this warp busy issuing, not waiting.
       // D f32, A/B tf32, B MN-major (bit 16), N = 256, M = 256 over the pair
       const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((unsigned)(256 >> 3) << 17) | ((unsigned)(256 >> 4) << 24);
+      const unsigned long long adesc0 = umma_desc(smem_u32(smem));                      // stage 0: A_hi
+      const unsigned long long bdesc0 = umma_desc_mn(smem_u32(smem) + 2 * TF_A_TILE);   // stage 0: B_hi
       unsigned it = 0, g = 0;
       for (int t = pair; t < total_tiles; t += npairs) {
         int kt = 0;
@@ -716,24 +722,27 @@ __global__ void __launch_bounds__(F2_THREADS, 1) gemm_tf32x3_fused2_kernel(const
           tc_fence_after();
           const unsigned d_tmem = tmem_base + (unsigned)(buf * TF_BN);
           const int kend = (kt + TF_CHUNK_KB < KT) ? kt + TF_CHUNK_KB : KT;
-          for (int first = 1; kt < kend; kt++, it++) {
-            int s = it % F2_STAGES; unsigned ph = (it / F2_STAGES) & 1;
+          for (unsigned first = 1; kt < kend; kt++, it++, first = 0) {
+            const int s = it % F2_STAGES; const unsigned ph = (it / F2_STAGES) & 1;
             mbar_wait(full0 + 8 * s, ph);                  // this CTA's converters
             mbar_wait_cluster(pfull0 + 8 * s, ph);         // the peer's, relayed
             tc_fence_after();
-            unsigned a_hi = smem_u32(smem) + s * F2_STAGE_BYTES, a_lo = a_hi + TF_A_TILE;
-            unsigned b_hi = a_hi + 2 * TF_A_TILE, b_lo = b_hi + F2_B_TILE;
+            const unsigned so = (unsigned)s * (F2_STAGE_BYTES >> 4);      // descriptor address field counts 16-byte units
+            if (lane == 0) {
 #pragma unroll
-            for (int ks = 0; ks < TF_BK / 8; ks++) {
-              unsigned aoff = ks * 32, boff = ks * 1024;
-              tc_mma2_tf32(d_tmem, umma_desc(a_lo + aoff), umma_desc_mn(b_hi + boff), idesc, first ? 0u : 1u);
-              first = 0;
-              tc_mma2_tf32(d_tmem, umma_desc(a_hi + aoff), umma_desc_mn(b_lo + boff), idesc, 1u);
-              tc_mma2_tf32(d_tmem, umma_desc(a_hi + aoff), umma_desc_mn(b_hi + boff), idesc, 1u);
+              for (int ks = 0; ks < TF_BK / 8; ks++) {
+                const unsigned long long a_hi = adesc0 + so + ks * (32 >> 4), a_lo = a_hi + (TF_A_TILE >> 4);       // A: 32 B along the row
+                const unsigned long long b_hi = bdesc0 + so + ks * (1024 >> 4), b_lo = b_hi + (F2_B_TILE >> 4);     // B: the next 8 k-rows
+                tc_mma2_tf32(d_tmem, a_lo, b_hi, idesc, (ks == 0 && first) ? 0u : 1u);
+                tc_mma2_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                tc_mma2_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+              }
+              tc_commit2(empty0 + 8 * s);
             }
-            tc_commit2(empty0 + 8 * s);
+            __syncwarp();
           }
-          tc_commit2(tfull0 + 8 * buf);
+          if (lane == 0) tc_commit2(tfull0 + 8 * buf);
+          __syncwarp();
         }
       }
     }
