@@ -171,3 +171,54 @@ def test_full_vectorised_fill_with_displacement(nc, dt, value, n, offset):
     assert np.all(raw[: offset * sb] == 0xAB) and np.all(raw[(offset + n) * sb:] == 0xAB)
     if n * sb >= 4096:
         assert nc.lib().ncl_last_kernel() == b"fill_vec"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,k,n,kernel", [(256, 64, 256, b"gemm_tf32x3_fused_2cta_tcgen05"), (128, 96, 512, b"gemm_tf32x3_fused_tcgen05"),
+                                          (200, 96, 300, b"gemm_tf32x3_tcgen05"), (40, 24, 56, b"gemm_fma_simt")])
+def test_gemm_writes_only_its_output_region(nc, m, k, n, kernel):
+    """C-ABI level: the result tensor is a displaced window (elem_offset 16) into a larger base vector filled
+    with a canary; every single-float GEMM kernel must leave the bytes before and after the window alone"""
+    import ctypes as C
+    from numcl_b200 import _lib
+    from numcl_b200.array import NArray
+    from numcl_b200.einsum import _memoized
+    rng = np.random.default_rng(11)
+    A = rng.uniform(-1, 1, (m, k)).astype(np.float32); B = rng.uniform(-1, 1, (k, n)).astype(np.float32)
+    a, b = nc.asarray(A, type="f32"), nc.asarray(B, type="f32")
+    off, tail = 16, 40
+    store = NArray((off + m * n + tail,), "f32")
+    store.set_raw(np.full(store.nbytes, 0xAB, dtype=np.uint8))
+    t = store.tensor()
+    t.rank = 2; t.dims[0] = m; t.dims[1] = n; t.elem_offset = off
+    _, desc = _memoized("ij jk -> ik")
+    tin = (_lib.Tensor * 2)(a.tensor(), b.tensor()); tout = (_lib.Tensor * 1)(t)
+    _lib.check(_lib.lib().ncl_einsum(C.byref(desc), tin, 2, tout, 1, _lib.OUT_FRESH))
+    assert nc.lib().ncl_last_kernel() == kernel
+    raw = store.raw()
+    assert np.all(raw[: off * 4] == 0xAB) and np.all(raw[(off + m * n) * 4: (off + m * n + tail) * 4] == 0xAB)
+    got = raw[off * 4: (off + m * n) * 4].view(np.float32).reshape(m, n)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_widening_kernel_writes_only_its_output_region(nc, oracle):
+    """same canary check for the widening integer family and a ragged element count"""
+    import ctypes as C
+    from numcl_b200 import _lib
+    from numcl_b200.array import NArray
+    n = 128 * 2 * 37 + 6                       # not a multiple of the 256-element warp item
+    x = rand(oracle, (n,), "ub8", SEED, 0, 0, 255); y = rand(oracle, (n,), "fixnum", SEED + 1, 0, -(2 ** 40), 2 ** 40)
+    want = refsem.arith(oracle, "*", [x, y])
+    off, tail = 2, 10
+    store = NArray((off + n + tail,), "fixnum")
+    store.set_raw(np.full(store.nbytes, 0xAB, dtype=np.uint8))
+    t = store.tensor(); t.rank = 1; t.dims[0] = n; t.elem_offset = off
+    gx, gy = to_gpu(nc, x), to_gpu(nc, y)
+    tx, ty = gx.tensor(), gy.tensor()
+    _lib.check(_lib.lib().ncl_broadcast(_lib.OPS["MUL"], C.byref(tx), C.byref(ty), C.byref(t)))
+    assert nc.lib().ncl_last_kernel() == b"bcast_widen"
+    raw = store.raw()
+    assert np.all(raw[: off * 8] == 0xAB) and np.all(raw[(off + n) * 8: (off + n + tail) * 8] == 0xAB)
+    assert np.array_equal(raw[off * 8: (off + n) * 8].view(np.int64), want.storage[: n * 8].view(np.int64))
