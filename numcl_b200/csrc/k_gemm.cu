@@ -6,7 +6,8 @@
 // one strided dimension, with K contiguous in A, N contiguous in B and C (row-major operands, the
 // layout of `matmul` and `(bij bjk -> bik)`).  Anything else stays on the generic nest kernel.
 //   double-float            -> DMMA          (k_gemm_f64.cu)
-//   single-float, large     -> 3xTF32 tcgen05 (k_gemm_tf32.cu)
+//   single-float, large     -> 3xTF32 tcgen05 (k_gemm_tf32.cu: pack + GEMM, or the split fused into the GEMM
+//                              -- on CTA pairs when M % 256 == 0 -- for small tile-aligned matrices)
 //   single-float skinny/odd, all integer types -> FMA / IMAD tiles (k_gemm_simt.cu)
 #include "k_gemm.cuh"
 

@@ -8,7 +8,11 @@
 // accumulated in fp32 in TMEM: ~5e-7 relative, about as good as the reference's own sequential
 // single-float accumulation.
 //
-// Two kernels:
+// Three variants, chosen by gemm_f32_tf32x3 (bottom of this file) from measured crossovers:
+//   * pack + gemm_tf32x3_kernel            large matrices (operands are re-used by many tiles)
+//   * gemm_tf32x3_fused_kernel             small tile-aligned matrices: the split happens inside the GEMM
+//   * gemm_tf32x3_fused2_kernel            the same on CTA pairs (tcgen05 cta_group::2), M % 256 == 0
+// The first one is two kernels:
 //  1. pack (HBM-bound pre-pass): splits A and B and writes them as PACKED TILES, byte-for-byte
 //     the shared-memory image tcgen05 wants -- K-major, 128-byte rows of 32 k-values, 8-row
 //     swizzle atoms (16-byte chunk c of row r stored at chunk c ^ (r & 7): UMMA SWIZZLE_128B) --
