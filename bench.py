@@ -380,12 +380,12 @@ def run_ours(args):
     others = {}
     if world == 1:
         from oracle import oracle as O
-        sample_rows = 4096
+        sample_rows = N_ROWS                  # the whole slab: ~0.35 s per pass of both scans, ~10 s in total with the host fill
         ah = O.fill_random((sample_rows, N_COLS), "f32", SEED, 0, -1.0, 1.0).values()
-        reps = 6
+        reps = 12
         ct = min(cpu_reference_step(O, ah)[0] for _ in range(reps))
         cpu = {"value": (BYTES_ROW + BYTES_ALL) * (sample_rows / N_ROWS) / ct / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-               "sample": f"{sample_rows} of {N_ROWS} rows (256 MiB), best of {reps}; C transcription of numcl's sequential reduce nest, not SBCL",
+               "sample": f"{sample_rows} of {N_ROWS} rows ({sample_rows * N_COLS * 4 >> 20} MiB), best of {reps}; C transcription of numcl's sequential reduce nest, not SBCL",
                "host_cores": os.cpu_count()}
         # parity spot check of the timed arrays against the oracle on the same synthetic stream
         got = rows.numpy()[:sample_rows].astype(np.float64)
