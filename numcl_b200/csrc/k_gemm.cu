@@ -51,6 +51,7 @@ int try_gemm(const Nest& n) {
   GemmParams p; memset(&p, 0, sizeof p);
   p.M = nm ? (int)gm[0].ext : 1; p.N = nn ? (int)gn[0].ext : 1; p.K = (int)gk[0].ext; p.batch = nb ? (int)gb[0].ext : 1;
   if ((nm && gm[0].ext > 0x7fffffffLL) || (nn && gn[0].ext > 0x7fffffffLL) || gk[0].ext > 0x7fffffffLL || (nb && gb[0].ext > 0x7fffffffLL)) return NCL_ERR_UNSUPPORTED;
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.batch <= 0) return NCL_ERR_UNSUPPORTED;   // empty loops: the generic kernel defines them
   if (gk[0].sa != 1) return NCL_ERR_UNSUPPORTED;                        // A must be k-contiguous
   if (nn && (gn[0].sb != 1 || gn[0].sc != 1)) return NCL_ERR_UNSUPPORTED; // B and C n-contiguous
   p.lda = nm ? gm[0].sa : 0; p.ldb = gk[0].sb; p.ldc = nm ? gm[0].sc : 0;

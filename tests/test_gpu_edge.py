@@ -222,3 +222,16 @@ def test_widening_kernel_writes_only_its_output_region(nc, oracle):
     raw = store.raw()
     assert np.all(raw[: off * 8] == 0xAB) and np.all(raw[(off + n) * 8: (off + n + tail) * 8] == 0xAB)
     assert np.array_equal(raw[off * 8: (off + n) * 8].view(np.int64), want.storage[: n * 8].view(np.int64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum"])
+def test_matmul_with_empty_contraction(nc, oracle, dt):
+    """(ij jk -> ik) with an empty j: the reference's loops never run and the fresh `zeros` output stays zero;
+    tile-aligned shapes must not reach the GEMM kernels with K = 0"""
+    a = nc.empty((256, 0), dt); b = nc.empty((0, 256), dt)
+    r = nc.matmul(a, b)
+    assert r.shape == (256, 256) and np.all(r.numpy() == 0)
+    c = nc.full((256, 256), 3, type=dt)
+    nc.matmul(a, b, c)
+    assert np.all(c.numpy() == 3)
