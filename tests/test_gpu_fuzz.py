@@ -111,3 +111,29 @@ def test_fuzz_einsum_bit_exact(nc, oracle, case):
         assert g == w, (spec, g, w)
     else:
         assert_bit_exact(got, want)
+
+
+@pytest.mark.parametrize("case", range(48))
+def test_fuzz_gemm_shapes_bit_exact(nc, oracle, case):
+    """GEMM-shaped specs over random tile-aligned and ragged sizes; integer-valued float data make the tensor-core
+    paths (DMMA, 3xTF32 on tcgen05 -- packed, fused, fused on CTA pairs) exact, so they too are compared bit for bit
+    with numcl's nest"""
+    rng = np.random.default_rng(SEED + 3000 + case)
+    dt = "f32" if case % 2 == 0 else "f64"
+    b = int(rng.choice([1, 1, 2, 3]))
+    m = int(rng.choice([128, 256, 384, 512, 130, 200, 64]))
+    n = int(rng.choice([256, 512, 300, 64, 768]))
+    k = int(rng.choice([32, 64, 96, 128, 512, 1024, 70, 2048]))
+    A = _mk(oracle, rng, (b, m, k), dt, -3, 3)
+    B = _mk(oracle, rng, (b, k, n), dt, -3, 3)
+    if dt == "f32":
+        ref = oracle.fast_bmm_f32(A.values(), B.values())
+    else:
+        ref = np.stack([oracle.fast_matmul(A.values()[i], B.values()[i]) for i in range(b)])
+    if b == 1 and rng.random() < 0.5:
+        got = nc.matmul(to_gpu(nc, oracle.OArr.from_values(A.values()[0], dt)), to_gpu(nc, oracle.OArr.from_values(B.values()[0], dt)))
+        ref = ref[0]
+    else:
+        got = nc.einsum("bij bjk -> bik", to_gpu(nc, A), to_gpu(nc, B))
+    assert got.dtype.name == dt
+    assert np.array_equal(got.numpy(), ref), (nc.lib().ncl_last_kernel(), b, m, n, k)
