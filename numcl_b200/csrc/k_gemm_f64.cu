@@ -29,6 +29,19 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// mbarrier helpers: the k-loop synchronises per STAGE (full: this stage's cp.asyncs have landed; empty: all eight
+// warps have read it) instead of with one CTA-wide barrier per k-tile, so warps may drift by a k-tile
+__device__ __forceinline__ unsigned dg_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dg_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void dg_mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void dg_cp_async_arrive(unsigned bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void dg_mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -74,15 +87,27 @@ __global__ void __launch_bounds__(256, 1) dgemm_dmma_kernel(const __grid_constan
     }
   };
 
+  __shared__ __align__(8) unsigned long long bars[2 * DG_STAGES];
+  const unsigned full0 = dg_smem_u32(&bars[0]), empty0 = dg_smem_u32(&bars[DG_STAGES]);
+  if (tid == 0) {
+    for (int s = 0; s < DG_STAGES; s++) { dg_mbar_init(full0 + 8 * s, 256); dg_mbar_init(empty0 + 8 * s, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 #pragma unroll
-  for (int s = 0; s < DG_STAGES - 1; s++) { load_tile(s, s); cp_async_commit(); }
+  for (int s = 0; s < DG_STAGES - 1; s++) { load_tile(s, s); dg_cp_async_arrive(full0 + 8 * s); }
 
   for (int kt = 0; kt < ktiles; kt++) {
-    cp_async_wait<DG_STAGES - 2>();
-    __syncthreads();
-    load_tile((kt + DG_STAGES - 1) % DG_STAGES, kt + DG_STAGES - 1);
-    cp_async_commit();
-    const double* sA = smem + (kt % DG_STAGES) * DG_STAGE_DOUBLES;
+    {
+      // refill the stage k-tile kt-1 was read from (with k-tile kt+3) once every warp has released it
+      const int ls = (kt + DG_STAGES - 1) % DG_STAGES;
+      if (kt > 0) dg_mbar_wait(empty0 + 8 * ls, ((kt - 1) / DG_STAGES) & 1);
+      load_tile(ls, kt + DG_STAGES - 1);
+      dg_cp_async_arrive(full0 + 8 * ls);
+    }
+    const int cs = kt % DG_STAGES;
+    dg_mbar_wait(full0 + 8 * cs, (kt / DG_STAGES) & 1);
+    const double* sA = smem + cs * DG_STAGE_DOUBLES;
     const double* sB = sA + DG_BM * DG_PA;
     const double* pa = sA + (wm * 64 + g) * DG_PA + t4;
     const double* pb = sB + t4 * DG_PB + wn * 32 + g;
@@ -98,6 +123,8 @@ __global__ void __launch_bounds__(256, 1) dgemm_dmma_kernel(const __grid_constan
 #pragma unroll
         for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
     }
+    __syncwarp();
+    if (lane == 0) dg_mbar_arrive(empty0 + 8 * cs);
   }
   cp_async_wait<0>();
 
