@@ -154,6 +154,9 @@ __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all
       for (int u = 0; u < 4; u++) acc[u] = fold_elems<T, OP, E>(acc[u], v[u]);
     }
     for (; c < nch; c += nthr) { T v[E]; load_elems<T, E>(p.in, p.in_off + c * E, p.lk, true, v); acc[0] = fold_elems<T, OP, E>(acc[0], v); }
+    // fewer than E trailing elements when the length is not a multiple of the chunk (odd-sized arrays)
+    const long long t0 = nch * E;
+    if (blockIdx.x == 0 && t0 + threadIdx.x < p.cols) acc[1] = Red<T, OP>::f(acc[1], load_scalar<T>(p.in, p.in_off + t0 + threadIdx.x, p.lk));
   } else {
     for (long long c = tid; c < p.cols; c += nthr) acc[0] = Red<T, OP>::f(acc[0], load_scalar<T>(p.in, p.in_off + c, p.lk));
   }
@@ -239,12 +242,15 @@ __global__ void __launch_bounds__(256) reduce_col_kernel(const __grid_constant__
   if (r0 >= r1) return;
   load_elems<T, E>(p.in, ibase + r0 * p.r_stride, p.lk, E > 1, acc);     // the first row seeds the accumulators
   long long r = r0 + 1;
-  for (; r + 3 < r1; r += 4) {
-    T v[4][E];
+  // rows in flight per thread: 4 x 16 bytes on the vector path; the scalar path (ragged column count) moves only one
+  // element per load and needs 16 rows to keep a comparable number of bytes in flight (0.17 -> of the HBM peak with 4)
+  constexpr int UR = E == 1 ? 16 : 4;
+  for (; r + UR - 1 < r1; r += UR) {
+    T v[UR][E];
 #pragma unroll
-    for (int u = 0; u < 4; u++) load_elems<T, E>(p.in, ibase + (r + u) * p.r_stride, p.lk, E > 1, v[u]);
+    for (int u = 0; u < UR; u++) load_elems<T, E>(p.in, ibase + (r + u) * p.r_stride, p.lk, E > 1, v[u]);
 #pragma unroll
-    for (int u = 0; u < 4; u++)
+    for (int u = 0; u < UR; u++)
 #pragma unroll
       for (int i = 0; i < E; i++) acc[i] = Red<T, OP>::f(acc[i], v[u][i]);
   }
@@ -384,7 +390,7 @@ int try_reduce(const Nest& n) {
   if (sR == 1 && nk == 0) {
     // ---- full reduce --------------------------------------------------------------------------
     p.cols = R;
-    p.vec = (R % Evec == 0) && aligned16(in, in.offset);
+    p.vec = R >= Evec && aligned16(in, in.offset);          // a ragged tail (< Evec elements) is folded by block 0
     int E = p.vec ? Evec : 1;
     long long work = p.vec ? R / E : R;
     RedKernel kfn = kernel_for(cls, E, op, KALL);
@@ -468,7 +474,7 @@ int reduce_all_p2p(int op, const Operand& a, int64_t count, const Operand& r, un
     else p.ident_i = mx ? 0 : (d.value_bits >= 63 ? INT64_MAX : (1ll << d.value_bits) - 1);
   }
   int Evec = 128 / sb;
-  p.vec = (count % Evec == 0) && aligned16(a, a.offset);
+  p.vec = count >= Evec && aligned16(a, a.offset);
   int E = p.vec ? Evec : 1;
   long long work = p.vec ? count / E : count;
   RedKernel kfn = kernel_for(cls, E, rop, KALL);
@@ -491,7 +497,7 @@ int reduce_all_to_partial(int op, const Operand& a, int64_t count, void* partial
   RedParams p; memset(&p, 0, sizeof p);
   p.in = a.base; p.in_off = a.offset; p.lk = dtype_load_kind(a.dtype); p.cols = count;
   int Evec = 128 / sb;
-  p.vec = (count % Evec == 0) && aligned16(a, a.offset);
+  p.vec = count >= Evec && aligned16(a, a.offset);
   int E = p.vec ? Evec : 1;
   long long work = p.vec ? count / E : count;
   RedKernel kfn = kernel_for(cls, E, rop, KALL);
