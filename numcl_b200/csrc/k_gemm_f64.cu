@@ -27,6 +27,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
 }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {     // rows that start on odd doubles
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
@@ -47,6 +51,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+template <bool A16>
 __global__ void __launch_bounds__(256, 1) dgemm_dmma_kernel(const __grid_constant__ GemmParams p, int tiles_m, int tiles_n, int cvec) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -70,21 +75,41 @@ __global__ void __launch_bounds__(256, 1) dgemm_dmma_kernel(const __grid_constan
     double* sA = smem + stage * DG_STAGE_DOUBLES;
     double* sB = sA + DG_BM * DG_PA;
     const int k0 = kt * DG_BK;
+    if constexpr (A16) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {                                     // A: 128 rows x 8 chunks of 2 doubles
-      int idx = tid + i * 256; int row = idx >> 3, c = idx & 7;
-      int m = m0 + row, k = k0 + c * 2;
-      int bytes = (m < p.M && kt < ktiles) ? ((p.K - k) >= 2 ? 16 : ((p.K - k) == 1 ? 8 : 0)) : 0;
-      const double* src = bytes ? A + (long long)m * p.lda + k : A;
-      cp_async16(sA + row * DG_PA + c * 2, src, bytes);
-    }
+      for (int i = 0; i < 4; i++) {                                   // A: 128 rows x 8 chunks of 2 doubles
+        int idx = tid + i * 256; int row = idx >> 3, c = idx & 7;
+        int m = m0 + row, k = k0 + c * 2;
+        int bytes = (m < p.M && kt < ktiles) ? ((p.K - k) >= 2 ? 16 : ((p.K - k) == 1 ? 8 : 0)) : 0;
+        const double* src = bytes ? A + (long long)m * p.lda + k : A;
+        cp_async16(sA + row * DG_PA + c * 2, src, bytes);
+      }
 #pragma unroll
-    for (int i = 0; i < 4; i++) {                                     // B: 16 rows x 64 chunks of 2 doubles
-      int idx = tid + i * 256; int row = idx >> 6, c = idx & 63;
-      int k = k0 + row, n = n0 + c * 2;
-      int bytes = (k < p.K && kt < ktiles) ? ((p.N - n) >= 2 ? 16 : ((p.N - n) == 1 ? 8 : 0)) : 0;
-      const double* src = bytes ? B + (long long)k * p.ldb + n : B;
-      cp_async16(sB + row * DG_PB + c * 2, src, bytes);
+      for (int i = 0; i < 4; i++) {                                   // B: 16 rows x 64 chunks of 2 doubles
+        int idx = tid + i * 256; int row = idx >> 6, c = idx & 63;
+        int k = k0 + row, n = n0 + c * 2;
+        int bytes = (k < p.K && kt < ktiles) ? ((p.N - n) >= 2 ? 16 : ((p.N - n) == 1 ? 8 : 0)) : 0;
+        const double* src = bytes ? B + (long long)k * p.ldb + n : B;
+        cp_async16(sB + row * DG_PB + c * 2, src, bytes);
+      }
+    } else {
+      // leading dimensions / bases that are only 8-byte aligned (odd-sized matrices): one double per copy
+#pragma unroll
+      for (int i = 0; i < 8; i++) {                                   // A: 128 rows x 16 doubles
+        int idx = tid + i * 256; int row = idx >> 4, c = idx & 15;
+        int m = m0 + row, k = k0 + c;
+        int bytes = (m < p.M && k < p.K && kt < ktiles) ? 8 : 0;
+        const double* src = bytes ? A + (long long)m * p.lda + k : A;
+        cp_async8(sA + row * DG_PA + c, src, bytes);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {                                   // B: 16 rows x 128 doubles
+        int idx = tid + i * 256; int row = idx >> 7, c = idx & 127;
+        int k = k0 + row, n = n0 + c;
+        int bytes = (k < p.K && n < p.N && kt < ktiles) ? 8 : 0;
+        const double* src = bytes ? B + (long long)k * p.ldb + n : B;
+        cp_async8(sB + row * DG_PB + c, src, bytes);
+      }
     }
   };
 
@@ -155,16 +180,22 @@ __global__ void __launch_bounds__(256, 1) dgemm_dmma_kernel(const __grid_constan
 }
 
 int gemm_f64_dmma(const GemmParams& p) {
-  // cp.async moves 16-byte chunks: rows must start 16B aligned
-  if ((p.lda & 1) || (p.ldb & 1) || (p.sA & 1) || (p.sB & 1) || ((uintptr_t)p.A & 15) || ((uintptr_t)p.B & 15) || ((uintptr_t)p.C & 7)) return NCL_ERR_UNSUPPORTED;
+  // cp.async moves 16-byte chunks when every row starts 16B aligned, single doubles otherwise (odd-sized matrices)
+  if (((uintptr_t)p.A & 7) || ((uintptr_t)p.B & 7) || ((uintptr_t)p.C & 7)) return NCL_ERR_UNSUPPORTED;
+  const bool a16 = !((p.lda & 1) || (p.ldb & 1) || (p.sA & 1) || (p.sB & 1) || ((uintptr_t)p.A & 15) || ((uintptr_t)p.B & 15));
   int cvec = ((p.ldc & 1) == 0 && (p.sC & 1) == 0 && ((uintptr_t)p.C & 15) == 0) ? 1 : 0;   // double2 stores allowed
   Context& c = ctx();
   static bool attr_set = false;
-  if (!attr_set) { NCL_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM)); attr_set = true; }
+  if (!attr_set) {
+    NCL_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
+    NCL_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
+    attr_set = true;
+  }
   int tiles_m = (p.M + DG_BM - 1) / DG_BM, tiles_n = (p.N + DG_BN - 1) / DG_BN;
   if ((long long)tiles_m * tiles_n > 0x7fffffffLL || p.batch > 65535) return NCL_ERR_UNSUPPORTED;
   dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)p.batch);
-  dgemm_dmma_kernel<<<grid, 256, DG_SMEM, c.stream>>>(p, tiles_m, tiles_n, cvec);
+  if (a16) dgemm_dmma_kernel<true><<<grid, 256, DG_SMEM, c.stream>>>(p, tiles_m, tiles_n, cvec);
+  else dgemm_dmma_kernel<false><<<grid, 256, DG_SMEM, c.stream>>>(p, tiles_m, tiles_n, cvec);
   note_launch("gemm_f64_dmma");
   return cuda_fail(cudaGetLastError(), "dgemm_dmma_kernel");
 }
