@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
 #include <mutex>
 #include <vector>
 #include "ncl_internal.h"
@@ -21,11 +22,28 @@ int cuda_fail(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return NCL_OK;
   return set_error(NCL_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
+// ---- device buffer cache (see "buffers" below) ----
+static std::multimap<size_t, void*> g_pool;
+static size_t g_pool_bytes = 0;
+static const size_t POOL_MAX_BYTES = (size_t)48 << 30;
+static size_t pool_round(size_t bytes) {
+  if (bytes <= ((size_t)1 << 20)) return bytes ? ((bytes + 511) & ~(size_t)511) : 512;
+  return (bytes + (((size_t)2 << 20) - 1)) & ~(((size_t)2 << 20) - 1);      // 2 MiB granules: few distinct sizes, little slack
+}
+static bool pool_enabled() { static int on = -1; if (on < 0) { const char* e = getenv("NUMCL_NO_POOL"); on = (e && atoi(e)) ? 0 : 1; } return on == 1; }
+static void pool_release_all() {
+  if (g_pool.empty()) return;
+  cudaStreamSynchronize(g_ctx.stream);
+  for (auto& kv : g_pool) cudaFree(kv.second);
+  g_pool.clear(); g_pool_bytes = 0;
+}
+
 static int grow(void** p, size_t* have, size_t want) {
   if (*have >= want) return NCL_OK;
   if (*p) { NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); NCL_CUDA(cudaFree(*p)); *p = nullptr; *have = 0; }
   size_t sz = want + want / 4 + (1u << 20);
-  NCL_CUDA(cudaMalloc(p, sz)); *have = sz; return NCL_OK;
+  if (cudaMalloc(p, sz) != cudaSuccess) { cudaGetLastError(); pool_release_all(); NCL_CUDA(cudaMalloc(p, sz)); }
+  *have = sz; return NCL_OK;
 }
 int ensure_scratch(size_t bytes) { return grow(&g_ctx.scratch, &g_ctx.scratch_bytes, bytes); }
 int ensure_scratch2(size_t bytes) { return grow(&g_ctx.scratch2, &g_ctx.scratch2_bytes, bytes); }
@@ -68,6 +86,7 @@ void ncl_shutdown(void) {
   LOCK;
   if (!g_ctx.inited) return;
   cudaStreamSynchronize(g_ctx.stream);
+  pool_release_all();
   if (g_ctx.scratch) cudaFree(g_ctx.scratch);
   if (g_ctx.scratch2) cudaFree(g_ctx.scratch2);
   if (g_ctx.ticket) cudaFree(g_ctx.ticket);
@@ -78,7 +97,19 @@ void ncl_shutdown(void) {
 }
 
 int ncl_device_count(void) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) return 0; return c; }
-int ncl_set_stream(void* s) { LOCK; NEED_INIT; g_ctx.stream = s ? (cudaStream_t)s : g_ctx.own_stream; return NCL_OK; }
+int ncl_set_stream(void* s) {
+  LOCK; NEED_INIT;
+  cudaStream_t ns = s ? (cudaStream_t)s : g_ctx.own_stream;
+  if (ns != g_ctx.stream) {
+    // blocks recycled by the buffer cache (and the scratch arenas) were last used on the old stream: order the new one after it
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+      cudaEventRecord(ev, g_ctx.stream); cudaStreamWaitEvent(ns, ev, 0); cudaEventDestroy(ev);
+    }
+    g_ctx.stream = ns;
+  }
+  return NCL_OK;
+}
 void* ncl_get_stream(void) { return (void*)g_ctx.stream; }
 int ncl_sync(void) { NEED_INIT; ncl_comm_join(); NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); return NCL_OK; }
 int64_t ncl_launch_count(void) { return g_ctx.launches; }
@@ -86,21 +117,32 @@ const char* ncl_last_kernel(void) { return g_ctx.last_kernel; }
 int ncl_force_generic(int on) { g_ctx.force_generic = on != 0; return NCL_OK; }
 
 // ---- buffers ----------------------------------------------------------------------------------
+// Every numcl operation returns a fresh array (src/1instantiate.lisp:81-96), so allocation is on the path of every
+// call.  cudaMalloc / cudaFree cost 0.1..1 ms and cudaFree synchronises the device; freed base vectors are therefore
+// kept in a size-bucketed cache and handed out again.  Re-use is stream-ordered: all work of the library is issued
+// on one stream, so a kernel writing a recycled block is ordered after every kernel that still reads it
+// (ncl_set_stream chains the old and the new stream with an event).  NUMCL_NO_POOL=1 disables the cache.
 ncl_buf* ncl_alloc(size_t bytes, int dev_slot) {
   LOCK;
   if (!g_ctx.inited) { set_error(NCL_ERR_STATE, "ncl_init has not been called"); return nullptr; }
   if (dev_slot < 0 || dev_slot >= g_ctx.ndev) { set_error(NCL_ERR_INVALID, "bad device slot %d", dev_slot); return nullptr; }
   void* p = nullptr;
-  size_t sz = bytes ? ((bytes + 255) & ~(size_t)255) : 256;
+  const size_t sz = pool_round(bytes);
+  auto it = g_pool.find(sz);
+  if (it != g_pool.end()) { p = it->second; g_pool.erase(it); g_pool_bytes -= sz; return new ncl_buf{p, sz, dev_slot, true}; }
   cudaError_t e = cudaMalloc(&p, sz);
-  if (e != cudaSuccess) { set_error(NCL_ERR_NOMEM, "cudaMalloc(%zu): %s", sz, cudaGetErrorString(e)); return nullptr; }
-  ncl_buf* b = new ncl_buf{p, sz, dev_slot, true};
-  return b;
+  if (e != cudaSuccess && !g_pool.empty()) { cudaGetLastError(); pool_release_all(); e = cudaMalloc(&p, sz); }   // give the cache back first
+  if (e != cudaSuccess) { cudaGetLastError(); set_error(NCL_ERR_NOMEM, "cudaMalloc(%zu): %s", sz, cudaGetErrorString(e)); return nullptr; }
+  return new ncl_buf{p, sz, dev_slot, true};
 }
 int ncl_free(ncl_buf* b) {
   LOCK;
   if (!b) return NCL_OK;
-  if (b->owned && b->ptr) { cudaStreamSynchronize(g_ctx.stream); cudaFree(b->ptr); }
+  if (b->owned && b->ptr) {
+    if (g_ctx.inited && pool_enabled() && g_pool_bytes + b->bytes <= POOL_MAX_BYTES && b->bytes == pool_round(b->bytes)) {
+      g_pool.emplace(b->bytes, b->ptr); g_pool_bytes += b->bytes;
+    } else { cudaStreamSynchronize(g_ctx.stream); cudaFree(b->ptr); }
+  }
   delete b; return NCL_OK;
 }
 void* ncl_buf_ptr(const ncl_buf* b) { return b ? b->ptr : nullptr; }
