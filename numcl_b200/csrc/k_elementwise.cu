@@ -95,6 +95,9 @@ int try_elementwise(const Nest& n) {
   }
   int out_cls = g_dt[out.dtype].cls;
   int shape = m.shape;
+  // astype / copy into a float type (src/3copy.lisp:27-43): the operand is converted on load exactly as `coerce` does
+  // (integer -> float and double -> single round to nearest, single -> double is exact), so the copy runs in the output's class
+  if (shape == S_COPY && out_cls != cc && out_cls != CLS_I) cc = out_cls;
   bool is_cmp = shape >= S_EQ && shape <= S_GT;
   if (shape == S_DIV && cc == CLS_I) { shape = S_IDIV; if (out_cls != CLS_F) return NCL_ERR_UNSUPPORTED; }
   else if (is_cmp) { if (out_cls != CLS_I) return NCL_ERR_UNSUPPORTED; }
@@ -168,10 +171,35 @@ int try_elementwise(const Nest& n) {
       int rc = try_elementwise(nb);
       if (rc != NCL_OK) return rc;
       Nest nt = piece(tail, body);
-      return try_elementwise(nt);
+      rc = try_elementwise(nt);
+      return rc == NCL_ERR_UNSUPPORTED ? launch_generic(nt) : rc;      // the body is done: never hand the whole nest on
     }
   }
-  if (E > 1 && !aligned(E)) { if (out_bits < 8) return NCL_ERR_UNSUPPORTED; E = 1; }
+  // Element-granular flat mode: the output is contiguous over a (rows x P) nest whose row length P is not a multiple of
+  // the chunk (a trailing axis of 3, an odd-length row vector), every operand is either the same contiguous shape (streamed
+  // as flat vectors) or anything else with one stride per loop (a row vector, one value per row, a scalar: gathered per
+  // element, (row, col) decoded once per chunk).  Without it these nests ran element-wise, 3 lanes of a warp busy:
+  // (16M,3) + (3) at 0.018 of the HBM peak.
+  bool eflat = false; int gather[3] = {0, 0, 0}; long long g_outer[3] = {0, 0, 0}; long long eflat_tail = 0, eflat_P = 0, eflat_R = 0;
+  if (E > 1 && out_bits >= 8 && nd == 2 && !aligned(E) && d[0].st[0] == d[1].ext && d[1].st[0] == 1) {
+    const long long P = d[1].ext, R = d[0].ext, total = P * R;
+    bool ok = total < 0x7fffffffLL && total >= 64LL * E && P < 0x40000000LL;
+    ok = ok && (((uintptr_t)out.base + (out.offset * out_bits) / 8) % 16) == 0;
+    for (int k = 0; k < m.n && ok; k++) {
+      const long long s_o = d[0].st[1 + k], s_i = d[1].st[1 + k];
+      const int sb = g_dt[ops[k].dtype].slot_bits;
+      const long long cb = (long long)E * sb / 8;
+      if (s_i == 1 && s_o == P && sb >= 8 && (((uintptr_t)ops[k].base + (ops[k].offset * sb) / 8) % (cb >= 16 ? 16 : cb)) == 0) gather[k] = 0;
+      else { gather[k] = 1; g_outer[k] = s_o; }
+    }
+    if (ok) {
+      eflat = true; eflat_P = P; eflat_R = R; eflat_tail = total % E;
+      d[0].ext = total - eflat_tail; d[0].st[0] = 1;
+      for (int k = 0; k < m.n; k++) d[0].st[1 + k] = gather[k] ? d[1].st[1 + k] : 1;
+      nd = 1;
+    }
+  }
+  if (!eflat && E > 1 && !aligned(E)) { if (out_bits < 8) return NCL_ERR_UNSUPPORTED; E = 1; }
 
   EwKernel kfn = nullptr;
   if (shape == S_IDIV) kfn = ew_pick_idiv(E);
@@ -209,7 +237,7 @@ int try_elementwise(const Nest& n) {
     }
   }
   // ---- widening integer family (k_ew_widen.cu): narrow int array (op) 64-bit operand -> 64-bit result, flat ----
-  if (nd == 1 && E == 2 && cc == CLS_I && out_cls == CLS_I && m.n == 2 && !is_cmp && d[0].ext / 2 < 0x7fffffffLL) {
+  if (nd == 1 && !eflat && E == 2 && cc == CLS_I && out_cls == CLS_I && m.n == 2 && !is_cmp && d[0].ext / 2 < 0x7fffffffLL) {
     int wop = shape == S_ADD || shape == S_ADD0 ? 0 : shape == S_SUB ? 1 : shape == S_MUL || shape == S_MUL0 ? 2 : shape == S_MAX ? 3 : shape == S_MIN ? 4 : -1;
     int lk0 = dtype_load_kind(ops[0].dtype), lk1 = dtype_load_kind(ops[1].dtype);
     auto narrow = [&](int k, int lk) { return lk >= LK_U8 && lk <= LK_S32 && d[0].st[1 + k] == 1 && p.period[k] == 0; };
@@ -244,7 +272,13 @@ int try_elementwise(const Nest& n) {
   }
   p.base[0] = out.base; p.off[0] = out.offset;
   for (int k = 0; k < m.n; k++) { p.base[1 + k] = ops[k].base; p.off[1 + k] = ops[k].offset; p.lk[k] = dtype_load_kind(ops[k].dtype); }
-  int U = E == 32 ? 1 : 4;
+  if (eflat) {
+    p.eper = (unsigned)eflat_P;
+    unsigned s2 = 0; while ((1ull << s2) < p.eper) s2++;
+    p.epmul = (unsigned)(((1ull << (31 + s2)) + p.eper - 1) / p.eper); p.epshr = s2 - 1;
+    for (int k = 0; k < m.n; k++) { p.gather[k] = gather[k]; p.gst[k] = (int)g_outer[k]; }
+  }
+  int U = ew_u_host(cc == CLS_I, E);
   unsigned long long rows = 1; for (int i = 1; i < nd; i++) rows *= p.ext[i];
   unsigned segs = (p.ext[0] + 32 * U - 1) / (32 * U);
   unsigned long long nitems = rows * segs;
@@ -263,6 +297,27 @@ int try_elementwise(const Nest& n) {
   unsigned long long cap = (unsigned long long)c.sm_count * per_sm * over;
   if (blocks > cap) blocks = cap;
   kfn<<<(unsigned)blocks, EW_THREADS, 0, c.stream>>>(p);
-  note_launch(E == 1 ? "bcast_scalar" : "bcast_vec");
-  return cuda_fail(cudaGetLastError(), "ew_kernel");
+  NCL_TRY(cuda_fail(cudaGetLastError(), "ew_kernel"));
+  if (eflat && eflat_tail) {
+    // fewer than E trailing elements: the end of the last partial row, then whole rows, as two tiny nests
+    const long long P = eflat_P, R = eflat_R, fr = eflat_tail / P, part = eflat_tail - fr * P, body = P * R - eflat_tail;
+    auto piece = [&](int loops, long long e0, long long e1, long long row, long long col, long long out_shift) {
+      Nest x = n;
+      x.nloops = loops; x.extent[0] = e0; x.extent[1] = e1;
+      for (int i = 0; i < x.n_in; i++) {
+        long long so = 0, si = 0;
+        for (int k = 0; k < m.n; k++) if (m.s[k].kind == 0 && m.s[k].idx == i) { so = gather[k] ? g_outer[k] : P; si = gather[k] ? d[0].st[1 + k] : 1; }
+        x.in[i].offset += row * so + col * si;
+        if (loops == 1) x.in[i].stride[0] = si; else { x.in[i].stride[0] = so; x.in[i].stride[1] = si; }
+      }
+      x.out[0].offset += out_shift;
+      if (loops == 1) x.out[0].stride[0] = 1; else { x.out[0].stride[0] = P; x.out[0].stride[1] = 1; }
+      return x;
+    };
+    auto run_piece = [&](Nest& t) { int rc = try_elementwise(t); return rc == NCL_ERR_UNSUPPORTED ? launch_generic(t) : rc; };
+    if (part) { Nest t = piece(1, part, 1, R - fr - 1, P - part, body); NCL_TRY(run_piece(t)); }
+    if (fr) { Nest t = piece(2, fr, P, R - fr, 0, body + part); NCL_TRY(run_piece(t)); }
+  }
+  note_launch(eflat ? "bcast_vec_flat" : E == 1 ? "bcast_scalar" : "bcast_vec");
+  return NCL_OK;
 }

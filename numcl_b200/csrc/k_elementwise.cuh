@@ -34,6 +34,10 @@ struct EwParams {
   unsigned period[3], pmul[3], pshr[3]; // flat mode: input k repeats every period[k] chunks (0 = not periodic)
   unsigned segs_per_row, seg_mul, seg_shr;   // a row of ext[0] chunks is cut into warp segments of 32*U chunks
   unsigned nitems;                     // rows * segs_per_row, < 2^31
+  // element-granular flat mode: the output is one contiguous run over a (rows x eper) nest whose row length is not a
+  // multiple of the chunk; operand k with gather[k] is addressed per element at (f / eper) * gst[k] + (f % eper) * st[1+k][0]
+  // (a row vector: gst 0, st 1; one value per row: gst s, st 0), the others stream as flat vectors
+  unsigned eper, epmul, epshr; int gather[3]; int gst[3];
 };
 __device__ __forceinline__ unsigned ew_div(unsigned q, unsigned mul, unsigned shr) { return mul ? (__umulhi(q, mul) >> shr) : q; }
 
@@ -98,6 +102,30 @@ __device__ __forceinline__ void load_operand_periodic(const char* base, long lon
     unsigned q = q0 + u * 32;
     if (q < ext0) { unsigned qm = q - ew_div(q, pmul, pshr) * period; load_elems<T, E>(base, elem0 + (long long)qm * E, lk, true, x[u]); }
   }
+}
+// operand addressed per element in element-granular flat mode: chunk q covers flat elements q*E .. q*E+E-1 of a
+// (rows x P) nest; (row, col) are decoded once per chunk and stepped with a wrap
+template <class T, int E, int U>
+__device__ __forceinline__ void load_operand_gather(const char* base, long long elem0, int lk, int s_in, int s_out, unsigned q0, unsigned ext0,
+                                                    unsigned P, unsigned mul, unsigned shr, T (&x)[U][E]) {
+  dispatch_lk(lk, [&](auto K) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const unsigned q = q0 + u * 32;
+      if (q < ext0) {
+        const unsigned f = q * E, r = ew_div(f, mul, shr);
+        unsigned e = f - r * P;
+        long long idx = elem0 + (long long)r * s_out + (long long)e * s_in;
+        const long long wrap = (long long)s_out - (long long)P * s_in;
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+          x[u][i] = load_scalar_k<T, decltype(K)::value>(base, idx);
+          e++; idx += s_in;
+          if (e >= P) { e = 0; idx += wrap; }
+        }
+      }
+    }
+  });
 }
 template <class T, int E, int U>
 __device__ __forceinline__ void load_operand(const char* base, long long elem0, int st0, int lk, unsigned q0, unsigned ext0, T (&x)[U][E]) {
@@ -218,7 +246,8 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
         unsigned s0 = seg * SEG;
         unsigned base_chunk = s0 - ew_div(s0, p.pmul[k], p.pshr[k]) * p.period[k];
         load_operand<TI, E, U>(p.base[1 + k], rowoff[1 + k] + ((long long)base_chunk - (long long)s0) * E, 1, p.lk[k], q0, p.ext[0], x[k]);
-      } else if (p.period[k]) load_operand_periodic<TI, E, U>(p.base[1 + k], rowoff[1 + k], p.lk[k], q0, p.ext[0], p.period[k], p.pmul[k], p.pshr[k], x[k]);
+      } else if (p.gather[k]) load_operand_gather<TI, E, U>(p.base[1 + k], p.off[1 + k], p.lk[k], p.st[1 + k][0], p.gst[k], q0, p.ext[0], p.eper, p.epmul, p.epshr, x[k]);
+      else if (p.period[k]) load_operand_periodic<TI, E, U>(p.base[1 + k], rowoff[1 + k], p.lk[k], q0, p.ext[0], p.period[k], p.pmul[k], p.pshr[k], x[k]);
       else load_operand<TI, E, U>(p.base[1 + k], rowoff[1 + k], p.st[1 + k][0], p.lk[k], q0, p.ext[0], x[k]);
     }
     if (p.nd == 1) {
@@ -228,7 +257,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
       const unsigned nq0 = q0 + nwarps * SEG;
 #pragma unroll
       for (int k = 0; k < NIN; k++) {
-        if (p.period[k] == 0 && p.st[1 + k][0] == 1) {
+        if (p.period[k] == 0 && p.st[1 + k][0] == 1 && !p.gather[k]) {
           const int bytes = lk_bits(p.lk[k]) >> 3;
           const char* a = p.base[1 + k] + (p.off[1 + k] + (long long)nq0 * E) * bytes;
 #pragma unroll
@@ -251,8 +280,11 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
 }
 
 typedef void (*EwKernel)(const EwParams);
-template <int E> constexpr int ew_u() { return E == 32 ? 1 : 4; }
-template <class TI, class F, int NIN, int E> static EwKernel kern() { return (EwKernel)ew_kernel<TI, F, NIN, E, ew_u<E>()>; }
+// chunks per thread and item.  The integer class computes in 64-bit lanes: 4 chunks of 8 or 16 narrow elements took 244
+// registers / spilled, so wide chunks get fewer of them.
+template <class TI, int E> constexpr int ew_u() { return E == 32 ? 1 : (std::is_integral<TI>::value ? (E >= 16 ? 1 : E >= 4 ? 2 : 4) : 4); }
+inline int ew_u_host(bool int_class, int E) { return E == 32 ? 1 : (int_class ? (E >= 16 ? 1 : E >= 4 ? 2 : 4) : 4); }
+template <class TI, class F, int NIN, int E> static EwKernel kern() { return (EwKernel)ew_kernel<TI, F, NIN, E, ew_u<TI, E>()>; }
 
 template <class T, int E> static EwKernel pick_arith(int shape) {     // T-class in, T-class out
   switch (shape) {

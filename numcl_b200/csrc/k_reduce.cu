@@ -50,7 +50,31 @@ struct RedParams {
   // into every other rank; the LAST block of this kernel pushes the local partial into all peers'
   // mailboxes, waits for theirs, folds them in rank order and stores the final value itself.
   unsigned long long* const* peers; int rank, world; unsigned long long seq;
+  // second operand of a contraction that is really a reduction (DOT kernels: r[kept] += a[..] * b[..]; vdot, inner,
+  // row-wise dot, matrix x vector).  b may be broadcast (stride 0) along any kept loop and along the reduced one.
+  const char* in2; long long in2_off; int lk2;
+  long long kin2[4];                               // strides of b along the outer kept dims
+  long long r_stride2;                             // stride of b along the reduced loop (row form: 0 or 1)
+  long long c_stride2;                             // col form: stride of b along the contiguous kept loop (0 or 1)
 };
+
+// element fetch of the reductions: a[i], or the product a[i] * b[i] of the einsum leaf (+ @1 (* $1 $2)) -- each product
+// rounded on its own, then added (common-lisp.lisp:226-240; no FMA contraction)
+template <class T, int E, bool DOT>
+__device__ __forceinline__ void fetch_elems(const RedParams& p, long long ia, long long ib, bool b_contig, T (&v)[E]) {
+  load_elems<T, E>(p.in, ia, p.lk, E > 1, v);
+  if constexpr (DOT) {
+    T w[E]; load_elems<T, E>(p.in2, ib, p.lk2, b_contig && E > 1, w);
+#pragma unroll
+    for (int i = 0; i < E; i++) v[i] = Ops<T>::mul(v[i], w[i]);
+  }
+}
+template <class T, bool DOT>
+__device__ __forceinline__ T fetch_scalar(const RedParams& p, long long ia, long long ib) {
+  T x = load_scalar<T>(p.in, ia, p.lk);
+  if constexpr (DOT) x = Ops<T>::mul(x, load_scalar<T>(p.in2, ib, p.lk2));
+  return x;
+}
 
 template <class T> __device__ __forceinline__ T ident_of(const RedParams& p) {
   if constexpr (std::is_integral<T>::value) return (T)p.ident_i; else return (T)p.ident_f;
@@ -87,14 +111,21 @@ __device__ __forceinline__ T block_combine(T v) {
 }
 
 // ---- row reduce: TPR threads cooperate on one row -----------------------------------------------------
-template <class T, int OP, int E, int TPR>
+// TPR = 1 / 4: short rows, one thread (four threads) per row -- a warp then covers 32 (8) consecutive rows, and with one
+// thread per row the fold is the reference's own left-to-right order.  vec == 2: rows whose length or start is not a
+// multiple of the 16-byte chunk: scalar head up to the first aligned element, vector body, scalar tail.
+template <class T, int OP, int E, int TPR, bool DOT>
 __global__ void __launch_bounds__(256) reduce_row_kernel(const __grid_constant__ RedParams p) {
   constexpr int RPB = 256 / TPR;
   long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR;
   int t = threadIdx.x % TPR;
   bool live = row < p.rows;
-  long long ibase = p.in_off, obase = p.out_off;
-  if (live) { long long r = row; for (int k = p.nk - 1; k >= 0; k--) { long long c = r % p.kext[k]; r /= p.kext[k]; ibase += c * p.kin[k]; obase += c * p.kout[k]; } }
+  long long ibase = p.in_off, obase = p.out_off, ibase2 = p.in2_off;
+  if (live) {
+    if (p.nk == 1) { ibase += row * p.kin[0]; obase += row * p.kout[0]; if constexpr (DOT) ibase2 += row * p.kin2[0]; }
+    else { long long r = row; for (int k = p.nk - 1; k >= 0; k--) { long long c = r % p.kext[k]; r /= p.kext[k]; ibase += c * p.kin[k]; obase += c * p.kout[k]; if constexpr (DOT) ibase2 += c * p.kin2[k]; } }
+  }
+  const long long rs2 = DOT ? p.r_stride2 : 0; const bool bc = rs2 == 1;
   // first element seeds max/min so that no artificial neutral value is needed
   T acc[4];
   T seed = (OP == R_ADD || OP == R_MUL) ? neutral<T, OP>() : (live && p.cols > 0 ? load_scalar<T>(p.in, ibase, p.lk) : (T)0);
@@ -102,29 +133,81 @@ __global__ void __launch_bounds__(256) reduce_row_kernel(const __grid_constant__
   for (int u = 0; u < 4; u++) acc[u] = seed;
   if (live) {
     if (p.vec && E > 1) {
-      long long nch = p.cols / E;
+      long long head = 0;
+      if (p.vec == 2) { head = (E - (ibase & (E - 1))) & (E - 1); if (head > p.cols) head = p.cols; }   // the base vector is 16-byte aligned
+      const long long nch = (p.cols - head) / E, vbase = ibase + head, vbase2 = ibase2 + head * rs2;
       long long c = t;
       for (; c + 3 * TPR < nch; c += 4 * TPR) {
         T v[4][E];
 #pragma unroll
-        for (int u = 0; u < 4; u++) load_elems<T, E>(p.in, ibase + (c + u * TPR) * E, p.lk, true, v[u]);
+        for (int u = 0; u < 4; u++) fetch_elems<T, E, DOT>(p, vbase + (c + u * TPR) * E, vbase2 + (c + u * TPR) * E * rs2, bc, v[u]);
 #pragma unroll
         for (int u = 0; u < 4; u++) acc[u] = fold_elems<T, OP, E>(acc[u], v[u]);
       }
-      for (; c < nch; c += TPR) { T v[E]; load_elems<T, E>(p.in, ibase + c * E, p.lk, true, v); acc[0] = fold_elems<T, OP, E>(acc[0], v); }
+      for (; c < nch; c += TPR) { T v[E]; fetch_elems<T, E, DOT>(p, vbase + c * E, vbase2 + c * E * rs2, bc, v); acc[0] = fold_elems<T, OP, E>(acc[0], v); }
+      if (p.vec == 2) {
+        const long long t0 = head + nch * E, extra = head + (p.cols - t0);       // fewer than 2E scalar elements
+        for (long long j = t; j < extra; j += TPR) { const long long e = j < head ? j : t0 + (j - head); acc[1] = Red<T, OP>::f(acc[1], fetch_scalar<T, DOT>(p, ibase + e, ibase2 + e * rs2)); }
+      }
     } else {
-      for (long long c = t; c < p.cols; c += TPR) acc[0] = Red<T, OP>::f(acc[0], load_scalar<T>(p.in, ibase + c, p.lk));
+      for (long long c = t; c < p.cols; c += TPR) acc[0] = Red<T, OP>::f(acc[0], fetch_scalar<T, DOT>(p, ibase + c, ibase2 + c * rs2));
     }
   }
   T a = Red<T, OP>::f(Red<T, OP>::f(acc[0], acc[1]), Red<T, OP>::f(acc[2], acc[3]));
-  if constexpr (TPR == 32) {
-    a = warp_reduce(a, [](T x, T y) { return Red<T, OP>::f(x, y); });
+  if constexpr (TPR <= 32) {
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) a = Red<T, OP>::f(a, __shfl_xor_sync(0xffffffffu, a, o));
   } else {
     a = block_combine<T, OP, 256>(a);
   }
   if (live && t == 0) {
     T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, obase, p.out_lk);
     store_scalar<T>(p.out, obase, p.sk, Red<T, OP>::f(init, a));          // r <- fn(r, partial)
+  }
+}
+
+// ---- short rows: one thread per row, four rows per thread ---------------------------------------------------
+// A row is at most 16 elements (or 4 chunks).  Thread t of a block folds rows t, t+256, t+512, t+768 of the block's 1024,
+// left to right (the reference's own order); the four rows' loads are issued together, and a warp's loads of one step
+// cover 32 adjacent rows, so every sector fetched is consumed through L1 by the following steps.
+template <class T, int OP, int E, bool DOT>
+__global__ void __launch_bounds__(256) reduce_row_thread_kernel(const __grid_constant__ RedParams p) {
+  long long ib[4], ob[4], ib2[4]; bool live[4]; T acc[4];
+  const long long rs2 = DOT ? p.r_stride2 : 0; const bool bc = rs2 == 1;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const long long row = (long long)blockIdx.x * 1024 + j * 256 + threadIdx.x;
+    live[j] = row < p.rows; ib[j] = p.in_off; ob[j] = p.out_off; ib2[j] = p.in2_off;      // dead rows read row 0: no branch around the loads
+    if (live[j]) {
+      if (p.nk == 1) { ib[j] += row * p.kin[0]; ob[j] += row * p.kout[0]; if constexpr (DOT) ib2[j] += row * p.kin2[0]; }
+      else { long long r = row; for (int k = p.nk - 1; k >= 0; k--) { long long c = r % p.kext[k]; r /= p.kext[k]; ib[j] += c * p.kin[k]; ob[j] += c * p.kout[k]; if constexpr (DOT) ib2[j] += c * p.kin2[k]; } }
+    }
+    acc[j] = (OP == R_ADD || OP == R_MUL) ? neutral<T, OP>() : (p.cols > 0 ? load_scalar<T>(p.in, ib[j], p.lk) : (T)0);
+  }
+  if (p.vec && E > 1) {
+    const int nch = (int)(p.cols / E);
+    for (int c = 0; c < nch; c++) {
+      T v[4][E];
+#pragma unroll
+      for (int j = 0; j < 4; j++) fetch_elems<T, E, DOT>(p, ib[j] + (long long)c * E, ib2[j] + (long long)c * E * rs2, bc, v[j]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[j] = fold_elems<T, OP, E>(acc[j], v[j]);
+    }
+  } else {
+    const int nc = (int)p.cols;
+#pragma unroll 4
+    for (int c = 0; c < nc; c++) {
+      T v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = fetch_scalar<T, DOT>(p, ib[j] + c, ib2[j] + c * rs2);
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[j] = Red<T, OP>::f(acc[j], v[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) if (live[j]) {
+    T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, ob[j], p.out_lk);
+    store_scalar<T>(p.out, ob[j], p.sk, Red<T, OP>::f(init, acc[j]));
   }
 }
 
@@ -135,7 +218,7 @@ template <> struct Wide<long long> { typedef long long W; };
 // 48 registers -> five resident CTAs per SM: the stream needs the occupancy (0.93 -> 1.00 of the measured HBM peak
 // on C2b); narrow integer inputs unpack 4..16 elements per chunk into 64-bit lanes and keep the default budget.
 template <class T, int E> constexpr int reduce_all_min_blocks() { return (sizeof(T) * E <= 16) ? 5 : 1; }
-template <class T, int OP, int E>
+template <class T, int OP, int E, bool DOT>
 __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all_kernel(const __grid_constant__ RedParams p) {
   typedef typename Wide<T>::W W;
   T seed = (OP == R_ADD || OP == R_MUL) ? neutral<T, OP>() : load_scalar<T>(p.in, p.in_off, p.lk);
@@ -149,16 +232,16 @@ __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all
     for (; c + 3 * nthr < nch; c += 4 * nthr) {
       T v[4][E];
 #pragma unroll
-      for (int u = 0; u < 4; u++) load_elems<T, E>(p.in, p.in_off + (c + u * nthr) * E, p.lk, true, v[u]);
+      for (int u = 0; u < 4; u++) fetch_elems<T, E, DOT>(p, p.in_off + (c + u * nthr) * E, p.in2_off + (c + u * nthr) * E, true, v[u]);
 #pragma unroll
       for (int u = 0; u < 4; u++) acc[u] = fold_elems<T, OP, E>(acc[u], v[u]);
     }
-    for (; c < nch; c += nthr) { T v[E]; load_elems<T, E>(p.in, p.in_off + c * E, p.lk, true, v); acc[0] = fold_elems<T, OP, E>(acc[0], v); }
+    for (; c < nch; c += nthr) { T v[E]; fetch_elems<T, E, DOT>(p, p.in_off + c * E, p.in2_off + c * E, true, v); acc[0] = fold_elems<T, OP, E>(acc[0], v); }
     // fewer than E trailing elements when the length is not a multiple of the chunk (odd-sized arrays)
     const long long t0 = nch * E;
-    if (blockIdx.x == 0 && t0 + threadIdx.x < p.cols) acc[1] = Red<T, OP>::f(acc[1], load_scalar<T>(p.in, p.in_off + t0 + threadIdx.x, p.lk));
+    if (blockIdx.x == 0 && t0 + threadIdx.x < p.cols) acc[1] = Red<T, OP>::f(acc[1], fetch_scalar<T, DOT>(p, p.in_off + t0 + threadIdx.x, p.in2_off + t0 + threadIdx.x));
   } else {
-    for (long long c = tid; c < p.cols; c += nthr) acc[0] = Red<T, OP>::f(acc[0], load_scalar<T>(p.in, p.in_off + c, p.lk));
+    for (long long c = tid; c < p.cols; c += nthr) acc[0] = Red<T, OP>::f(acc[0], fetch_scalar<T, DOT>(p, p.in_off + c, p.in2_off + c));
   }
   // thread partials leave the element type here: float sums continue in float64
   W a = Red<W, OP>::f(Red<W, OP>::f((W)acc[0], (W)acc[1]), Red<W, OP>::f((W)acc[2], (W)acc[3]));
@@ -226,21 +309,106 @@ __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all
   }
 }
 
+// ---- few columns: (sum a :axes 0) of an (N,3) array ------------------------------------------------------------------
+// The array is ONE contiguous stream of R*ncols elements and a row is far shorter than a warp's worth of chunks, so the
+// column form below would keep 3 lanes busy.  Here the stream is read exactly like the full reduce (persistent grid,
+// 4 x 16 bytes in flight per thread), with the grid sized so that (threads x E) is a multiple of ncols: every chunk a
+// thread visits then starts at the same column, and its E accumulators stay with fixed columns.  Thread partials widen to
+// float64 / int64, fold per column inside the block through shared memory, block partials per column go to global
+// memory and the last block (ticket) folds them in block order: deterministic, one rounding.
+template <class T, int OP, int E>
+__global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_fewcols_kernel(const __grid_constant__ RedParams p) {
+  typedef typename Wide<T>::W W;
+  __shared__ W S[256 * E];
+  __shared__ W S2[256];
+  __shared__ bool H2[256];
+  __shared__ bool last;
+  const int nc = (int)p.ncols;
+  const long long tid = (long long)blockIdx.x * 256 + threadIdx.x, nthr = (long long)gridDim.x * 256;
+  const long long nch = p.cols / E;                        // p.cols: elements in the stream, a multiple of E
+  const int ph0 = (int)((tid * E) % nc);
+  T acc[4][E];
+#pragma unroll
+  for (int i = 0; i < E; i++) {
+    // max / min start from the row-0 element of the accumulator's own column: no artificial neutral value
+    T seed = (OP == R_ADD || OP == R_MUL) ? neutral<T, OP>() : load_scalar<T>(p.in, p.in_off + (ph0 + i) % nc, p.lk);
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc[u][i] = seed;
+  }
+  long long c = tid;
+  for (; c + 3 * nthr < nch; c += 4 * nthr) {
+    T v[4][E];
+#pragma unroll
+    for (int u = 0; u < 4; u++) load_elems<T, E>(p.in, p.in_off + (c + u * nthr) * E, p.lk, true, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int i = 0; i < E; i++) acc[u][i] = Red<T, OP>::f(acc[u][i], v[u][i]);
+  }
+  for (; c < nch; c += nthr) {
+    T v[E]; load_elems<T, E>(p.in, p.in_off + c * E, p.lk, true, v);
+#pragma unroll
+    for (int i = 0; i < E; i++) acc[0][i] = Red<T, OP>::f(acc[0][i], v[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < E; i++)
+    S[threadIdx.x * E + i] = Red<W, OP>::f(Red<W, OP>::f((W)acc[0][i], (W)acc[1][i]), Red<W, OP>::f((W)acc[2][i], (W)acc[3][i]));
+  __syncthreads();
+  // fold per column: thread -> (column j, group g); group g takes every ng-th of the block's positions of that column
+  const int j = threadIdx.x % nc, g = threadIdx.x / nc, ng = 256 / nc;
+  {
+    int f0 = j - (int)(((long long)blockIdx.x * 256 * E) % nc); if (f0 < 0) f0 += nc;
+    W part = (W)0; bool has = false;
+    if (g < ng) for (int f = f0 + g * nc; f < 256 * E; f += ng * nc) { part = has ? Red<W, OP>::f(part, S[f]) : S[f]; has = true; }
+    S2[threadIdx.x] = part; H2[threadIdx.x] = has;
+  }
+  __syncthreads();
+  W* partials = (W*)p.block_partials;
+  if (threadIdx.x < nc) {
+    W tot = S2[j];                                          // group 0 always holds at least one position
+    for (int gg = 1; gg < ng; gg++) if (H2[gg * nc + j]) tot = Red<W, OP>::f(tot, S2[gg * nc + j]);
+    partials[(long long)blockIdx.x * nc + j] = tot;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned int done = atomicAdd(p.ticket, 1u); last = (done == gridDim.x - 1); }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  {
+    W part = (W)0; bool has = false;
+    if (g < ng) for (int b = g; b < (int)gridDim.x; b += ng) { W x = ((volatile W*)partials)[(long long)b * nc + j]; part = has ? Red<W, OP>::f(part, x) : x; has = true; }
+    S2[threadIdx.x] = part; H2[threadIdx.x] = has;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *p.ticket = 0;                      // re-arm for the next launch on this stream
+  if (threadIdx.x < nc) {
+    W tot = S2[j];
+    for (int gg = 1; gg < ng; gg++) if (H2[gg * nc + j]) tot = Red<W, OP>::f(tot, S2[gg * nc + j]);
+    const long long o = p.out_off + (long long)j * p.kout[0];
+    W init = p.fresh ? (W)ident_of<T>(p) : (W)load_scalar<T>(p.out, o, p.out_lk);
+    W r = Red<W, OP>::f(init, tot);
+    if constexpr (std::is_integral<T>::value) store_scalar<long long>(p.out, o, p.sk, r);
+    else store_scalar<double>(p.out, o, p.sk, r);           // one rounding to the element type
+  }
+}
+
 // ---- column reduce ---------------------------------------------------------------------------------------------
 // thread -> one chunk of E contiguous kept columns of one outer-kept coordinate; walks rows [r0, r1)
-template <class T, int OP, int E>
+template <class T, int OP, int E, bool DOT>
 __global__ void __launch_bounds__(256) reduce_col_kernel(const __grid_constant__ RedParams p) {
   long long chunks_per_row = p.ncols / E;
   long long q = (long long)blockIdx.x * 256 + threadIdx.x;
   long long nq = p.rows * chunks_per_row;              // rows = prod of the outer kept dims
   if (q >= nq) return;
   long long cc = q % chunks_per_row, orow = q / chunks_per_row;
-  long long ibase = p.in_off + cc * E, obase = p.out_off + cc * E;
-  { long long r = orow; for (int k = p.nk - 1; k >= 0; k--) { long long c = r % p.kext[k]; r /= p.kext[k]; ibase += c * p.kin[k]; obase += c * p.kout[k]; } }
+  long long ibase = p.in_off + cc * E, obase = p.out_off + cc * E, ibase2 = DOT ? p.in2_off + cc * E * p.c_stride2 : 0;
+  { long long r = orow; for (int k = p.nk - 1; k >= 0; k--) { long long c = r % p.kext[k]; r /= p.kext[k]; ibase += c * p.kin[k]; obase += c * p.kout[k]; if constexpr (DOT) ibase2 += c * p.kin2[k]; } }
+  const long long rs2 = DOT ? p.r_stride2 : 0; const bool bc = DOT && p.c_stride2 == 1;
   long long r0 = (long long)blockIdx.y * p.seg, r1 = r0 + p.seg; if (r1 > p.r_ext) r1 = p.r_ext;
   T acc[E];
   if (r0 >= r1) return;
-  load_elems<T, E>(p.in, ibase + r0 * p.r_stride, p.lk, E > 1, acc);     // the first row seeds the accumulators
+  fetch_elems<T, E, DOT>(p, ibase + r0 * p.r_stride, ibase2 + r0 * rs2, bc, acc);     // the first row seeds the accumulators
   long long r = r0 + 1;
   // rows in flight per thread: 4 x 16 bytes on the vector path; the scalar path (ragged column count) moves only one
   // element per load and needs 16 rows to keep a comparable number of bytes in flight (0.17 -> of the HBM peak with 4)
@@ -248,14 +416,14 @@ __global__ void __launch_bounds__(256) reduce_col_kernel(const __grid_constant__
   for (; r + UR - 1 < r1; r += UR) {
     T v[UR][E];
 #pragma unroll
-    for (int u = 0; u < UR; u++) load_elems<T, E>(p.in, ibase + (r + u) * p.r_stride, p.lk, E > 1, v[u]);
+    for (int u = 0; u < UR; u++) fetch_elems<T, E, DOT>(p, ibase + (r + u) * p.r_stride, ibase2 + (r + u) * rs2, bc, v[u]);
 #pragma unroll
     for (int u = 0; u < UR; u++)
 #pragma unroll
       for (int i = 0; i < E; i++) acc[i] = Red<T, OP>::f(acc[i], v[u][i]);
   }
   for (; r < r1; r++) {
-    T v[E]; load_elems<T, E>(p.in, ibase + r * p.r_stride, p.lk, E > 1, v);
+    T v[E]; fetch_elems<T, E, DOT>(p, ibase + r * p.r_stride, ibase2 + r * rs2, bc, v);
 #pragma unroll
     for (int i = 0; i < E; i++) acc[i] = Red<T, OP>::f(acc[i], v[i]);
   }
@@ -292,20 +460,41 @@ __global__ void __launch_bounds__(256) reduce_col_finish_kernel(const __grid_con
 
 // ---- host ---------------------------------------------------------------------------------------------------------
 typedef void (*RedKernel)(const RedParams);
-enum { KROW32, KROW256, KALL, KCOL, KCOLFIN };
+enum { KROW1, KROW4, KROW32, KROW256, KALL, KCOL, KCOLFIN, KFEWCOLS };
 
 template <class T, int OP, int E> static RedKernel kget(int which) {
   switch (which) {
-    case KROW32: return (RedKernel)reduce_row_kernel<T, OP, E, 32>;
-    case KROW256: return (RedKernel)reduce_row_kernel<T, OP, E, 256>;
-    case KALL: return (RedKernel)reduce_all_kernel<T, OP, E>;
-    case KCOL: return (RedKernel)reduce_col_kernel<T, OP, E>;
+    case KROW1: return (RedKernel)reduce_row_thread_kernel<T, OP, E, false>;
+    case KFEWCOLS: if constexpr (E > 1) return (RedKernel)reduce_fewcols_kernel<T, OP, E>; else return nullptr;
+    case KROW4: return (RedKernel)reduce_row_kernel<T, OP, E, 4, false>;
+    case KROW32: return (RedKernel)reduce_row_kernel<T, OP, E, 32, false>;
+    case KROW256: return (RedKernel)reduce_row_kernel<T, OP, E, 256, false>;
+    case KALL: return (RedKernel)reduce_all_kernel<T, OP, E, false>;
+    case KCOL: return (RedKernel)reduce_col_kernel<T, OP, E, false>;
     default: return (RedKernel)reduce_col_finish_kernel<T, OP, E>;
+  }
+}
+template <class T, int E> static RedKernel kget_dot(int which) {       // r += a * b: the sum only
+  switch (which) {
+    case KROW1: return (RedKernel)reduce_row_thread_kernel<T, R_ADD, E, true>;
+    case KROW4: return (RedKernel)reduce_row_kernel<T, R_ADD, E, 4, true>;
+    case KROW32: return (RedKernel)reduce_row_kernel<T, R_ADD, E, 32, true>;
+    case KROW256: return (RedKernel)reduce_row_kernel<T, R_ADD, E, 256, true>;
+    case KALL: return (RedKernel)reduce_all_kernel<T, R_ADD, E, true>;
+    case KCOL: return (RedKernel)reduce_col_kernel<T, R_ADD, E, true>;
+    case KCOLFIN: return (RedKernel)reduce_col_finish_kernel<T, R_ADD, E>;
+    default: return nullptr;
   }
 }
 template <class T, int E> static RedKernel kget_op(int op, int which) {
   switch (op) { case R_ADD: return kget<T, R_ADD, E>(which); case R_MUL: return kget<T, R_MUL, E>(which);
     case R_MAX: return kget<T, R_MAX, E>(which); default: return kget<T, R_MIN, E>(which); }
+}
+static RedKernel kernel_for_dot(int cls, int E, int which) {
+  if (cls == CLS_F) return E == 4 ? kget_dot<float, 4>(which) : kget_dot<float, 1>(which);
+  if (cls == CLS_D) return E == 2 ? kget_dot<double, 2>(which) : kget_dot<double, 1>(which);
+  switch (E) { case 16: return kget_dot<long long, 16>(which); case 8: return kget_dot<long long, 8>(which);
+    case 4: return kget_dot<long long, 4>(which); case 2: return kget_dot<long long, 2>(which); default: return kget_dot<long long, 1>(which); }
 }
 static RedKernel kernel_for(int cls, int E, int op, int which) {
   if (cls == CLS_F) return E == 4 ? kget_op<float, 4>(op, which) : kget_op<float, 1>(op, which);
@@ -326,17 +515,17 @@ static bool match_reduce(const Expr& e, int* op) {
   *op = o; return true;
 }
 
-struct RDim { long long ext, sin, sout; };
+struct RDim { long long ext, sin, sout, sin2; };       // sin2: stride of the second operand (DOT), 0 otherwise
 static void sort_merge(RDim* d, int& n, bool kept) {
   for (int i = 1; i < n; i++) { RDim t = d[i]; int j = i - 1; while (j >= 0 && llabs(d[j].sin) < llabs(t.sin)) { d[j + 1] = d[j]; j--; } d[j + 1] = t; }
   for (int i = n - 1; i > 0; i--) {
-    bool ok = d[i - 1].sin == d[i].sin * d[i].ext && (!kept || d[i - 1].sout == d[i].sout * d[i].ext);
-    if (ok) { d[i - 1].ext *= d[i].ext; d[i - 1].sin = d[i].sin; d[i - 1].sout = d[i].sout; for (int j = i; j + 1 < n; j++) d[j] = d[j + 1]; n--; }
+    bool ok = d[i - 1].sin == d[i].sin * d[i].ext && (!kept || d[i - 1].sout == d[i].sout * d[i].ext) && d[i - 1].sin2 == d[i].sin2 * d[i].ext;
+    if (ok) { d[i - 1].ext *= d[i].ext; d[i - 1].sin = d[i].sin; d[i - 1].sout = d[i].sout; d[i - 1].sin2 = d[i].sin2; for (int j = i; j + 1 < n; j++) d[j] = d[j + 1]; n--; }
   }
 }
 
-static int fill_common(RedParams& p, const Nest& n, int op) {
-  const Operand& in = n.in[0]; const Operand& out = n.out[0];
+static int fill_common(RedParams& p, const Nest& n, int op, int ia) {
+  const Operand& in = n.in[ia]; const Operand& out = n.out[0];
   memset(&p, 0, sizeof p);
   p.in = in.base; p.in_off = in.offset; p.lk = dtype_load_kind(in.dtype);
   p.out = out.base; p.out_off = out.offset; p.sk = dtype_store_spec(out.dtype); p.out_lk = dtype_load_kind(out.dtype);
@@ -360,11 +549,49 @@ static bool aligned16(const Operand& o, long long elem_off) {
   return (((uintptr_t)o.base + (elem_off * sb) / 8) % 16) == 0;
 }
 
+static int reduce_impl(const Nest& n, int op, int ia, int ib);
+
 int try_reduce(const Nest& n) {
   if (n.n_out != 1 || n.n_in != 1) return NCL_ERR_UNSUPPORTED;
   int op;
   if (!match_reduce(n.transform[0], &op)) return NCL_ERR_UNSUPPORTED;
-  const Operand& in = n.in[0]; const Operand& out = n.out[0];
+  return reduce_impl(n, op, 0, -1);
+}
+
+// Contractions that are really reductions: the default transform (+ @1 (* $1 $2)) over two arrays of one element type
+// where no loop is private to one input and kept (no M x N outer structure, k_gemm.cu): vdot / inner `(i i ->)`, row-wise
+// dots `(ij ij -> i)`, matrix x vector `(ij j -> i)`, vector x matrix `(i ij -> j)`.  Every element of the larger input is
+// used once, so they are HBM-bound streams and run on the reduction kernels with the product formed on load.
+int try_dot_reduce(const Nest& n) {
+  if (n.n_in != 2 || n.n_out != 1) return NCL_ERR_UNSUPPORTED;
+  const Expr& e = n.transform[0];
+  if (e.n != 5) return NCL_ERR_UNSUPPORTED;
+  const XNode& root = e.node[4];
+  if (root.op != NCL_OP_ADD || e.node[root.a].op != NCL_X_OUTPUT || e.node[root.b].op != NCL_OP_MUL) return NCL_ERR_UNSUPPORTED;
+  const XNode& mul = e.node[root.b];
+  if (e.node[mul.a].op != NCL_X_INPUT || e.node[mul.b].op != NCL_X_INPUT || e.node[mul.a].a == e.node[mul.b].a) return NCL_ERR_UNSUPPORTED;
+  const int i0 = e.node[mul.a].a - 1, i1 = e.node[mul.b].a - 1;
+  const Operand& A = n.in[i0]; const Operand& B = n.in[i1];
+  if (A.dtype != B.dtype) return NCL_ERR_UNSUPPORTED;
+  bool a_all = true, b_all = true, m_loop = false, n_loop = false, k_loop = false;
+  for (int l = 0; l < n.nloops; l++) {
+    if (n.extent[l] == 1) continue;
+    const bool a = A.stride[l] != 0, b = B.stride[l] != 0, c = n.out[0].stride[l] != 0;
+    if (!a) a_all = false;
+    if (!b) b_all = false;
+    if (a && !b && c) m_loop = true;
+    if (!a && b && c) n_loop = true;
+    if (!c) k_loop = true;
+    if (!a && !b) return NCL_ERR_UNSUPPORTED;
+  }
+  if (!k_loop || (m_loop && n_loop) || (!a_all && !b_all)) return NCL_ERR_UNSUPPORTED;
+  return a_all ? reduce_impl(n, R_ADD, i0, i1) : reduce_impl(n, R_ADD, i1, i0);
+}
+
+// ia: the array every loop moves; ib: second operand of a DOT (or -1)
+static int reduce_impl(const Nest& n, int op, int ia, int ib) {
+  const bool dot = ib >= 0;
+  const Operand& in = n.in[ia]; const Operand& out = n.out[0];
   int icls = g_dt[in.dtype].cls, ocls = g_dt[out.dtype].cls;
   if (icls != ocls) return NCL_ERR_UNSUPPORTED;                       // e.g. integer sum into a float array: generic path
   if (g_dt[in.dtype].slot_bits < 8) return NCL_ERR_UNSUPPORTED;       // packed inputs: generic path
@@ -372,7 +599,7 @@ int try_reduce(const Nest& n) {
   RDim kd[NCL_MAX_LOOPS], rd[NCL_MAX_LOOPS]; int nk = 0, nr = 0;
   for (int l = 0; l < n.nloops; l++) {
     if (n.extent[l] == 1) continue;
-    RDim d = {n.extent[l], in.stride[l], out.stride[l]};
+    RDim d = {n.extent[l], in.stride[l], out.stride[l], dot ? n.in[ib].stride[l] : 0};
     if (out.stride[l] != 0) kd[nk++] = d; else rd[nr++] = d;
   }
   if (nr == 0) return NCL_ERR_UNSUPPORTED;
@@ -383,23 +610,32 @@ int try_reduce(const Nest& n) {
   Context& c = ctx();
   int sb = g_dt[in.dtype].slot_bits;
   int Evec = 128 / sb;
-  RedParams p; fill_common(p, n, op);
+  RedParams p; fill_common(p, n, op, ia);
   long long R = rd[0].ext, sR = rd[0].sin;
   int cls = icls;
+  if (dot) {
+    const Operand& b = n.in[ib];
+    p.in2 = b.base; p.in2_off = b.offset; p.lk2 = dtype_load_kind(b.dtype);
+    p.r_stride2 = rd[0].sin2;
+  }
+  // second operand: vector loads need the same 16-byte phase as the first along every loop it moves with
+  auto b_vec_ok = [&](long long s2) { return (((s2 * sb) / 8) % 16) == 0; };
+  auto kfor = [&](int E, int which) { return dot ? kernel_for_dot(cls, E, which) : kernel_for(cls, E, op, which); };
 
   if (sR == 1 && nk == 0) {
     // ---- full reduce --------------------------------------------------------------------------
     p.cols = R;
-    p.vec = R >= Evec && aligned16(in, in.offset);          // a ragged tail (< Evec elements) is folded by block 0
+    if (dot && rd[0].sin2 != 1) return NCL_ERR_UNSUPPORTED;
+    p.vec = R >= Evec && aligned16(in, in.offset) && (!dot || aligned16(n.in[ib], n.in[ib].offset));   // a ragged tail (< Evec elements) is folded by block 0
     int E = p.vec ? Evec : 1;
     long long work = p.vec ? R / E : R;
-    RedKernel kfn = kernel_for(cls, E, op, KALL);
+    RedKernel kfn = kfor(E, KALL);
     long long blocks = (work + 256 * 4 - 1) / (256 * 4);
     long long cap = persistent_blocks((const void*)kfn); if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
     NCL_TRY(ensure_scratch((size_t)blocks * 8));
     p.block_partials = c.scratch; p.ticket = c.ticket; p.nblocks = (int)blocks;
     kfn<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
-    note_launch("reduce_all");
+    note_launch(dot ? "dot_all" : "reduce_all");
     return cuda_fail(cudaGetLastError(), "reduce_all_kernel");
   }
   // the contiguous kept dim must be the innermost of the kept group for the column form
@@ -408,17 +644,62 @@ int try_reduce(const Nest& n) {
     // ---- row reduce: kept dims (any strides) x contiguous reduced axis ------------------------------
     if (nk > 4) return NCL_ERR_UNSUPPORTED;
     p.nk = nk; p.rows = 1;
-    for (int i = 0; i < nk; i++) { p.kext[i] = kd[i].ext; p.kin[i] = kd[i].sin; p.kout[i] = kd[i].sout; p.rows *= kd[i].ext; }
+    for (int i = 0; i < nk; i++) { p.kext[i] = kd[i].ext; p.kin[i] = kd[i].sin; p.kout[i] = kd[i].sout; p.kin2[i] = kd[i].sin2; p.rows *= kd[i].ext; }
     p.cols = R;
+    if (dot && rd[0].sin2 != 1 && rd[0].sin2 != 0) return NCL_ERR_UNSUPPORTED;
+    // ---- few long rows ((sum a :axes 1) of a (3,N) array): one CTA per row would leave the GPU empty.  Every row is cut into
+    // S pieces of L elements (L a multiple of the chunk): [rows x S x L] reduces over L into a scratch [rows x S], which then
+    // reduces over S into the result; the R - S*L trailing elements of every row are accumulated last.
+    if (!dot && p.rows < 2LL * c.sm_count && R >= 65536 && (n.fresh || op == R_ADD) && nk <= 3) {
+      long long S = (8LL * c.sm_count + p.rows - 1) / p.rows; if (S > R / 16384) S = R / 16384;
+      const long long L = R / S / (4 * Evec) * (4 * Evec), rem = R - S * L;
+      if (S >= 2 && L > 0) {
+        const int osb = g_dt[out.dtype].slot_bits;
+        NCL_TRY(ensure_scratch3((size_t)(p.rows * S) * osb / 8 + 64));
+        auto run = [&](Nest& x) { int r2 = try_reduce(x); return r2 == NCL_ERR_UNSUPPORTED ? launch_generic(x) : r2; };
+        long long tst[4]; { long long acc = S; for (int i = nk - 1; i >= 0; i--) { tst[i] = acc; acc *= kd[i].ext; } }
+        Nest a = n;                                         // kept..., S, L -> scratch[kept..., S]
+        a.nloops = nk + 2;
+        for (int i = 0; i < nk; i++) { a.extent[i] = kd[i].ext; a.in[0].stride[i] = kd[i].sin; a.out[0].stride[i] = tst[i]; }
+        a.extent[nk] = S; a.in[0].stride[nk] = L; a.out[0].stride[nk] = 1;
+        a.extent[nk + 1] = L; a.in[0].stride[nk + 1] = 1; a.out[0].stride[nk + 1] = 0;
+        a.out[0].base = (char*)c.scratch3; a.out[0].offset = 0; a.out[0].n_storage = p.rows * S;
+        a.fresh = true; if (!n.fresh) a.has_identity = false;
+        NCL_TRY(run(a));
+        Nest b = n;                                         // scratch[kept..., S] -> result
+        b.nloops = nk + 1;
+        for (int i = 0; i < nk; i++) { b.extent[i] = kd[i].ext; b.in[0].stride[i] = tst[i]; b.out[0].stride[i] = kd[i].sout; }
+        b.extent[nk] = S; b.in[0].stride[nk] = 1; b.out[0].stride[nk] = 0;
+        b.in[0].base = (char*)c.scratch3; b.in[0].dtype = out.dtype; b.in[0].offset = 0; b.in[0].n_storage = p.rows * S;
+        NCL_TRY(run(b));
+        if (rem > 0) {
+          Nest r3 = n;
+          r3.nloops = nk + 1;
+          for (int i = 0; i < nk; i++) { r3.extent[i] = kd[i].ext; r3.in[0].stride[i] = kd[i].sin; r3.out[0].stride[i] = kd[i].sout; }
+          r3.extent[nk] = rem; r3.in[0].stride[nk] = 1; r3.out[0].stride[nk] = 0;
+          r3.in[0].offset += S * L; r3.fresh = false;
+          NCL_TRY(run(r3));
+        }
+        return NCL_OK;
+      }
+    }
     bool vec = (R % Evec == 0) && aligned16(in, in.offset);
     for (int i = 0; i < nk && vec; i++) if (((kd[i].sin * sb) / 8) % 16) vec = false;
-    p.vec = vec; int E = vec ? Evec : 1;
-    long long chunks = vec ? R / E : R;
-    bool wide = chunks >= 512;
-    long long blocks = wide ? p.rows : (p.rows + 7) / 8;
+    if (dot && vec && rd[0].sin2 == 1) { vec = aligned16(n.in[ib], n.in[ib].offset); for (int i = 0; i < nk && vec; i++) if (!b_vec_ok(kd[i].sin2)) vec = false; }
+    // rows that do not start / end on a chunk boundary: scalar head and tail around an aligned vector body (vec = 2),
+    // unless they are so short that one thread folds a whole row element by element
+    int vmode = vec ? 1 : ((!dot && R > 16 && Evec > 1 && ((uintptr_t)in.base % 16) == 0) ? 2 : 0);
+    p.vec = vmode; int E = vmode ? Evec : 1;
+    long long chunks = vmode ? R / E : R;
+    int which; long long blocks;
+    if (vmode == 0 && R <= 16) { which = KROW1; blocks = (p.rows + 1023) / 1024; }
+    else if (vmode == 1 && chunks <= 4) { which = KROW1; blocks = (p.rows + 1023) / 1024; }
+    else if (chunks <= 16 && vmode) { which = KROW4; blocks = (p.rows + 63) / 64; }
+    else if (chunks >= 512) { which = KROW256; blocks = p.rows; }
+    else { which = KROW32; blocks = (p.rows + 7) / 8; }
     if (blocks > 0x7fffffffLL) return NCL_ERR_UNSUPPORTED;
-    kernel_for(cls, E, op, wide ? KROW256 : KROW32)<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
-    note_launch(wide ? "reduce_row_block" : "reduce_row_warp");
+    kfor(E, which)<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+    note_launch(dot ? "dot_rows" : which == KROW256 ? "reduce_row_block" : which == KROW32 ? "reduce_row_warp" : which == KROW4 ? "reduce_row_quad" : "reduce_row_thread");
     return cuda_fail(cudaGetLastError(), "reduce_row_kernel");
   }
   // ---- column reduce: [outer kept...][R][contiguous kept] ---------------------------------------------
@@ -427,14 +708,45 @@ int try_reduce(const Nest& n) {
   long long ncols = kd[nk - 1].ext;
   p.ncols = ncols; p.r_ext = R; p.r_stride = sR;
   p.nk = nk - 1; p.rows = 1;
-  for (int i = 0; i < nk - 1; i++) { p.kext[i] = kd[i].ext; p.kin[i] = kd[i].sin; p.kout[i] = kd[i].sout; p.rows *= kd[i].ext; }
+  for (int i = 0; i < nk - 1; i++) { p.kext[i] = kd[i].ext; p.kin[i] = kd[i].sin; p.kout[i] = kd[i].sout; p.kin2[i] = kd[i].sin2; p.rows *= kd[i].ext; }
+  if (dot) { p.c_stride2 = kd[nk - 1].sin2; if (p.c_stride2 != 0 && p.c_stride2 != 1) return NCL_ERR_UNSUPPORTED; }
+  // ---- few columns ((sum a :axes 0) of an (N,3) array): the whole array as one stream, reduce_fewcols_kernel ----------
+  if (!dot && nk == 1 && sR == ncols && ncols <= 128 && Evec > 1 && aligned16(in, in.offset) && R * ncols >= 32768 && R * ncols < (1LL << 40)) {
+    const long long Rr = (R * ncols) % Evec ? R % Evec : 0, Rm = R - Rr;      // Rm * ncols is a multiple of the chunk
+    RedKernel kfn = kernel_for(cls, Evec, op, KFEWCOLS);
+    if (kfn && Rm > 0) {
+      p.cols = Rm * ncols; p.vec = 1; p.kout[0] = kd[0].sout;
+      long long work = p.cols / Evec, blocks = (work + 1023) / 1024;
+      long long cap = persistent_blocks((const void*)kfn); if (blocks > cap) blocks = cap;
+      long long g = ncols, x = 256LL * Evec; while (x) { long long t = g % x; g = x; x = t; }     // gcd(ncols, 256 * Evec)
+      const long long m = ncols / g;                                        // grid must be a multiple of m
+      blocks = blocks / m * m; if (blocks < m) blocks = m;
+      NCL_TRY(ensure_scratch((size_t)blocks * ncols * 8));
+      p.block_partials = c.scratch; p.ticket = c.ticket; p.nblocks = (int)blocks;
+      kfn<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+      note_launch("reduce_fewcols");
+      NCL_TRY(cuda_fail(cudaGetLastError(), "reduce_fewcols_kernel"));
+      if (Rr > 0) {                                                         // fewer than Evec left-over rows, accumulated
+        Nest r3 = n;
+        r3.nloops = 2; r3.extent[0] = Rr; r3.extent[1] = ncols;
+        r3.in[0].offset += Rm * ncols; r3.in[0].stride[0] = ncols; r3.in[0].stride[1] = 1;
+        r3.out[0].stride[0] = 0; r3.out[0].stride[1] = kd[0].sout;
+        r3.fresh = false;
+        int rc = try_reduce(r3);
+        if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(r3);
+        NCL_TRY(rc);
+      }
+      return NCL_OK;
+    }
+  }
   bool vec = (ncols % Evec == 0) && aligned16(in, in.offset) && ((sR * sb) / 8) % 16 == 0;
   for (int i = 0; i < nk - 1 && vec; i++) if (((kd[i].sin * sb) / 8) % 16) vec = false;
+  if (dot && vec && p.c_stride2 == 1) { vec = aligned16(n.in[ib], n.in[ib].offset) && b_vec_ok(rd[0].sin2); for (int i = 0; i < nk - 1 && vec; i++) if (!b_vec_ok(kd[i].sin2)) vec = false; }
   int E = vec ? Evec : 1; p.vec = vec;
   long long nq = p.rows * (ncols / E);
   // split R so that the grid is ONE resident wave of equal segments (2048 threads per SM assumed here before: two
   // uneven waves at 60 registers)
-  long long want = persistent_blocks((const void*)kernel_for(cls, E, op, KCOL)) * 256;
+  long long want = persistent_blocks((const void*)kfor(E, KCOL)) * 256;
   int nseg = 1;
   if (nq < want && R >= 128) { nseg = (int)((want + nq - 1) / nq); long long maxseg = R / 32; if (nseg > maxseg) nseg = (int)maxseg; if (nseg > 1024) nseg = 1024; if (nseg < 1) nseg = 1; }
   p.nseg = nseg; p.seg = (R + nseg - 1) / nseg;
@@ -443,12 +755,12 @@ int try_reduce(const Nest& n) {
   if (bx > 0x7fffffffLL) return NCL_ERR_UNSUPPORTED;
   if (p.nseg > 1) { NCL_TRY(ensure_scratch((size_t)p.nseg * nq * E * 8)); p.partial = c.scratch; }
   dim3 grid((unsigned)bx, (unsigned)p.nseg);
-  kernel_for(cls, E, op, KCOL)<<<grid, 256, 0, c.stream>>>(p);
-  note_launch("reduce_col");
+  kfor(E, KCOL)<<<grid, 256, 0, c.stream>>>(p);
+  note_launch(dot ? "dot_cols" : "reduce_col");
   NCL_TRY(cuda_fail(cudaGetLastError(), "reduce_col_kernel"));
   if (p.nseg > 1) {
-    kernel_for(cls, E, op, KCOLFIN)<<<(unsigned)bx, 256, 0, c.stream>>>(p);
-    note_launch("reduce_col");
+    kfor(E, KCOLFIN)<<<(unsigned)bx, 256, 0, c.stream>>>(p);
+    note_launch(dot ? "dot_cols" : "reduce_col");
     NCL_TRY(cuda_fail(cudaGetLastError(), "reduce_col_finish_kernel"));
   }
   return NCL_OK;

@@ -98,6 +98,64 @@ __global__ void __launch_bounds__(256) transpose_raw_kernel(const __grid_constan
   }
 }
 
+// Thin planes: one of the two contiguous loops is short (a trailing axis of 3: (N,3) -> (3,N)).  Square tiles would be
+// mostly empty, so the tile is TI x TO with TI*TO = 4096 (16 independent loads per thread: a CTA's only latency hiding is
+// what it has in flight before its barrier) and the short side covering the whole short loop; the long side
+// keeps every warp access on contiguous memory (rows of the short loop are adjacent when the array is contiguous).
+// MODE 0: raw words, 1 / 2: raw single / double floats through x + 0.0, 3: through the value class V (type-changing).
+template <class V, int TI, int TO, int MODE>
+__global__ void __launch_bounds__(256) transpose_thin_kernel(const __grid_constant__ TrParams p) {
+  constexpr bool I_SHORT = TI <= TO;
+  constexpr int PITCH = I_SHORT ? TO + 32 / TI : TI + 32 / TO;      // conflict-free for both phases
+  __shared__ V tile[(I_SHORT ? TI : TO) * PITCH];
+  long long b = blockIdx.x;
+  long long ti = b % p.tiles_i; b /= p.tiles_i;
+  long long to = b % p.tiles_o; b /= p.tiles_o;
+  long long ibase = p.in_off, obase = p.out_off;
+  for (int k = p.nb - 1; k >= 0; k--) { long long c = b % p.bext[k]; b /= p.bext[k]; ibase += c * p.bin[k]; obase += c * p.bout[k]; }
+  const long long i0 = ti * TI, o0 = to * TO;
+  auto slot = [](int i, int o) { return I_SHORT ? i * PITCH + o : o * PITCH + i; };
+  // load: threads run along i (input-contiguous) first.  All of a thread's loads are issued before the first shared-memory
+  // store: out-of-range positions read a valid dummy address instead of branching around the load (with a branch per element
+  // ptxas kept ONE load in flight per thread).
+  constexpr int N = TI * TO / 256;
+  V v[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const int e = threadIdx.x + k * 256, i = e % TI, o = e / TI;
+    const bool ok = i0 + i < p.ni && o0 + o < p.no;
+    const long long idx = ok ? ibase + (o0 + o) * p.in_so + i0 + i : p.in_off;
+    if constexpr (MODE == 3) v[k] = load_scalar<V>(p.in, idx, p.lk);
+    else v[k] = __ldg((const V*)p.in + idx);
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) { const int e = threadIdx.x + k * 256; tile[slot(e % TI, e / TI)] = v[k]; }
+  __syncthreads();
+  // store: threads run along o (output-contiguous) first
+#pragma unroll
+  for (int k = 0; k < N; k++) { const int e = threadIdx.x + k * 256; v[k] = tile[slot(e / TO, e % TO)]; }
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const int e = threadIdx.x + k * 256, o = e % TO, i = e / TO;
+    if (i0 + i < p.ni && o0 + o < p.no) {
+      V w = v[k];
+      const long long idx = obase + (i0 + i) * p.out_si + o0 + o;
+      if constexpr (MODE == 1) w = (V)__float_as_uint(__fadd_rn(0.0f, __uint_as_float((unsigned)w)));
+      if constexpr (MODE == 2) w = (V)__double_as_longlong(__dadd_rn(0.0, __longlong_as_double((long long)w)));
+      if constexpr (MODE == 3) { if (p.add_zero) w = Ops<V>::add(Ops<V>::zero(), w); store_scalar<V>(p.out, idx, p.sk, w); }
+      else ((V*)p.out)[idx] = w;
+    }
+  }
+}
+typedef void (*TrKernel)(const TrParams);
+template <class V, int MODE> static TrKernel thin_pick(int ti) {
+  switch (ti) {
+    case 4: return transpose_thin_kernel<V, 4, 1024, MODE>;  case 8: return transpose_thin_kernel<V, 8, 512, MODE>;
+    case 16: return transpose_thin_kernel<V, 16, 256, MODE>; case 256: return transpose_thin_kernel<V, 256, 16, MODE>;
+    case 512: return transpose_thin_kernel<V, 512, 8, MODE>; default: return transpose_thin_kernel<V, 1024, 4, MODE>;
+  }
+}
+
 int try_transpose(const Nest& n) {
   if (n.n_out != 1 || n.n_in != 1) return NCL_ERR_UNSUPPORTED;
   const Operand& in = n.in[0]; const Operand& out = n.out[0];
@@ -140,6 +198,26 @@ int try_transpose(const Nest& n) {
              g_dt[in.dtype].tagged == g_dt[out.dtype].tagged && g_dt[out.dtype].value_bits >= g_dt[in.dtype].value_bits &&
              g_dt[in.dtype].is_signed == g_dt[out.dtype].is_signed);
   int wbytes = g_dt[in.dtype].slot_bits / 8;
+  if ((p.ni <= 16 || p.no <= 16) && (p.ni >= 128 || p.no >= 128)) {
+    // thin plane: rectangular tiles, short side first
+    const long long sh = p.ni <= p.no ? p.ni : p.no;
+    const int ts = sh <= 4 ? 4 : sh <= 8 ? 8 : 16, tl = 4096 / ts;
+    const int TI = p.ni <= p.no ? ts : tl, TO = p.ni <= p.no ? tl : ts;
+    p.tiles_i = (p.ni + TI - 1) / TI; p.tiles_o = (p.no + TO - 1) / TO;
+    long long blocks = p.tiles_i * p.tiles_o * batch;
+    if (blocks > 0x7fffffffLL || blocks <= 0) return NCL_ERR_UNSUPPORTED;
+    TrKernel k;
+    if (raw) {
+      int fz = (add_zero && icls == CLS_F) ? 1 : (add_zero && icls == CLS_D) ? 2 : 0;
+      if (wbytes == 8) k = fz == 2 ? thin_pick<unsigned long long, 2>(TI) : thin_pick<unsigned long long, 0>(TI);
+      else if (wbytes == 4) k = fz == 1 ? thin_pick<unsigned int, 1>(TI) : thin_pick<unsigned int, 0>(TI);
+      else if (wbytes == 2) k = thin_pick<unsigned short, 0>(TI);
+      else k = thin_pick<unsigned char, 0>(TI);
+    } else k = icls == CLS_F ? thin_pick<float, 3>(TI) : icls == CLS_D ? thin_pick<double, 3>(TI) : thin_pick<long long, 3>(TI);
+    k<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+    note_launch("transpose_thin");
+    return cuda_fail(cudaGetLastError(), "transpose_thin_kernel");
+  }
   if (raw) {
     int tile = wbytes >= 4 ? 32 : 64;
     p.tiles_i = (p.ni + tile - 1) / tile; p.tiles_o = (p.no + tile - 1) / tile;

@@ -47,6 +47,7 @@ static int grow(void** p, size_t* have, size_t want) {
 }
 int ensure_scratch(size_t bytes) { return grow(&g_ctx.scratch, &g_ctx.scratch_bytes, bytes); }
 int ensure_scratch2(size_t bytes) { return grow(&g_ctx.scratch2, &g_ctx.scratch2_bytes, bytes); }
+int ensure_scratch3(size_t bytes) { return grow(&g_ctx.scratch3, &g_ctx.scratch3_bytes, bytes); }
 
 #define LOCK std::lock_guard<std::recursive_mutex> lock__(g_mu)
 #define NEED_INIT if (!g_ctx.inited) return set_error(NCL_ERR_STATE, "ncl_init has not been called")
@@ -89,6 +90,7 @@ void ncl_shutdown(void) {
   pool_release_all();
   if (g_ctx.scratch) cudaFree(g_ctx.scratch);
   if (g_ctx.scratch2) cudaFree(g_ctx.scratch2);
+  if (g_ctx.scratch3) cudaFree(g_ctx.scratch3);
   if (g_ctx.ticket) cudaFree(g_ctx.ticket);
   if (g_ctx.consts) cudaFree(g_ctx.consts);
   if (g_ctx.pinned) cudaFreeHost(g_ctx.pinned);
@@ -496,6 +498,33 @@ int ncl_reduce(int op, const ncl_tensor* a, const int* axes, int n_axes, ncl_ten
   for (int ax = 0; ax < a->rank; ax++) if (!summed[ax]) { if (rk >= r->rank || r->dims[rk] != a->dims[ax]) return set_error(NCL_ERR_SHAPE, "reduce: result shape mismatch"); rk++; }
   if (rk != r->rank) return set_error(NCL_ERR_SHAPE, "reduce: result rank %d, expected %d", r->rank, rk);
   bool fresh = (flags & NCL_OUT_FRESH) != 0;
+  {
+    // Summed axes that do not form ONE run of adjacent axes (e.g. axes (0 2) of a rank-3 array) cannot be merged into a
+    // single reduced dimension, and the nest used to fall to the thread-per-output generic kernel (130 ms for
+    // 256x512x512).  Peel the last run off into a temporary of the result's element type, then reduce the rest from
+    // there: two fast kernels.  Exact for integers (modular) and max/min; floats round once more, within tolerance.
+    int runs = 0, t0 = -1, t1 = -1; bool empty = false;
+    for (int ax = 0; ax < a->rank; ax++) {
+      if (a->dims[ax] == 0) empty = true;
+      if (summed[ax] && (ax == 0 || !summed[ax - 1])) { runs++; t0 = ax; }
+      if (summed[ax]) t1 = ax;
+    }
+    if (runs > 1 && !empty && !a->host && !r->host && a->buf && r->buf) {
+      ncl_tensor tmp; memset(&tmp, 0, sizeof tmp);
+      tmp.dtype = r->dtype; tmp.rank = 0;
+      int64_t n = 1;
+      for (int ax = 0; ax < a->rank; ax++) if (ax < t0 || ax > t1) { tmp.dims[tmp.rank++] = a->dims[ax]; n *= a->dims[ax]; }
+      tmp.buf = ncl_alloc(ncl_storage_bytes(r->dtype, n), 0);
+      if (!tmp.buf) return NCL_ERR_NOMEM;
+      int ax1[NCL_MAX_RANK], n1 = 0, ax2[NCL_MAX_RANK], n2 = 0;
+      for (int ax = t0; ax <= t1; ax++) ax1[n1++] = ax;
+      for (int ax = 0; ax < t0; ax++) if (summed[ax]) ax2[n2++] = ax;
+      int rc = ncl_reduce(op, a, ax1, n1, &tmp, NCL_OUT_FRESH);
+      if (rc == NCL_OK) rc = ncl_reduce(op, &tmp, ax2, n2, r, flags);
+      ncl_free(tmp.buf);
+      return rc;
+    }
+  }
   return with_staging(a, 1, r, 1, !fresh, [&](Stager& st) {
     Nest* nest = new Nest;
     nest->nloops = a->rank; nest->n_in = 1; nest->n_out = 1; nest->fresh = fresh;

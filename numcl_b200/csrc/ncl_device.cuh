@@ -88,6 +88,37 @@ __device__ __forceinline__ T load_scalar(const char* base, long long idx, int lk
   }
 }
 
+// the same with the element kind known at compile time (callers hoist the kind switch out of their element loops)
+template <class T, int LK>
+__device__ __forceinline__ T load_scalar_k(const char* base, long long idx) {
+  if constexpr (LK == LK_U8)  return from_i64<T>(((const unsigned char*)base)[idx]);
+  else if constexpr (LK == LK_S8)  return from_i64<T>(((const signed char*)base)[idx]);
+  else if constexpr (LK == LK_U16) return from_i64<T>(((const unsigned short*)base)[idx]);
+  else if constexpr (LK == LK_S16) return from_i64<T>(((const short*)base)[idx]);
+  else if constexpr (LK == LK_U32) return from_i64<T>(((const unsigned int*)base)[idx]);
+  else if constexpr (LK == LK_S32) return from_i64<T>(((const int*)base)[idx]);
+  else if constexpr (LK == LK_W64) return from_i64<T>(((const long long*)base)[idx]);
+  else if constexpr (LK == LK_T64) return from_i64<T>(((const long long*)base)[idx] >> 1);
+  else if constexpr (LK == LK_F32) return from_f32<T>(((const float*)base)[idx]);
+  else if constexpr (LK == LK_F64) return from_f64<T>(((const double*)base)[idx]);
+  else if constexpr (LK == LK_P1)  return from_i64<T>((((const unsigned char*)base)[idx >> 3] >> (idx & 7)) & 1);
+  else if constexpr (LK == LK_P2)  return from_i64<T>((((const unsigned char*)base)[idx >> 2] >> ((idx & 3) * 2)) & 3);
+  else return from_i64<T>((((const unsigned char*)base)[idx >> 1] >> ((idx & 1) * 4)) & 15);
+}
+template <int K> struct LkTag { static constexpr int value = K; };
+// calls f(LkTag<kind>()) for the runtime kind lk: one warp-uniform switch, the body compiled per kind
+template <class F> __device__ __forceinline__ void dispatch_lk(int lk, F f) {
+  switch (lk) {
+    case LK_U8: f(LkTag<LK_U8>()); break;   case LK_S8: f(LkTag<LK_S8>()); break;
+    case LK_U16: f(LkTag<LK_U16>()); break; case LK_S16: f(LkTag<LK_S16>()); break;
+    case LK_U32: f(LkTag<LK_U32>()); break; case LK_S32: f(LkTag<LK_S32>()); break;
+    case LK_W64: f(LkTag<LK_W64>()); break; case LK_T64: f(LkTag<LK_T64>()); break;
+    case LK_F32: f(LkTag<LK_F32>()); break; case LK_F64: f(LkTag<LK_F64>()); break;
+    case LK_P1: f(LkTag<LK_P1>()); break;   case LK_P2: f(LkTag<LK_P2>()); break;
+    default: f(LkTag<LK_P4>()); break;
+  }
+}
+
 // %coerce of a class value into an integer slot (src/1type.lisp:673-694): (round x) half-even, then wrap.
 __device__ __forceinline__ long long round_to_i64(long long v) { return v; }
 __device__ __forceinline__ long long round_to_i64(float v) { return __float2ll_rn(v); }

@@ -62,7 +62,8 @@ struct Context {
   bool force_generic = false;
   // scratch: reduction partials, GEMM operand splits, host staging
   void* scratch = nullptr; size_t scratch_bytes = 0;
-  void* scratch2 = nullptr; size_t scratch2_bytes = 0;
+  void* scratch2 = nullptr; size_t scratch2_bytes = 0;   // host staging arena: lives for the whole call
+  void* scratch3 = nullptr; size_t scratch3_bytes = 0;   // intermediate rows of multi-pass reductions
   unsigned int* ticket = nullptr;       // zero-initialised counters for last-block reductions
   void* consts = nullptr;               // [sb64 0][sb64 1]
   void* pinned = nullptr; size_t pinned_bytes = 0;
@@ -74,6 +75,7 @@ int  cuda_fail(cudaError_t e, const char* what);
 #define NCL_TRY(call) do { int r__ = (call); if (r__ != NCL_OK) return r__; } while (0)
 int  ensure_scratch(size_t bytes);       // ctx().scratch  >= bytes
 int  ensure_scratch2(size_t bytes);
+int  ensure_scratch3(size_t bytes);
 inline void note_launch(const char* name, int n = 1) { ctx().launches += n; ctx().last_kernel = name; }
 
 // ---- expression helpers (ncl_plan.cu) -------------------------------------------------------------
@@ -85,6 +87,7 @@ bool expr_reads_output(const Expr& e);
 int launch_generic(const Nest& n);                        // k_generic.cu
 int try_elementwise(const Nest& n);                       // k_elementwise.cu
 int try_reduce(const Nest& n);                            // k_reduce.cu
+int try_dot_reduce(const Nest& n);                        // k_reduce.cu: contractions without an M x N structure
 int try_transpose(const Nest& n);                         // k_transpose.cu
 int try_gemm(const Nest& n);                              // k_gemm.cu (dispatch to f64/tf32/simt)
 int run_nest(Nest& n);                                    // ncl_plan.cu: canonicalise + dispatch

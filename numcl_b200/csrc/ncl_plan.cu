@@ -97,6 +97,7 @@ int run_nest(Nest& n) {
   for (int l = 0; l < n.nloops; l++) if (n.extent[l] == 0) empty = true;
   if (!ctx().force_generic && !empty) {
     int rc;
+    if ((rc = try_dot_reduce(n)) != NCL_ERR_UNSUPPORTED) return rc;
     if ((rc = try_gemm(n)) != NCL_ERR_UNSUPPORTED) return rc;
     if ((rc = try_reduce(n)) != NCL_ERR_UNSUPPORTED) return rc;
     if ((rc = try_transpose(n)) != NCL_ERR_UNSUPPORTED) return rc;

@@ -267,7 +267,7 @@ def test_transpose_abcd_dbca_bit_exact(nc, oracle, shape, dt):
     got = nc.einsum("abcd -> dbca", to_gpu(nc, a))
     assert_bit_exact(got, want)
     if a.size > 1000:      # ub8 -> fixnum changes the element type on the way: the converting variant of the tiled kernel
-        assert nc.lib().ncl_last_kernel() == (b"transpose_convert" if dt == "ub8" else b"transpose_tile")
+        assert nc.lib().ncl_last_kernel() in ((b"transpose_convert",) if dt == "ub8" else (b"transpose_tile", b"transpose_thin"))
 
 
 def test_transpose_c5_chain(nc, oracle):
