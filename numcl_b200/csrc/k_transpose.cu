@@ -219,13 +219,14 @@ int try_transpose(const Nest& n) {
     return cuda_fail(cudaGetLastError(), "transpose_thin_kernel");
   }
   if (raw) {
-    int tile = wbytes >= 4 ? 32 : 64;
+    int tile = wbytes >= 8 ? 32 : 64;      // 4-byte words: 64 x 64 (16 loads in flight per thread: abc -> cab 0.66 -> 1.0 of the HBM peak)
     p.tiles_i = (p.ni + tile - 1) / tile; p.tiles_o = (p.no + tile - 1) / tile;
     long long blocks = p.tiles_i * p.tiles_o * batch;
     if (blocks > 0x7fffffffLL || blocks <= 0) return NCL_ERR_UNSUPPORTED;
     int fz = (add_zero && icls == CLS_F) ? 1 : (add_zero && icls == CLS_D) ? 2 : 0;
     unsigned g = (unsigned)blocks;
     if (wbytes == 8) { if (fz == 2) transpose_raw_kernel<unsigned long long, 32, 2><<<g, 256, 0, c.stream>>>(p); else transpose_raw_kernel<unsigned long long, 32, 0><<<g, 256, 0, c.stream>>>(p); }
+    else if (wbytes == 4 && tile == 64) { if (fz == 1) transpose_raw_kernel<unsigned int, 64, 1><<<g, 256, 0, c.stream>>>(p); else transpose_raw_kernel<unsigned int, 64, 0><<<g, 256, 0, c.stream>>>(p); }
     else if (wbytes == 4) { if (fz == 1) transpose_raw_kernel<unsigned int, 32, 1><<<g, 256, 0, c.stream>>>(p); else transpose_raw_kernel<unsigned int, 32, 0><<<g, 256, 0, c.stream>>>(p); }
     else if (wbytes == 2) transpose_raw_kernel<unsigned short, 64, 0><<<g, 256, 0, c.stream>>>(p);
     else transpose_raw_kernel<unsigned char, 64, 0><<<g, 256, 0, c.stream>>>(p);

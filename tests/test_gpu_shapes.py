@@ -95,7 +95,7 @@ def test_thin_transpose_bit_exact(nc, oracle, shape, dt):
 DOTS = [("i i -> ", [(70001,), (70001,)]), ("ij ij -> i", [(300, 1000), (300, 1000)]), ("ij ij -> i", [(20000, 3), (20000, 3)]),
         ("ij ij -> ", [(300, 1001), (300, 1001)]), ("ij ij -> j", [(1000, 300), (1000, 300)]), ("ij j -> i", [(300, 1000), (1000,)]),
         ("ij j -> i", [(301, 999), (999,)]), ("i ij -> j", [(1000,), (1000, 300)]), ("i ij -> j", [(999,), (999, 301)]),
-        ("bij bj -> bi", [(40, 30, 52), (40, 52)]), ("ij i -> i", [(300, 1000), (300,)]), ("j ij -> i", [(1000,), (300, 1000)])]
+        ("ij j -> i", [(67, 4096), (4096,)]), ("bij bj -> bi", [(40, 30, 52), (40, 52)]), ("ij i -> i", [(300, 1000), (300,)]), ("j ij -> i", [(1000,), (300, 1000)])]
 
 
 @pytest.mark.parametrize("spec,shapes", DOTS)
@@ -111,7 +111,7 @@ def test_dot_like_contractions_bit_exact(nc, oracle, spec, shapes, dt):
         assert_bit_exact(got, want)
 
 
-@pytest.mark.parametrize("spec,shapes", [DOTS[0], DOTS[1], DOTS[4], DOTS[5], DOTS[7]])
+@pytest.mark.parametrize("spec,shapes", [DOTS[0], DOTS[1], DOTS[4], DOTS[5], DOTS[7], DOTS[9]])
 @pytest.mark.parametrize("dt,tol", [("f32", 1e-5), ("f64", 1e-12)])
 def test_dot_like_contractions_random_floats(nc, oracle, spec, shapes, dt, tol):
     ins = [rand(oracle, s, dt, SEED + 20 + i, 0, -1.0, 1.0) for i, s in enumerate(shapes)]
