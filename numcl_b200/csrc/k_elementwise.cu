@@ -201,8 +201,23 @@ int try_elementwise(const Nest& n) {
   }
   if (!eflat && E > 1 && !aligned(E)) { if (out_bits < 8) return NCL_ERR_UNSUPPORTED; E = 1; }
 
+  // 32-bit lanes when every slot involved is at most 32 bits wide (ub8 + ub8 -> ub15, sb16 * sb16 -> sb32, ub8 < ub8 -> bit):
+  // half the registers and no 64-bit multiply / add pairs
+  bool i32 = false;
+  if (cc == CLS_I && E > 1 && shape != S_IDIV && (is_cmp || (out_bits <= 32 && !g_dt[out.dtype].tagged))) {
+    i32 = true;
+    const bool ordered = is_cmp || shape == S_MAX || shape == S_MIN || shape == S_ABS;      // needs the true value in a signed 32-bit lane
+    for (int k = 0; k < m.n; k++) {
+      if (m.s[k].kind >= 2) continue;                                                      // the constants 0 / 1
+      const int lk = dtype_load_kind(ops[k].dtype);
+      const bool packed_scalar = lk >= LK_P1;                                                // (full nil 3) is a rank-0 ub2 array: read through load_scalar
+      if (!((lk >= LK_U8 && lk <= LK_S32) || packed_scalar) || (ordered && lk == LK_U32)) i32 = false;
+    }
+  }
   EwKernel kfn = nullptr;
-  if (shape == S_IDIV) kfn = ew_pick_idiv(E);
+  if (i32) { kfn = is_cmp ? (E == 32 ? ew_pick_cmp(shape, 4) : nullptr) : ew_pick_i32(shape, E); if (!kfn) i32 = false; }
+  if (kfn) {}
+  else if (shape == S_IDIV) kfn = ew_pick_idiv(E);
   else if (is_cmp) { if (E != 32) return NCL_ERR_UNSUPPORTED; kfn = ew_pick_cmp(shape, cc); }
   else if (cc == CLS_F) kfn = ew_pick_f32(shape, E);
   else if (cc == CLS_D) kfn = ew_pick_f64(shape, E);
@@ -278,7 +293,7 @@ int try_elementwise(const Nest& n) {
     p.epmul = (unsigned)(((1ull << (31 + s2)) + p.eper - 1) / p.eper); p.epshr = s2 - 1;
     for (int k = 0; k < m.n; k++) { p.gather[k] = gather[k]; p.gst[k] = (int)g_outer[k]; }
   }
-  int U = ew_u_host(cc == CLS_I, E);
+  int U = ew_u_host(cc != CLS_I ? 0 : i32 ? 2 : 1, E);
   unsigned long long rows = 1; for (int i = 1; i < nd; i++) rows *= p.ext[i];
   unsigned segs = (p.ext[0] + 32 * U - 1) / (32 * U);
   unsigned long long nitems = rows * segs;

@@ -57,22 +57,25 @@ template <class T> struct FnAdd0 { typedef T R; static __device__ __forceinline_
 // (+ 0 (* a b)): default transform into a fresh output
 template <class T> struct FnMul0 { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return Ops<T>::add(Ops<T>::zero(), Ops<T>::mul(a, b)); } };
 struct FnIDiv { typedef float R; static __device__ __forceinline__ float f(long long a, long long b) { return ratio_to_f32(a, b); } };
-template <class T> struct FnEq { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a == b; } };
-template <class T> struct FnNe { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a != b; } };
-template <class T> struct FnLe { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a <= b; } };
-template <class T> struct FnGe { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a >= b; } };
-template <class T> struct FnLt { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a < b; } };
-template <class T> struct FnGt { typedef long long R; static __device__ __forceinline__ long long f(T a, T b) { return a > b; } };
-struct FnAnd { typedef long long R; static __device__ __forceinline__ long long f(long long a, long long b) { return a & b; } };
-struct FnIor { typedef long long R; static __device__ __forceinline__ long long f(long long a, long long b) { return a | b; } };
-struct FnXor { typedef long long R; static __device__ __forceinline__ long long f(long long a, long long b) { return a ^ b; } };
+// comparisons produce 0 / 1 for a packed bit array: 32-bit results (32 of them per thread) keep the register count down
+template <class T> struct FnEq { typedef int R; static __device__ __forceinline__ int f(T a, T b) { return a == b; } };
+template <class T> struct FnNe { typedef int R; static __device__ __forceinline__ int f(T a, T b) { return a != b; } };
+template <class T> struct FnLe { typedef int R; static __device__ __forceinline__ int f(T a, T b) { return a <= b; } };
+template <class T> struct FnGe { typedef int R; static __device__ __forceinline__ int f(T a, T b) { return a >= b; } };
+template <class T> struct FnLt { typedef int R; static __device__ __forceinline__ int f(T a, T b) { return a < b; } };
+template <class T> struct FnGt { typedef int R; static __device__ __forceinline__ int f(T a, T b) { return a > b; } };
+template <class T> struct FnAndT { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return a & b; } };
+template <class T> struct FnIorT { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return a | b; } };
+template <class T> struct FnXorT { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return a ^ b; } };
+typedef FnAndT<long long> FnAnd; typedef FnIorT<long long> FnIor; typedef FnXorT<long long> FnXor;
 // unary
 template <class T> struct FnCopy { typedef T R; static __device__ __forceinline__ T f(T a) { return a; } };
 template <class T> struct FnAdd0U { typedef T R; static __device__ __forceinline__ T f(T a) { return Ops<T>::add(Ops<T>::zero(), a); } };
 template <class T> struct FnNeg { typedef T R; static __device__ __forceinline__ T f(T a) { return Ops<T>::neg(a); } };
 template <class T> struct FnAbs { typedef T R; static __device__ __forceinline__ T f(T a) { return Ops<T>::abs_(a); } };
 template <class T> struct FnSquare { typedef T R; static __device__ __forceinline__ T f(T a) { return Ops<T>::mul(a, a); } };
-struct FnNot { typedef long long R; static __device__ __forceinline__ long long f(long long a) { return ~a; } };
+template <class T> struct FnNotT { typedef T R; static __device__ __forceinline__ T f(T a) { return ~a; } };
+typedef FnNotT<long long> FnNot;
 template <class T> struct FnSqrt;
 template <> struct FnSqrt<float> { typedef float R; static __device__ __forceinline__ float f(float a) { return __fsqrt_rn(a); } };
 template <> struct FnSqrt<double> { typedef double R; static __device__ __forceinline__ double f(double a) { return __dsqrt_rn(a); } };
@@ -282,8 +285,11 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
 typedef void (*EwKernel)(const EwParams);
 // chunks per thread and item.  The integer class computes in 64-bit lanes: 4 chunks of 8 or 16 narrow elements took 244
 // registers / spilled, so wide chunks get fewer of them.
-template <class TI, int E> constexpr int ew_u() { return E == 32 ? 1 : (std::is_integral<TI>::value ? (E >= 16 ? 1 : E >= 4 ? 2 : 4) : 4); }
-inline int ew_u_host(bool int_class, int E) { return E == 32 ? 1 : (int_class ? (E >= 16 ? 1 : E >= 4 ? 2 : 4) : 4); }
+template <class TI, int E> constexpr int ew_u() {
+  return E == 32 ? 1 : !std::is_integral<TI>::value ? 4 : sizeof(TI) == 4 ? (E >= 8 ? 2 : 4) : (E >= 16 ? 1 : E >= 4 ? 2 : 4);
+}
+// lanes: 0 = float / double, 1 = 64-bit integer lanes, 2 = 32-bit integer lanes
+inline int ew_u_host(int lanes, int E) { return E == 32 ? 1 : lanes == 0 ? 4 : lanes == 2 ? (E >= 8 ? 2 : 4) : (E >= 16 ? 1 : E >= 4 ? 2 : 4); }
 template <class TI, class F, int NIN, int E> static EwKernel kern() { return (EwKernel)ew_kernel<TI, F, NIN, E, ew_u<TI, E>()>; }
 
 template <class T, int E> static EwKernel pick_arith(int shape) {     // T-class in, T-class out
@@ -313,6 +319,14 @@ template <int E> static EwKernel pick_int(int shape) {
     default: return nullptr;
   }
 }
+template <int E> static EwKernel pick_int32(int shape) {
+  if (EwKernel k = pick_arith<int, E>(shape)) return k;
+  switch (shape) {
+    case S_AND: return kern<int, FnAndT<int>, 2, E>(); case S_IOR: return kern<int, FnIorT<int>, 2, E>(); case S_XOR: return kern<int, FnXorT<int>, 2, E>();
+    case S_NOT: return kern<int, FnNotT<int>, 1, E>();
+    default: return nullptr;
+  }
+}
 template <class T, int E> static EwKernel pick_cmp(int shape) {
   switch (shape) {
     case S_EQ: return kern<T, FnEq<T>, 2, E>(); case S_NE: return kern<T, FnNe<T>, 2, E>(); case S_LE: return kern<T, FnLe<T>, 2, E>();
@@ -326,5 +340,6 @@ template <class T, int E> static EwKernel pick_cmp(int shape) {
 EwKernel ew_pick_f32(int shape, int E);
 EwKernel ew_pick_f64(int shape, int E);
 EwKernel ew_pick_int(int shape, int E);
+EwKernel ew_pick_i32(int shape, int E);      // 32-bit lanes, E = 4 / 8 / 16
 EwKernel ew_pick_cmp(int shape, int cls);
 EwKernel ew_pick_idiv(int E);

@@ -167,7 +167,13 @@ __global__ void __launch_bounds__(256) reduce_row_kernel(const __grid_constant__
 #pragma unroll
         for (int u = 0; u < 4; u++) acc[u] = fold_elems<T, OP, E>(acc[u], v[u]);
       }
-      for (; c < nch; c += TPR) { T v[E]; fetch_elems<T, E, DOT>(p, vbase + c * E, vbase2 + c * E * rs2, bc, v); acc[0] = fold_elems<T, OP, E>(acc[0], v); }
+      if (c < nch) {                                        // up to three chunks left for this thread: issued together
+        T v[3][E]; bool ok[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) { ok[u] = c + u * TPR < nch; const long long cc = ok[u] ? c + u * TPR : c; fetch_elems<T, E, DOT>(p, vbase + cc * E, vbase2 + cc * E * rs2, bc, v[u]); }
+#pragma unroll
+        for (int u = 0; u < 3; u++) if (ok[u]) acc[u] = fold_elems<T, OP, E>(acc[u], v[u]);
+      }
       }
       if (p.vec == 2) {
         const long long t0 = head + nch * E, extra = head + (p.cols - t0);       // fewer than 2E scalar elements
@@ -828,17 +834,6 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
         return NCL_OK;
       }
     }
-    // ---- rows back to back and at most 2 KB long: the staged kernel --------------------------------------------------
-    if (!dot && nk == 1 && kd[0].sin == R && R * sb / 8 <= 2048 && p.rows >= 64 && aligned16(in, in.offset)) {
-      const long long row_bytes = R * sb / 8;
-      long long RT = 32768 / row_bytes / Evec * Evec;
-      p.seg = RT; p.nseg = R <= 8 ? 1 : R <= 16 ? 2 : R <= 32 ? 4 : R <= 64 ? 8 : R <= 128 ? 16 : 32;
-      RedKernel kfn = cls == CLS_F ? staged_pick<float>(op) : cls == CLS_D ? staged_pick<double>(op) : staged_pick<long long>(op);
-      long long tiles = (p.rows + RT - 1) / RT, cap = persistent_blocks((const void*)kfn);
-      kfn<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, c.stream>>>(p);
-      note_launch("reduce_rows_staged");
-      return cuda_fail(cudaGetLastError(), "reduce_rows_staged_kernel");
-    }
     bool vec = (R % Evec == 0) && aligned16(in, in.offset);
     for (int i = 0; i < nk && vec; i++) if (((kd[i].sin * sb) / 8) % 16) vec = false;
     if (dot && vec && rd[0].sin2 == 1) { vec = aligned16(n.in[ib], n.in[ib].offset); for (int i = 0; i < nk && vec; i++) if (!b_vec_ok(kd[i].sin2)) vec = false; }
@@ -851,13 +846,24 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
       note_launch("dot_matvec");
       return cuda_fail(cudaGetLastError(), "dot_matvec_kernel");
     }
+    // ---- rows back to back, at most 2 KB long and not on chunk boundaries: the staged kernel -------------------------------
+    if (!dot && !vec && nk == 1 && kd[0].sin == R && R * sb / 8 <= 2048 && p.rows >= 64 && aligned16(in, in.offset)) {
+      const long long row_bytes = R * sb / 8;
+      long long RT = 32768 / row_bytes / Evec * Evec;
+      p.seg = RT; p.nseg = R <= 8 ? 1 : R <= 16 ? 2 : R <= 32 ? 4 : R <= 64 ? 8 : R <= 128 ? 16 : 32;
+      RedKernel kfn = cls == CLS_F ? staged_pick<float>(op) : cls == CLS_D ? staged_pick<double>(op) : staged_pick<long long>(op);
+      long long tiles = (p.rows + RT - 1) / RT, cap = persistent_blocks((const void*)kfn);
+      kfn<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, c.stream>>>(p);
+      note_launch("reduce_rows_staged");
+      return cuda_fail(cudaGetLastError(), "reduce_rows_staged_kernel");
+    }
     int vmode = vec ? 1 : ((!dot && R > 16 && Evec > 1 && ((uintptr_t)in.base % 16) == 0) ? 2 : 0);
     p.vec = vmode; int E = vmode ? Evec : 1;
     long long chunks = vmode ? R / E : R;
     int which; long long blocks;
     if (vmode == 0 && R <= 16) { which = KROW1; blocks = (p.rows + 1023) / 1024; }
     else if (vmode == 1 && chunks <= 4) { which = KROW1; blocks = (p.rows + 1023) / 1024; }
-    else if (chunks <= 16 && vmode) { which = KROW4; blocks = (p.rows + 63) / 64; }
+    else if (chunks <= 32 && vmode) { which = KROW4; blocks = (p.rows + 63) / 64; }      // up to 8 chunks per thread, 4 + 3 in flight
     else if (chunks >= 512) { which = KROW256; blocks = p.rows; }
     else { which = KROW32; blocks = (p.rows + 7) / 8; }
     if (blocks > 0x7fffffffLL) return NCL_ERR_UNSUPPORTED;

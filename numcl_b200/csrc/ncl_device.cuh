@@ -56,14 +56,17 @@ template <> struct ClsT<CLS_D> { typedef double T; };
 
 template <class T> __device__ __forceinline__ T from_i64(long long v);
 template <> __device__ __forceinline__ long long from_i64<long long>(long long v) { return v; }
+template <> __device__ __forceinline__ int from_i64<int>(long long v) { return (int)v; }     // 32-bit lane class: values mod 2^32
 template <> __device__ __forceinline__ float from_i64<float>(long long v) { return __ll2float_rn(v); }
 template <> __device__ __forceinline__ double from_i64<double>(long long v) { return __ll2double_rn(v); }
 template <class T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ long long from_f32<long long>(float v) { return (long long)v; }   // unreachable by typing
+template <> __device__ __forceinline__ int from_f32<int>(float v) { return (int)v; }                        // unreachable by typing
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ double from_f32<double>(float v) { return (double)v; }
 template <class T> __device__ __forceinline__ T from_f64(double v);
 template <> __device__ __forceinline__ long long from_f64<long long>(double v) { return (long long)v; }   // unreachable
+template <> __device__ __forceinline__ int from_f64<int>(double v) { return (int)v; }                      // unreachable
 template <> __device__ __forceinline__ float from_f64<float>(double v) { return __double2float_rn(v); }   // unreachable
 template <> __device__ __forceinline__ double from_f64<double>(double v) { return v; }
 
@@ -121,12 +124,15 @@ template <class F> __device__ __forceinline__ void dispatch_lk(int lk, F f) {
 
 // %coerce of a class value into an integer slot (src/1type.lisp:673-694): (round x) half-even, then wrap.
 __device__ __forceinline__ long long round_to_i64(long long v) { return v; }
+__device__ __forceinline__ long long round_to_i64(int v) { return v; }
 __device__ __forceinline__ long long round_to_i64(float v) { return __float2ll_rn(v); }
 __device__ __forceinline__ long long round_to_i64(double v) { return __double2ll_rn(v); }
 __device__ __forceinline__ float to_f32(long long v) { return __ll2float_rn(v); }
+__device__ __forceinline__ float to_f32(int v) { return __int2float_rn(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(double v) { return __double2float_rn(v); }
 __device__ __forceinline__ double to_f64(long long v) { return __ll2double_rn(v); }
+__device__ __forceinline__ double to_f64(int v) { return (double)v; }
 __device__ __forceinline__ double to_f64(float v) { return (double)v; }
 __device__ __forceinline__ double to_f64(double v) { return v; }
 
@@ -205,6 +211,20 @@ template <> struct Ops<long long> {
   static __device__ __forceinline__ T mx(T a, T b) { return a >= b ? a : b; }
   static __device__ __forceinline__ T mn(T a, T b) { return a <= b ? a : b; }
   static __device__ __forceinline__ T neg(T a) { return (T)(0ull - (U)a); }
+  static __device__ __forceinline__ T abs_(T a) { return a < 0 ? neg(a) : a; }
+  static __device__ __forceinline__ T zero() { return 0; }
+};
+// 32-bit lanes for integer arrays whose slots (inputs and result) are at most 32 bits wide: + - * and the bitwise functions
+// are exact modulo 2^32, which is all a store into a <= 32-bit slot keeps (%coerce masks / wraps to the slot's width);
+// max / min / abs / comparisons are only routed here when every operand fits a signed 32-bit value.
+template <> struct Ops<int> {
+  typedef int T; typedef unsigned int U;
+  static __device__ __forceinline__ T add(T a, T b) { return (T)((U)a + (U)b); }
+  static __device__ __forceinline__ T sub(T a, T b) { return (T)((U)a - (U)b); }
+  static __device__ __forceinline__ T mul(T a, T b) { return (T)((U)a * (U)b); }
+  static __device__ __forceinline__ T mx(T a, T b) { return a >= b ? a : b; }
+  static __device__ __forceinline__ T mn(T a, T b) { return a <= b ? a : b; }
+  static __device__ __forceinline__ T neg(T a) { return (T)(0u - (U)a); }
   static __device__ __forceinline__ T abs_(T a) { return a < 0 ? neg(a) : a; }
   static __device__ __forceinline__ T zero() { return 0; }
 };
