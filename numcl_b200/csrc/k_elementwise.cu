@@ -216,12 +216,13 @@ int try_elementwise(const Nest& n) {
   }
   EwKernel kfn = nullptr;
   if (i32) { kfn = is_cmp ? (E == 32 ? ew_pick_cmp(shape, 4) : nullptr) : ew_pick_i32(shape, E); if (!kfn) i32 = false; }
-  if (kfn) {}
-  else if (shape == S_IDIV) kfn = ew_pick_idiv(E);
-  else if (is_cmp) { if (E != 32) return NCL_ERR_UNSUPPORTED; kfn = ew_pick_cmp(shape, cc); }
-  else if (cc == CLS_F) kfn = ew_pick_f32(shape, E);
-  else if (cc == CLS_D) kfn = ew_pick_f64(shape, E);
-  else kfn = ew_pick_int(shape, E);
+  if (!kfn) {
+    if (shape == S_IDIV) kfn = ew_pick_idiv(E);
+    else if (is_cmp) { if (E != 32) return NCL_ERR_UNSUPPORTED; kfn = ew_pick_cmp(shape, cc); }
+    else if (cc == CLS_F) kfn = ew_pick_f32(shape, E);
+    else if (cc == CLS_D) kfn = ew_pick_f64(shape, E);
+    else kfn = ew_pick_int(shape, E);
+  }
   if (!kfn) return NCL_ERR_UNSUPPORTED;
 
   EwParams p; memset(&p, 0, sizeof p);

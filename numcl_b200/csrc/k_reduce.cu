@@ -127,10 +127,7 @@ __device__ __forceinline__ T block_combine(T v) {
 // thread per row the fold is the reference's own left-to-right order.  vec == 2: rows whose length or start is not a
 // multiple of the 16-byte chunk: scalar head up to the first aligned element, vector body, scalar tail.
 template <class T, int OP, int E, int TPR, bool DOT>
-__global__ void __launch_bounds__(256) reduce_row_kernel(const __grid_constant__ RedParams p) {
-  constexpr int RPB = 256 / TPR;
-  long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR;
-  int t = threadIdx.x % TPR;
+__device__ __forceinline__ void reduce_one_row(const RedParams& p, const long long row, const int t) {
   bool live = row < p.rows;
   long long ibase = p.in_off, obase = p.out_off, ibase2 = p.in2_off;
   if (live) {
@@ -167,7 +164,9 @@ __global__ void __launch_bounds__(256) reduce_row_kernel(const __grid_constant__
 #pragma unroll
         for (int u = 0; u < 4; u++) acc[u] = fold_elems<T, OP, E>(acc[u], v[u]);
       }
-      if (c < nch) {                                        // up to three chunks left for this thread: issued together
+      if constexpr (DOT) {                                  // (two operands: the batch below doubled the register count)
+        for (; c < nch; c += TPR) { T v[E]; fetch_elems<T, E, DOT>(p, vbase + c * E, vbase2 + c * E * rs2, bc, v); acc[0] = fold_elems<T, OP, E>(acc[0], v); }
+      } else if (c < nch) {                                 // up to three chunks left for this thread: issued together
         T v[3][E]; bool ok[3];
 #pragma unroll
         for (int u = 0; u < 3; u++) { ok[u] = c + u * TPR < nch; const long long cc = ok[u] ? c + u * TPR : c; fetch_elems<T, E, DOT>(p, vbase + cc * E, vbase2 + cc * E * rs2, bc, v[u]); }
@@ -194,6 +193,12 @@ __global__ void __launch_bounds__(256) reduce_row_kernel(const __grid_constant__
     T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, obase, p.out_lk);
     store_scalar<T>(p.out, obase, p.sk, Red<T, OP>::f(init, a));          // r <- fn(r, partial)
   }
+}
+// 256 / TPR rows per CTA.  (Persistent warps walking the short rows with a grid stride were tried for TPR <= 32: no gain,
+// 0.64 -> 0.61 on rows of 512 floats.)
+template <class T, int OP, int E, int TPR, bool DOT>
+__global__ void __launch_bounds__(256) reduce_row_kernel(const __grid_constant__ RedParams p) {
+  reduce_one_row<T, OP, E, TPR, DOT>(p, (long long)blockIdx.x * (256 / TPR) + threadIdx.x / TPR, threadIdx.x % TPR);
 }
 
 // ---- short rows: one thread per row, four rows per thread ---------------------------------------------------
@@ -574,10 +579,23 @@ __global__ void __launch_bounds__(256) reduce_col_kernel(const __grid_constant__
 #pragma unroll
       for (int i = 0; i < E; i++) acc[i] = Red<T, OP>::f(acc[i], v[u][i]);
   }
-  for (; r < r1; r++) {
-    T v[E]; fetch_elems<T, E, DOT>(p, ibase + r * p.r_stride, ibase2 + r * rs2, bc, v);
+  if constexpr (DOT) {
+    for (; r < r1; r++) {
+      T v[E]; fetch_elems<T, E, DOT>(p, ibase + r * p.r_stride, ibase2 + r * rs2, bc, v);
 #pragma unroll
-    for (int i = 0; i < E; i++) acc[i] = Red<T, OP>::f(acc[i], v[i]);
+      for (int i = 0; i < E; i++) acc[i] = Red<T, OP>::f(acc[i], v[i]);
+    }
+  } else if (r < r1) {                                      // fewer than UR rows left: issued together, not one latency each
+    constexpr int TR = E == 1 ? 15 : 3;
+    T v[TR][E]; bool ok[TR];
+#pragma unroll
+    for (int u = 0; u < TR; u++) { ok[u] = r + u < r1; const long long rr = ok[u] ? r + u : r; fetch_elems<T, E, DOT>(p, ibase + rr * p.r_stride, ibase2 + rr * rs2, bc, v[u]); }
+#pragma unroll
+    for (int u = 0; u < TR; u++)
+      if (ok[u]) {
+#pragma unroll
+        for (int i = 0; i < E; i++) acc[i] = Red<T, OP>::f(acc[i], v[u][i]);
+      }
   }
   if (p.nseg > 1) {
     T* part = (T*)p.partial + ((long long)blockIdx.y * nq + q) * E;
