@@ -569,6 +569,8 @@ __global__ void __launch_bounds__(256) reduce_col_kernel(const __grid_constant__
   long long r = r0 + 1;
   // rows in flight per thread: 4 x 16 bytes on the vector path; the scalar path (ragged column count) moves only one
   // element per load and needs 16 rows to keep a comparable number of bytes in flight (0.17 -> of the HBM peak with 4)
+  // (8 rows in flight for 16-byte chunks was tried after ncu showed the kernel latency-bound at 49 % of DRAM bandwidth: worse everywhere,
+  // 0.96 -> 0.73 on (1024,512,512) axis 1 and 0.57 -> 0.25 on 8192^2 fixnum -- more rows per thread means more DRAM pages open at once)
   constexpr int UR = E == 1 ? 16 : 4;
   for (; r + UR - 1 < r1; r += UR) {
     T v[UR][E];

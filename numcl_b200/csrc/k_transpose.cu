@@ -117,37 +117,115 @@ __global__ void __launch_bounds__(256) transpose_thin_kernel(const __grid_consta
   auto slot = [](int i, int o) { return I_SHORT ? i * PITCH + o : o * PITCH + i; };
   // load: threads run along i (input-contiguous) first.  All of a thread's loads are issued before the first shared-memory
   // store: out-of-range positions read a valid dummy address instead of branching around the load (with a branch per element
-  // ptxas kept ONE load in flight per thread).
+  // ptxas kept ONE load in flight per thread).  Element e = tid + 256 k of the tile is (i, o) = (e % TI, e / TI): the part
+  // that depends on k is a compile-time constant, so an address is one multiply-add from a per-thread base (ncu on the first
+  // version: 84 % issue-slot utilisation -- index arithmetic, not memory, was the limit).
   constexpr int N = TI * TO / 256;
+  const int tid = threadIdx.x;
   V v[N];
+  {
+    constexpr bool NARROW = TI <= 256;                      // one i per thread, o advances by 256 / TI per step
+    const int ti0 = NARROW ? tid % TI : tid, to0 = NARROW ? tid / TI : 0;
+    const long long base = ibase + (o0 + to0) * p.in_so + i0 + ti0;
 #pragma unroll
-  for (int k = 0; k < N; k++) {
-    const int e = threadIdx.x + k * 256, i = e % TI, o = e / TI;
-    const bool ok = i0 + i < p.ni && o0 + o < p.no;
-    const long long idx = ok ? ibase + (o0 + o) * p.in_so + i0 + i : p.in_off;
-    if constexpr (MODE == 3) v[k] = load_scalar<V>(p.in, idx, p.lk);
-    else v[k] = __ldg((const V*)p.in + idx);
+    for (int k = 0; k < N; k++) {
+      const int di = NARROW ? 0 : 256 * (k % (TI / 256 > 0 ? TI / 256 : 1)), dO = NARROW ? k * (256 / (TI < 256 ? TI : 256)) : k / (TI / 256 > 0 ? TI / 256 : 1);
+      const bool ok = i0 + ti0 + di < p.ni && o0 + to0 + dO < p.no;
+      const long long idx = ok ? base + (long long)dO * p.in_so + di : p.in_off;
+      if constexpr (MODE == 3) v[k] = load_scalar<V>(p.in, idx, p.lk);
+      else v[k] = __ldg((const V*)p.in + idx);
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const int di = NARROW ? 0 : 256 * (k % (TI / 256 > 0 ? TI / 256 : 1)), dO = NARROW ? k * (256 / (TI < 256 ? TI : 256)) : k / (TI / 256 > 0 ? TI / 256 : 1);
+      tile[slot(ti0 + di, to0 + dO)] = v[k];
+    }
   }
-#pragma unroll
-  for (int k = 0; k < N; k++) { const int e = threadIdx.x + k * 256; tile[slot(e % TI, e / TI)] = v[k]; }
   __syncthreads();
   // store: threads run along o (output-contiguous) first
+  {
+    constexpr bool NARROW = TO <= 256;
+    const int so0 = NARROW ? tid % TO : tid, si0 = NARROW ? tid / TO : 0;
+    const long long base = obase + (i0 + si0) * p.out_si + o0 + so0;
 #pragma unroll
-  for (int k = 0; k < N; k++) { const int e = threadIdx.x + k * 256; v[k] = tile[slot(e / TO, e % TO)]; }
+    for (int k = 0; k < N; k++) {
+      const int dO = NARROW ? 0 : 256 * (k % (TO / 256 > 0 ? TO / 256 : 1)), di = NARROW ? k * (256 / (TO < 256 ? TO : 256)) : k / (TO / 256 > 0 ? TO / 256 : 1);
+      v[k] = tile[slot(si0 + di, so0 + dO)];
+    }
 #pragma unroll
-  for (int k = 0; k < N; k++) {
-    const int e = threadIdx.x + k * 256, o = e % TO, i = e / TO;
-    if (i0 + i < p.ni && o0 + o < p.no) {
-      V w = v[k];
-      const long long idx = obase + (i0 + i) * p.out_si + o0 + o;
-      if constexpr (MODE == 1) w = (V)__float_as_uint(__fadd_rn(0.0f, __uint_as_float((unsigned)w)));
-      if constexpr (MODE == 2) w = (V)__double_as_longlong(__dadd_rn(0.0, __longlong_as_double((long long)w)));
-      if constexpr (MODE == 3) { if (p.add_zero) w = Ops<V>::add(Ops<V>::zero(), w); store_scalar<V>(p.out, idx, p.sk, w); }
-      else ((V*)p.out)[idx] = w;
+    for (int k = 0; k < N; k++) {
+      const int dO = NARROW ? 0 : 256 * (k % (TO / 256 > 0 ? TO / 256 : 1)), di = NARROW ? k * (256 / (TO < 256 ? TO : 256)) : k / (TO / 256 > 0 ? TO / 256 : 1);
+      if (i0 + si0 + di < p.ni && o0 + so0 + dO < p.no) {
+        V w = v[k];
+        const long long idx = base + (long long)di * p.out_si + dO;
+        if constexpr (MODE == 1) w = (V)__float_as_uint(__fadd_rn(0.0f, __uint_as_float((unsigned)w)));
+        if constexpr (MODE == 2) w = (V)__double_as_longlong(__dadd_rn(0.0, __longlong_as_double((long long)w)));
+        if constexpr (MODE == 3) { if (p.add_zero) w = Ops<V>::add(Ops<V>::zero(), w); store_scalar<V>(p.out, idx, p.sk, w); }
+        else ((V*)p.out)[idx] = w;
+      }
     }
   }
 }
+// (N, C) <-> (C, N) with C <= 8, entirely in registers: a thread owns E = 16 / sizeof(V) consecutive positions of the long
+// loop, i.e. C whole chunks on the side where the short loop is contiguous and one chunk of each of the C rows on the other
+// side; every index below is a compile-time constant.  No shared memory, no barrier, C 128-bit loads in flight per thread and
+// fully coalesced 128-bit accesses on both sides.  FWD: input (N, C) rows back to back -> output C rows of length N.
+template <class V, int C, bool FWD, int MODE>
+__global__ void __launch_bounds__(256) transpose_reg_kernel(const __grid_constant__ TrParams p) {
+  constexpr int E = 16 / (int)sizeof(V);
+  const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long n_long = FWD ? p.no : p.ni;
+  if (q * E >= n_long) return;
+  auto fix = [](V w) {
+    if constexpr (MODE == 1) return (V)__float_as_uint(__fadd_rn(0.0f, __uint_as_float((unsigned)w)));
+    else if constexpr (MODE == 2) return (V)__double_as_longlong(__dadd_rn(0.0, __longlong_as_double((long long)w)));
+    else return w;
+  };
+  const V* in = (const V*)p.in + p.in_off; V* out = (V*)p.out + p.out_off;
+  if (q * E + E <= n_long) {
+    V a[C][E], b[C][E];
+    if constexpr (FWD) {
+#pragma unroll
+      for (int k = 0; k < C; k++) { Chunk<16> c; ld_chunk(c, (const char*)(in + (q * E * C + k * E))); 
+#pragma unroll
+        for (int j = 0; j < E; j++) a[k][j] = (V)chunk_get<8 * (int)sizeof(V)>(c, j); }
+#pragma unroll
+      for (int f = 0; f < C * E; f++) b[f % C][f / C] = fix(a[f / E][f % E]);           // flat f = o_local * C + i
+#pragma unroll
+      for (int i = 0; i < C; i++) { Chunk<16> c;
+#pragma unroll
+        for (int j = 0; j < E; j++) chunk_put<8 * (int)sizeof(V)>(c, j, (unsigned long long)b[i][j]);
+        st_chunk(c, (char*)(out + (i * p.out_si + q * E))); }
+    } else {
+#pragma unroll
+      for (int o = 0; o < C; o++) { Chunk<16> c; ld_chunk(c, (const char*)(in + (o * p.in_so + q * E)));
+#pragma unroll
+        for (int j = 0; j < E; j++) a[o][j] = (V)chunk_get<8 * (int)sizeof(V)>(c, j); }
+#pragma unroll
+      for (int f = 0; f < C * E; f++) b[f / E][f % E] = fix(a[f % C][f / C]);           // flat f = i_local * C + o
+#pragma unroll
+      for (int k = 0; k < C; k++) { Chunk<16> c;
+#pragma unroll
+        for (int j = 0; j < E; j++) chunk_put<8 * (int)sizeof(V)>(c, j, (unsigned long long)b[k][j]);
+        st_chunk(c, (char*)(out + (q * E * C + k * E))); }
+    }
+  } else {                                                  // fewer than E positions left on the long loop
+    for (long long l = q * E; l < n_long; l++)
+      for (int s = 0; s < C; s++) {
+        if constexpr (FWD) out[s * p.out_si + l] = fix(in[l * C + s]);
+        else out[l * C + s] = fix(in[s * p.in_so + l]);
+      }
+  }
+}
 typedef void (*TrKernel)(const TrParams);
+template <class V, bool FWD, int MODE> static TrKernel reg_pick(int c) {
+  switch (c) {
+    case 2: return transpose_reg_kernel<V, 2, FWD, MODE>; case 3: return transpose_reg_kernel<V, 3, FWD, MODE>;
+    case 4: return transpose_reg_kernel<V, 4, FWD, MODE>; case 5: return transpose_reg_kernel<V, 5, FWD, MODE>;
+    case 6: return transpose_reg_kernel<V, 6, FWD, MODE>; case 7: return transpose_reg_kernel<V, 7, FWD, MODE>;
+    case 8: return transpose_reg_kernel<V, 8, FWD, MODE>; default: return nullptr;
+  }
+}
 template <class V, int MODE> static TrKernel thin_pick(int ti) {
   switch (ti) {
     case 4: return transpose_thin_kernel<V, 4, 1024, MODE>;  case 8: return transpose_thin_kernel<V, 8, 512, MODE>;
@@ -198,6 +276,28 @@ int try_transpose(const Nest& n) {
              g_dt[in.dtype].tagged == g_dt[out.dtype].tagged && g_dt[out.dtype].value_bits >= g_dt[in.dtype].value_bits &&
              g_dt[in.dtype].is_signed == g_dt[out.dtype].is_signed);
   int wbytes = g_dt[in.dtype].slot_bits / 8;
+  if (raw && nb == 0 && (wbytes == 4 || wbytes == 8) && ((p.ni >= 2 && p.ni <= 8 && p.no >= 1024) || (p.no >= 2 && p.no <= 8 && p.ni >= 1024))) {
+    // (N, C) <-> (C, N), C <= 8: the register kernel, when both sides allow 128-bit accesses
+    const bool fwd = p.ni <= 8;
+    auto al = [&](const Operand& o, long long off) { return (((uintptr_t)o.base + off * wbytes) % 16) == 0; };
+    const bool ok = al(in, in.offset) && al(out, out.offset) &&
+                    (fwd ? (p.in_so == p.ni && (p.out_si * wbytes) % 16 == 0) : (p.out_si == p.no && (p.in_so * wbytes) % 16 == 0));
+    if (ok) {
+      const int fz = (add_zero && icls == CLS_F) ? 1 : (add_zero && icls == CLS_D) ? 2 : 0;
+      const int cshort = (int)(fwd ? p.ni : p.no); const long long nlong = fwd ? p.no : p.ni;
+      TrKernel k;
+      if (wbytes == 4) k = fwd ? (fz ? reg_pick<unsigned int, true, 1>(cshort) : reg_pick<unsigned int, true, 0>(cshort))
+                               : (fz ? reg_pick<unsigned int, false, 1>(cshort) : reg_pick<unsigned int, false, 0>(cshort));
+      else k = fwd ? (fz ? reg_pick<unsigned long long, true, 2>(cshort) : reg_pick<unsigned long long, true, 0>(cshort))
+                   : (fz ? reg_pick<unsigned long long, false, 2>(cshort) : reg_pick<unsigned long long, false, 0>(cshort));
+      const long long threads = (nlong + 16 / wbytes - 1) / (16 / wbytes), blocks = (threads + 255) / 256;
+      if (k && blocks <= 0x7fffffffLL) {
+        k<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+        note_launch("transpose_reg");
+        return cuda_fail(cudaGetLastError(), "transpose_reg_kernel");
+      }
+    }
+  }
   if ((p.ni <= 16 || p.no <= 16) && (p.ni >= 128 || p.no >= 128)) {
     // thin plane: rectangular tiles, short side first
     const long long sh = p.ni <= p.no ? p.ni : p.no;

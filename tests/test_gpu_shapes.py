@@ -84,7 +84,8 @@ def test_reduce_into_supplied_output_accumulates(nc, oracle):
 
 
 # ---- tall-and-thin transposes ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(50000, 3), (3, 50000), (20000, 48), (48, 20000), (4099, 7), (7, 4099), (1000, 33), (70001, 2), (2, 70001)])
+@pytest.mark.parametrize("shape", [(50000, 3), (3, 50000), (20000, 48), (48, 20000), (4099, 7), (7, 4099), (1000, 33), (70001, 2), (2, 70001),
+                                   (40000, 5), (5, 40000), (40000, 8), (8, 40000), (2, 40000), (40000, 2), (40004, 6), (6, 40004), (7, 40000), (4, 4096), (4096, 4)])
 @pytest.mark.parametrize("dt", ["f32", "f64", "fixnum", "ub8", "sb16"])
 def test_thin_transpose_bit_exact(nc, oracle, shape, dt):
     a = rand(oracle, shape, dt, SEED + 7, 1 if dt in ("f32", "f64") else 0, *((-8, 8) if dt != "ub8" else (0, 255)))
