@@ -304,6 +304,50 @@ __global__ void __launch_bounds__(256) dot_matvec_kernel(const __grid_constant__
   }
 }
 
+// ---- rows of 2..8 elements, back to back: entirely in registers ---------------------------------------------------------
+// A thread owns E = (elements per 16-byte chunk) consecutive rows = C whole chunks: C 128-bit loads in flight, every element
+// index a compile-time constant, each row folded left to right (the reference's own order), E adjacent results stored.
+// No shared memory, no barrier, no idle lanes whatever C is ((sum a :axes 1) of an (N,3) array: 0.56 staged -> this).
+template <class T, int OP, int E, int C>
+__global__ void __launch_bounds__(256) reduce_rows_reg_kernel(const __grid_constant__ RedParams p) {
+  const long long row0 = ((long long)blockIdx.x * 256 + threadIdx.x) * E;
+  if (row0 >= p.rows) return;
+  if (row0 + E <= p.rows) {
+    T a[C][E];
+#pragma unroll
+    for (int k = 0; k < C; k++) load_elems<T, E>(p.in, p.in_off + row0 * C + k * E, p.lk, true, a[k]);
+#pragma unroll
+    for (int j = 0; j < E; j++) {
+      T r = a[(j * C) / E][(j * C) % E];
+#pragma unroll
+      for (int i = 1; i < C; i++) r = Red<T, OP>::f(r, a[(j * C + i) / E][(j * C + i) % E]);
+      const long long ob = p.out_off + (row0 + j) * p.kout[0];
+      T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, ob, p.out_lk);
+      store_scalar<T>(p.out, ob, p.sk, Red<T, OP>::f(init, r));
+    }
+  } else {                                                  // fewer than E rows left
+    for (long long row = row0; row < p.rows; row++) {
+      T r = load_scalar<T>(p.in, p.in_off + row * C, p.lk);
+      for (int i = 1; i < C; i++) r = Red<T, OP>::f(r, load_scalar<T>(p.in, p.in_off + row * C + i, p.lk));
+      const long long ob = p.out_off + row * p.kout[0];
+      T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, ob, p.out_lk);
+      store_scalar<T>(p.out, ob, p.sk, Red<T, OP>::f(init, r));
+    }
+  }
+}
+template <class T, int OP, int E> static RedKernel rows_reg_pick_c(int c) {
+  switch (c) {
+    case 2: return (RedKernel)reduce_rows_reg_kernel<T, OP, E, 2>; case 3: return (RedKernel)reduce_rows_reg_kernel<T, OP, E, 3>;
+    case 4: return (RedKernel)reduce_rows_reg_kernel<T, OP, E, 4>; case 5: return (RedKernel)reduce_rows_reg_kernel<T, OP, E, 5>;
+    case 6: return (RedKernel)reduce_rows_reg_kernel<T, OP, E, 6>; case 7: return (RedKernel)reduce_rows_reg_kernel<T, OP, E, 7>;
+    case 8: return (RedKernel)reduce_rows_reg_kernel<T, OP, E, 8>; default: return nullptr;
+  }
+}
+template <class T, int E> static RedKernel rows_reg_pick(int op, int c) {
+  switch (op) { case R_ADD: return rows_reg_pick_c<T, R_ADD, E>(c); case R_MUL: return rows_reg_pick_c<T, R_MUL, E>(c);
+    case R_MAX: return rows_reg_pick_c<T, R_MAX, E>(c); default: return rows_reg_pick_c<T, R_MIN, E>(c); }
+}
+
 // ---- short / ragged rows of a contiguous array: staged through shared memory -----------------------------------------
 // When the rows lie back to back the whole input is one stream, whatever the row length.  A CTA copies a tile of p.seg
 // consecutive rows (<= 32 KB, a whole number of 16-byte chunks) into shared memory with coalesced 128-bit loads -- up to
@@ -865,6 +909,18 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
       if (cls == CLS_F) dot_matvec_kernel<float, 4><<<blocks4, 256, 0, c.stream>>>(p); else dot_matvec_kernel<double, 2><<<blocks4, 256, 0, c.stream>>>(p);
       note_launch("dot_matvec");
       return cuda_fail(cudaGetLastError(), "dot_matvec_kernel");
+    }
+    // ---- rows of 2..8 elements of at least 4 bytes, back to back: the register kernel -------------------------------------------
+    if (!dot && nk == 1 && kd[0].sin == R && R >= 2 && R <= 8 && sb >= 32 && p.rows >= 1024 && aligned16(in, in.offset)) {
+      RedKernel kfn = cls == CLS_F ? rows_reg_pick<float, 4>(op, (int)R) : cls == CLS_D ? rows_reg_pick<double, 2>(op, (int)R)
+                    : sb == 32 ? rows_reg_pick<long long, 4>(op, (int)R) : rows_reg_pick<long long, 2>(op, (int)R);
+      const long long threads = (p.rows + Evec - 1) / Evec, blocks = (threads + 255) / 256;
+      if (kfn && blocks <= 0x7fffffffLL) {
+        p.vec = 1;
+        kfn<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+        note_launch("reduce_rows_reg");
+        return cuda_fail(cudaGetLastError(), "reduce_rows_reg_kernel");
+      }
     }
     // ---- rows back to back, at most 2 KB long and not on chunk boundaries: the staged kernel -------------------------------
     if (!dot && !vec && nk == 1 && kd[0].sin == R && R * sb / 8 <= 2048 && p.rows >= 64 && aligned16(in, in.offset)) {
