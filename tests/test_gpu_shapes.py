@@ -132,3 +132,17 @@ def test_dot_accumulates_into_supplied_output(nc, oracle):
     want = refsem.einsum(oracle, "ij j -> i", [a, x], [o])
     nc.einsum("ij j -> i", to_gpu(nc, a), to_gpu(nc, x), go)
     assert_bit_exact(go, want if not isinstance(want, (list, tuple)) else want[0])
+
+
+# ---- comparisons into packed bit arrays (words assembled across lanes) ------------------------------------------------------
+@pytest.mark.parametrize("sa,sb", [((64, 128), (128,)), ((33, 5, 64), (5, 64)), ((1000, 96), (96,)), ((1000, 96), (1000, 1)), ((7, 1056), (7, 1056)),
+                                   ((129, 2048), ()), ((3, 40000), (3, 1)), ((50, 33), (33,)), ((2049, 32), (32,))])
+@pytest.mark.parametrize("ta,tb", [("f32", "f32"), ("f64", "f64"), ("ub8", "ub8"), ("fixnum", "fixnum"), ("sb16", "ub8"), ("f32", "ub8"), ("ub31", "sb32")])
+@pytest.mark.parametrize("op", ["</bit", ">=/bit", "=/bit"])
+def test_comparisons_broadcast_shapes(nc, oracle, sa, sb, ta, tb, op):
+    lo_hi = lambda t: (-3, 3) if t in ("f32", "f64", "fixnum", "sb16", "sb32") else (0, 6)
+    x = rand(oracle, sa, ta, SEED + 40, 1, *lo_hi(ta))
+    y = rand(oracle, sb, tb, SEED + 41, 1, *lo_hi(tb))
+    want = refsem.broadcast(oracle, op, x, y)
+    assert want.dtype == "bit"
+    assert_bit_exact(nc.broadcast(op, to_gpu(nc, x), to_gpu(nc, y)), want)
