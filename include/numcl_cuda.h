@@ -174,8 +174,9 @@ void* ncl_get_stream(void);
 int  ncl_sync(void);
 /* Number of kernels the library has launched since ncl_init (bench.py's gpu_launches). */
 int64_t ncl_launch_count(void);
-/* Name of the kernel family the last compute call dispatched to ("bcast_vec", "reduce_row",
- * "transpose_tile", "gemm_f64_dmma", "gemm_tf32x3_tcgen05", "generic_nest", ...). */
+/* Name of the kernel family the last compute call dispatched to ("bcast_vec", "bcast_vec_flat", "bcast_widen",
+ * "reduce_row_block", "reduce_rows_reg", "reduce_fewcols", "reduce_all", "reduce_col", "dot_all", "dot_rows",
+ * "dot_matvec", "transpose_tile", "transpose_reg", "gemm_f64_dmma", "gemm_tf32x3_tcgen05", "generic_nest", ...). */
 const char* ncl_last_kernel(void);
 /* Force the generic (thread-per-output, reference-ordered) nest kernel: test hook. */
 int  ncl_force_generic(int on);

@@ -1,19 +1,26 @@
 // k_reduce.cu -- K3: axis reductions (replaces reduce-lambda's nest, src/5reduce.lisp:67-87, and
-// einsum specs whose only work is a reduction, e.g. `(ij -> i)`, `(i ->)`).
+// einsum specs whose only work is a reduction, e.g. `(ij -> i)`, `(i ->)`), plus the contractions that are
+// really reductions (`(i i ->)` vdot / inner, `(ij ij -> i)`, `(ij j -> i)`: DOT variants, product formed on load).
 //
-// All three shapes are HBM-bound streams over the input (1 GiB at config C2), read exactly once
-// with 128-bit loads, several independent loads in flight per thread:
+// All of them are HBM-bound streams over the input (1 GiB at config C2), read exactly once, with 128-bit loads and
+// several independent loads in flight per thread.  The basic forms:
 //   reduce_row  : kept x reduced with the reduced axis contiguous   ((sum a :axes 1))
-//                 one row per warp (short rows) or per 256-thread block (long rows), warp-shuffle +
-//                 shared-memory tree, one store per row;
-//   reduce_all  : everything reduced ((sum a)): persistent grid of sm_count*8 blocks, per-thread
-//                 accumulators -> float64/int64 block partials -> the last block to finish (ticket)
-//                 folds the partials in a fixed order, so the result is deterministic;
-//   reduce_col  : reduced x kept with the kept axis contiguous ((sum a :axes 0)): one thread per
-//                 16-byte column chunk walking down the reduced axis; when there are too few
-//                 columns to fill the GPU the reduced axis is split and a second pass folds the slabs.
-// Accumulation order differs from the reference's sequential row-major scan (5reduce.lisp:78-87):
-// bit-exact for integers (wrap-around add/mul are associative) and for exactly representable
+//                 256 / 32 / 4 threads per row by row length, warp-shuffle + shared-memory tree, one store per row;
+//   reduce_all  : everything reduced ((sum a)): persistent grid, per-thread accumulators -> float64/int64 block
+//                 partials -> the last block to finish (ticket) folds the partials in a fixed order: deterministic;
+//   reduce_col  : reduced x kept with the kept axis contiguous ((sum a :axes 0)): one thread per 16-byte column
+//                 chunk walking down the reduced axis; when there are too few columns to fill the GPU the reduced
+//                 axis is split into one resident wave of slabs and a second pass folds them.
+// Shapes those forms handle badly have their own paths ("Shapes off the headline configs"):
+//   reduce_rows_reg     rows of 2..8 elements, back to back: E rows per thread, entirely in registers;
+//   reduce_row_thread   rows of at most 4 chunks / 16 elements: one thread per row, four rows per thread;
+//   reduce_rows_staged  ragged rows up to 2 KB, back to back: 32 KB tiles through shared memory;
+//   few long rows       host split [rows x S x L] -> scratch [rows x S] -> result (three launches);
+//   reduce_fewcols      <= 128 columns, back to back: the array as ONE stream, accumulators with fixed column phase;
+//   dot_matvec          matrix x vector: four rows per CTA, every chunk of the vector loaded once per four rows;
+//   8-bit `+`           a chunk's 16 bytes are summed with four dp4a.
+// Accumulation order differs from the reference's sequential row-major scan (5reduce.lisp:78-87) except where one
+// thread folds a whole row: bit-exact for integers (wrap-around add/mul are associative) and for exactly representable
 // float sums, within tolerance otherwise (north_star: 1e-5 single, 1e-12 double).
 #include "ncl_device.cuh"
 

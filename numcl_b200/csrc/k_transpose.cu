@@ -3,13 +3,15 @@
 // `(ij -> ji)`, `(abcd -> dbca)` (config C5b).
 //
 // HBM-bound copy.  A direct kernel would be coalesced on one side only, so the (input-contiguous,
-// output-contiguous) plane is tiled through shared memory: a 256-thread block reads a 64 x 64
-// tile along the input's contiguous loop (512-byte runs for 8-byte elements, 16 independent loads
-// per thread), parks it in a padded tile (row pitch 65: conflict-free for both phases) and
-// writes it out along the output's contiguous loop.  All remaining loops are batch coordinates
-// decoded from the block index.  Elements pass through the value class, so element-type
-// changing copies (ub8 -> fixnum: an integer einsum output is always fixnum, 3einsum.lisp:517-518)
-// and the `0 + x` of the default transform into a fresh output (-0.0 -> +0.0) cost nothing extra.
+// output-contiguous) plane is tiled through shared memory: a 256-thread block reads a square tile
+// along the input's contiguous loop (64 x 64 for words of up to 4 bytes: 16 independent loads per
+// thread; 32 x 32 for 8-byte words), parks it in a padded tile (odd row pitch: conflict-free for both
+// phases) and writes it out along the output's contiguous loop.  All remaining loops are batch
+// coordinates decoded from the block index.  Elements pass through the value class in the converting
+// variant, so element-type changing copies (ub8 -> fixnum: an integer einsum output is always fixnum,
+// 3einsum.lisp:517-518) and the `0 + x` of the default transform into a fresh output (-0.0 -> +0.0)
+// cost nothing extra.  Planes with one short side: transpose_reg_kernel ((N,C) <-> (C,N), C <= 8, in
+// registers) and transpose_thin_kernel (C <= 16, rectangular tiles).
 #include "ncl_device.cuh"
 
 #define TR_MAXB 6
