@@ -1,23 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- the hot path's headline benchmark (contract: see the task statement, section (4)).
 
-Workload (BASELINE.json configs[1]): numcl:sum over axis 1 AND over the full array of a
-16384 x 16384 single-float array.  One "step" = both reductions over one per-GPU slab.  With
-N GPUs the array is the row-concatenation of N such slabs (weak scaling: (16384*N) x 16384), the
-axis-1 sums need no exchange and the full sum combines one float64 partial per GPU with an NCCL
-all-reduce (ncl_reduce_all_sharded).
+Workload (BASELINE.json configs[1]): numcl:sum over axis 1 AND over the full array of ONE
+16384 x 16384 single-float array.  One "step" = both reductions.  With N GPUs the array is sharded by
+rows, 16384/N rows per rank (STRONG scaling: the global shape is fixed); the axis-1 sums need no
+exchange, the full sum combines one float64 partial per GPU over NVLink (peer-mapped mailboxes written
+by the reduction kernel itself, ncl_reduce_all_sharded_async; ncclAllReduce if peer access is missing).
+Steps rotate over 3 arrays (3 seeds) so that a 128 MiB shard is not served from the 126 MB L2.
 
-  metric/value : GB/s of ALGORITHMIC bytes over all ranks, inputs resident in HBM
-  e2e          : the same through the C ABI with the slab in pinned HOST memory, copies inside
-  roofline     : the dominant kernel (reduce_row_block) vs the measured HBM peak
+  metric/value : GB/s of ALGORITHMIC bytes of the whole job, inputs resident in HBM; the
+                 timed region replays CUDA graphs of the step's C-ABI calls (ncl_capture_begin/end)
+  e2e          : the same through the C ABI with the shard in pinned HOST memory, copies inside
+  roofline     : the dominant kernel (reduce_row_block) vs the measured HBM peak, CUDA events
   cpu_baseline : the oracle's typed C loops (numcl's sequential scans), 1 thread, on the host
-  others       : the remaining BASELINE configs timed the same way (device resident)
+  others       : the remaining BASELINE configs timed the same way (device resident); at N > 1 the
+                 shardable ones (C1 and C5a by rows, C4 along b) on each rank's shard, max over ranks,
+                 plus the weak-scaling variant of the headline (one whole 16384^2 array per GPU)
 
 `--impl reference` times the reference's own algorithm on the host CPU (the oracle port: the
-reference is Common Lisp and no Lisp exists in this image).
+reference is Common Lisp and no Lisp exists in this image) on the same array.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -32,7 +37,16 @@ N_ROWS = N_COLS = 16384
 BYTES_ROW = N_ROWS * N_COLS * 4 + N_ROWS * 4          # read a, write the row sums      (1 073 807 360)
 BYTES_ALL = N_ROWS * N_COLS * 4 + 4                    # read a, write one element       (1 073 741 828)
 SEED = 20261019
+N_ARRAYS = 3                                           # rotating arrays (seeds SEED, SEED+1, SEED+2)
 METRIC = "einsum GB/s (elementwise/reduce) & TFLOP/s (matmul) vs B200 roofline"
+WORKLOAD = "numcl:sum axis 1 + numcl:sum full of a 16384x16384 single-float array (BASELINE configs[1])"
+
+
+def workload_config(world):
+    return {"workload": WORKLOAD, "global_shape": [N_ROWS, N_COLS],
+            "sharding": f"rows (outer axis), {N_ROWS // max(world, 1)} per GPU; axis-1 sums need no exchange, the full sum combines one float64 partial per GPU",
+            "l2": f"steps rotate over {N_ARRAYS} arrays: consecutive steps never read the same bytes (a shard is {N_ROWS * N_COLS * 4 // max(world, 1) >> 20} MiB, L2 is 126 MB)",
+            "algorithmic_bytes_per_step": BYTES_ROW + BYTES_ALL}
 
 
 def measured_peaks():
@@ -98,27 +112,26 @@ def cpu_reference_step(O, a_host):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path, timed on the host cores."""
+    """--impl reference: the reference's CPU implementation of the path, timed on the host cores, on the
+    same 16384 x 16384 array (all of it) as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
     from oracle import oracle as O
-    sample_rows = 4096                                   # bounded sample: a quarter of the slab per step
-    a = O.fill_random((sample_rows, N_COLS), "f32", SEED, 0, -1.0, 1.0).values()
+    a = O.fill_random((N_ROWS, N_COLS), "f32", SEED, 0, -1.0, 1.0).values()
     for _ in range(min(args.warmup, 1)):
         cpu_reference_step(O, a)
     ts = [cpu_reference_step(O, a)[0] for _ in range(args.steps)]
-    frac = sample_rows / N_ROWS
     t = sum(ts) / len(ts)
-    value = (BYTES_ROW + BYTES_ALL) * frac / t / 1e9
+    value = (BYTES_ROW + BYTES_ALL) / t / 1e9
+    cfg = workload_config(args.gpus)
+    cfg["note"] = "reference = C transcription of numcl's reduce-array nest (oracle port), 1 thread because numcl is single-threaded; SBCL is not installed in this image"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t / frac * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "numcl:sum axis 1 + full, 16384x16384 single-float (BASELINE configs[1])",
-                   "note": "reference = C transcription of numcl's reduce-array nest (oracle port); SBCL is not installed in this image"},
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port",
-                         "sample": f"{sample_rows} of {N_ROWS} rows per step, {args.steps} steps, ms_per_step scaled to the full slab"},
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+                         "sample": f"the whole {N_ROWS}x{N_COLS} array (1 GiB) per step, {args.steps} steps, mean"},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -126,79 +139,88 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------
-def time_other_configs(nc, L, torch, stream, peak, contractions=True):
+def time_other_configs(nc, L, torch, stream, peak, rank, world, dist, sampler_dev, contractions=True):
     """C1, C3, C4, C5 of BASELINE.json, device resident, rotating buffer sets so that no operand of
-    the next launch is still in L2 (126 MB)."""
+    the next launch is still in L2 (126 MB).  world > 1: only what shards without an exchange runs
+     -- C1 and C5a by rows of the outer axis, C4 along b -- every rank on its own shard,
+    the time is the max over ranks, the figure is the whole job's."""
     from numcl_b200 import _lib
     out = {}
+    sampler = ClockSampler(sampler_dev)
+    if rank == 0:
+        sampler.start()
 
     def timed(make_call, nsets, iters, warm=3, batch=None):
         """median over `iters` event pairs of the average duration of a back-to-back batch of
-        launches (one per rotating buffer set).  The batch is captured once into a CUDA graph and
-        replayed, so host-side launch cost (ctypes + planning, ~20 us per call) cannot starve the
-        stream: the figure is kernel time.  Falls back to direct launches if capture is refused."""
+        launches (one per rotating buffer set).  The batch is recorded once into a CUDA graph
+        (ncl_capture_begin/end) and replayed, so host-side launch cost (ctypes + planning, ~20 us per
+        call) cannot starve the stream: the figure is kernel time."""
         calls = [make_call(i) for i in range(nsets)]
         batch = batch or nsets
         for i in range(max(warm, nsets)):
             calls[i % nsets]()
         stream.synchronize()
-        graph = None
-        try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
-                for j in range(batch):
-                    calls[j % nsets]()
-        except Exception:
-            graph = None
-            torch.cuda.synchronize()
+        with _lib.Graph() as graph:
+            for j in range(batch):
+                calls[j % nsets]()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-        with torch.cuda.stream(stream):
-            if graph is not None:
-                graph.replay()
-            for i in range(iters):
-                ev[i][0].record(stream)
-                if graph is not None:
-                    graph.replay()
-                else:
-                    for j in range(batch):
-                        calls[j % nsets]()
-                ev[i][1].record(stream)
+        graph.launch()
+        for i in range(iters):
+            ev[i][0].record(stream)
+            graph.launch()
+            ev[i][1].record(stream)
         stream.synchronize()
         ts = sorted(e0.elapsed_time(e1) * 1e-3 / batch for e0, e1 in ev)
-        timed.graph_used = graph is not None
-        return ts[len(ts) // 2], L.ncl_last_kernel().decode()
+        t = ts[len(ts) // 2]
+        if world > 1:
+            tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = tt.item()
+        return t, L.ncl_last_kernel().decode()
 
     def fold_call(op, arrs, r):
         ts = (_lib.Tensor * len(arrs))(*[a.tensor() for a in arrs])
         tr = r.tensor()
         keep = (ts, tr, arrs, r)
-        return lambda: (L.ncl_fold(op, 1, keep[0], len(arrs), C.byref(keep[1])))
+        return lambda: _lib.check(L.ncl_fold(op, 1, keep[0], len(arrs), C.byref(keep[1])))
 
-    # C1: (numcl:+ a b), 4096x4096 f32 + 4096 row vector
+    out["timing"] = "CUDA-graph replay (ncl_capture_begin/end) of back-to-back launches over rotating buffer sets; max over ranks"
+    shard = f", sharded by rows: {4096 // world} per GPU" if world > 1 else ""
+    # C1: (numcl:+ a b), 4096x4096 f32 + 4096 row vector; rank r owns rows [r*4096/world, (r+1)*4096/world)
+    r1 = 4096 // world
     b = nc.random_array((4096,), "f32", SEED + 1, 2, -1.0, 1.0)
-    sets = [(nc.random_array((4096, 4096), "f32", SEED + 10 + i, 2, -1.0, 1.0), nc.empty((4096, 4096), "f32")) for i in range(4)]
-    t, k = timed(lambda i: fold_call(_lib.OPS["ADD"], [sets[i][0], b], sets[i][1]), 4, 12, batch=8)
-    out["timing"] = "CUDA-graph replay of back-to-back launches over rotating buffer sets" if getattr(timed, "graph_used", False) else "direct back-to-back launches over rotating buffer sets"
-    out["C1 (numcl:+ a b) 4096x4096 f32 + 4096"] = {"us": t * 1e6, "GB/s": 134234112 / t / 1e9, "frac_hbm": 134234112 / t / 1e9 / peak, "kernel": k}
+    nset = 4 if world == 1 else 8
+    sets = [(nc.random_array((r1, 4096), "f32", SEED + 10 + i, 2, -1.0, 1.0, first=rank * r1 * 4096), nc.empty((r1, 4096), "f32")) for i in range(nset)]
+    t, k = timed(lambda i: fold_call(_lib.OPS["ADD"], [sets[i][0], b], sets[i][1]), nset, 12, batch=2 * nset)
+    byt = 2 * 4096 * 4096 * 4 + 4096 * 4 * world
+    out["C1 (numcl:+ a b) 4096x4096 f32 + 4096" + shard] = {"us": t * 1e6, "GB/s": byt / t / 1e9, "frac_hbm": byt / t / 1e9 / (peak * world), "kernel": k}
     del sets
-    # C5a: (numcl:* u8 fixnum) -> fixnum, (64,32,32,256); C5b: (abcd -> dbca) of the result
+    # C5a: (numcl:* u8 fixnum) -> fixnum, (64,32,32,256), outer axis sharded; C5b: (abcd -> dbca) of the result (1 GPU only:
+    # the permutation moves the sharded axis, SURVEY 8e)
+    a5 = 64 // world
     y = nc.random_array((256,), "fixnum", SEED + 2, 0, -(2 ** 40), 2 ** 40)
-    sets = [(nc.random_array((64, 32, 32, 256), "ub8", SEED + 20 + i, 0, 0, 255), nc.empty((64, 32, 32, 256), "fixnum")) for i in range(3)]
-    t, k = timed(lambda i: fold_call(_lib.OPS["MUL"], [sets[i][0], y], sets[i][1]), 3, 12, batch=6)
-    out["C5a (numcl:* ub8 fixnum) (64,32,32,256)"] = {"us": t * 1e6, "GB/s": 150996992 / t / 1e9, "frac_hbm": 150996992 / t / 1e9 / peak, "kernel": k}
+    nset = 3 if world == 1 else 8
+    sets = [(nc.random_array((a5, 32, 32, 256), "ub8", SEED + 20 + i, 0, 0, 255, first=rank * a5 * 32 * 32 * 256), nc.empty((a5, 32, 32, 256), "fixnum")) for i in range(nset)]
+    t, k = timed(lambda i: fold_call(_lib.OPS["MUL"], [sets[i][0], y], sets[i][1]), nset, 12, batch=2 * nset)
+    byt = 16777216 + 134217728 + 2048 * world
+    out["C5a (numcl:* ub8 fixnum) (64,32,32,256)" + (f", outer axis sharded: {a5} per GPU" if world > 1 else "")] = {"us": t * 1e6, "GB/s": byt / t / 1e9, "frac_hbm": byt / t / 1e9 / (peak * world), "kernel": k}
     from numcl_b200.einsum import _memoized
-    _, desc = _memoized("abcd -> dbca")
-    outs = [nc.empty((256, 32, 32, 64), "fixnum") for _ in range(3)]
+    if world == 1:
+        _, desc = _memoized("abcd -> dbca")
+        outs = [nc.empty((256, 32, 32, 64), "fixnum") for _ in range(3)]
 
-    def tr_call(i):
-        tin = (_lib.Tensor * 1)(sets[i][1].tensor())
-        tout = (_lib.Tensor * 1)(outs[i].tensor())
-        keep = (tin, tout)
-        return lambda: L.ncl_einsum(C.byref(desc), keep[0], 1, keep[1], 1, _lib.OUT_FRESH)
-    t, k = timed(tr_call, 3, 12, batch=6)
-    out["C5b (einsum '(abcd -> dbca)) fixnum"] = {"us": t * 1e6, "GB/s": 268435456 / t / 1e9, "frac_hbm": 268435456 / t / 1e9 / peak, "kernel": k}
-    del sets, outs
-    # C3 / C4: contractions (TFLOP/s; denominators measured with cuBLAS in the same run)
+        def tr_call(i):
+            tin = (_lib.Tensor * 1)(sets[i][1].tensor())
+            tout = (_lib.Tensor * 1)(outs[i].tensor())
+            keep = (tin, tout)
+            return lambda: _lib.check(L.ncl_einsum(C.byref(desc), keep[0], 1, keep[1], 1, _lib.OUT_FRESH))
+        t, k = timed(tr_call, 3, 12, batch=6)
+        out["C5b (einsum '(abcd -> dbca)) fixnum"] = {"us": t * 1e6, "GB/s": 268435456 / t / 1e9, "frac_hbm": 268435456 / t / 1e9 / peak, "kernel": k}
+        del outs
+    del sets
+    out["clocks_elementwise"] = sampler.stop() if rank == 0 else None
+
+    # C3 / C4: contractions (TFLOP/s; denominators measured with cuBLAS in the same run, clocks sampled around them)
     def cublas_peak(dt, tf32, n=8192):
         torch.backends.cuda.matmul.allow_tf32 = tf32
         A = torch.randn(n, n, device="cuda", dtype=dt)
@@ -218,24 +240,57 @@ def time_other_configs(nc, L, torch, stream, peak, contractions=True):
     try:
         _, mm = _memoized("ij jk -> ik")
         _, bmm = _memoized("bij bjk -> bik")
-        peaks = {"f64": cublas_peak(torch.float64, False), "tf32": cublas_peak(torch.float32, True)}
-        for name, dt, spec_desc, shp_a, shp_b, shp_c, flops, denom, iters in [
-            ("C3 matmul 8192^3 f64", "f64", mm, (8192, 8192), (8192, 8192), (8192, 8192), 2 * 8192 ** 3, peaks["f64"], 3),
-            ("C3 matmul 8192^3 f32", "f32", mm, (8192, 8192), (8192, 8192), (8192, 8192), 2 * 8192 ** 3, peaks["tf32"] / 3, 5),
-            ("C4 (bij bjk -> bik) b=256 512^3 f32", "f32", bmm, (256, 512, 512), (256, 512, 512), (256, 512, 512), 2 * 256 * 512 ** 3, peaks["tf32"] / 3, 10),
-        ]:
-            A = nc.random_array(shp_a, dt, SEED + 30, 0, -1.0, 1.0)
-            B = nc.random_array(shp_b, dt, SEED + 31, 0, -1.0, 1.0)
-            Cc = nc.empty(shp_c, dt)
-            tin = (_lib.Tensor * 2)(A.tensor(), B.tensor())
-            tout = (_lib.Tensor * 1)(Cc.tensor())
-            t, k = timed(lambda i: (lambda: L.ncl_einsum(C.byref(spec_desc), tin, 2, tout, 1, _lib.OUT_FRESH)), 1, iters, warm=1)
+        sampler = ClockSampler(sampler_dev)
+        if rank == 0:
+            sampler.start()
+        peaks = {"tf32": cublas_peak(torch.float32, True)}
+        if world == 1:
+            peaks["f64"] = cublas_peak(torch.float64, False)
+        out["clocks_cublas_denominators"] = sampler.stop() if rank == 0 else None
+        sampler = ClockSampler(sampler_dev)
+        if rank == 0:
+            sampler.start()
+        bl = 256 // world
+        cases = []
+        if world == 1:
+            cases += [("C3 matmul 8192^3 f64", "f64", mm, (8192, 8192), (8192, 8192), (8192, 8192), 2 * 8192 ** 3, peaks["f64"], 3),
+                      ("C3 matmul 8192^3 f32", "f32", mm, (8192, 8192), (8192, 8192), (8192, 8192), 2 * 8192 ** 3, peaks["tf32"] / 3, 5)]
+        cases += [("C4 (bij bjk -> bik) b=256 512^3 f32" + (f", sharded along b: {bl} per GPU" if world > 1 else ""), "f32", bmm,
+                   (bl, 512, 512), (bl, 512, 512), (bl, 512, 512), 2 * 256 * 512 ** 3, peaks["tf32"] / 3 * world, 10)]
+        for name, dt, spec_desc, shp_a, shp_b, shp_c, flops, denom, iters in cases:
+            first = rank * shp_a[0] * shp_a[1] * shp_a[2] if len(shp_a) == 3 else 0
+            nset = 1 if world == 1 else 4                  # a b/8 shard (96 MiB) would otherwise be served from L2
+            ABC = [(nc.random_array(shp_a, dt, SEED + 30 + 2 * i, 0, -1.0, 1.0, first=first), nc.random_array(shp_b, dt, SEED + 31 + 2 * i, 0, -1.0, 1.0, first=first),
+                    nc.empty(shp_c, dt)) for i in range(nset)]
+
+            def mk(i):
+                tin = (_lib.Tensor * 2)(ABC[i][0].tensor(), ABC[i][1].tensor())
+                tout = (_lib.Tensor * 1)(ABC[i][2].tensor())
+                keep = (tin, tout)
+                return lambda: _lib.check(L.ncl_einsum(C.byref(spec_desc), keep[0], 2, keep[1], 1, _lib.OUT_FRESH))
+            t, k = timed(mk, nset, iters, warm=1)
             out[name] = {"ms": t * 1e3, "TFLOP/s": flops / t / 1e12, "denominator_TFLOP/s": denom, "frac_tensor": flops / t / 1e12 / denom, "kernel": k,
-                         "denominator": "cuBLAS f64 GEMM measured in this run" if dt == "f64" else "cuBLAS TF32 GEMM measured in this run / 3"}
-            del A, B, Cc
+                         "denominator": ("cuBLAS f64 GEMM measured in this run" if dt == "f64" else "cuBLAS TF32 GEMM measured in this run / 3") + (f" x {world} GPUs" if world > 1 else "")}
+            del ABC
+        out["clocks_contractions"] = sampler.stop() if rank == 0 else None
     except Exception as e:                                   # never lose the headline line to an auxiliary config
         out["contractions"] = {"error": repr(e)[:300]}
     return out
+
+
+class _CudaView:
+    """A library buffer seen through __cuda_array_interface__, so that torch can read it (the in-bench fp64 check)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def source_stamp():
+    """hash of the reduction kernels' sources: roofline.traffic is an ncu figure taken from a build with this stamp"""
+    h = hashlib.sha256()
+    for f in ("k_reduce.cuh", "k_reduce.cu", "ncl_device.cuh"):
+        h.update(open(os.path.join(ROOT, "numcl_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def run_ours(args):
@@ -268,34 +323,55 @@ def run_ours(args):
 
     stream = torch.cuda.Stream()
     _lib.check(L.ncl_set_stream(C.c_void_p(stream.cuda_stream)))
-    # this rank's slab of the (16384*world, 16384) array: rows [rank*16384, (rank+1)*16384)
-    a = nc.random_array((N_ROWS, N_COLS), "f32", SEED + 1000 * rank, 0, -1.0, 1.0)
-    rows = nc.empty((N_ROWS,), "f32")
-    total = nc.empty((), "f32")
-    ta, trows, ttot = a.tensor(), rows.tensor(), total.tensor()
     ax1 = (C.c_int * 1)(1)
+    from numcl_b200.dist import row_partition
 
-    sync_a = nc.zeros((8,), type="f32")
-    sync_r = nc.empty((), type="f32")
-    tsync_a, tsync_r = sync_a.tensor(), sync_r.tensor()
+    class Job:
+        """this rank's row shards of `narr` synthetic (rows x 16384) arrays + the step over them"""
 
-    def step(ev=None):
-        # N > 1: the full sum goes first so that its one-element all-reduce (communication stream)
-        # hides behind the axis-1 kernel, which needs no exchange; ncl_comm_join closes the step.
-        if ev:
-            ev[1].record(stream)
-        if world > 1:
-            _lib.check(L.ncl_reduce_all_sharded_async(_lib.OPS["ADD"], C.byref(ta), C.byref(ttot)))          # (sum a): local partial, async all-reduce
-        else:
-            _lib.check(L.ncl_reduce(_lib.OPS["ADD"], C.byref(ta), ax1, 0, C.byref(ttot), _lib.OUT_FRESH))    # (sum a)
-        if ev:
-            ev[2].record(stream)
-            ev[0].record(stream)
-        _lib.check(L.ncl_reduce(_lib.OPS["ADD"], C.byref(ta), ax1, 1, C.byref(trows), _lib.OUT_FRESH))       # (sum a :axes 1)
-        if ev:
-            ev[3].record(stream)
-        if world > 1:
-            _lib.check(L.ncl_comm_join())
+        def __init__(self, rows_global, narr):
+            self.start, self.rows = row_partition(rows_global, world)[rank]
+            self.narr = narr
+            self.a = [nc.random_array((self.rows, N_COLS), "f32", SEED + s, 0, -1.0, 1.0, first=self.start * N_COLS) for s in range(narr)]
+            self.rowsum = [nc.empty((self.rows,), "f32") for _ in range(narr)]
+            self.total = [nc.empty((), "f32") for _ in range(narr)]
+            self.ta = [x.tensor() for x in self.a]
+            self.tr = [x.tensor() for x in self.rowsum]
+            self.tt = [x.tensor() for x in self.total]
+            self.graph = None
+
+        def step(self, i, ev=None):
+            # N > 1: the full sum goes first: its kernel pushes the partial into every rank's mailbox and the
+            # one-CTA collect runs on the communication stream BESIDE the axis-1 kernel, which needs no
+            # exchange; ncl_comm_join closes the step.
+            s = i % self.narr
+            if ev:
+                ev[1].record(stream)
+            if world > 1:
+                _lib.check(L.ncl_reduce_all_sharded_async(_lib.OPS["ADD"], C.byref(self.ta[s]), C.byref(self.tt[s])))     # (sum a)
+            else:
+                _lib.check(L.ncl_reduce(_lib.OPS["ADD"], C.byref(self.ta[s]), ax1, 0, C.byref(self.tt[s]), _lib.OUT_FRESH))  # (sum a)
+            if ev:
+                ev[2].record(stream)
+                ev[0].record(stream)
+            _lib.check(L.ncl_reduce(_lib.OPS["ADD"], C.byref(self.ta[s]), ax1, 1, C.byref(self.tr[s]), _lib.OUT_FRESH))      # (sum a :axes 1)
+            if ev:
+                ev[3].record(stream)
+            if world > 1:
+                _lib.check(L.ncl_comm_join())
+
+        def capture(self):
+            with _lib.Graph() as g:
+                for s in range(self.narr):
+                    self.step(s)
+            self.graph = g
+
+        def run(self, steps):
+            """exactly `steps` steps: graph replays of narr steps each, the remainder eagerly"""
+            for _ in range(steps // self.narr):
+                self.graph.launch()
+            for i in range(steps % self.narr):
+                self.step(i)
 
     def barrier():
         stream.synchronize()
@@ -303,60 +379,93 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    sync_a = nc.zeros((8,), type="f32")
+    sync_r = nc.empty((), type="f32")
+    tsync_a, tsync_r = sync_a.tensor(), sync_r.tensor()
+
+    def timed_steps(job, steps):
+        """device time of `steps` steps, max over ranks"""
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            # device-side alignment: ranks leave the host barrier up to milliseconds apart; a one-element
+            # exchange enqueued BEFORE the start event makes every GPU begin its timed region together,
+            # so the max-over-ranks time does not charge the first rank for the last rank's late start
+            _lib.check(L.ncl_reduce_all_sharded(_lib.OPS["ADD"], C.byref(tsync_a), C.byref(tsync_r)))
+        t_start.record(stream)
+        h0 = time.perf_counter()
+        job.run(steps)
+        host = time.perf_counter() - h0
+        t_end.record(stream)
+        barrier()
+        el = t_start.elapsed_time(t_end) * 1e-3
+        if world > 1:
+            tt = torch.tensor([el], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el = tt.item()
+        return el, host
+
+    job = Job(N_ROWS, N_ARRAYS)
+    for i in range(max(args.warmup, N_ARRAYS)):
+        job.step(i)
+    barrier()
+    job.capture()
+    job.run(N_ARRAYS)                                       # one replay as warm-up of the graph itself
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # per-kernel events on every 4th step only: with N ranks in lock-step the host side of a step must
-    # stay far below the 0.34 ms of device work, or the slowest rank's launch loop sets the pace
-    ev_steps = [i for i in range(args.steps) if i % 4 == 0]
-    evmap = {i: [torch.cuda.Event(enable_timing=True) for _ in range(4)] for i in ev_steps}
-    evs = list(evmap.values())
     l0 = L.ncl_launch_count()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        # device-side alignment: ranks leave the host barrier up to milliseconds apart; a one-element
-        # all-reduce enqueued BEFORE the start event makes every GPU begin its timed region together,
-        # so the max-over-ranks time does not charge the first rank for the last rank's late start
-        _lib.check(L.ncl_reduce_all_sharded(_lib.OPS["ADD"], C.byref(tsync_a), C.byref(tsync_r)))
-    t_start.record(stream)
-    h0 = time.perf_counter()
-    for i in range(args.steps):
-        step(evmap.get(i))
-    host_enqueue = time.perf_counter() - h0
-    t_end.record(stream)
-    barrier()
+    elapsed, host_enqueue = timed_steps(job, args.steps)
     launches = L.ncl_launch_count() - l0
+    # per-kernel durations: the same steps issued one call at a time with CUDA events around each kernel
+    ev_n = max(6, min(30, args.steps))
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(ev_n)]
+    for i in range(ev_n):
+        job.step(i, evs[i])
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
-    elapsed = t_start.elapsed_time(t_end) * 1e-3
-    t_row = sum(e[0].elapsed_time(e[3]) for e in evs) * 1e-3 / len(evs)
-    t_all = sum(e[1].elapsed_time(e[2]) for e in evs) * 1e-3 / len(evs)
+    t_row = sorted(e[0].elapsed_time(e[3]) for e in evs)[ev_n // 2] * 1e-3
+    t_all = sorted(e[1].elapsed_time(e[2]) for e in evs)[ev_n // 2] * 1e-3
     per_rank = None
+    parity = None
     if world > 1:
-        mine = torch.tensor([elapsed, t_row, t_all, host_enqueue / args.steps], device="cuda", dtype=torch.float64)
+        mine = torch.tensor([t_row, t_all, host_enqueue / args.steps], device="cuda", dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        per_rank = {"ms_per_step": [round(x[0].item() / args.steps * 1e3, 4) for x in allr], "row_us": [round(x[1].item() * 1e6, 1) for x in allr],
-                    "full_us": [round(x[2].item() * 1e6, 1) for x in allr], "host_enqueue_us": [round(x[3].item() * 1e6, 1) for x in allr]}
-        tt = torch.tensor([elapsed, t_row, t_all], device="cuda", dtype=torch.float64)
+        per_rank = {"row_us": [round(x[0].item() * 1e6, 1) for x in allr], "full_local_us": [round(x[1].item() * 1e6, 1) for x in allr],
+                    "host_enqueue_us_per_step": [round(x[2].item() * 1e6, 1) for x in allr]}
+        tt = torch.tensor([t_row, t_all], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed, t_row, t_all = tt.tolist()
-    value = (BYTES_ROW + BYTES_ALL) * world * args.steps / elapsed / 1e9
+        t_row, t_all = tt.tolist()
+        # correctness of the NVLink exchange, checked in the run: every rank's result of (sum a) against the float64
+        # sum of float64 per-rank partials computed by torch from the same device buffers
+        errs, same = [], True
+        for s in range(N_ARRAYS):
+            view = torch.as_tensor(_CudaView(job.a[s].device_ptr(), job.rows * N_COLS), device="cuda")
+            part = view.double().sum().reshape(1)
+            dist.all_reduce(part)
+            got = torch.tensor([float(job.total[s].numpy().reshape(-1)[0])], device="cuda", dtype=torch.float64)
+            gl = [torch.zeros_like(got) for _ in range(world)]
+            dist.all_gather(gl, got)
+            same = same and all(g.item() == gl[0].item() for g in gl)
+            errs.append(abs(got.item() - part.item()) / abs(part.item()))
+        parity = {"parity_full_sum_rel_err": max(errs), "same_bits_on_every_rank": same,
+                  "how": "float32 result of the sharded (sum a) vs torch float64 sum of the same shards, all-reduced; per array, max"}
+    value = (BYTES_ROW + BYTES_ALL) * args.steps / elapsed / 1e9
 
-    # ---- e2e: slab in pinned host memory, copies inside the timed region, through the C ABI ----------
-    host = nc.NArray((N_ROWS, N_COLS), "f32", where="host")
-    host.set_raw(a.raw())
-    rows_h = np.empty(N_ROWS, dtype=np.float32)
+    # ---- e2e: this rank's shard in pinned host memory, copies inside the timed region, through the C ABI ----------
+    host = nc.NArray((job.rows, N_COLS), "f32", where="host")
+    host.set_raw(job.a[0].raw())
+    rows_h = np.empty(job.rows, dtype=np.float32)
     tot_h = np.empty(1, dtype=np.float32)
     e2e_steps = max(1, min(args.steps, 5))
+    shard_bytes = job.rows * N_COLS * 4
 
     def e2e_step():
-        _lib.check(L.ncl_h2d(a._buf, 0, host._host.ctypes.data, N_ROWS * N_COLS * 4))
-        step()
-        _lib.check(L.ncl_d2h(rows_h.ctypes.data, rows._buf, 0, N_ROWS * 4))
-        _lib.check(L.ncl_d2h(tot_h.ctypes.data, total._buf, 0, 4))
+        _lib.check(L.ncl_h2d(job.a[0]._buf, 0, host._host.ctypes.data, shard_bytes))
+        job.step(0)
+        _lib.check(L.ncl_d2h(rows_h.ctypes.data, job.rowsum[0]._buf, 0, job.rows * 4))
+        _lib.check(L.ncl_d2h(tot_h.ctypes.data, job.total[0]._buf, 0, 4))
     e2e_step()
     barrier()
     w0 = time.perf_counter()
@@ -368,55 +477,80 @@ def run_ours(args):
         tt = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_t = tt.item()
-    e2e_value = (BYTES_ROW + BYTES_ALL) * world * e2e_steps / e2e_t / 1e9
+    e2e_value = (BYTES_ROW + BYTES_ALL) * e2e_steps / e2e_t / 1e9
+    del host
 
+    # ---- the other configs (every rank takes part: sharded), the weak-scaling variant, the CPU baseline ------------
+    others = {}
+    if not args.skip_others:
+        others = time_other_configs(nc, L, torch, stream, peak, rank, world, dist, local, contractions=not args.no_contractions)
+    if world > 1 and not args.skip_others:
+        del job
+        wjob = Job(N_ROWS * world, N_ARRAYS)               # weak scaling: one whole 16384^2 array per GPU
+        for i in range(N_ARRAYS):
+            wjob.step(i)
+        barrier()
+        wjob.capture()
+        wjob.run(N_ARRAYS)
+        barrier()
+        wsteps = max(N_ARRAYS, min(args.steps, 30))
+        wel, _ = timed_steps(wjob, wsteps)
+        others["weak scaling: one 16384x16384 array per GPU"] = {"ms_per_step": wel / wsteps * 1e3, "GB/s": (BYTES_ROW + BYTES_ALL) * world * wsteps / wel / 1e9,
+                                                                  "global_shape": [N_ROWS * world, N_COLS]}
+        del wjob
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
-    # ---- rank 0 only: CPU baseline, the other configs, the JSON line -----------------------------------
     cpu = None
-    others = {}
     if world == 1:
         from oracle import oracle as O
-        sample_rows = N_ROWS                  # the whole slab: ~0.35 s per pass of both scans, ~10 s in total with the host fill
-        ah = O.fill_random((sample_rows, N_COLS), "f32", SEED, 0, -1.0, 1.0).values()
+        ah = O.fill_random((N_ROWS, N_COLS), "f32", SEED, 0, -1.0, 1.0).values()
         reps = 12
         ct = min(cpu_reference_step(O, ah)[0] for _ in range(reps))
-        cpu = {"value": (BYTES_ROW + BYTES_ALL) * (sample_rows / N_ROWS) / ct / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-               "sample": f"{sample_rows} of {N_ROWS} rows ({sample_rows * N_COLS * 4 >> 20} MiB), best of {reps}; C transcription of numcl's sequential reduce nest, not SBCL",
+        cpu = {"value": (BYTES_ROW + BYTES_ALL) / ct / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+               "sample": f"the whole {N_ROWS}x{N_COLS} array (1 GiB), best of {reps}; C transcription of numcl's sequential reduce nest, not SBCL",
                "host_cores": os.cpu_count()}
         # parity spot check of the timed arrays against the oracle on the same synthetic stream
-        got = rows.numpy()[:sample_rows].astype(np.float64)
+        got = job.rowsum[0].numpy().astype(np.float64)
         want = O.fast_sum_axis1_f32(ah).astype(np.float64)
         cpu["parity_rel_err_axis1_vs_port"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
-        if not args.skip_others:
-            others = time_other_configs(nc, L, torch, stream, peak, contractions=not args.no_contractions)
-    traffic = None
+        truth = float(ah.astype(np.float64).sum())
+        cpu["parity_full_sum_rel_err_vs_fp64"] = abs(float(job.total[0].numpy().reshape(-1)[0]) - truth) / abs(truth)
+        cpu["port_full_sum_rel_err_vs_fp64"] = abs(float(O.fast_sum_all_f32(ah)) - truth) / abs(truth)
+    traffic, traffic_note = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("reduce_row_block")
-    achieved = BYTES_ROW / t_row / 1e9
+        tj = json.load(open(tp))
+        traffic = tj.get("reduce_row_block")
+        traffic_note = {"source": tj.get("source"), "taken_at_source_stamp": tj.get("source_stamp"), "current_source_stamp": source_stamp(),
+                        "stale": tj.get("source_stamp") != source_stamp()}
+    bytes_row_local = BYTES_ROW / world
+    achieved = bytes_row_local / t_row / 1e9
+    cfg = workload_config(world)
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "numcl:sum axis 1 + numcl:sum full, 16384x16384 single-float slab per GPU (BASELINE configs[1])",
-                   "global_shape": [N_ROWS * world, N_COLS], "sharding": "rows (outer axis); full sum = NCCL all-reduce of one float64 partial per GPU",
-                   "l2": "input slab (1 GiB) is 8x the 126 MB L2, no flush needed", "algorithmic_bytes_per_step_per_gpu": BYTES_ROW + BYTES_ALL},
-        "roofline": {"bound": "hbm", "kernel": "reduce_row_kernel (sum :axes 1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "second_kernel": {"kernel": "reduce_all_kernel (sum full)" + (" local phase; the all-reduce overlaps the axis-1 kernel" if world > 1 else ""),
-                                       "achieved": BYTES_ALL / t_all / 1e9, "frac": BYTES_ALL / t_all / 1e9 / peak}},
-        "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": N_ROWS * N_COLS * 4 * 1, "d2h_bytes_per_step": N_ROWS * 4 + 4,
-                "steps": e2e_steps, "api": "ncl_h2d + ncl_reduce x2 + ncl_d2h (pinned host slab)"},
+        "config": cfg,
+        "roofline": {"bound": "hbm", "kernel": "reduce_row_kernel (sum :axes 1)" + (f" on a {N_ROWS // world}-row shard" if world > 1 else ""),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic if world == 1 else None, "traffic_note": traffic_note, "peak_source": peak_src,
+                     "how": f"median of {ev_n} CUDA-event pairs around the kernel in eager steps issued right after the timed region",
+                     "second_kernel": {"kernel": "reduce_all_kernel (sum full)" + (" local phase + push into the peers' mailboxes; the collect runs beside the axis-1 kernel" if world > 1 else ""),
+                                       "achieved": BYTES_ALL / world / t_all / 1e9, "frac": BYTES_ALL / world / t_all / 1e9 / peak}},
+        "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": shard_bytes * world, "d2h_bytes_per_step": (job.rows * 4 + 4) * world if world == 1 else (N_ROWS * 4 + 4 * world),
+                "steps": e2e_steps, "api": "ncl_h2d + ncl_reduce x2 + ncl_d2h (pinned host shard per rank)"},
         "gpu_launches": int(launches),
+        "timed_region": f"{args.steps // N_ARRAYS} replays of a CUDA graph of {N_ARRAYS} steps + {args.steps % N_ARRAYS} eager steps",
         "host_enqueue_us_per_step": host_enqueue / args.steps * 1e6,
         "clocks": clocks,
     }
     if per_rank:
         line["per_rank"] = per_rank
+    if parity:
+        line.update(parity)
     if cpu:
         line["cpu_baseline"] = cpu
     if others:

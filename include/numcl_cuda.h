@@ -161,7 +161,8 @@ typedef struct {
                                    reading them, so no host/device fill pass is needed       */
 
 /* ---- context ---------------------------------------------------------------------------- */
-/* Bind this process to `ndev` CUDA devices (one process per GPU: ndev = 1). */
+/* Bind this process to its CUDA device: one process per GPU, so ndev must be 1 (devs[0] = the
+ * device ordinal); ndev > 1 returns NCL_ERR_UNSUPPORTED. */
 int  ncl_init(int ndev, const int* devs);
 void ncl_shutdown(void);
 const char* ncl_last_error(void);
@@ -172,6 +173,13 @@ int  ncl_device_count(void);
 int  ncl_set_stream(void* cuda_stream);
 void* ncl_get_stream(void);
 int  ncl_sync(void);
+/* The library caches freed device blocks for re-use (every numcl operation returns a fresh array,
+ * src/1instantiate.lisp:81-96); ncl_trim gives the cache back to the driver. */
+int  ncl_trim(void);
+/* Bytes the library itself has copied host->device / device->host since ncl_init (ncl_h2d, ncl_d2h,
+ * staging of host-resident tensors, the residency table below): lets a caller verify that a warm
+ * call moved nothing over PCIe. */
+void ncl_transfer_stats(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 /* Number of kernels the library has launched since ncl_init (bench.py's gpu_launches). */
 int64_t ncl_launch_count(void);
 /* Name of the kernel family the last compute call dispatched to ("bcast_vec", "bcast_vec_flat", "bcast_widen",
@@ -180,6 +188,20 @@ int64_t ncl_launch_count(void);
 const char* ncl_last_kernel(void);
 /* Force the generic (thread-per-output, reference-ordered) nest kernel: test hook. */
 int  ncl_force_generic(int on);
+
+/* ---- CUDA graphs: a launch-bound sequence of calls recorded once and replayed with one launch --
+ * (no reference counterpart: the reference compiles its loop nests with `compile` and caches them,
+ * src/3einsum.lisp:30-31; the GPU analogue of that cache for a whole call sequence is a graph).
+ * Between begin and end every compute call on DEVICE-resident tensors is recorded, not run; host
+ * tensors, ncl_h2d/ncl_d2h/ncl_sync and anything that must allocate return NCL_ERR_STATE: run the
+ * sequence once eagerly first.  The sharded reduce (mailbox exchange on the communication stream)
+ * is captured too. */
+typedef struct ncl_graph ncl_graph;
+int     ncl_capture_begin(void);
+int     ncl_capture_end(ncl_graph** out);
+int     ncl_graph_launch(ncl_graph* g);
+int64_t ncl_graph_kernels(const ncl_graph* g);   /* kernels one replay launches */
+int     ncl_graph_free(ncl_graph* g);
 
 /* ---- buffers: what src/1instantiate.lisp:81-96 (%make-array) gains ----------------------- */
 ncl_buf* ncl_alloc(size_t bytes, int dev_slot);
@@ -202,6 +224,9 @@ int ncl_fill(ncl_tensor* t, int value_is_float, int64_t ival, double fval);
  *  dist 2: as 0 for floats, but 2^-10 of the elements replaced by specials
  *          {+0,-0,+inf,-inf,min denormal,max finite/2} (set R of SURVEY 8d)              */
 int ncl_fill_random(ncl_tensor* t, uint64_t seed, int dist, double lo, double hi);
+/* Same stream, but element k of t is stream element first_index + k: a rank generates its own row
+ * shard of a larger synthetic array. */
+int ncl_fill_random_at(ncl_tensor* t, uint64_t seed, uint64_t first_index, int dist, double lo, double hi);
 
 /* ---- compute ---------------------------------------------------------------------------- */
 /* The form a (defmethod einsum-body ((*compiler* (eql :cuda)) ev)) returns calls this:
@@ -247,9 +272,11 @@ int ncl_allreduce(int op, ncl_tensor* t);
 /* Full reduce of a row-sharded array: local two-phase reduce to a float64/int64 partial,
  * all-reduce of that one element, one final rounding into r (rank-0 tensor, every rank). */
 int ncl_reduce_all_sharded(int op, const ncl_tensor* a_local, ncl_tensor* r);
-/* Same, but the all-reduce and the final rounding are issued on the library's communication
- * stream and overlap with later work on the compute stream; ncl_comm_join() (or ncl_sync / any
- * d2h) orders the compute stream after them. */
+/* Same, but the exchange and the final rounding are issued on the library's communication stream
+ * and overlap with later work on the compute stream; ncl_comm_join() (or ncl_sync / any d2h)
+ * orders the compute stream after them.  With NVLink peer access the local kernel's last block
+ * stores the partial into every rank's mailbox (P2P stores) and a one-CTA kernel on the
+ * communication stream collects them; without it the partial goes through ncclAllReduce. */
 int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a_local, ncl_tensor* r);
 int ncl_comm_join(void);
 

@@ -31,6 +31,8 @@ EXPORTS = [
     "ncl_einsum", "ncl_broadcast", "ncl_fold", "ncl_map", "ncl_reduce", "ncl_convert",
     "ncl_comm_unique_id", "ncl_comm_init", "ncl_comm_destroy", "ncl_allreduce", "ncl_reduce_all_sharded",
     "ncl_reduce_all_sharded_async", "ncl_comm_join",
+    "ncl_trim", "ncl_transfer_stats", "ncl_capture_begin", "ncl_capture_end", "ncl_graph_launch", "ncl_graph_kernels",
+    "ncl_graph_free", "ncl_fill_random_at",
 ]
 
 
@@ -117,6 +119,14 @@ def load():
     L.ncl_storage_bytes.argtypes = [C.c_int, C.c_int64]
     L.ncl_fill.argtypes = [C.POINTER(Tensor), C.c_int, C.c_int64, C.c_double]
     L.ncl_fill_random.argtypes = [C.POINTER(Tensor), C.c_uint64, C.c_int, C.c_double, C.c_double]
+    L.ncl_fill_random_at.argtypes = [C.POINTER(Tensor), C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_double]
+    L.ncl_transfer_stats.restype = None
+    L.ncl_transfer_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.ncl_capture_end.argtypes = [C.POINTER(C.c_void_p)]
+    L.ncl_graph_launch.argtypes = [C.c_void_p]
+    L.ncl_graph_kernels.restype = C.c_int64
+    L.ncl_graph_kernels.argtypes = [C.c_void_p]
+    L.ncl_graph_free.argtypes = [C.c_void_p]
     L.ncl_einsum.argtypes = [C.POINTER(EinsumDesc), C.POINTER(Tensor), C.c_int, C.POINTER(Tensor), C.c_int, C.c_uint]
     L.ncl_broadcast.argtypes = [C.c_int, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor)]
     L.ncl_fold.argtypes = [C.c_int, C.c_int, C.POINTER(Tensor), C.c_int, C.POINTER(Tensor)]
@@ -160,3 +170,40 @@ def shutdown():
     if _lib is not None and _inited:
         _lib.ncl_shutdown()
         _inited = False
+
+
+class Graph:
+    """A recorded call sequence (ncl_capture_begin .. ncl_capture_end): `with Graph() as g: <calls>`; then g.launch()."""
+
+    def __init__(self):
+        self._g = C.c_void_p()
+
+    def __enter__(self):
+        check(lib().ncl_capture_begin())
+        return self
+
+    def __exit__(self, et, ev, tb):
+        rc = lib().ncl_capture_end(C.byref(self._g))
+        if et is None:
+            check(rc)
+        return False
+
+    def launch(self):
+        check(lib().ncl_graph_launch(self._g))
+
+    @property
+    def kernels(self):
+        return lib().ncl_graph_kernels(self._g)
+
+    def __del__(self):
+        try:
+            if self._g:
+                load().ncl_graph_free(self._g)
+        except Exception:
+            pass
+
+
+def transfer_stats():
+    h, d = C.c_uint64(), C.c_uint64()
+    lib().ncl_transfer_stats(C.byref(h), C.byref(d))
+    return h.value, d.value

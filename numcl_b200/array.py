@@ -205,11 +205,12 @@ def arange(*args, type=None, where="device") -> NArray:
     return asarray(v, type=type, where=where)
 
 
-def random_array(shape, type, seed, dist=0, lo=0.0, hi=1.0) -> NArray:
-    """Synthetic input generated on the device (splitmix64(seed ^ index))."""
+def random_array(shape, type, seed, dist=0, lo=0.0, hi=1.0, first=0) -> NArray:
+    """Synthetic input generated on the device (splitmix64(seed ^ index)).  `first`: index of this array's
+    first element in the stream, so that a rank can generate its row shard of a larger array."""
     a = NArray(_shape(shape), type)
     t = a.tensor()
-    _lib.check(_lib.lib().ncl_fill_random(C.byref(t), C.c_uint64(seed), dist, float(lo), float(hi)))
+    _lib.check(_lib.lib().ncl_fill_random_at(C.byref(t), C.c_uint64(seed), C.c_uint64(first), dist, float(lo), float(hi)))
     return a
 
 

@@ -9,6 +9,7 @@ struct FillParams {
   StoreSpec st; int slot_bits; int cls;
   int is_float; long long iv; double fv;        // constant fill
   unsigned long long seed; int dist; double lo, hi; int random;
+  unsigned long long first;                     // element k of the tensor is element first + k of the synthetic stream
 };
 
 template <class T> __device__ __forceinline__ void fill_store_direct(char* base, long long idx, const StoreSpec& s, T v) {
@@ -26,7 +27,7 @@ template <class T> __device__ __forceinline__ void fill_store_direct(char* base,
 
 // element i of the synthetic stream; mirrors nco_fill_random in oracle/numcl_oracle.c exactly
 __device__ __forceinline__ void synth(const FillParams& p, long long i, long long& iv, float& f, double& d) {
-  unsigned long long h = splitmix64(p.seed ^ (unsigned long long)i);
+  unsigned long long h = splitmix64(p.seed ^ (p.first + (unsigned long long)i));
   if (p.cls != CLS_I && p.dist != 1) {
     if (p.cls == CLS_F) {
       float u = __fmul_rn((float)(h >> 40), 0x1p-24f);
@@ -155,10 +156,10 @@ int fill_const(void* base, int dtype, int64_t offset, int64_t n, bool is_float, 
   return launch_fill(p);
 }
 
-int fill_random(void* base, int dtype, int64_t offset, int64_t n, uint64_t seed, int dist, double lo, double hi) {
+int fill_random(void* base, int dtype, int64_t offset, int64_t n, uint64_t seed, uint64_t first_index, int dist, double lo, double hi) {
   FillParams p; memset(&p, 0, sizeof p);
   p.base = (char*)base; p.offset = offset; p.n = n; p.st = dtype_store_spec(dtype);
   p.slot_bits = g_dt[dtype].slot_bits; p.cls = g_dt[dtype].cls;
-  p.seed = seed; p.dist = dist; p.lo = lo; p.hi = hi; p.random = 1;
+  p.seed = seed; p.first = first_index; p.dist = dist; p.lo = lo; p.hi = hi; p.random = 1;
   return launch_fill(p);
 }

@@ -313,14 +313,7 @@ int reduce_all_p2p(int op, const Operand& a, int64_t count, const Operand& r, un
   RedParams p; memset(&p, 0, sizeof p);
   p.in = a.base; p.in_off = a.offset; p.lk = dtype_load_kind(a.dtype); p.cols = count;
   p.out = r.base; p.out_off = r.offset; p.sk = dtype_store_spec(r.dtype); p.out_lk = dtype_load_kind(r.dtype);
-  p.fresh = 1; p.ident_i = rop == R_MUL ? 1 : 0; p.ident_f = rop == R_MUL ? 1.0 : 0.0;
-  if (rop == R_MAX || rop == R_MIN) {
-    const DtInfo& d = g_dt[r.dtype]; bool mx = rop == R_MAX;
-    if (d.cls == CLS_F) p.ident_f = mx ? -3.4028234663852886e38 : 3.4028234663852886e38;
-    else if (d.cls == CLS_D) p.ident_f = mx ? -1.7976931348623157e308 : 1.7976931348623157e308;
-    else if (d.is_signed) p.ident_i = mx ? (d.value_bits >= 64 ? INT64_MIN : -(1ll << (d.value_bits - 1))) : (d.value_bits >= 64 ? INT64_MAX : (1ll << (d.value_bits - 1)) - 1);
-    else p.ident_i = mx ? 0 : (d.value_bits >= 63 ? INT64_MAX : (1ll << d.value_bits) - 1);
-  }
+  p.fresh = 1; reduce_identity(op, r.dtype, &p.ident_i, &p.ident_f);
   int Evec = 128 / sb;
   p.vec = count >= Evec && aligned16(a, a.offset);
   int E = p.vec ? Evec : 1;
@@ -352,6 +345,7 @@ int reduce_all_to_partial(int op, const Operand& a, int64_t count, void* partial
   long long blocks = (work + 1023) / 1024; long long cap = persistent_blocks((const void*)kfn); if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
   NCL_TRY(ensure_scratch((size_t)blocks * 8));
   p.block_partials = c.scratch; p.ticket = c.ticket; p.nblocks = (int)blocks; p.raw_partial = partial8; p.fresh = 1;
+  reduce_identity(op, a.dtype, &p.ident_i, &p.ident_f);       // an empty slab contributes the identity (max / min seed)
   kfn<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
   note_launch("reduce_all");
   return cuda_fail(cudaGetLastError(), "reduce_all_kernel");

@@ -418,7 +418,9 @@ template <class T, int E> constexpr int reduce_all_min_blocks() { return (sizeof
 template <class T, int OP, int E, bool DOT>
 __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all_kernel(const __grid_constant__ RedParams p) {
   typedef typename Wide<T>::W W;
-  T seed = (OP == R_ADD || OP == R_MUL) ? neutral<T, OP>() : load_scalar<T>(p.in, p.in_off, p.lk);
+  // max / min start from the first element; an EMPTY slab (a rank that owns no rows of a sharded array) has none and
+  // contributes the identity instead of reading in[0]
+  T seed = (OP == R_ADD || OP == R_MUL) ? neutral<T, OP>() : (p.cols > 0 ? load_scalar<T>(p.in, p.in_off, p.lk) : ident_of<T>(p));
   T acc[4];
 #pragma unroll
   for (int u = 0; u < 4; u++) acc[u] = seed;
@@ -470,42 +472,21 @@ __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all
   for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) s = Red<W, OP>::f(s, ((volatile W*)partials)[i]);
   s = block_combine<W, OP, 256>(s);
   if (p.world > 1) {
-    // ---- compute + collective in ONE kernel: P2P stores / loads on NVLink-mapped mailboxes -------
-    // mailbox layout per rank: [parity 2][source rank world]{value bits, sequence}; the parity slot of
-    // call n cannot be overwritten by call n+2 before every rank has consumed call n (each rank only
-    // reaches n+2 after receiving everybody's n+1, which is sent after n was read).
-    __shared__ unsigned long long xch[64];
-    if (threadIdx.x == 0) { *p.ticket = 0; xch[63] = (unsigned long long)(std::is_integral<T>::value ? (long long)s : __double_as_longlong((double)s)); }
+    // ---- compute + collective push in ONE kernel: P2P stores into NVLink-mapped mailboxes -----------------
+    // Every rank's mailbox (layout: mbox_* helpers in ncl_device.cuh) is mapped into every other rank.  The last block
+    // takes the next sequence number from the rank's own device-resident counter (so the launch is identical every time
+    // and can sit in a CUDA graph), and W threads store the partial into all W mailboxes.  A message is two 8-byte words,
+    // each {sequence : 32 | half of the value : 32}: every word is published atomically by its own store, so there is no
+    // fence and no second "flag" store on the critical path -- the kernel ends right after issuing the stores.
+    // Nobody waits here: mailbox_finalize_kernel (k_reduce.cu), one small CTA on the communication stream, collects the W
+    // messages, folds them in rank order and stores the result while the compute stream already runs the next kernel.
+    __shared__ unsigned long long xseq;
+    if (threadIdx.x == 0) { *p.ticket = 0; xseq = mbox_push_seq(p.peers[p.rank], p.world) + 1ull; }
     __syncthreads();
-    const int t = threadIdx.x;
-    if (t < p.world) {
-      const size_t slot = (((size_t)(p.seq & 1) * p.world) + p.rank) * 2;
-      volatile unsigned long long* remote = p.peers[t] + slot;
-      remote[0] = xch[63];
-      __threadfence_system();
-      remote[1] = p.seq;                                                   // publish
-      volatile unsigned long long* mine = p.peers[p.rank] + (((size_t)(p.seq & 1) * p.world) + t) * 2;
-      long long t0 = clock64();
-      unsigned long long seen;
-      do {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine + 1) : "memory");
-        if (seen != p.seq && clock64() - t0 > 20000000000LL) { printf("numcl-cuda: peer %d did not arrive (rank %d)\n", t, p.rank); __trap(); }
-      } while (seen != p.seq);
-      xch[t] = mine[0];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      W tot;
-      if constexpr (std::is_integral<T>::value) tot = (W)(long long)xch[0]; else tot = (W)__longlong_as_double((long long)xch[0]);
-      for (int r = 1; r < p.world; r++) {
-        W v; if constexpr (std::is_integral<T>::value) v = (W)(long long)xch[r]; else v = (W)__longlong_as_double((long long)xch[r]);
-        tot = Red<W, OP>::f(tot, v);                                       // rank order: every rank gets the same bits
-      }
-      W init = p.fresh ? (W)ident_of<T>(p) : (W)load_scalar<T>(p.out, p.out_off, p.out_lk);
-      W r = Red<W, OP>::f(init, tot);
-      if constexpr (std::is_integral<T>::value) store_scalar<long long>(p.out, p.out_off, p.sk, r);
-      else store_scalar<double>(p.out, p.out_off, p.sk, r);
-    }
+    const unsigned long long seq = xseq;
+    const unsigned long long bits = (unsigned long long)(std::is_integral<T>::value ? (long long)s : __double_as_longlong((double)s));
+    if (threadIdx.x < p.world) mbox_send(p.peers[threadIdx.x], p.world, seq, p.rank, bits);
+    if (threadIdx.x == 0) mbox_set_push_seq(p.peers[p.rank], p.world, seq);
     return;
   }
   if (threadIdx.x == 0) {

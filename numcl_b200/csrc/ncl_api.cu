@@ -40,6 +40,7 @@ static void pool_release_all() {
 
 static int grow(void** p, size_t* have, size_t want) {
   if (*have >= want) return NCL_OK;
+  if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "a scratch arena must grow (%zu bytes) inside ncl_capture_begin/end: run the sequence once before capturing it", want);
   if (*p) { NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); NCL_CUDA(cudaFree(*p)); *p = nullptr; *have = 0; }
   size_t sz = want + want / 4 + (1u << 20);
   if (cudaMalloc(p, sz) != cudaSuccess) { cudaGetLastError(); pool_release_all(); NCL_CUDA(cudaMalloc(p, sz)); }
@@ -48,6 +49,21 @@ static int grow(void** p, size_t* have, size_t want) {
 int ensure_scratch(size_t bytes) { return grow(&g_ctx.scratch, &g_ctx.scratch_bytes, bytes); }
 int ensure_scratch2(size_t bytes) { return grow(&g_ctx.scratch2, &g_ctx.scratch2_bytes, bytes); }
 int ensure_scratch3(size_t bytes) { return grow(&g_ctx.scratch3, &g_ctx.scratch3_bytes, bytes); }
+
+void reduce_identity(int op, int dtype, long long* ident_i, double* ident_f) {
+  const DtInfo& d = g_dt[dtype];
+  *ident_i = op == NCL_OP_MUL ? 1 : 0; *ident_f = op == NCL_OP_MUL ? 1.0 : 0.0;
+  if (op != NCL_OP_MAX && op != NCL_OP_MIN) return;
+  const bool mx = op == NCL_OP_MAX;
+  if (d.cls == CLS_F) *ident_f = mx ? -3.4028234663852886e38 : 3.4028234663852886e38;
+  else if (d.cls == CLS_D) *ident_f = mx ? -1.7976931348623157e308 : 1.7976931348623157e308;
+  else {
+    long long lo, hi;
+    if (d.is_signed) { lo = d.value_bits >= 64 ? INT64_MIN : -((long long)1 << (d.value_bits - 1)); hi = d.value_bits >= 64 ? INT64_MAX : ((long long)1 << (d.value_bits - 1)) - 1; }
+    else { lo = 0; hi = d.value_bits >= 63 ? INT64_MAX : ((long long)1 << d.value_bits) - 1; }
+    *ident_i = mx ? lo : hi;
+  }
+}
 
 #define LOCK std::lock_guard<std::recursive_mutex> lock__(g_mu)
 #define NEED_INIT if (!g_ctx.inited) return set_error(NCL_ERR_STATE, "ncl_init has not been called")
@@ -65,7 +81,8 @@ int ncl_init(int ndev, const int* devs) {
   if (e != cudaSuccess || count == 0)
     return set_error(NCL_ERR_CUDA, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
   if (ndev <= 0) ndev = 1;
-  if (ndev > 16) return set_error(NCL_ERR_INVALID, "ndev > 16");
+  // one process per GPU: the buffer cache, the scratch arenas and the stream all belong to ONE device
+  if (ndev > 1) return set_error(NCL_ERR_UNSUPPORTED, "ndev = %d: bind one process to one GPU (one rank per device) and shard across processes", ndev);
   g_ctx.ndev = ndev;
   for (int i = 0; i < ndev; i++) g_ctx.devs[i] = devs ? devs[i] : i;
   NCL_CUDA(cudaSetDevice(g_ctx.devs[0]));
@@ -113,7 +130,64 @@ int ncl_set_stream(void* s) {
   return NCL_OK;
 }
 void* ncl_get_stream(void) { return (void*)g_ctx.stream; }
-int ncl_sync(void) { NEED_INIT; ncl_comm_join(); NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); return NCL_OK; }
+int ncl_sync(void) {
+  LOCK; NEED_INIT;
+  if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_sync inside ncl_capture_begin/end");
+  ncl_comm_join(); NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); return NCL_OK;
+}
+// Give every cached device block back to the driver (the cache keeps freed base vectors for re-use and would otherwise
+// only shrink when one of the library's own allocations fails): for hosts that share the GPU with another allocator.
+int ncl_trim(void) { LOCK; NEED_INIT; if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_trim inside a capture"); pool_release_all(); return NCL_OK; }
+void ncl_transfer_stats(uint64_t* h2d_bytes, uint64_t* d2h_bytes) { if (h2d_bytes) *h2d_bytes = g_ctx.h2d_bytes; if (d2h_bytes) *d2h_bytes = g_ctx.d2h_bytes; }
+
+// ---- CUDA graphs: a launch-bound sequence of calls recorded once, replayed with ONE launch ---------------------------------
+// Between ncl_capture_begin and ncl_capture_end every compute call on device-resident tensors is recorded into a CUDA
+// graph instead of being executed (the library's communication stream joins the capture through its events, so the sharded
+// reduce with its mailbox exchange is captured too).  Host-resident tensors, ncl_d2h, ncl_sync and anything that has to
+// allocate are refused while capturing: run the sequence once eagerly first.  ncl_graph_launch replays on the library
+// stream; the arrays named at capture time are the ones read and written on every replay.
+struct ncl_graph { cudaGraph_t g; cudaGraphExec_t e; int64_t launches; };
+int ncl_capture_begin(void) {
+  LOCK; NEED_INIT;
+  if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_capture_begin: already capturing");
+  NCL_TRY(ncl_comm_join());
+  NCL_CUDA(cudaStreamBeginCapture(g_ctx.stream, cudaStreamCaptureModeRelaxed));
+  g_ctx.capturing = true; g_ctx.capture_launch0 = g_ctx.launches;
+  return NCL_OK;
+}
+int ncl_capture_end(ncl_graph** out) {
+  LOCK; NEED_INIT;
+  if (!g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_capture_end without ncl_capture_begin");
+  int jrc = ncl_comm_join();                               // the communication stream must re-join before the capture ends
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(g_ctx.stream, &g);
+  g_ctx.capturing = false;
+  if (jrc != NCL_OK) { if (g) cudaGraphDestroy(g); return jrc; }
+  if (e != cudaSuccess || !g) { cudaGetLastError(); return set_error(NCL_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e)); }
+  cudaGraphExec_t x = nullptr;
+  e = cudaGraphInstantiate(&x, g, 0);
+  if (e != cudaSuccess) { cudaGraphDestroy(g); cudaGetLastError(); return set_error(NCL_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+  if (!out) { cudaGraphExecDestroy(x); cudaGraphDestroy(g); return set_error(NCL_ERR_INVALID, "ncl_capture_end: out is NULL"); }
+  *out = new ncl_graph{g, x, g_ctx.launches - g_ctx.capture_launch0};
+  g_ctx.launches = g_ctx.capture_launch0;                  // nothing ran yet: replays are what gets counted
+  return NCL_OK;
+}
+int ncl_graph_launch(ncl_graph* gr) {
+  LOCK; NEED_INIT;
+  if (!gr) return set_error(NCL_ERR_INVALID, "ncl_graph_launch: NULL graph");
+  if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_graph_launch inside a capture");
+  NCL_TRY(ncl_comm_join());
+  NCL_CUDA(cudaGraphLaunch(gr->e, g_ctx.stream));
+  g_ctx.launches += gr->launches;
+  return NCL_OK;
+}
+int64_t ncl_graph_kernels(const ncl_graph* gr) { return gr ? gr->launches : 0; }
+int ncl_graph_free(ncl_graph* gr) {
+  LOCK;
+  if (!gr) return NCL_OK;
+  if (g_ctx.inited) cudaStreamSynchronize(g_ctx.stream);
+  cudaGraphExecDestroy(gr->e); cudaGraphDestroy(gr->g); delete gr; return NCL_OK;
+}
 int64_t ncl_launch_count(void) { return g_ctx.launches; }
 const char* ncl_last_kernel(void) { return g_ctx.last_kernel; }
 int ncl_force_generic(int on) { g_ctx.force_generic = on != 0; return NCL_OK; }
@@ -151,14 +225,18 @@ void* ncl_buf_ptr(const ncl_buf* b) { return b ? b->ptr : nullptr; }
 size_t ncl_buf_bytes(const ncl_buf* b) { return b ? b->bytes : 0; }
 ncl_buf* ncl_wrap(void* p, size_t bytes, int dev_slot) { return new ncl_buf{p, bytes, dev_slot, false}; }
 int ncl_h2d(ncl_buf* dst, size_t off, const void* host, size_t bytes) {
-  NEED_INIT;
+  LOCK; NEED_INIT;
   if (!dst || off + bytes > dst->bytes) return set_error(NCL_ERR_INVALID, "ncl_h2d out of range");
+  if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_h2d inside ncl_capture_begin/end");
   NCL_CUDA(cudaMemcpyAsync((char*)dst->ptr + off, host, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+  g_ctx.h2d_bytes += bytes;
   return NCL_OK;
 }
 int ncl_d2h(void* host, const ncl_buf* src, size_t off, size_t bytes) {
-  NEED_INIT;
+  LOCK; NEED_INIT;
   if (!src || off + bytes > src->bytes) return set_error(NCL_ERR_INVALID, "ncl_d2h out of range");
+  if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_d2h inside ncl_capture_begin/end");
+  g_ctx.d2h_bytes += bytes;
   ncl_comm_join();
   NCL_CUDA(cudaMemcpyAsync(host, (const char*)src->ptr + off, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
   NCL_CUDA(cudaStreamSynchronize(g_ctx.stream));
@@ -200,24 +278,40 @@ struct Stager {
     for (int i = 0; i < n; i++) if (ts[i].host) { items.push_back({&ts[i], nullptr, need(&ts[i]), is_out}); used += items.back().bytes; }
     return NCL_OK;
   }
+  // byte window of the base vector a tensor's elements occupy: [lo, hi)
+  static void window(const ncl_tensor* t, size_t* lo, size_t* hi, bool* ragged) {
+    const size_t bits = (size_t)g_dt[t->dtype].slot_bits, b0 = (size_t)t->elem_offset * bits, b1 = ((size_t)t->elem_offset + (size_t)total_elems(t)) * bits;
+    *lo = b0 / 8; *hi = (b1 + 7) / 8; *ragged = (b0 % 8) != 0 || (b1 % 8) != 0;
+  }
   int upload(bool outputs_too) {
     if (!used) return NCL_OK;
+    if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "host-resident tensors cannot be staged inside ncl_capture_begin/end");
     NCL_TRY(ensure_scratch2(used));
     size_t off = 0;
     for (auto& it : items) {
       it.dev = (char*)g_ctx.scratch2 + off; off += it.bytes;
       size_t live = ncl_storage_bytes(it.t->dtype, it.t->elem_offset + total_elems(it.t));
-      if (!it.is_out || outputs_too)
+      if (!it.is_out || outputs_too) {
         NCL_CUDA(cudaMemcpyAsync(it.dev, it.t->host, live, cudaMemcpyHostToDevice, g_ctx.stream));
+        g_ctx.h2d_bytes += live;
+      } else {
+        // a write-only output is not uploaded; but a packed (bit / ub2 / ub4) window that does not start and end on byte
+        // boundaries shares its first / last byte with neighbouring elements of the base vector, which the download
+        // must hand back unchanged: stage those bytes (the kernels update sub-byte fields read-modify-write)
+        size_t lo, hi; bool ragged; window(it.t, &lo, &hi, &ragged);
+        if (ragged && hi > lo) NCL_CUDA(cudaMemcpyAsync(it.dev + lo, (const char*)it.t->host + lo, hi - lo, cudaMemcpyHostToDevice, g_ctx.stream));
+      }
     }
     return NCL_OK;
   }
   char* dev_of(const ncl_tensor* t) { for (auto& it : items) if (it.t == t) return it.dev; return nullptr; }
+  // Only the bytes of the tensor's own window travel back: the arena in front of a displaced view (elem_offset > 0) and the
+  // padding behind it were never initialised when the output was not uploaded, and must not overwrite the host base vector.
   int download() {
     bool any = false;
     for (auto& it : items) if (it.is_out) {
-      size_t live = ncl_storage_bytes(it.t->dtype, it.t->elem_offset + total_elems(it.t));
-      NCL_CUDA(cudaMemcpyAsync(it.t->host, it.dev, live, cudaMemcpyDeviceToHost, g_ctx.stream)); any = true;
+      size_t lo, hi; bool ragged; window(it.t, &lo, &hi, &ragged);
+      if (hi > lo) { NCL_CUDA(cudaMemcpyAsync((char*)it.t->host + lo, it.dev + lo, hi - lo, cudaMemcpyDeviceToHost, g_ctx.stream)); any = true; g_ctx.d2h_bytes += hi - lo; }
     }
     if (any) NCL_CUDA(cudaStreamSynchronize(g_ctx.stream));
     return NCL_OK;
@@ -422,6 +516,23 @@ int ncl_einsum(const ncl_einsum_desc* desc, const ncl_tensor* in, int n_in, ncl_
   return with_staging(in, n_in, out, n_out, !(flags & NCL_OUT_FRESH), [&](Stager& st) {
     Nest* nest = new Nest;
     int rc = build_einsum_nest(desc, in, out, flags, st, nest);
+    // A fresh output stands for the `zeros` the wrapper would have made (src/3einsum.lisp:468), but the nest only writes
+    // the elements it visits.  When it cannot visit all of them -- an index repeated in the o-spec (`i -> ii` writes the
+    // diagonal only) or an o-option (:start / :end / :step) -- the rest must read as 0, not as whatever the recycled
+    // block held: make the zeros for real and accumulate into them.
+    if (rc == NCL_OK && nest->fresh) {
+      bool sparse = false;
+      for (int o = 0; o < desc->n_out && !sparse; o++) {
+        if (desc->out_nopt[o] > 0) sparse = true;
+        for (int k = 0; k < desc->out_rank[o] && !sparse; k++)
+          for (int k2 = k + 1; k2 < desc->out_rank[o]; k2++) if (desc->out_spec[o][k] >= 0 && desc->out_spec[o][k] == desc->out_spec[o][k2]) sparse = true;
+      }
+      if (sparse) {
+        for (int o = 0; o < desc->n_out && rc == NCL_OK; o++)
+          rc = fill_const(nest->out[o].base, out[o].dtype, out[o].elem_offset, total_elems(&out[o]), false, 0, 0.0);
+        nest->fresh = false;
+      }
+    }
     if (rc == NCL_OK) rc = run_nest(*nest);
     delete nest; return rc;
   });
@@ -537,20 +648,8 @@ int ncl_reduce(int op, const ncl_tensor* a, const int* axes, int n_axes, ncl_ten
     }
     if (fresh) {                                                  // identities of sum / prod / amax / amin, :103-126 + 1constants.lisp
       nest->has_identity = true;
-      const DtInfo& d = g_dt[r->dtype];
-      if (op == NCL_OP_ADD) { nest->ident_i = 0; nest->ident_f = 0.0; }
-      else if (op == NCL_OP_MUL) { nest->ident_i = 1; nest->ident_f = 1.0; }
-      else {
-        bool mx = op == NCL_OP_MAX;
-        if (d.cls == CLS_F) nest->ident_f = mx ? -3.4028234663852886e38 : 3.4028234663852886e38;
-        else if (d.cls == CLS_D) nest->ident_f = mx ? -1.7976931348623157e308 : 1.7976931348623157e308;
-        else {
-          int64_t lo, hi;
-          if (d.is_signed) { lo = d.value_bits >= 64 ? INT64_MIN : -((int64_t)1 << (d.value_bits - 1)); hi = d.value_bits >= 64 ? INT64_MAX : ((int64_t)1 << (d.value_bits - 1)) - 1; }
-          else { lo = 0; hi = d.value_bits >= 63 ? INT64_MAX : ((int64_t)1 << d.value_bits) - 1; }
-          nest->ident_i = mx ? lo : hi;
-        }
-      }
+      long long ii; double ff; reduce_identity(op, r->dtype, &ii, &ff);
+      nest->ident_i = ii; nest->ident_f = ff;
     }
     ncl_expr e; e.n = 0; x_leaf(&e, NCL_X_OUTPUT, 1); x_leaf(&e, NCL_X_INPUT, 1); x_op(&e, op, 0, 1);   // (funcall fn r a)
     int in_dt = a->dtype, out_dt = r->dtype;
@@ -565,10 +664,11 @@ int ncl_fill(ncl_tensor* t, int value_is_float, int64_t ival, double fval) {
   if (!t->buf) return set_error(NCL_ERR_UNSUPPORTED, "ncl_fill works on device-resident tensors");
   return fill_const(t->buf->ptr, t->dtype, t->elem_offset, total_elems(t), value_is_float != 0, ival, fval);
 }
-int ncl_fill_random(ncl_tensor* t, uint64_t seed, int dist, double lo, double hi) {
+int ncl_fill_random_at(ncl_tensor* t, uint64_t seed, uint64_t first_index, int dist, double lo, double hi) {
   LOCK; NEED_INIT; NCL_TRY(check_tensor(t, "tensor"));
   if (!t->buf) return set_error(NCL_ERR_UNSUPPORTED, "ncl_fill_random works on device-resident tensors");
-  return fill_random(t->buf->ptr, t->dtype, t->elem_offset, total_elems(t), seed, dist, lo, hi);
+  return fill_random(t->buf->ptr, t->dtype, t->elem_offset, total_elems(t), seed, first_index, dist, lo, hi);
 }
+int ncl_fill_random(ncl_tensor* t, uint64_t seed, int dist, double lo, double hi) { return ncl_fill_random_at(t, seed, 0, dist, lo, hi); }
 
 }  // extern "C"

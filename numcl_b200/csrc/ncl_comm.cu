@@ -21,7 +21,7 @@ typedef const char* (*fn_errstr)(int);
 static struct {
   void* h; fn_get_uid get_uid; fn_init_rank init_rank; fn_allreduce allreduce; fn_destroy destroy; fn_errstr errstr; fn_allgather allgather;
   // peer mailboxes for the fused one-element all-reduce (NVLink P2P, CUDA IPC)
-  unsigned long long* mbox; unsigned long long** peers_host; unsigned long long** peers_dev; bool p2p; unsigned long long seq;
+  unsigned long long* mbox; unsigned long long** peers_host; unsigned long long** peers_dev; bool p2p;
   nccl_comm comm; int rank, world; void* partial;   // 8-byte device slot for the sharded full reduce
   cudaStream_t comm_stream; cudaEvent_t ev_partial, ev_done; bool pending;
 } g_nccl;
@@ -61,19 +61,40 @@ static int finalize_partial_on(cudaStream_t stream, int op, const void* partial8
 int finalize_partial(int op, const void* partial8, int cls, Operand& r, bool fresh) { return finalize_partial_on(ctx().stream, op, partial8, cls, r, fresh); }
 static int finalize_partial_on(cudaStream_t stream, int op, const void* partial8, int cls, Operand& r, bool fresh) {
   StoreSpec sk = dtype_store_spec(r.dtype); int lk = dtype_load_kind(r.dtype);
-  long long ident_i = op == NCL_OP_MUL ? 1 : 0; double ident_f = op == NCL_OP_MUL ? 1.0 : 0.0;
-  const DtInfo& d = g_dt[r.dtype];
-  if (op == NCL_OP_MAX || op == NCL_OP_MIN) {
-    bool mx = op == NCL_OP_MAX;
-    if (d.cls == CLS_F) ident_f = mx ? -3.4028234663852886e38 : 3.4028234663852886e38;
-    else if (d.cls == CLS_D) ident_f = mx ? -1.7976931348623157e308 : 1.7976931348623157e308;
-    else ident_i = mx ? (d.is_signed ? -(1ll << (d.value_bits >= 64 ? 62 : d.value_bits - 1)) : 0)
-                      : (d.is_signed ? (1ll << (d.value_bits >= 64 ? 62 : d.value_bits - 1)) - 1 : (d.value_bits >= 63 ? INT64_MAX : (1ll << d.value_bits) - 1));
-  }
+  long long ident_i; double ident_f; reduce_identity(op, r.dtype, &ident_i, &ident_f);
   if (cls == CLS_I) finalize_kernel<long long><<<1, 1, 0, stream>>>((const long long*)partial8, r.base, r.offset, sk, lk, fresh, op, ident_i, ident_f);
   else finalize_kernel<double><<<1, 1, 0, stream>>>((const double*)partial8, r.base, r.offset, sk, lk, fresh, op, ident_i, ident_f);
   note_launch("reduce_finalize");
   return cuda_fail(cudaGetLastError(), "finalize_kernel");
+}
+
+// The collective half of the sharded full reduce when the mailboxes are mapped (k_reduce.cuh: reduce_all_kernel pushes):
+// one CTA on the communication stream waits for the W messages of the current sequence number, folds them in rank order
+// (every rank computes the same bits) and stores the result with one rounding.  It runs beside whatever the compute
+// stream launched after the local reduction, so neither the NVLink latency nor the skew between ranks is on that stream.
+template <class W>
+__global__ void mailbox_finalize_kernel(unsigned long long* const* peers, int rank, int world, char* out, long long off, StoreSpec sk, int op,
+                                        long long ident_i, double ident_f) {
+  __shared__ unsigned long long xch[64];
+  const unsigned long long* mb = peers[rank];
+  const unsigned long long seq = mbox_push_seq(mb, world);            // the message this rank's reduction just pushed
+  const int t = threadIdx.x;
+  if (t < world) {
+    unsigned long long bits = 0;
+    if (!mbox_recv(mb, world, seq, t, &bits)) { printf("numcl-cuda: rank %d never received partial %llu of rank %d\n", rank, seq, t); __trap(); }
+    xch[t] = bits;
+  }
+  __syncthreads();
+  if (t != 0) return;
+  auto val = [&](int r) -> W { if constexpr (std::is_integral<W>::value) return (W)(long long)xch[r]; else return (W)__longlong_as_double((long long)xch[r]); };
+  W tot = val(0);
+  for (int r = 1; r < world; r++) {
+    const W v = val(r);
+    tot = op == NCL_OP_ADD ? Ops<W>::add(tot, v) : op == NCL_OP_MUL ? Ops<W>::mul(tot, v) : op == NCL_OP_MAX ? Ops<W>::mx(tot, v) : Ops<W>::mn(tot, v);
+  }
+  const W init = std::is_integral<W>::value ? (W)ident_i : (W)ident_f;
+  const W res = op == NCL_OP_ADD ? Ops<W>::add(init, tot) : op == NCL_OP_MUL ? Ops<W>::mul(init, tot) : op == NCL_OP_MAX ? Ops<W>::mx(init, tot) : Ops<W>::mn(init, tot);
+  store_scalar<W>(out, off, sk, res);
 }
 
 // Map every rank's mailbox into this process (CUDA IPC over NVLink).  The 64-byte IPC handles travel
@@ -82,7 +103,7 @@ static void setup_p2p() {
   g_nccl.p2p = false;
   if (!g_nccl.allgather || g_nccl.world < 2 || g_nccl.world > 63 || getenv("NUMCL_CUDA_NO_P2P")) return;
   const int W = g_nccl.world; cudaStream_t st = ctx().stream;
-  size_t mbytes = (size_t)2 * W * 16;
+  size_t mbytes = mbox_words(W) * 8;
   if (cudaMalloc((void**)&g_nccl.mbox, mbytes) != cudaSuccess) return;
   cudaMemset(g_nccl.mbox, 0, mbytes);
   cudaIpcMemHandle_t mine;
@@ -115,7 +136,7 @@ static void setup_p2p() {
   bool synced = g_nccl.allreduce(flag, flag, 1, 2 /* ncclInt32 */, 0 /* sum */, g_nccl.comm, st) == 0 && cudaStreamSynchronize(st) == cudaSuccess;
   cudaFree(flag);
   if (!synced) return;
-  g_nccl.seq = 0; g_nccl.p2p = true;
+  g_nccl.p2p = true;
 }
 
 extern "C" {
@@ -205,11 +226,25 @@ int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a, ncl_tensor* r) {
     return rc;
   }
   if (g_nccl.p2p) {
-    // ONE kernel: local reduce, then its last block exchanges partials with the peers over NVLink-mapped
-    // mailboxes and writes the final value.  No NCCL call, no second launch.
-    int rc = reduce_all_p2p(op, ao, n, ro, g_nccl.peers_dev, g_nccl.rank, g_nccl.world, ++g_nccl.seq);
-    if (rc != NCL_ERR_UNSUPPORTED) return rc;
-    --g_nccl.seq;
+    // The local reduction's last block pushes the partial into every rank's mailbox over NVLink (P2P stores, no NCCL
+    // call); the one-CTA finalize collects the W messages on the communication stream.  A rank's push n + 1 is ordered
+    // after its own finalize n (two-parity mailbox, see ncl_device.cuh).
+    if (g_nccl.pending) NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done, 0));
+    int rc = reduce_all_p2p(op, ao, n, ro, g_nccl.peers_dev, g_nccl.rank, g_nccl.world, 0);
+    if (rc != NCL_ERR_UNSUPPORTED) {
+      NCL_TRY(rc);
+      NCL_CUDA(cudaEventRecord(g_nccl.ev_partial, ctx().stream));
+      NCL_CUDA(cudaStreamWaitEvent(g_nccl.comm_stream, g_nccl.ev_partial, 0));
+      long long ident_i; double ident_f; reduce_identity(op, ro.dtype, &ident_i, &ident_f);
+      const StoreSpec sk = dtype_store_spec(ro.dtype);
+      if (cls == CLS_I) mailbox_finalize_kernel<long long><<<1, 64, 0, g_nccl.comm_stream>>>(g_nccl.peers_dev, g_nccl.rank, g_nccl.world, ro.base, ro.offset, sk, op, ident_i, ident_f);
+      else mailbox_finalize_kernel<double><<<1, 64, 0, g_nccl.comm_stream>>>(g_nccl.peers_dev, g_nccl.rank, g_nccl.world, ro.base, ro.offset, sk, op, ident_i, ident_f);
+      note_launch("reduce_all_p2p");
+      NCL_TRY(cuda_fail(cudaGetLastError(), "mailbox_finalize_kernel"));
+      NCL_CUDA(cudaEventRecord(g_nccl.ev_done, g_nccl.comm_stream));
+      g_nccl.pending = true;
+      return NCL_OK;
+    }
   }
   if (g_nccl.pending) NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done, 0));   // the slot is single-buffered
   NCL_TRY(reduce_all_to_partial(op, ao, n, g_nccl.partial));

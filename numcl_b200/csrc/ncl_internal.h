@@ -60,6 +60,8 @@ struct Context {
   int64_t launches = 0;
   const char* last_kernel = "";
   bool force_generic = false;
+  bool capturing = false; int64_t capture_launch0 = 0;   // ncl_capture_begin .. ncl_capture_end
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;                 // bytes the library itself copied over PCIe (ncl_transfer_stats)
   // scratch: reduction partials, GEMM operand splits, host staging
   void* scratch = nullptr; size_t scratch_bytes = 0;
   void* scratch2 = nullptr; size_t scratch2_bytes = 0;   // host staging arena: lives for the whole call
@@ -93,7 +95,7 @@ int try_gemm(const Nest& n);                              // k_gemm.cu (dispatch
 int run_nest(Nest& n);                                    // ncl_plan.cu: canonicalise + dispatch
 
 int fill_const(void* base, int dtype, int64_t offset, int64_t n, bool is_float, int64_t iv, double fv);   // k_fill.cu
-int fill_random(void* base, int dtype, int64_t offset, int64_t n, uint64_t seed, int dist, double lo, double hi);
+int fill_random(void* base, int dtype, int64_t offset, int64_t n, uint64_t seed, uint64_t first_index, int dist, double lo, double hi);
 
 // full reduce of a contiguous array into a float64/int64 partial on the device (k_reduce.cu):
 // used by ncl_reduce_all_sharded before the all-reduce.
@@ -101,3 +103,7 @@ int reduce_all_to_partial(int op, const Operand& a, int64_t n, void* partial8);
 int finalize_partial(int op, const void* partial8, int cls, Operand& r, bool fresh);
 int reduce_all_p2p(int op, const Operand& a, int64_t n, const Operand& r, unsigned long long* const* peers, int rank, int world,
                    unsigned long long seq);
+// numcl's identity of a reduction into element type `dtype` (src/5reduce.lisp:103-126, src/1constants.lisp:30-89): sum 0,
+// prod 1, amax most-negative-value, amin most-positive-value.  ONE definition for ncl_reduce, the sharded reduce and
+// both of its finalize paths.
+void reduce_identity(int op, int dtype, long long* ident_i, double* ident_f);

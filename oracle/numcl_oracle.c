@@ -1126,10 +1126,12 @@ static uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
-int nco_fill_random(nco_tensor* t, uint64_t seed, int dist, double lo, double hi) {
+int nco_fill_random(nco_tensor* t, uint64_t seed, int dist, double lo, double hi) { return nco_fill_random_at(t, seed, 0, dist, lo, hi); }
+/* element k of the tensor is element first + k of the synthetic stream (a row shard of a larger array) */
+int nco_fill_random_at(nco_tensor* t, uint64_t seed, uint64_t first, int dist, double lo, double hi) {
   int64_t n = total_size(t); const dtinfo* d = &DT[t->dtype];
   for (int64_t i = 0; i < n; i++) {
-    uint64_t h = splitmix64(seed ^ (uint64_t)i);
+    uint64_t h = splitmix64(seed ^ (first + (uint64_t)i));
     val v;
     if (d->is_float && dist != 1) {
       if (d->is_float == 1) { float u = (float)(h >> 40) * 0x1p-24f; float w = (float)hi - (float)lo; float m = w * u; v = v_f32((float)lo + m); }

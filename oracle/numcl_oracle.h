@@ -121,6 +121,7 @@ void nco_fast_transpose_abcd_dbca_w64(const int64_t* in_tagged, int64_t* out_tag
 /* counter-based generator shared with the CUDA fill kernel:
  * splitmix64(seed ^ index). dist as in ncl_fill_random. */
 int nco_fill_random(nco_tensor* t, uint64_t seed, int dist, double lo, double hi);
+int nco_fill_random_at(nco_tensor* t, uint64_t seed, uint64_t first, int dist, double lo, double hi);
 
 #ifdef __cplusplus
 }

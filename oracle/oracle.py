@@ -52,6 +52,7 @@ def lib():
         L.nco_fast_sum_all_f32.restype = C.c_float
         L.nco_fast_sum_all_f32.argtypes = [C.c_void_p, C.c_int64]
         L.nco_fill_random.argtypes = [C.POINTER(_Tensor), C.c_uint64, C.c_int, C.c_double, C.c_double]
+        L.nco_fill_random_at.argtypes = [C.POINTER(_Tensor), C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_double]
         _lib = L
     return _lib
 
@@ -203,10 +204,11 @@ def plan_broadcast(shapes):
     return np.array(list(plan), dtype=np.int64).reshape(2, n + 1, M)
 
 
-def fill_random(shape, dtype: str, seed: int, dist: int, lo: float, hi: float) -> OArr:
+def fill_random(shape, dtype: str, seed: int, dist: int, lo: float, hi: float, first: int = 0) -> OArr:
+    """Synthetic stream element first + k for element k (first > 0: a row shard of a larger array)."""
     a = OArr(shape, dtype)
     t = a.c()
-    _check(lib().nco_fill_random(C.byref(t), C.c_uint64(seed), dist, lo, hi))
+    _check(lib().nco_fill_random_at(C.byref(t), C.c_uint64(seed), C.c_uint64(first), dist, lo, hi))
     return a
 
 
