@@ -41,7 +41,15 @@ typedef enum {
   NCL_ERR_UNSUPPORTED = -3,  /* outside the CUDA whitelist (no CPU fallback)             */
   NCL_ERR_CUDA        = -4,  /* CUDA runtime / driver error, text in ncl_last_error()    */
   NCL_ERR_NOMEM       = -5,
-  NCL_ERR_STATE       = -6   /* ncl_init not called, wrong device, ...                   */
+  NCL_ERR_STATE       = -6,  /* ncl_init not called, wrong device, ...                   */
+  NCL_ERR_DOMAIN      = -7   /* an element left the real domain of the function applied to it, where the
+                                reference would have signalled a Lisp error or produced a complex number:
+                                sqrt / log / log2 of a negative, asin / acos outside [-1,1], acosh below 1,
+                                atanh outside [-1,1], isqrt of a negative, integer division / mod / rem by
+                                zero, (expt 0 negative), an integer power that does not fit 64 bits.
+                                Kernels record it in a sticky device flag; the next ncl_sync, ncl_d2h or
+                                call with host-resident tensors reports it (and clears it).  The arrays
+                                written by the offending call hold NaN / 0 in those elements.            */
 } ncl_status;
 
 /* Element types = SBCL's specialized array element types, in SBCL's storage format
@@ -81,10 +89,21 @@ typedef enum {
   NCL_OP_EQ, NCL_OP_NE, NCL_OP_LE, NCL_OP_GE, NCL_OP_LT, NCL_OP_GT,
   /* bitwise, integers only (src/4numeric.lisp:584-602) */
   NCL_OP_LOGAND, NCL_OP_LOGIOR, NCL_OP_LOGXOR,
+  NCL_OP_LOGANDC1, NCL_OP_LOGANDC2, NCL_OP_LOGEQV, NCL_OP_LOGNAND, NCL_OP_LOGNOR, NCL_OP_LOGORC1, NCL_OP_LOGORC2,
+  /* rounding family (src/4numeric.lisp:568-581): (floor number divisor) etc. -> the INTEGER quotient (first value);
+   * mod / rem -> the remainder.  Integers: exact.  Floats: SBCL's definitions (truncate of the rounded quotient
+   * number/divisor, then the adjustment by the sign of the remainder; numbers.lisp), each float op rounded on its own. */
+  NCL_OP_FLOOR, NCL_OP_CEILING, NCL_OP_ROUND, NCL_OP_TRUNCATE, NCL_OP_MOD, NCL_OP_REM,
+  /* (expt base power), src/4numeric.lisp:533: integer power -> SBCL's intexp (repeated squaring, exact for integers,
+   * every multiplication rounded for floats; negative power = reciprocal); float power -> pow (tolerance only). */
+  NCL_OP_EXPT,
   NCL_OP_BINARY_END,
   /* unary (src/4numeric.lisp:455-519) */
   NCL_OP_NEG = 32, NCL_OP_ABS, NCL_OP_SQUARE, NCL_OP_SQRT, NCL_OP_LOGNOT, NCL_OP_IDENTITY,
   NCL_OP_EXP, NCL_OP_LOG, NCL_OP_SIN, NCL_OP_COS, NCL_OP_TAN, NCL_OP_TANH, NCL_OP_SIGNUM,
+  NCL_OP_ASIN, NCL_OP_ACOS, NCL_OP_ATAN, NCL_OP_SINH, NCL_OP_COSH, NCL_OP_ASINH, NCL_OP_ACOSH, NCL_OP_ATANH,
+  NCL_OP_LOG2,                                   /* %log2 = (log x 2), src/4numeric.lisp:514-516 */
+  NCL_OP_ISQRT, NCL_OP_LOGCOUNT, NCL_OP_INTEGER_LENGTH,   /* integers only, exact */
   /* leaves of an expression */
   NCL_X_INPUT = 64,  /* $a : element of input  number a (1-based)  */
   NCL_X_OUTPUT,      /* @a : element of output number a (1-based)  */

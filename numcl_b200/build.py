@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import concurrent.futures as cf
 import os
+import re
 import subprocess
 import sys
 
@@ -27,10 +28,21 @@ def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _deps_mtime():
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
-    hdrs.append(os.path.join(HERE, "..", "include", "numcl_cuda.h"))
-    return max(os.path.getmtime(h) for h in hdrs)
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _deps_mtime(src, _seen=None):
+    """newest mtime among `src` and the local headers it includes, transitively (a header change rebuilds only the
+    translation units that see it: the kernel instantiation files take minutes)"""
+    seen = _seen if _seen is not None else set()
+    path = os.path.normpath(os.path.join(CSRC, src))
+    if path in seen or not os.path.exists(path):
+        return 0.0
+    seen.add(path)
+    m = os.path.getmtime(path)
+    for inc in _INC.findall(open(path, errors="replace").read()):
+        m = max(m, _deps_mtime(os.path.join(os.path.dirname(src), inc), seen))
+    return m
 
 
 def _compile(src, verbose):
@@ -49,12 +61,11 @@ def _compile(src, verbose):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    hdr_m = _deps_mtime()
     todo, objs = [], []
     for src in _sources():
         obj = os.path.join(OBJ, src[:-3] + ".o")
         objs.append(obj)
-        sm = max(os.path.getmtime(os.path.join(CSRC, src)), hdr_m)
+        sm = _deps_mtime(src)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < sm:
             todo.append(src)
     if todo:

@@ -9,7 +9,7 @@
 // claims (diagonals `ii`, kron `ij kl -> ikjl`, multi-output specs, iteration options, odd
 // transforms) runs here -- not a fast path: operands are read with whatever strides the spec
 // gives and the transform is interpreted.
-#include "ncl_device.cuh"
+#include "ncl_fn.cuh"
 
 struct GNode { short op, a, b, cls; long long c; };
 
@@ -21,6 +21,7 @@ struct GenericParams {
   StoreSpec st; int out_cls, out_bits, out_signed;
   int fresh; int has_identity; long long ident_i; double ident_f;
   long long total;
+  unsigned int* fault;                                // sticky DOMAIN flag (ncl_fn.cuh)
   GNode node[NCL_MAX_EXPR];
 };
 
@@ -49,8 +50,8 @@ __device__ inline double gv_to_f64(GV g, int cls) {
 __device__ inline long long gv_round(GV g, int cls) {
   switch (cls) {
     case CLS_I: return g.i;
-    case CLS_F: return __float2ll_rn(gf(g));
-    case CLS_D: return __double2ll_rn(gd(g));
+    case CLS_F: return round_to_i64(gf(g));
+    case CLS_D: return round_to_i64(gd(g));
     default: {
       long long n = g.i, d = g.j; if (d < 0) { n = -n; d = -d; }
       if (d == 0) return 0;
@@ -79,11 +80,48 @@ __device__ inline GV coerce_out(GV v, int cls, const GenericParams& p) {
   return gv_i(x);
 }
 
-__device__ inline GV eval_node(const GNode& nd, const GV* val, const GNode* nodes) {
+__device__ inline GV eval_node(const GNode& nd, const GV* val, const GNode* nodes, unsigned int* flt) {
   int op = nd.op;
   if (op < NCL_OP_BINARY_END) {
     int ca = nodes[nd.a].cls, cb = nodes[nd.b].cls;
     GV a = val[nd.a], b = val[nd.b];
+    // comparisons between an integer and a float are exact in Common Lisp (CLHS 12.1.4.1), not after contagion
+    if (op >= NCL_OP_EQ && op <= NCL_OP_GT && ((ca == CLS_I) != (cb == CLS_I)) && ca != CLS_R && cb != CLS_R) {
+      int c;
+      if (ca == CLS_I) c = cmp_i64_f64(a.i, cb == CLS_F ? (double)gf(b) : gd(b));
+      else { c = cmp_i64_f64(b.i, ca == CLS_F ? (double)gf(a) : gd(a)); if (c != 2) c = -c; }
+      return gv_i(cmp_result(op, c));
+    }
+    if (op == NCL_OP_EXPT) {
+      if (cb == CLS_I) {                                                  // integer power: intexp
+        const long long pw = b.i;
+        if (ca == CLS_I) {
+          if (pw >= 0) return gv_i(int_expt(a.i, pw, flt));
+          if (a.i == 0) { ncl_fault(flt, FAULT_DIV0); return gv_i(0); }
+          GV g; g.i = 1; g.j = int_expt(a.i, -pw, flt); if (g.j < 0) { g.i = -1; g.j = -g.j; } return g;      // exact ratio until %coerce
+        }
+        if (ca == CLS_F) return gv_f(float_intexp<float>(gf(a), pw));
+        return gv_d(float_intexp<double>(gd(a), pw));
+      }
+      // float power: real-expt (pow in double-float, coerced back): tolerance only
+      const double x = gv_to_f64(a, ca), y = gv_to_f64(b, cb);
+      if (x < 0.0 && y != rint(y)) ncl_fault(flt, FAULT_DOMAIN);
+      const double r = pow(x, y);
+      return (ca == CLS_D || cb == CLS_D) ? gv_d(r) : gv_f((float)r);
+    }
+    if (op >= NCL_OP_FLOOR && op <= NCL_OP_REM) {
+      const bool want_rem = op == NCL_OP_MOD || op == NCL_OP_REM;
+      const int dop = op == NCL_OP_REM ? NCL_OP_TRUNCATE : op;
+      if (ca == CLS_I && cb == CLS_I) { long long r; const long long q = int_divide(dop, a.i, b.i, &r, flt); return gv_i(want_rem ? r : q); }
+      if (ca == CLS_D || cb == CLS_D) {
+        const double x = gv_to_f64(a, ca), y = gv_to_f64(b, cb); double r;
+        if (op == NCL_OP_ROUND && cb == CLS_I && b.i == 1) return gv_i(float_round_unary<double>(x));
+        const long long q = float_divide<double>(dop, x, y, &r); return want_rem ? gv_d(r) : gv_i(q);
+      }
+      const float x = gv_to_f32(a, ca), y = gv_to_f32(b, cb); float r;
+      if (op == NCL_OP_ROUND && cb == CLS_I && b.i == 1) return gv_i(float_round_unary<float>(x));
+      const long long q = float_divide<float>(dop, x, y, &r); return want_rem ? gv_f(r) : gv_i(q);
+    }
     int cc = (ca == CLS_D || cb == CLS_D) ? CLS_D : (ca == CLS_F || cb == CLS_F) ? CLS_F : CLS_I;   // contagion
     if (cc == CLS_I && (ca == CLS_R || cb == CLS_R)) cc = CLS_F;       // rejected by the host typer; defensive
     if (cc == CLS_I) {
@@ -98,8 +136,7 @@ __device__ inline GV eval_node(const GNode& nd, const GV* val, const GNode* node
         case NCL_OP_EQ: return gv_i(x == y); case NCL_OP_NE: return gv_i(x != y);
         case NCL_OP_LE: return gv_i(x <= y); case NCL_OP_GE: return gv_i(x >= y);
         case NCL_OP_LT: return gv_i(x < y);  case NCL_OP_GT: return gv_i(x > y);
-        case NCL_OP_LOGAND: return gv_i(x & y); case NCL_OP_LOGIOR: return gv_i(x | y);
-        default: return gv_i(x ^ y);
+        default: return gv_i(int_bitwise(op, x, y));
       }
     } else if (cc == CLS_F) {
       float x = gv_to_f32(a, ca), y = gv_to_f32(b, cb);
@@ -128,6 +165,9 @@ __device__ inline GV eval_node(const GNode& nd, const GV* val, const GNode* node
   switch (op) {
     case NCL_OP_IDENTITY: return a;
     case NCL_OP_LOGNOT: return gv_i(~a.i);
+    case NCL_OP_ISQRT: return gv_i(int_isqrt(a.i, flt));
+    case NCL_OP_LOGCOUNT: return gv_i(int_logcount(a.i));
+    case NCL_OP_INTEGER_LENGTH: return gv_i(int_length(a.i));
     case NCL_OP_NEG:
       if (ca == CLS_I) return gv_i(Ops<long long>::neg(a.i));
       if (ca == CLS_F) return gv_f(-gf(a));
@@ -148,20 +188,8 @@ __device__ inline GV eval_node(const GNode& nd, const GV* val, const GNode* node
   }
   // irrational functions: rationals are substituted by single-floats (src/1type.lisp:358-416);
   // SBCL calls libm, so these are tolerance-checked, never bit-checked
-  if (nd.cls == CLS_D) {
-    double x = gv_to_f64(a, ca);
-    switch (op) {
-      case NCL_OP_SQRT: return gv_d(__dsqrt_rn(x)); case NCL_OP_EXP: return gv_d(exp(x)); case NCL_OP_LOG: return gv_d(log(x));
-      case NCL_OP_SIN: return gv_d(sin(x)); case NCL_OP_COS: return gv_d(cos(x)); case NCL_OP_TAN: return gv_d(tan(x));
-      default: return gv_d(tanh(x));
-    }
-  }
-  float x = gv_to_f32(a, ca);
-  switch (op) {
-    case NCL_OP_SQRT: return gv_f(__fsqrt_rn(x)); case NCL_OP_EXP: return gv_f(expf(x)); case NCL_OP_LOG: return gv_f(logf(x));
-    case NCL_OP_SIN: return gv_f(sinf(x)); case NCL_OP_COS: return gv_f(cosf(x)); case NCL_OP_TAN: return gv_f(tanf(x));
-    default: return gv_f(tanhf(x));
-  }
+  if (nd.cls == CLS_D) return gv_d(float_unary<double>(op, gv_to_f64(a, ca), flt));
+  return gv_f(float_unary<float>(op, gv_to_f32(a, ca), flt));
 }
 
 __device__ inline GV load_gv(const char* base, long long idx, int lk, int cls) {
@@ -200,7 +228,7 @@ __global__ void __launch_bounds__(128) generic_nest_kernel(const __grid_constant
         case NCL_X_CONST_INT: val[k] = gv_i(nd.c); break;
         case NCL_X_CONST_F32: val[k] = gv_f((float)__longlong_as_double(nd.c)); break;
         case NCL_X_CONST_F64: val[k] = gv_d(__longlong_as_double(nd.c)); break;
-        default: val[k] = eval_node(nd, val, p.node);
+        default: val[k] = eval_node(nd, val, p.node, p.fault);
       }
     }
     acc = coerce_out(val[p.n_nodes - 1], p.node[p.n_nodes - 1].cls, p);     // (setf @k (%coerce transform type))
@@ -256,7 +284,8 @@ int launch_generic(const Nest& n) {
     for (int i = 0; i < n.n_in; i++) fill_arr(1 + i, n.in[i]);
     p.st = dtype_store_spec(out.dtype); p.out_cls = g_dt[out.dtype].cls; p.out_bits = g_dt[out.dtype].value_bits; p.out_signed = g_dt[out.dtype].is_signed;
     p.fresh = n.fresh ? 1 : 0; p.has_identity = n.has_identity ? 1 : 0; p.ident_i = n.ident_i; p.ident_f = n.ident_f;
-    p.n_nodes = e.n;
+    p.n_nodes = e.n; p.fault = c.fault;
+    for (int k = 0; k < e.n; k++) if (op_may_fault(e.node[k].op)) c.fault_possible = true;
     for (int k = 0; k < e.n; k++) {
       const XNode& x = e.node[k]; GNode& g = p.node[k];
       g.op = (short)x.op; g.a = (short)x.a; g.b = (short)x.b; g.cls = (short)x.cls;

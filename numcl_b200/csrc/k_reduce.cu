@@ -58,6 +58,21 @@ static bool aligned16(const Operand& o, long long elem_off) {
 
 static int reduce_impl(const Nest& n, int op, int ia, int ib);
 
+// Launch of a streaming reduction kernel that takes part in programmatic dependent launch (ncl_internal.h): `reads` are
+// the arrays it starts streaming right away, `write` the array it stores into after griddepcontrol.wait.
+static int launch_red(RedKernel kfn, dim3 grid, const RedParams& p, const Operand* in_a, const Operand* in_b, const Operand& out, const char* name) {
+  PdlRange reads[2]; int nr = 0;
+  if (in_a) reads[nr++] = pdl_range(*in_a);
+  if (in_b) reads[nr++] = pdl_range(*in_b);
+  const bool early = pdl_eligible(reads, nr);
+  void* args[1] = {(void*)&p};
+  NCL_TRY(pdl_launch((const void*)kfn, grid, dim3(256), args, ctx().stream, early));
+  note_launch(name);
+  PdlRange w = pdl_range(out);
+  pdl_commit(early, &w, 1);
+  return NCL_OK;
+}
+
 int try_reduce(const Nest& n) {
   if (n.n_out != 1 || n.n_in != 1) return NCL_ERR_UNSUPPORTED;
   int op;
@@ -141,9 +156,7 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
     long long cap = persistent_blocks((const void*)kfn); if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
     NCL_TRY(ensure_scratch((size_t)blocks * 8));
     p.block_partials = c.scratch; p.ticket = c.ticket; p.nblocks = (int)blocks;
-    kfn<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
-    note_launch(dot ? "dot_all" : "reduce_all");
-    return cuda_fail(cudaGetLastError(), "reduce_all_kernel");
+    return launch_red(kfn, dim3((unsigned)blocks), p, &in, dot ? &n.in[ib] : nullptr, out, dot ? "dot_all" : "reduce_all");
   }
   // the contiguous kept dim must be the innermost of the kept group for the column form
   bool inner_reduced = (sR == 1);
@@ -234,8 +247,10 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
     else if (chunks >= 512) { which = KROW256; blocks = p.rows; }
     else { which = KROW32; blocks = (p.rows + 7) / 8; }
     if (blocks > 0x7fffffffLL) return NCL_ERR_UNSUPPORTED;
+    const char* kname = dot ? "dot_rows" : which == KROW256 ? "reduce_row_block" : which == KROW32 ? "reduce_row_warp" : which == KROW4 ? "reduce_row_quad" : "reduce_row_thread";
+    if (which != KROW1) return launch_red(kfor(E, which), dim3((unsigned)blocks), p, &in, dot ? &n.in[ib] : nullptr, out, kname);
     kfor(E, which)<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
-    note_launch(dot ? "dot_rows" : which == KROW256 ? "reduce_row_block" : which == KROW32 ? "reduce_row_warp" : which == KROW4 ? "reduce_row_quad" : "reduce_row_thread");
+    note_launch(kname);
     return cuda_fail(cudaGetLastError(), "reduce_row_kernel");
   }
   // ---- column reduce: [outer kept...][R][contiguous kept] ---------------------------------------------
@@ -323,9 +338,9 @@ int reduce_all_p2p(int op, const Operand& a, int64_t count, const Operand& r, un
   NCL_TRY(ensure_scratch((size_t)blocks * 8));
   p.block_partials = c.scratch; p.ticket = c.ticket; p.nblocks = (int)blocks;
   p.peers = peers; p.rank = rank; p.world = world; p.seq = seq;
-  kfn<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
-  note_launch("reduce_all_p2p");
-  return cuda_fail(cudaGetLastError(), "reduce_all_kernel (p2p)");
+  Operand ain = a; if (ain.n_storage == 0) ain.n_storage = a.offset + count;
+  Operand rout = r; if (rout.n_storage == 0) rout.n_storage = r.offset + 1;
+  return launch_red(kfn, dim3((unsigned)blocks), p, &ain, nullptr, rout, "reduce_all_p2p");
 }
 
 // local phase of a sharded full reduce: contiguous a -> one float64 / int64 partial on the device

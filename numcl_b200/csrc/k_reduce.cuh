@@ -68,14 +68,43 @@ struct RedParams {
 
 // element fetch of the reductions: a[i], or the product a[i] * b[i] of the einsum leaf (+ @1 (* $1 $2)) -- each product
 // rounded on its own, then added (common-lisp.lisp:226-240; no FMA contraction)
+// E > 1: raw 16-byte loads first (all of a step's loads can be issued back to back), conversion afterwards, no branch.
+template <class T, int E> struct RawPair { uint4 a, b; T bs; };
 template <class T, int E, bool DOT>
-__device__ __forceinline__ void fetch_elems(const RedParams& p, long long ia, long long ib, bool b_contig, T (&v)[E]) {
-  load_elems<T, E>(p.in, ia, p.lk, E > 1, v);
+__device__ __forceinline__ void fetch_raw(const RedParams& p, long long ia, long long ib, bool b_contig, RawPair<T, E>& r) {
+  r.a = load_raw16(p.in + ia * (16 / E));
+  if constexpr (DOT) { if (b_contig) r.b = load_raw16(p.in2 + ib * (16 / E)); else r.bs = load_scalar<T>(p.in2, ib, p.lk2); }
+}
+template <class T, int E, bool DOT>
+__device__ __forceinline__ void fetch_convert(const RedParams& p, const RawPair<T, E>& r, bool b_contig, T (&v)[E]) {
+  convert_raw16<T, E>(r.a, lk_flags(p.lk), v);
   if constexpr (DOT) {
-    T w[E]; load_elems<T, E>(p.in2, ib, p.lk2, b_contig && E > 1, w);
+    T w[E];
+    if (b_contig) convert_raw16<T, E>(r.b, lk_flags(p.lk2), w);
+    else {
+#pragma unroll
+      for (int i = 0; i < E; i++) w[i] = r.bs;
+    }
 #pragma unroll
     for (int i = 0; i < E; i++) v[i] = Ops<T>::mul(v[i], w[i]);
   }
+}
+template <class T, int E, bool DOT>
+__device__ __forceinline__ void fetch_elems(const RedParams& p, long long ia, long long ib, bool b_contig, T (&v)[E]) {
+  if constexpr (E > 1) {
+    RawPair<T, E> r; fetch_raw<T, E, DOT>(p, ia, ib, b_contig, r); fetch_convert<T, E, DOT>(p, r, b_contig, v);
+  } else {
+    load_elems<T, E>(p.in, ia, p.lk, false, v);
+    if constexpr (DOT) {
+      T w[E]; load_elems<T, E>(p.in2, ib, p.lk2, false, w);
+      v[0] = Ops<T>::mul(v[0], w[0]);
+    }
+  }
+}
+template <class T, int E>
+__device__ __forceinline__ void load_vec(const char* base, long long idx, int lk, T (&v)[E]) {
+  if constexpr (E > 1) convert_raw16<T, E>(load_raw16(base + idx * (16 / E)), lk_flags(lk), v);
+  else v[0] = load_scalar<T>(base, idx, lk);
 }
 template <class T, bool DOT>
 __device__ __forceinline__ T fetch_scalar(const RedParams& p, long long ia, long long ib) {
@@ -197,6 +226,7 @@ __device__ __forceinline__ void reduce_one_row(const RedParams& p, const long lo
   } else {
     a = block_combine<T, OP, 256>(a);
   }
+  pdl_wait();                                                                // nothing is written before every earlier kernel has completed
   if (live && t == 0) {
     T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, obase, p.out_lk);
     store_scalar<T>(p.out, obase, p.sk, Red<T, OP>::f(init, a));          // r <- fn(r, partial)
@@ -206,6 +236,7 @@ __device__ __forceinline__ void reduce_one_row(const RedParams& p, const long lo
 // 0.64 -> 0.61 on rows of 512 floats.)
 template <class T, int OP, int E, int TPR, bool DOT>
 __global__ void __launch_bounds__(256) reduce_row_kernel(const __grid_constant__ RedParams p) {
+  pdl_trigger();                                                             // the next kernel may start filling the SMs this one leaves
   reduce_one_row<T, OP, E, TPR, DOT>(p, (long long)blockIdx.x * (256 / TPR) + threadIdx.x / TPR, threadIdx.x % TPR);
 }
 
@@ -274,9 +305,9 @@ __global__ void __launch_bounds__(256) dot_matvec_kernel(const __grid_constant__
     T y[2][E], a[2][RB][E];
 #pragma unroll
     for (int u = 0; u < 2; u++) {
-      load_elems<T, E>(p.in2, p.in2_off + (c + u * 256) * E, p.lk2, true, y[u]);
+      load_vec<T, E>(p.in2, p.in2_off + (c + u * 256) * E, p.lk2, y[u]);
 #pragma unroll
-      for (int j = 0; j < RB; j++) load_elems<T, E>(p.in, ib[j] + (c + u * 256) * E, p.lk, true, a[u][j]);
+      for (int j = 0; j < RB; j++) load_vec<T, E>(p.in, ib[j] + (c + u * 256) * E, p.lk, a[u][j]);
     }
 #pragma unroll
     for (int u = 0; u < 2; u++)
@@ -287,9 +318,9 @@ __global__ void __launch_bounds__(256) dot_matvec_kernel(const __grid_constant__
   }
   for (; c < nch; c += 256) {
     T y[E], a[RB][E];
-    load_elems<T, E>(p.in2, p.in2_off + c * E, p.lk2, true, y);
+    load_vec<T, E>(p.in2, p.in2_off + c * E, p.lk2, y);
 #pragma unroll
-    for (int j = 0; j < RB; j++) load_elems<T, E>(p.in, ib[j] + c * E, p.lk, true, a[j]);
+    for (int j = 0; j < RB; j++) load_vec<T, E>(p.in, ib[j] + c * E, p.lk, a[j]);
 #pragma unroll
     for (int j = 0; j < RB; j++)
 #pragma unroll
@@ -323,7 +354,7 @@ __global__ void __launch_bounds__(256) reduce_rows_reg_kernel(const __grid_const
   if (row0 + E <= p.rows) {
     T a[C][E];
 #pragma unroll
-    for (int k = 0; k < C; k++) load_elems<T, E>(p.in, p.in_off + row0 * C + k * E, p.lk, true, a[k]);
+    for (int k = 0; k < C; k++) load_vec<T, E>(p.in, p.in_off + row0 * C + k * E, p.lk, a[k]);
 #pragma unroll
     for (int j = 0; j < E; j++) {
       T r = a[(j * C) / E][(j * C) % E];
@@ -418,6 +449,7 @@ template <class T, int E> constexpr int reduce_all_min_blocks() { return (sizeof
 template <class T, int OP, int E, bool DOT>
 __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all_kernel(const __grid_constant__ RedParams p) {
   typedef typename Wide<T>::W W;
+  pdl_trigger();
   // max / min start from the first element; an EMPTY slab (a rank that owns no rows of a sharded array) has none and
   // contributes the identity instead of reading in[0]
   T seed = (OP == R_ADD || OP == R_MUL) ? neutral<T, OP>() : (p.cols > 0 ? load_scalar<T>(p.in, p.in_off, p.lk) : ident_of<T>(p));
@@ -459,6 +491,7 @@ __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all
   a = block_combine<W, OP, 256>(a);
   __shared__ bool last;
   W* partials = (W*)p.block_partials;
+  pdl_wait();                                          // scratch, ticket and the result are shared with earlier kernels: they must be done
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = a;
     __threadfence();
@@ -480,11 +513,13 @@ __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all
     // fence and no second "flag" store on the critical path -- the kernel ends right after issuing the stores.
     // Nobody waits here: mailbox_finalize_kernel (k_reduce.cu), one small CTA on the communication stream, collects the W
     // messages, folds them in rank order and stores the result while the compute stream already runs the next kernel.
-    __shared__ unsigned long long xseq;
-    if (threadIdx.x == 0) { *p.ticket = 0; xseq = mbox_push_seq(p.peers[p.rank], p.world) + 1ull; }
+    __shared__ unsigned long long xseq, xbits;
+    if (threadIdx.x == 0) {                                  // the combined partial is valid in thread 0 only
+      *p.ticket = 0; xseq = mbox_push_seq(p.peers[p.rank], p.world) + 1ull;
+      xbits = (unsigned long long)(std::is_integral<T>::value ? (long long)s : __double_as_longlong((double)s));
+    }
     __syncthreads();
-    const unsigned long long seq = xseq;
-    const unsigned long long bits = (unsigned long long)(std::is_integral<T>::value ? (long long)s : __double_as_longlong((double)s));
+    const unsigned long long seq = xseq, bits = xbits;
     if (threadIdx.x < p.world) mbox_send(p.peers[threadIdx.x], p.world, seq, p.rank, bits);
     if (threadIdx.x == 0) mbox_set_push_seq(p.peers[p.rank], p.world, seq);
     return;
@@ -529,14 +564,14 @@ __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_few
   for (; c + 3 * nthr < nch; c += 4 * nthr) {
     T v[4][E];
 #pragma unroll
-    for (int u = 0; u < 4; u++) load_elems<T, E>(p.in, p.in_off + (c + u * nthr) * E, p.lk, true, v[u]);
+    for (int u = 0; u < 4; u++) load_vec<T, E>(p.in, p.in_off + (c + u * nthr) * E, p.lk, v[u]);
 #pragma unroll
     for (int u = 0; u < 4; u++)
 #pragma unroll
       for (int i = 0; i < E; i++) acc[u][i] = Red<T, OP>::f(acc[u][i], v[u][i]);
   }
   for (; c < nch; c += nthr) {
-    T v[E]; load_elems<T, E>(p.in, p.in_off + c * E, p.lk, true, v);
+    T v[E]; load_vec<T, E>(p.in, p.in_off + c * E, p.lk, v);
 #pragma unroll
     for (int i = 0; i < E; i++) acc[0][i] = Red<T, OP>::f(acc[0][i], v[i]);
   }

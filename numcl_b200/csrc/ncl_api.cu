@@ -127,6 +127,7 @@ int ncl_set_stream(void* s) {
     }
     g_ctx.stream = ns;
   }
+  pdl().unknown = true;
   return NCL_OK;
 }
 void* ncl_get_stream(void) { return (void*)g_ctx.stream; }
@@ -153,6 +154,7 @@ int ncl_capture_begin(void) {
   NCL_TRY(ncl_comm_join());
   NCL_CUDA(cudaStreamBeginCapture(g_ctx.stream, cudaStreamCaptureModeRelaxed));
   g_ctx.capturing = true; g_ctx.capture_launch0 = g_ctx.launches;
+  pdl().unknown = true;                                    // the first recorded kernel is fully serialised
   return NCL_OK;
 }
 int ncl_capture_end(ncl_graph** out) {
@@ -161,7 +163,7 @@ int ncl_capture_end(ncl_graph** out) {
   int jrc = ncl_comm_join();                               // the communication stream must re-join before the capture ends
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(g_ctx.stream, &g);
-  g_ctx.capturing = false;
+  g_ctx.capturing = false; pdl().unknown = true;
   if (jrc != NCL_OK) { if (g) cudaGraphDestroy(g); return jrc; }
   if (e != cudaSuccess || !g) { cudaGetLastError(); return set_error(NCL_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e)); }
   cudaGraphExec_t x = nullptr;
@@ -178,6 +180,7 @@ int ncl_graph_launch(ncl_graph* gr) {
   if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_graph_launch inside a capture");
   NCL_TRY(ncl_comm_join());
   NCL_CUDA(cudaGraphLaunch(gr->e, g_ctx.stream));
+  pdl().unknown = true;
   g_ctx.launches += gr->launches;
   return NCL_OK;
 }
@@ -229,7 +232,7 @@ int ncl_h2d(ncl_buf* dst, size_t off, const void* host, size_t bytes) {
   if (!dst || off + bytes > dst->bytes) return set_error(NCL_ERR_INVALID, "ncl_h2d out of range");
   if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_h2d inside ncl_capture_begin/end");
   NCL_CUDA(cudaMemcpyAsync((char*)dst->ptr + off, host, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
-  g_ctx.h2d_bytes += bytes;
+  g_ctx.h2d_bytes += bytes; pdl().unknown = true;
   return NCL_OK;
 }
 int ncl_d2h(void* host, const ncl_buf* src, size_t off, size_t bytes) {

@@ -239,7 +239,7 @@ int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a, ncl_tensor* r) {
       const StoreSpec sk = dtype_store_spec(ro.dtype);
       if (cls == CLS_I) mailbox_finalize_kernel<long long><<<1, 64, 0, g_nccl.comm_stream>>>(g_nccl.peers_dev, g_nccl.rank, g_nccl.world, ro.base, ro.offset, sk, op, ident_i, ident_f);
       else mailbox_finalize_kernel<double><<<1, 64, 0, g_nccl.comm_stream>>>(g_nccl.peers_dev, g_nccl.rank, g_nccl.world, ro.base, ro.offset, sk, op, ident_i, ident_f);
-      note_launch("reduce_all_p2p");
+      note_side_launch("reduce_all_p2p");
       NCL_TRY(cuda_fail(cudaGetLastError(), "mailbox_finalize_kernel"));
       NCL_CUDA(cudaEventRecord(g_nccl.ev_done, g_nccl.comm_stream));
       g_nccl.pending = true;

@@ -125,8 +125,20 @@ template <class F> __device__ __forceinline__ void dispatch_lk(int lk, F f) {
 // %coerce of a class value into an integer slot (src/1type.lisp:673-694): (round x) half-even, then wrap.
 __device__ __forceinline__ long long round_to_i64(long long v) { return v; }
 __device__ __forceinline__ long long round_to_i64(int v) { return v; }
-__device__ __forceinline__ long long round_to_i64(float v) { return __float2ll_rn(v); }
-__device__ __forceinline__ long long round_to_i64(double v) { return __double2ll_rn(v); }
+// an integer-valued double of any magnitude -> its value modulo 2^64 (what %coerce keeps after wrapping)
+__device__ __forceinline__ long long f64_integer_to_i64_wrap(double v) {
+  if (fabs(v) < 9223372036854775808.0) return (long long)v;
+  if (!(fabs(v) <= 1.7976931348623157e308)) return 0;                       // inf / nan: the reference signals
+  const long long bits = __double_as_longlong(v);
+  const int e = (int)((bits >> 52) & 0x7ff) - 1075;                          // v = m * 2^e, e >= 11 here
+  const unsigned long long m = ((unsigned long long)bits & 0xfffffffffffffull) | 0x10000000000000ull;
+  const unsigned long long mag = e >= 64 ? 0ull : (m << e);
+  return (long long)(bits < 0 ? 0ull - mag : mag);
+}
+// (round x) of a float of ANY magnitude, then modulo 2^64 -- the conversion intrinsics saturate at +-2^63, while the reference
+// rounds to the exact (big) integer and %coerce wraps it
+__device__ __forceinline__ long long round_to_i64(double v) { return fabs(v) < 9223372036854775808.0 ? __double2ll_rn(v) : f64_integer_to_i64_wrap(v); }
+__device__ __forceinline__ long long round_to_i64(float v) { return round_to_i64((double)v); }
 __device__ __forceinline__ float to_f32(long long v) { return __ll2float_rn(v); }
 __device__ __forceinline__ float to_f32(int v) { return __int2float_rn(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
@@ -334,6 +346,48 @@ __device__ __forceinline__ void load_elems(const char* base, long long idx, int 
     }
   }
 }
+
+// The same 16-byte chunk with the element kind reduced to two warp-uniform flags (bit 0: signed slots, bit 1: tagged
+// words) and NO branch: within one (value class, E) instance the slot width is fixed, so a chunk is one LDG.128 followed by
+// selects / shifts.  The kernels that stream (reductions) use this instead of load_elems: with the kind switch of
+// load_elems around every load, consecutive loads of an unrolled step were ~30 instructions apart and, for integer
+// kinds, each was followed directly by its conversion -- ONE load in flight per thread (profiles/r01_sass_reduce_row_kind_switch.txt).
+__host__ __device__ inline unsigned lk_flags(int lk) {
+  return ((lk == LK_S8 || lk == LK_S16 || lk == LK_S32 || lk == LK_W64 || lk == LK_T64) ? 1u : 0u) | (lk == LK_T64 ? 2u : 0u);
+}
+__device__ __forceinline__ uint4 load_raw16(const char* p) { return __ldg((const uint4*)p); }
+template <class T, int E>
+__device__ __forceinline__ void convert_raw16(const uint4 w, unsigned kf, T (&v)[E]) {
+  static_assert(E == 2 || E == 4 || E == 8 || E == 16, "a 16-byte chunk holds 2, 4, 8 or 16 elements");
+  const unsigned x[4] = {w.x, w.y, w.z, w.w};
+  if constexpr (std::is_same<T, float>::value) {
+    static_assert(E == 4, "float lanes read f32 slots");
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = __uint_as_float(x[i]);
+  } else if constexpr (std::is_same<T, double>::value) {
+    static_assert(E == 2, "double lanes read f64 slots");
+    v[0] = __hiloint2double((int)x[1], (int)x[0]); v[1] = __hiloint2double((int)x[3], (int)x[2]);
+  } else {
+    const bool sg = (kf & 1u) != 0; const int tg = (int)((kf >> 1) & 1u);
+    if constexpr (E == 2) {
+#pragma unroll
+      for (int i = 0; i < 2; i++) v[i] = (T)((long long)(((unsigned long long)x[2 * i + 1] << 32) | x[2 * i]) >> tg);
+    } else if constexpr (E == 4) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) v[i] = sg ? (T)(long long)(int)x[i] : (T)(long long)x[i];
+    } else if constexpr (E == 8) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) { const unsigned h = (x[i >> 1] >> ((i & 1) * 16)) & 0xffffu; v[i] = sg ? (T)(long long)(short)h : (T)(long long)h; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i++) { const unsigned b = (x[i >> 2] >> ((i & 3) * 8)) & 0xffu; v[i] = sg ? (T)(long long)(signed char)b : (T)(long long)b; }
+    }
+  }
+}
+
+// programmatic dependent launch (ncl_internal.h: PdlTracker): no-ops unless the launch carries the attribute
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <class TO, int E>
 __device__ __forceinline__ void store_elems(char* base, long long idx, const StoreSpec& sk, const TO (&v)[E]) {

@@ -68,6 +68,8 @@ struct Context {
   void* scratch3 = nullptr; size_t scratch3_bytes = 0;   // intermediate rows of multi-pass reductions
   unsigned int* ticket = nullptr;       // zero-initialised counters for last-block reductions
   void* consts = nullptr;               // [sb64 0][sb64 1]
+  unsigned int* fault = nullptr;        // sticky DOMAIN flag written by kernels (ncl_fn.cuh); checked at sync points when fault_possible
+  bool fault_possible = false;
   void* pinned = nullptr; size_t pinned_bytes = 0;
 };
 Context& ctx();
@@ -78,12 +80,41 @@ int  cuda_fail(cudaError_t e, const char* what);
 int  ensure_scratch(size_t bytes);       // ctx().scratch  >= bytes
 int  ensure_scratch2(size_t bytes);
 int  ensure_scratch3(size_t bytes);
-inline void note_launch(const char* name, int n = 1) { ctx().launches += n; ctx().last_kernel = name; }
+// ---- programmatic dependent launch (PDL): consecutive INDEPENDENT kernels overlap their tail and ramp ----------------
+// The streaming reduction kernels execute griddepcontrol.launch_dependents when they start and griddepcontrol.wait before
+// their first write.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, such a kernel may begin READING its
+// inputs while the previous kernel of the stream is still draining (its blocks fill the SMs the predecessor's tail leaves
+// idle), but writes nothing until every earlier kernel has completed.  That is only legal when its inputs are not written
+// by a kernel that may still be in flight, so the host keeps the byte ranges written by every launch since the last fully
+// serialised one; a launch whose reads touch none of them gets the attribute, anything else is launched normally.  Every
+// launch site that does not take part (note_launch) marks the state unknown, which forces the next launch to serialise.
+struct PdlRange { const char* lo; const char* hi; };
+struct PdlTracker {
+  bool unknown = true; int n = 0; PdlRange w[16];
+  bool enabled = true;
+};
+PdlTracker& pdl();
+bool pdl_eligible(const PdlRange* reads, int nreads);
+void pdl_commit(bool launched_pdl, const PdlRange* writes, int nwrites);
+int  pdl_launch(const void* kfn, dim3 grid, dim3 block, void** args, cudaStream_t stream, bool with_attribute);
+inline PdlRange pdl_range(const Operand& o) { PdlRange r; r.lo = o.base; r.hi = o.base + (size_t)((o.n_storage * g_dt[o.dtype].slot_bits + 7) / 8); return r; }
+inline void note_launch(const char* name, int n = 1) { ctx().launches += n; ctx().last_kernel = name; pdl().unknown = true; }
+// a kernel on the communication stream: counted, but it does not sit between two kernels of the compute stream
+inline void note_side_launch(const char* name) { ctx().launches += 1; ctx().last_kernel = name; }
 
 // ---- expression helpers (ncl_plan.cu) -------------------------------------------------------------
 int  type_expr(const ncl_expr* src, const int* in_dtype, int n_in, const int* out_dtype, int n_out,
                int self_out, Expr* dst);
 bool expr_reads_output(const Expr& e);
+// functions whose kernels may raise the DOMAIN flag (NCL_ERR_DOMAIN)
+inline bool op_may_fault(int op) {
+  switch (op) {
+    case NCL_OP_SQRT: case NCL_OP_LOG: case NCL_OP_LOG2: case NCL_OP_ASIN: case NCL_OP_ACOS: case NCL_OP_ACOSH: case NCL_OP_ATANH: case NCL_OP_ISQRT:
+    case NCL_OP_FLOOR: case NCL_OP_CEILING: case NCL_OP_ROUND: case NCL_OP_TRUNCATE: case NCL_OP_MOD: case NCL_OP_REM: case NCL_OP_EXPT: return true;
+    default: return false;
+  }
+}
+int check_fault();                       // ncl_api.cu: reads and clears the flag; NCL_OK or NCL_ERR_DOMAIN (synchronises the stream)
 
 // ---- kernel families; each returns NCL_OK, an error, or NCL_ERR_UNSUPPORTED to fall through ------
 int launch_generic(const Nest& n);                        // k_generic.cu

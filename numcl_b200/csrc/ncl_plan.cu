@@ -1,6 +1,7 @@
 // ncl_plan.cu -- static typing of TRANSFORM expressions and kernel-family dispatch.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "ncl_internal.h"
 
@@ -14,6 +15,36 @@ const DtInfo g_dt[NCL_DTYPE_COUNT] = {
   {32, 0, 1, 0, CLS_F, "f32"},  {64, 0, 1, 0, CLS_D, "f64"},
 };
 
+// ---- PDL tracker (ncl_internal.h) ----------------------------------------------------------------------------
+static PdlTracker g_pdl;
+PdlTracker& pdl() {
+  static bool init = false;
+  if (!init) { init = true; const char* e = getenv("NUMCL_PDL"); if (e && atoi(e) == 0) g_pdl.enabled = false; }
+  return g_pdl;
+}
+bool pdl_eligible(const PdlRange* reads, int nreads) {
+  PdlTracker& t = pdl();
+  if (!t.enabled || t.unknown || t.n >= 14) return false;
+  for (int i = 0; i < nreads; i++)
+    for (int j = 0; j < t.n; j++)
+      if (reads[i].lo < t.w[j].hi && t.w[j].lo < reads[i].hi) return false;
+  return true;
+}
+void pdl_commit(bool launched_pdl, const PdlRange* writes, int nwrites) {
+  PdlTracker& t = pdl();
+  if (!launched_pdl) t.n = 0;                                  // a serialised launch: everything before it has completed when it starts
+  for (int i = 0; i < nwrites && t.n < 16; i++) t.w[t.n++] = writes[i];
+  t.unknown = false;
+}
+int pdl_launch(const void* kfn, dim3 grid, dim3 block, void** args, cudaStream_t stream, bool with_attribute) {
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = with_attribute ? 1 : 0;
+  return cuda_fail(cudaLaunchKernelExC(&cfg, kfn, args), "cudaLaunchKernelExC");
+}
+
 // ---- expression typing: Common Lisp contagion, decided once on the host ----------------------------
 static int contagion(int a, int b) {
   if (a == CLS_D || b == CLS_D) return CLS_D;
@@ -22,33 +53,53 @@ static int contagion(int a, int b) {
   return CLS_I;
 }
 
+// ub64 words at or above 2^63 do not fit the signed 64-bit lanes the integer class computes in.  Functions that only need
+// the value modulo 2^64 (+ - * and the bitwise family, whose results are wrapped by %coerce anyway) are exact regardless;
+// anything that looks at the ORDER or MAGNITUDE of such a value (max min comparisons / abs division conversion to float
+// rounding ...) would silently be wrong, so it is refused.
+static bool mod64_safe(int op) {
+  switch (op) {
+    case NCL_OP_ADD: case NCL_OP_SUB: case NCL_OP_MUL: case NCL_OP_LOGAND: case NCL_OP_LOGIOR: case NCL_OP_LOGXOR:
+    case NCL_OP_LOGANDC1: case NCL_OP_LOGANDC2: case NCL_OP_LOGEQV: case NCL_OP_LOGNAND: case NCL_OP_LOGNOR: case NCL_OP_LOGORC1: case NCL_OP_LOGORC2:
+    case NCL_OP_LOGNOT: case NCL_OP_NEG: case NCL_OP_SQUARE: case NCL_OP_IDENTITY: return true;
+    default: return false;
+  }
+}
+
 int type_expr(const ncl_expr* src, const int* in_dtype, int n_in, const int* out_dtype, int n_out,
               int self_out, Expr* dst) {
   if (src->n <= 0 || src->n > NCL_MAX_EXPR) return set_error(NCL_ERR_INVALID, "transform has %d nodes", src->n);
   dst->n = src->n;
+  bool u64[NCL_MAX_EXPR];
   for (int k = 0; k < src->n; k++) {
     const ncl_expr_node& s = src->node[k]; XNode& x = dst->node[k];
     x.op = s.op; x.a = s.a; x.b = s.b; x.ival = s.ival; x.fval = s.fval; x.cls = CLS_I;
+    u64[k] = false;
     switch (s.op) {
       case NCL_X_INPUT:
         if (s.a < 1 || s.a > n_in) return set_error(NCL_ERR_INVALID, "transform refers to $%d but there are %d inputs", s.a, n_in);
-        x.cls = g_dt[in_dtype[s.a - 1]].cls; break;
+        x.cls = g_dt[in_dtype[s.a - 1]].cls; u64[k] = in_dtype[s.a - 1] == NCL_UB64; break;
       case NCL_X_OUTPUT:
         if (s.a < 1 || s.a > n_out) return set_error(NCL_ERR_INVALID, "transform refers to @%d but there are %d outputs", s.a, n_out);
-        x.cls = g_dt[out_dtype[s.a - 1]].cls; break;
+        x.cls = g_dt[out_dtype[s.a - 1]].cls; u64[k] = out_dtype[s.a - 1] == NCL_UB64; break;
       case NCL_X_CONST_INT: x.cls = CLS_I; break;
       case NCL_X_CONST_F32: x.cls = CLS_F; break;
       case NCL_X_CONST_F64: x.cls = CLS_D; break;
       default: {
         if (s.a < 0 || s.a >= k) return set_error(NCL_ERR_INVALID, "transform node %d: bad child", k);
         int ca = dst->node[s.a].cls;
+        bool tainted = u64[s.a];
         if (s.op >= 0 && s.op < NCL_OP_BINARY_END) {
           if (s.b < 0 || s.b >= k) return set_error(NCL_ERR_INVALID, "transform node %d: bad child", k);
           int cb = dst->node[s.b].cls;
+          tainted = tainted || u64[s.b];
           int cc = contagion(ca, cb);
           if (cc == CLS_R) return set_error(NCL_ERR_UNSUPPORTED, "arithmetic on an unreduced integer ratio is outside the CUDA whitelist");
-          if (s.op >= NCL_OP_LOGAND) { if (ca != CLS_I || cb != CLS_I) return set_error(NCL_ERR_INVALID, "bitwise function on non-integers"); x.cls = CLS_I; }
-          else if (s.op >= NCL_OP_EQ) x.cls = CLS_I;
+          if (s.op >= NCL_OP_LOGAND && s.op <= NCL_OP_LOGORC2) { if (ca != CLS_I || cb != CLS_I) return set_error(NCL_ERR_INVALID, "bitwise function on non-integers"); x.cls = CLS_I; }
+          else if (s.op >= NCL_OP_EQ && s.op <= NCL_OP_GT) x.cls = CLS_I;
+          else if (s.op >= NCL_OP_FLOOR && s.op <= NCL_OP_TRUNCATE) x.cls = CLS_I;           // the integer quotient
+          else if (s.op == NCL_OP_MOD || s.op == NCL_OP_REM) x.cls = cc;
+          else if (s.op == NCL_OP_EXPT) x.cls = (cc == CLS_I) ? CLS_R : cc;                   // integer ^ negative integer is a ratio
           else if (s.op == NCL_OP_DIV && cc == CLS_I) x.cls = CLS_R;
           else x.cls = cc;
         } else {
@@ -56,18 +107,27 @@ int type_expr(const ncl_expr* src, const int* in_dtype, int n_in, const int* out
             case NCL_OP_NEG: case NCL_OP_ABS: case NCL_OP_SQUARE: case NCL_OP_SIGNUM: case NCL_OP_IDENTITY:
               if (ca == CLS_R && s.op != NCL_OP_IDENTITY) return set_error(NCL_ERR_UNSUPPORTED, "function of an integer ratio");
               x.cls = ca; break;
-            case NCL_OP_LOGNOT:
-              if (ca != CLS_I) return set_error(NCL_ERR_INVALID, "lognot of a non-integer"); x.cls = CLS_I; break;
+            case NCL_OP_LOGNOT: case NCL_OP_ISQRT: case NCL_OP_LOGCOUNT: case NCL_OP_INTEGER_LENGTH:
+              if (ca != CLS_I) return set_error(NCL_ERR_INVALID, "integer function of a non-integer"); x.cls = CLS_I; break;
             case NCL_OP_SQRT: case NCL_OP_EXP: case NCL_OP_LOG: case NCL_OP_SIN: case NCL_OP_COS: case NCL_OP_TAN: case NCL_OP_TANH:
+            case NCL_OP_ASIN: case NCL_OP_ACOS: case NCL_OP_ATAN: case NCL_OP_SINH: case NCL_OP_COSH: case NCL_OP_ASINH: case NCL_OP_ACOSH:
+            case NCL_OP_ATANH: case NCL_OP_LOG2:
               x.cls = (ca == CLS_D) ? CLS_D : CLS_F; break;      // float substitution: rational -> single-float
             default:
               return set_error(NCL_ERR_UNSUPPORTED, "function code %d is not on the CUDA whitelist", s.op);
           }
         }
+        if (tainted) {
+          if (!mod64_safe(s.op) || x.cls != CLS_I)
+            return set_error(NCL_ERR_UNSUPPORTED, "an (unsigned-byte 64) operand reaches a function that depends on its order or magnitude (function code %d): "
+                                                  "values >= 2^63 do not fit the signed 64-bit lanes; only + - * and the bitwise family are exact", s.op);
+          u64[k] = true;
+        }
       }
     }
   }
-  (void)self_out;
+  if (u64[src->n - 1] && self_out >= 0 && self_out < n_out && g_dt[out_dtype[self_out]].cls != CLS_I)
+    return set_error(NCL_ERR_UNSUPPORTED, "an (unsigned-byte 64) value is stored into a float array: values >= 2^63 do not fit the signed 64-bit lanes");
   return NCL_OK;
 }
 
