@@ -232,6 +232,23 @@ int      ncl_h2d(ncl_buf* dst, size_t dst_off, const void* host, size_t bytes);
 int      ncl_d2h(void* host, const ncl_buf* src, size_t src_off, size_t bytes);
 void*    ncl_host_alloc_pinned(size_t bytes);
 int      ncl_host_free(void* p);
+/* ---- residency: a device mirror that outlives the call, attached to a host base vector ------------------------
+ * (north_star: "3array.lisp gains pinned-host and device buffers behind numcl's specialized arrays"; the hook is
+ * %make-array, src/1instantiate.lisp:81-96: register the fresh base vector, unregister from its finalizer.)
+ * A host-resident ncl_tensor whose `host` equals a registered base is served from the mirror: it is uploaded only
+ * when the host copy is newer (after registration without NCL_RESIDENT_FRESH, or after ncl_host_dirty), so repeated
+ * calls on the same arrays move no input bytes over PCIe.  Outputs are written back into the host vector when the call
+ * returns (only the tensor's own window), unless the vector was registered NCL_RESIDENT_LAZY: then the result stays
+ * on the device -- usable as an input of later calls at no cost -- until ncl_host_fetch.
+ *   ncl_host_dirty : the host wrote into the vector ((setf aref) ...): the next use uploads it again.
+ *   ncl_host_state : 0 in sync, 1 host newer, 2 device newer, -1 not registered. */
+#define NCL_RESIDENT_FRESH 1u   /* the vector holds nothing yet (a result array): skip the first upload          */
+#define NCL_RESIDENT_LAZY  2u   /* results stay on the device until ncl_host_fetch / ncl_host_unregister        */
+int ncl_host_register(void* base, size_t bytes, unsigned flags);
+int ncl_host_unregister(void* base);      /* fetches a pending result first */
+int ncl_host_dirty(void* base);
+int ncl_host_fetch(void* base);
+int ncl_host_state(const void* base);
 /* numcl's base vectors are padded to a multiple of 8 elements (1instantiate.lisp:81-84). */
 size_t   ncl_storage_bytes(int dtype, int64_t n_elements);
 
@@ -276,6 +293,16 @@ int ncl_map(const ncl_expr* fn, const ncl_tensor* args, int n, ncl_tensor* r);
  * amax most-negative-value, amin most-positive-value; 5reduce.lisp:103-126). */
 int ncl_reduce(int op, const ncl_tensor* a, const int* axes, int n_axes,
                ncl_tensor* r, unsigned flags);
+
+/* numcl:mean / variance / standard-deviation (src/5reduce.lisp:128-167) as one fused launch: the sum kernels' final store
+ * divides by the element count (then takes the square root); bit-identical to the reference's composition
+ * (numcl:sqrt (numcl:/ (numcl:sum [(square a)] :axes axes) count)).  variance is the reference's mean of SQUARES.
+ * r: single-float for single-float and integer arrays (integer / integer is a single-float, 2typeinfer.lisp:134-139),
+ * double-float for double-float arrays. */
+#define NCL_STAT_MEAN     1
+#define NCL_STAT_VARIANCE 2
+#define NCL_STAT_STDEV    3
+int ncl_reduce_stat(int stat, const ncl_tensor* a, const int* axes, int n_axes, ncl_tensor* r);
 
 /* astype / copy (src/3copy.lisp:27-43): r = %coerce(a, r.dtype), same shape. */
 int ncl_convert(const ncl_tensor* a, ncl_tensor* r);

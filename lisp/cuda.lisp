@@ -20,14 +20,8 @@
 the left, max/min to the right (SBCL's source transform), (- x) is NEG, (/ x) is (/ 1 x)."
   (let ((nodes nil) (n 0))
     (labels ((emit (op a b ival fval) (push (list op a b ival fval) nodes) (1- (incf n)))
-             (binop (name) (ecase name
-                             (+ :add) (- :sub) (* :mul) (/ :div) (max :max) (min :min)
-                             (=/bit :eq) (/=/bit :ne) (<=/bit :le) (>=/bit :ge) (</bit :lt) (>/bit :gt)
-                             (logand :logand) (logior :logior) (logxor :logxor)))
-             (unop (name) (ecase name
-                            (abs :abs) (%square :square) (sqrt :sqrt) (lognot :lognot) (identity :identity)
-                            (exp :exp) (log :log) (%logr :log) (sin :sin) (cos :cos) (tan :tan) (tanh :tanh)
-                            (signum :signum)))
+             (binop (name) (binary-op name))          ; numcl-cuda-ffi.lisp: ONE table for every dispatch point
+             (unop (name) (unary-op name))
              (rec (f)
                (etypecase f
                  (integer (emit :x-const-int 0 0 f 0d0))
@@ -55,6 +49,10 @@ the left, max/min to the right (SBCL's source transform), (- x) is NEG, (/ x) is
                       ((max min) (let ((vals (mapcar #'rec args)))
                                    (reduce (lambda (x acc) (emit (binop head) x acc 0 0d0))
                                            (butlast vals) :initial-value (car (last vals)) :from-end t)))
+                      ;; (floor number &optional (divisor 1)) etc., src/4numeric.lisp:572-577
+                      ((floor ceiling round truncate mod rem)
+                       (emit (binop head) (rec (first args))
+                             (if (rest args) (rec (second args)) (emit :x-const-int 0 0 1 0d0)) 0 0d0))
                       (t (if (rest args)
                              (emit (binop head) (rec (first args)) (rec (second args)) 0 0d0)
                              (emit (unop head) (rec (first args)) 0 0 0d0)))))))))
@@ -153,8 +151,13 @@ there is no CPU fallback inside the :cuda backend."
                          (rec (cdr rest) (1+ k)))))))
         (rec arrays 0)))))
 
-(defun cuda-broadcast (function x y &key type)
-  "BROADCAST on the :cuda backend: same result type, same result shape, same (assert (broadcast-p ...))."
+(defun cuda-broadcast (function x y &key type (atomic function))
+  "BROADCAST on the :cuda backend: same result type, same result shape, same (assert (broadcast-p ...)).
+FUNCTION is any symbol the reference passes (src/4numeric.lisp:528-655: + - * / max min expt, mod rem round floor
+ceiling truncate, the ten bitwise functions, the six */bit comparisons); ATOMIC is what two bare numbers are
+combined with -- the comparisons pass #'= etc. there so that (numcl:< 1 2) is T, not 1 (:625-630)."
+  (when (and (numberp x) (numberp y))
+    (return-from cuda-broadcast (funcall atomic x y)))          ; :205-206: scalars never reach a kernel
   (let* ((x (if (arrayp x) x (full nil x)))
          (y (if (arrayp y) y (full nil y)))
          (type (or type (infer-type function (array-element-type x) (array-element-type y)))))
@@ -162,7 +165,7 @@ there is no CPU fallback inside the :cuda backend."
     (let ((r (empty (broadcast-result-shape x y) :type type)))
       (%cuda-call-with-arrays (list x y r)
         (lambda (ts)
-          (ncl-check (ncl-broadcast (ecase function (+ :add) (- :sub) (* :mul) (/ :div) (max :max) (min :min))
+          (ncl-check (ncl-broadcast (binary-op function)
                                     (cffi:mem-aptr ts '(:struct ncl-tensor) 0)
                                     (cffi:mem-aptr ts '(:struct ncl-tensor) 1)
                                     (cffi:mem-aptr ts '(:struct ncl-tensor) 2)))))
@@ -181,7 +184,7 @@ array decided exactly as the reference's chain of BROADCAST calls decides it."
          (r (empty rshape :type rtype)))
     (%cuda-call-with-arrays (append arrays (list r))
       (lambda (ts)
-        (ncl-check (ncl-fold (ecase function (+ :add) (- :sub) (* :mul) (/ :div) (max :max) (min :min))
+        (ncl-check (ncl-fold (binary-op function)
                              (if use-identity 1 0) ts (length arrays)
                              (cffi:mem-aptr ts '(:struct ncl-tensor) (length arrays))))))
     r))
@@ -203,3 +206,56 @@ array decided exactly as the reference's chain of BROADCAST calls decides it."
                                  (cffi:mem-aptr ts '(:struct ncl-tensor) 0) ax (length axes)
                                  (cffi:mem-aptr ts '(:struct ncl-tensor) 1) +ncl-out-accumulate+)))))
     (ensure-singleton result)))
+
+;;; 4. numcl:mean / variance / standard-deviation (src/5reduce.lisp:128-167): ONE fused launch instead of
+;;; sum -> broadcast '/ -> sqrt.  The reference's definition is kept: variance is the mean of SQUARES.  A full
+;;; reduction of an integer array is an exact Lisp rational in the reference, so that case stays on the composition.
+
+(defun cuda-statistic (stat array axes)
+  "STAT: 1 mean, 2 variance, 3 standard-deviation (NCL_STAT_*).  Result element type as the reference infers it for
+(numcl:/ (numcl:sum ...) count): double-float for double-float arrays, single-float otherwise."
+  (let* ((axes (etypecase axes (null (iota (rank array))) (fixnum (list axes)) (list (sort (copy-list axes) #'<))))
+         (remaining (sort (set-difference (iota (rank array)) axes) #'<))
+         (type (if (csubtypep (array-element-type array) 'double-float) 'double-float 'single-float))
+         (result (empty (mapcar (lambda (d) (array-dimension array d)) remaining) :type type)))
+    (cffi:with-foreign-object (ax :int (max 1 (length axes)))
+      (loop for a in axes for i from 0 do (setf (cffi:mem-aref ax :int i) a))
+      (%cuda-call-with-arrays (list array result)
+        (lambda (ts)
+          (ncl-check (ncl-reduce-stat stat (cffi:mem-aptr ts '(:struct ncl-tensor) 0) ax (length axes)
+                                      (cffi:mem-aptr ts '(:struct ncl-tensor) 1))))))
+    (ensure-singleton result)))
+
+;;; 5. Residency (north_star: "3array.lisp gains pinned-host and device buffers behind numcl's specialized arrays").
+;;; The choke point is %make-array (src/1instantiate.lisp:81-96), which creates every base vector.  With the :cuda
+;;; backend it allocates the vector in non-moving foreign memory (static-vectors style: the Lisp array header sits in
+;;; front of pinned memory from ncl_host_alloc_pinned), registers it, and unregisters it from a finalizer.  From then on
+;;; a call uploads the vector only when the Lisp side wrote into it since the last call.
+
+(defvar *resident-vectors* (make-hash-table :test 'eq :weakness :key)
+  "base vector -> its address, for the vectors that carry a device mirror")
+
+(defun cuda-register-base-vector (base &key fresh lazy)
+  "Called at the end of %make-array when *compiler* is :cuda.  FRESH: the vector holds nothing yet (EMPTY / a result):
+no first upload.  LAZY: results written into it stay on the device until CUDA-FETCH (used for intermediates)."
+  (let* ((sap (sb-sys:vector-sap base))
+         (bytes (* (ceiling (* (length base) (sb-vm::simple-array-widetag->bits-per-elt (sb-kernel:widetag-of base))) 8))))
+    (ncl-check (ncl-host-register sap bytes (logior (if fresh 1 0) (if lazy 2 0))))
+    (setf (gethash base *resident-vectors*) (sb-sys:sap-int sap))
+    (let ((address (sb-sys:sap-int sap)))
+      (sb-ext:finalize base (lambda () (ncl-host-unregister (sb-sys:int-sap address))) :dont-save t))
+    base))
+
+(defun cuda-touch (array)
+  "The Lisp side wrote into ARRAY ((setf aref), replace, fill ...): numcl's own (setf aref) (src/2aref.lisp:226-272) calls
+this; user code that writes through cl:aref directly must call it itself."
+  (let ((base (array-displacement array)))
+    (when (gethash (or base array) *resident-vectors*)
+      (sb-sys:with-pinned-objects (base) (ncl-check (ncl-host-dirty (sb-sys:vector-sap (or base array))))))))
+
+(defun cuda-fetch (array)
+  "Bring a lazily kept result back before the Lisp side reads ARRAY (numcl:aref, printing, to-simple-array)."
+  (let ((base (or (array-displacement array) array)))
+    (when (gethash base *resident-vectors*)
+      (ncl-check (ncl-host-fetch (sb-sys:vector-sap base))))
+    array))

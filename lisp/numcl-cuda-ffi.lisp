@@ -37,8 +37,35 @@
 
 (cffi:defcenum ncl-op
   (:add 0) :sub :mul :div :max :min :eq :ne :le :ge :lt :gt :logand :logior :logxor
+  :logandc1 :logandc2 :logeqv :lognand :lognor :logorc1 :logorc2
+  :floor :ceiling :round :truncate :mod :rem :expt
   (:neg 32) :abs :square :sqrt :lognot :identity :exp :log :sin :cos :tan :tanh :signum
+  :asin :acos :atan :sinh :cosh :asinh :acosh :atanh :log2 :isqrt :logcount :integer-length
   (:x-input 64) :x-output :x-const-int :x-const-f32 :x-const-f64)
+
+(defparameter *binary-ops*
+  '((+ . :add) (- . :sub) (* . :mul) (/ . :div) (max . :max) (min . :min)
+    (=/bit . :eq) (/=/bit . :ne) (<=/bit . :le) (>=/bit . :ge) (</bit . :lt) (>/bit . :gt)
+    (logand . :logand) (logior . :logior) (logxor . :logxor) (logandc1 . :logandc1) (logandc2 . :logandc2)
+    (logeqv . :logeqv) (lognand . :lognand) (lognor . :lognor) (logorc1 . :logorc1) (logorc2 . :logorc2)
+    (floor . :floor) (ceiling . :ceiling) (round . :round) (truncate . :truncate) (mod . :mod) (rem . :rem)
+    (expt . :expt))
+  "Every function numcl hands to BROADCAST (src/4numeric.lisp:528-655) -> ncl_op.  ONE table for the einsum transform
+compiler, cuda-broadcast and cuda-fold, so that the three dispatch points cannot drift apart.")
+
+(defparameter *unary-ops*
+  '((abs . :abs) (%square . :square) (sqrt . :sqrt) (lognot . :lognot) (identity . :identity) (exp . :exp)
+    (log . :log) (%logr . :log) (sin . :sin) (cos . :cos) (tan . :tan) (tanh . :tanh) (signum . :signum)
+    (asin . :asin) (acos . :acos) (atan . :atan) (sinh . :sinh) (cosh . :cosh) (asinh . :asinh) (acosh . :acosh)
+    (atanh . :atanh) (%log2 . :log2) (isqrt . :isqrt) (logcount . :logcount) (integer-length . :integer-length))
+  "The functions of define-simple-mapper (src/4numeric.lisp:466-519) -> ncl_op.")
+
+(defun binary-op (name)
+  (or (cdr (assoc name *binary-ops*))
+      (error "numcl-cuda: ~a is not on the CUDA whitelist of binary functions (there is no CPU fallback)" name)))
+(defun unary-op (name)
+  (or (cdr (assoc name *unary-ops*))
+      (error "numcl-cuda: ~a is not on the CUDA whitelist of unary functions (there is no CPU fallback)" name)))
 
 ;;; ---- structs ------------------------------------------------------------------------------
 (cffi:defcstruct ncl-expr-node
@@ -85,6 +112,18 @@
 (cffi:defcfun "ncl_reduce" :int
   (op ncl-op) (a :pointer) (axes :pointer) (n-axes :int) (r :pointer) (flags :unsigned-int))
 (cffi:defcfun "ncl_convert" :int (a :pointer) (r :pointer))
+(cffi:defcfun "ncl_reduce_stat" :int (stat :int) (a :pointer) (axes :pointer) (n-axes :int) (r :pointer))
+;; residency: a device mirror attached to a base vector in %make-array (src/1instantiate.lisp:81-96)
+(cffi:defcfun "ncl_host_register" :int (base :pointer) (bytes :size) (flags :unsigned-int))
+(cffi:defcfun "ncl_host_unregister" :int (base :pointer))
+(cffi:defcfun "ncl_host_dirty" :int (base :pointer))
+(cffi:defcfun "ncl_host_fetch" :int (base :pointer))
+;; CUDA graphs: a recorded call sequence
+(cffi:defcfun "ncl_capture_begin" :int)
+(cffi:defcfun "ncl_capture_end" :int (out :pointer))
+(cffi:defcfun "ncl_graph_launch" :int (graph :pointer))
+(cffi:defcfun "ncl_graph_free" :int (graph :pointer))
+(cffi:defcfun "ncl_trim" :int)
 
 (define-condition numcl-cuda-error (error)
   ((code :initarg :code :reader numcl-cuda-error-code)
@@ -92,12 +131,16 @@
   (:report (lambda (c s)
              (format s "numcl-cuda error ~a: ~a" (numcl-cuda-error-code c) (numcl-cuda-error-message c)))))
 
+(define-condition numcl-cuda-domain-error (numcl-cuda-error arithmetic-error) ()
+  (:documentation "NCL_ERR_DOMAIN (-7): an element left the real domain of its function -- where the :common-lisp
+backend would have signalled DIVISION-BY-ZERO or stored a complex number.  Reported at the first synchronisation point."))
+
 (declaim (inline ncl-check))
 (defun ncl-check (rc)
   "Every ncl_* returns 0 or a negative status; nothing aborts or throws across the ABI.
--2 (NCL_ERR_SHAPE) corresponds to the reference's failed (assert ...) forms."
+-2 (NCL_ERR_SHAPE) corresponds to the reference's failed (assert ...) forms, -7 to its arithmetic errors."
   (unless (zerop rc)
-    (error 'numcl-cuda-error :code rc :message (ncl-last-error)))
+    (error (if (= rc -7) 'numcl-cuda-domain-error 'numcl-cuda-error) :code rc :message (ncl-last-error)))
   rc)
 
 ;;; ---- element types ------------------------------------------------------------------------------

@@ -13,13 +13,19 @@ SO_PATH = os.path.join(HERE, "libnumcl_cuda.so")
 
 MAX_RANK, MAX_INDEX, MAX_OPERANDS, MAX_EXPR, MAX_OPTS = 8, 16, 8, 48, 8
 
-OK, ERR_INVALID, ERR_SHAPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
+OK, ERR_INVALID, ERR_SHAPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_DOMAIN = 0, -1, -2, -3, -4, -5, -6, -7
 OUT_ACCUMULATE, OUT_FRESH = 0, 1
+STAT_MEAN, STAT_VARIANCE, STAT_STDEV = 1, 2, 3
+RESIDENT_FRESH, RESIDENT_LAZY = 1, 2
 
 OPS = dict(ADD=0, SUB=1, MUL=2, DIV=3, MAX=4, MIN=5, EQ=6, NE=7, LE=8, GE=9, LT=10, GT=11,
            LOGAND=12, LOGIOR=13, LOGXOR=14,
+           LOGANDC1=15, LOGANDC2=16, LOGEQV=17, LOGNAND=18, LOGNOR=19, LOGORC1=20, LOGORC2=21,
+           FLOOR=22, CEILING=23, ROUND=24, TRUNCATE=25, MOD=26, REM=27, EXPT=28,
            NEG=32, ABS=33, SQUARE=34, SQRT=35, LOGNOT=36, IDENTITY=37, EXP=38, LOG=39, SIN=40, COS=41,
            TAN=42, TANH=43, SIGNUM=44,
+           ASIN=45, ACOS=46, ATAN=47, SINH=48, COSH=49, ASINH=50, ACOSH=51, ATANH=52, LOG2=53, ISQRT=54, LOGCOUNT=55,
+           INTEGER_LENGTH=56,
            X_INPUT=64, X_OUTPUT=65, X_CONST_INT=66, X_CONST_F32=67, X_CONST_F64=68)
 
 # every symbol include/numcl_cuda.h declares (tests/test_abi.py checks the .so exports them all)
@@ -32,7 +38,8 @@ EXPORTS = [
     "ncl_comm_unique_id", "ncl_comm_init", "ncl_comm_destroy", "ncl_allreduce", "ncl_reduce_all_sharded",
     "ncl_reduce_all_sharded_async", "ncl_comm_join",
     "ncl_trim", "ncl_transfer_stats", "ncl_capture_begin", "ncl_capture_end", "ncl_graph_launch", "ncl_graph_kernels",
-    "ncl_graph_free", "ncl_fill_random_at",
+    "ncl_graph_free", "ncl_fill_random_at", "ncl_reduce_stat",
+    "ncl_host_register", "ncl_host_unregister", "ncl_host_dirty", "ncl_host_fetch", "ncl_host_state",
 ]
 
 
@@ -81,6 +88,11 @@ class NumclShapeError(NumclCudaError, AssertionError):
 
 class NumclUnsupportedError(NumclCudaError, NotImplementedError):
     pass
+
+
+class NumclDomainError(NumclCudaError, ArithmeticError):
+    """An element left the real domain of its function (sqrt of a negative, division by zero ...): the reference signals a
+    Lisp error or produces a complex number there.  Reported at the first synchronisation point after the call."""
 
 
 _lib = None
@@ -133,6 +145,12 @@ def load():
     L.ncl_map.argtypes = [C.POINTER(Expr), C.POINTER(Tensor), C.c_int, C.POINTER(Tensor)]
     L.ncl_reduce.argtypes = [C.c_int, C.POINTER(Tensor), C.POINTER(C.c_int), C.c_int, C.POINTER(Tensor), C.c_uint]
     L.ncl_convert.argtypes = [C.POINTER(Tensor), C.POINTER(Tensor)]
+    L.ncl_host_register.argtypes = [C.c_void_p, C.c_size_t, C.c_uint]
+    L.ncl_host_unregister.argtypes = [C.c_void_p]
+    L.ncl_host_dirty.argtypes = [C.c_void_p]
+    L.ncl_host_fetch.argtypes = [C.c_void_p]
+    L.ncl_host_state.argtypes = [C.c_void_p]
+    L.ncl_reduce_stat.argtypes = [C.c_int, C.POINTER(Tensor), C.POINTER(C.c_int), C.c_int, C.POINTER(Tensor)]
     L.ncl_comm_unique_id.argtypes = [C.c_void_p]
     L.ncl_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ncl_allreduce.argtypes = [C.c_int, C.POINTER(Tensor)]
@@ -150,6 +168,8 @@ def check(rc):
         raise NumclShapeError(rc, msg)
     if rc == ERR_UNSUPPORTED:
         raise NumclUnsupportedError(rc, msg)
+    if rc == ERR_DOMAIN:
+        raise NumclDomainError(rc, msg)
     raise NumclCudaError(rc, msg)
 
 

@@ -53,6 +53,8 @@ class NArray:
 
     def __del__(self):
         try:
+            if getattr(self, "_resident", False) and self._host is not None:
+                _lib.load().ncl_host_unregister(self._host.ctypes.data)
             if getattr(self, "_owner", False):
                 L = _lib.load()
                 if self._buf:
@@ -82,9 +84,28 @@ class NArray:
         return _lib.lib().ncl_buf_ptr(self._buf)
 
     # ---- data movement ----------------------------------------------------------------------
+    # ---- residency (host arrays): what the `:cuda` glue does in %make-array, src/1instantiate.lisp:81-96 ---------
+    def make_resident(self, lazy: bool = False, fresh: bool = False) -> "NArray":
+        """Attach a device mirror that outlives the calls (ncl_host_register): the array is uploaded once, later calls
+        on it move nothing over PCIe.  lazy: results written into this array stay on the device until fetch()."""
+        assert self.where == "host" and self.offset == 0 and self._host is not None
+        flags = (_lib.RESIDENT_LAZY if lazy else 0) | (_lib.RESIDENT_FRESH if fresh else 0)
+        _lib.check(_lib.lib().ncl_host_register(self._host.ctypes.data, self.nbytes, flags))
+        self._resident = True
+        return self
+
+    def dirty(self):
+        """The host bytes were modified behind the library's back ((setf aref) in Lisp): upload again on next use."""
+        _lib.check(_lib.lib().ncl_host_dirty(self._host.ctypes.data))
+
+    def fetch(self):
+        _lib.check(_lib.lib().ncl_host_fetch(self._host.ctypes.data))
+
     def raw(self) -> np.ndarray:
         """The base vector's bytes (SBCL storage format)."""
         if self.where == "host":
+            if getattr(self, "_resident", False):
+                self.fetch()                                   # a lazily kept result comes back now
             return self._host.copy()
         out = np.empty(self.nbytes, dtype=np.uint8)
         _lib.check(_lib.lib().ncl_d2h(out.ctypes.data, self._buf, 0, self.nbytes))
@@ -95,6 +116,8 @@ class NArray:
         n = min(storage.size, self.nbytes)
         if self.where == "host":
             self._host[:n] = storage[:n]
+            if getattr(self, "_resident", False):
+                self.dirty()
         else:
             L = _lib.lib()
             _lib.check(L.ncl_h2d(self._buf, 0, storage.ctypes.data, n))

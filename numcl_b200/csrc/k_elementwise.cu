@@ -7,7 +7,7 @@
 
 
 struct Slot { int kind; int idx; };   // kind 0: input idx (0-based); 1: the output (read); 2: const 0; 3: const 1
-struct Match { int shape; int n; Slot s[3]; };
+struct Match { int shape; int n; Slot s[3]; int rt_op; };
 
 static bool leaf_slot(const Expr& e, int k, int self_out, Slot* s) {
   const XNode& x = e.node[k];
@@ -23,17 +23,24 @@ static int bin_shape(int op) {
   switch (op) { case NCL_OP_ADD: return S_ADD; case NCL_OP_SUB: return S_SUB; case NCL_OP_MUL: return S_MUL; case NCL_OP_DIV: return S_DIV;
     case NCL_OP_MAX: return S_MAX; case NCL_OP_MIN: return S_MIN; case NCL_OP_EQ: return S_EQ; case NCL_OP_NE: return S_NE;
     case NCL_OP_LE: return S_LE; case NCL_OP_GE: return S_GE; case NCL_OP_LT: return S_LT; case NCL_OP_GT: return S_GT;
-    case NCL_OP_LOGAND: return S_AND; case NCL_OP_LOGIOR: return S_IOR; case NCL_OP_LOGXOR: return S_XOR; default: return S_NONE; }
+    case NCL_OP_LOGAND: return S_AND; case NCL_OP_LOGIOR: return S_IOR; case NCL_OP_LOGXOR: return S_XOR;
+    case NCL_OP_LOGANDC1: case NCL_OP_LOGANDC2: case NCL_OP_LOGEQV: case NCL_OP_LOGNAND: case NCL_OP_LOGNOR: case NCL_OP_LOGORC1: case NCL_OP_LOGORC2:
+    case NCL_OP_FLOOR: case NCL_OP_CEILING: case NCL_OP_ROUND: case NCL_OP_TRUNCATE: case NCL_OP_MOD: case NCL_OP_REM: return S_RT2;
+    default: return S_NONE; }       // expt: generic kernel (integer and float powers take different algorithms)
 }
 static int un_shape(int op) {
   switch (op) { case NCL_OP_NEG: return S_NEG; case NCL_OP_ABS: return S_ABS; case NCL_OP_SQUARE: return S_SQUARE; case NCL_OP_LOGNOT: return S_NOT;
-    case NCL_OP_IDENTITY: return S_COPY; case NCL_OP_SQRT: return S_SQRT; case NCL_OP_EXP: return S_EXP; case NCL_OP_LOG: return S_LOG;
-    case NCL_OP_SIN: return S_SIN; case NCL_OP_COS: return S_COS; case NCL_OP_TAN: return S_TAN; case NCL_OP_TANH: return S_TANH; default: return S_NONE; }
+    case NCL_OP_IDENTITY: return S_COPY; case NCL_OP_EXP: return S_EXP;
+    case NCL_OP_SIN: return S_SIN; case NCL_OP_COS: return S_COS; case NCL_OP_TAN: return S_TAN; case NCL_OP_TANH: return S_TANH;
+    // the runtime-selected families (k_ew_rt.cu); sqrt and log live there too because they can raise the DOMAIN flag
+    case NCL_OP_SQRT: case NCL_OP_LOG: case NCL_OP_LOG2: case NCL_OP_ASIN: case NCL_OP_ACOS: case NCL_OP_ATAN: case NCL_OP_SINH: case NCL_OP_COSH:
+    case NCL_OP_ASINH: case NCL_OP_ACOSH: case NCL_OP_ATANH: case NCL_OP_ISQRT: case NCL_OP_LOGCOUNT: case NCL_OP_INTEGER_LENGTH: return S_RT1;
+    default: return S_NONE; }
 }
 
 static bool match_expr(const Expr& e, int self_out, bool fresh, Match* m) {
   int r = e.n - 1; const XNode& root = e.node[r];
-  m->n = 0; m->shape = S_NONE;
+  m->n = 0; m->shape = S_NONE; m->rt_op = root.op;
   if (root.op == NCL_X_INPUT) { m->shape = S_COPY; m->n = 1; return leaf_slot(e, r, self_out, &m->s[0]); }
   if (root.op >= 0 && root.op < NCL_OP_BINARY_END) {
     const XNode& A = e.node[root.a]; const XNode& B = e.node[root.b];
@@ -59,7 +66,7 @@ static bool match_expr(const Expr& e, int self_out, bool fresh, Match* m) {
     }
     return false;
   }
-  if (root.op >= NCL_OP_NEG && root.op <= NCL_OP_SIGNUM) {
+  if (root.op >= NCL_OP_NEG && root.op <= NCL_OP_INTEGER_LENGTH) {
     Slot a; if (!leaf_slot(e, root.a, self_out, &a) || a.kind != 0) return false;
     m->shape = un_shape(root.op); m->n = 1; m->s[0] = a; return m->shape != S_NONE;
   }
@@ -99,10 +106,31 @@ int try_elementwise(const Nest& n) {
   // (integer -> float and double -> single round to nearest, single -> double is exact), so the copy runs in the output's class
   if (shape == S_COPY && out_cls != cc && out_cls != CLS_I) cc = out_cls;
   bool is_cmp = shape >= S_EQ && shape <= S_GT;
+  int rt_family = -1;
+  if (shape == S_RT1) {
+    const int op = m.rt_op;
+    if (op == NCL_OP_ISQRT || op == NCL_OP_LOGCOUNT || op == NCL_OP_INTEGER_LENGTH) { if (cc != CLS_I) return NCL_ERR_UNSUPPORTED; rt_family = RT_UN_I; }
+    else { if (cc == CLS_I) cc = CLS_F; rt_family = cc == CLS_F ? RT_UN_F : RT_UN_D; }      // a rational argument is converted to single-float first
+  } else if (shape == S_RT2) {
+    const int op = m.rt_op;
+    if (cc == CLS_I) rt_family = RT_BIN_I;
+    else if (op == NCL_OP_MOD || op == NCL_OP_REM) rt_family = cc == CLS_F ? RT_BIN_F : RT_BIN_D;
+    else return NCL_ERR_UNSUPPORTED;                       // float -> integer quotients: generic kernel
+  }
+  if (is_cmp && cc != CLS_I) {
+    // Common Lisp compares an integer with a float EXACTLY (CLHS 12.1.4.1).  Converting the integer to the float's format first
+    // is only the same thing while every value of the integer's type is representable there: 24 bits in single-float lanes,
+    // 53 in double-float lanes.  Wider 32-bit integers against single-floats are compared in double-float lanes (exact for
+    // both); 64-bit integers against any float go to the generic kernel, which compares exactly (cmp_i64_f64).
+    int wide = 0;
+    for (int k = 0; k < m.n; k++) if (ocls[k] == CLS_I && m.s[k].kind < 2) { const int vb = g_dt[ops[k].dtype].value_bits; if (vb > wide) wide = vb; }
+    if (wide > 53) return NCL_ERR_UNSUPPORTED;
+    if (wide > 24 && cc == CLS_F) cc = CLS_D;
+  }
+  if ((shape >= S_SQRT && shape <= S_TANH) && cc == CLS_I) cc = CLS_F;      // a rational argument is converted to single-float first (float substitution)
   if (shape == S_DIV && cc == CLS_I) { shape = S_IDIV; if (out_cls != CLS_F) return NCL_ERR_UNSUPPORTED; }
   else if (is_cmp) { if (out_cls != CLS_I) return NCL_ERR_UNSUPPORTED; }
   else if (out_cls != cc) return NCL_ERR_UNSUPPORTED;                    // float->int rounding stores etc.: generic path
-  if ((shape >= S_SQRT && shape <= S_TANH) && cc == CLS_I) return NCL_ERR_UNSUPPORTED;   // typed F by the host: inputs convert first
 
   // ---- collapse the nest: drop unit loops, sort by output stride, merge ----
   struct D { long long ext; long long st[4]; };
@@ -204,7 +232,7 @@ int try_elementwise(const Nest& n) {
   // 32-bit lanes when every slot involved is at most 32 bits wide (ub8 + ub8 -> ub15, sb16 * sb16 -> sb32, ub8 < ub8 -> bit):
   // half the registers and no 64-bit multiply / add pairs
   bool i32 = false;
-  if (cc == CLS_I && E > 1 && shape != S_IDIV && (is_cmp || (out_bits <= 32 && !g_dt[out.dtype].tagged))) {
+  if (cc == CLS_I && E > 1 && shape != S_IDIV && rt_family < 0 && (is_cmp || (out_bits <= 32 && !g_dt[out.dtype].tagged))) {
     i32 = true;
     const bool ordered = is_cmp || shape == S_MAX || shape == S_MIN || shape == S_ABS;      // needs the true value in a signed 32-bit lane
     for (int k = 0; k < m.n; k++) {
@@ -217,7 +245,8 @@ int try_elementwise(const Nest& n) {
   EwKernel kfn = nullptr;
   if (i32) { kfn = is_cmp ? (E == 32 ? ew_pick_cmp(shape, 4) : nullptr) : ew_pick_i32(shape, E); if (!kfn) i32 = false; }
   if (!kfn) {
-    if (shape == S_IDIV) kfn = ew_pick_idiv(E);
+    if (rt_family >= 0) kfn = ew_pick_rt(rt_family, E);
+    else if (shape == S_IDIV) kfn = ew_pick_idiv(E);
     else if (is_cmp) { if (E != 32) return NCL_ERR_UNSUPPORTED; kfn = ew_pick_cmp(shape, cc); }
     else if (cc == CLS_F) kfn = ew_pick_f32(shape, E);
     else if (cc == CLS_D) kfn = ew_pick_f64(shape, E);
@@ -276,6 +305,8 @@ int try_elementwise(const Nest& n) {
     }
   }
   p.nd = nd; p.n_in = m.n; p.sk = sk;
+  p.rt_op = m.rt_op; p.fault = c.fault;
+  if (rt_family >= 0 && op_may_fault(m.rt_op)) c.fault_possible = true;
   for (int i = 0; i < nd; i++) {                      // reverse: params dim 0 is the innermost
     const D& s = d[nd - 1 - i];
     p.ext[i] = (unsigned)(i == 0 ? s.ext / E : s.ext);

@@ -19,7 +19,7 @@
 //     kind-specialised family in k_ew_widen.cu.
 // Arithmetic follows ncl_device.cuh (IEEE rn, no FMA contraction, CL max/min, exact integers).
 #pragma once
-#include "ncl_device.cuh"
+#include "ncl_fn.cuh"
 
 #define EW_MAXD 6
 #define EW_THREADS 256
@@ -38,12 +38,13 @@ struct EwParams {
   // multiple of the chunk; operand k with gather[k] is addressed per element at (f / eper) * gst[k] + (f % eper) * st[1+k][0]
   // (a row vector: gst 0, st 1; one value per row: gst s, st 0), the others stream as flat vectors
   unsigned eper, epmul, epshr; int gather[3]; int gst[3];
+  int rt_op; unsigned int* fault;       // runtime-selected function (FnRt*: an ncl_op) and the sticky DOMAIN flag it may raise
 };
 __device__ __forceinline__ unsigned ew_div(unsigned q, unsigned mul, unsigned shr) { return mul ? (__umulhi(q, mul) >> shr) : q; }
 
 enum Shape { S_NONE = 0, S_ADD, S_SUB, S_MUL, S_DIV, S_MAX, S_MIN, S_ADD0, S_MUL0, S_IDIV, S_EQ, S_NE, S_LE, S_GE, S_LT, S_GT,
              S_AND, S_IOR, S_XOR, S_COPY, S_ADD0U, S_NEG, S_ABS, S_SQUARE, S_NOT, S_SQRT, S_EXP, S_LOG, S_SIN, S_COS, S_TAN, S_TANH,
-             S_ADDMUL };
+             S_ADDMUL, S_RT1, S_RT2 };
 
 // ---- functors ------------------------------------------------------------------------------------------------
 template <class T> struct FnAdd { typedef T R; static __device__ __forceinline__ T f(T a, T b) { return Ops<T>::add(a, b); } };
@@ -84,6 +85,37 @@ template <> struct FnSqrt<double> { typedef double R; static __device__ __forcei
   template <> struct NAME<double> { typedef double R; static __device__ __forceinline__ double f(double a) { return DF(a); } };
 LIBM_FN(FnExp, expf, exp) LIBM_FN(FnLog, logf, log) LIBM_FN(FnSin, sinf, sin) LIBM_FN(FnCos, cosf, cos)
 LIBM_FN(FnTan, tanf, tan) LIBM_FN(FnTanh, tanhf, tanh)
+// ---- runtime-selected functions (ncl_fn.cuh): the rest of numcl's scalar-function surface (src/4numeric.lisp:466-519,568-602).
+// ONE kernel per (value class, E) covers a whole family; the function code is a kernel parameter and the switch on it is
+// warp-uniform.  These are HBM-bound like everything here, so the few extra instructions per element are free, and the
+// family costs 18 instantiations instead of ~150.
+struct FnRtBinI {          // integer x integer -> integer: bitwise family, floor ceiling round truncate mod rem
+  typedef long long R; static constexpr bool RT = true;
+  static __device__ __forceinline__ long long f(int op, unsigned int* flt, long long a, long long b) {
+    if (op >= NCL_OP_LOGAND && op <= NCL_OP_LOGORC2) return int_bitwise(op, a, b);
+    long long r; const long long q = int_divide(op == NCL_OP_REM ? NCL_OP_TRUNCATE : op, a, b, &r, flt);
+    return (op == NCL_OP_MOD || op == NCL_OP_REM) ? r : q;
+  }
+};
+struct FnRtUnI {           // integer -> integer: isqrt logcount integer-length
+  typedef long long R; static constexpr bool RT = true;
+  static __device__ __forceinline__ long long f(int op, unsigned int* flt, long long a) {
+    return op == NCL_OP_ISQRT ? int_isqrt(a, flt) : op == NCL_OP_LOGCOUNT ? int_logcount(a) : int_length(a);
+  }
+};
+template <class T> struct FnRtBinF {   // float x float -> float: mod rem
+  typedef T R; static constexpr bool RT = true;
+  static __device__ __forceinline__ T f(int op, unsigned int* flt, T a, T b) {
+    T r; float_divide<T>(op == NCL_OP_REM ? NCL_OP_TRUNCATE : NCL_OP_MOD, a, b, &r); (void)flt; return r;
+  }
+};
+template <class T> struct FnRtUnF {    // float -> float: sqrt log log2 and the inverse / hyperbolic functions, with the DOMAIN flag
+  typedef T R; static constexpr bool RT = true;
+  static __device__ __forceinline__ T f(int op, unsigned int* flt, T a) { return float_unary<T>(op, a, flt); }
+};
+template <class F, class = void> struct fn_is_rt : std::false_type {};
+template <class F> struct fn_is_rt<F, std::void_t<decltype(F::RT)>> : std::true_type {};
+
 // ternary: a + b*c, each op rounded on its own (the einsum leaf with a live accumulator)
 template <class T> struct FnAddMul { typedef T R; static __device__ __forceinline__ T f(T a, T b, T c) { return Ops<T>::add(a, Ops<T>::mul(b, c)); } };
 
@@ -274,7 +306,12 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
     for (int u = 0; u < U; u++)
 #pragma unroll
       for (int i = 0; i < E; i++) {
-        if constexpr (NIN == 1) y[u][i] = F::f(x[0][u][i]);
+        if constexpr (fn_is_rt<F>::value) {
+          // chunks past the end of the row were not loaded: their lanes hold junk, which must not raise the DOMAIN flag
+          if (q0 + u * 32 >= p.ext[0]) y[u][i] = (TO)0;
+          else if constexpr (NIN == 1) y[u][i] = F::f(p.rt_op, p.fault, x[0][u][i]);
+          else y[u][i] = F::f(p.rt_op, p.fault, x[0][u][i], x[1][u][i]);
+        } else if constexpr (NIN == 1) y[u][i] = F::f(x[0][u][i]);
         else if constexpr (NIN == 2) y[u][i] = F::f(x[0][u][i], x[1][u][i]);
         else y[u][i] = F::f(x[0][u][i], x[1][u][i], x[2][u][i]);
       }
@@ -305,8 +342,8 @@ template <class T, int E> static EwKernel pick_arith(int shape) {     // T-class
 template <class T, int E> static EwKernel pick_float(int shape) {
   if (EwKernel k = pick_arith<T, E>(shape)) return k;
   switch (shape) {
-    case S_DIV: return kern<T, FnDiv<T>, 2, E>(); case S_SQRT: return kern<T, FnSqrt<T>, 1, E>(); case S_EXP: return kern<T, FnExp<T>, 1, E>();
-    case S_LOG: return kern<T, FnLog<T>, 1, E>(); case S_SIN: return kern<T, FnSin<T>, 1, E>(); case S_COS: return kern<T, FnCos<T>, 1, E>();
+    case S_DIV: return kern<T, FnDiv<T>, 2, E>(); case S_EXP: return kern<T, FnExp<T>, 1, E>();
+    case S_SIN: return kern<T, FnSin<T>, 1, E>(); case S_COS: return kern<T, FnCos<T>, 1, E>();
     case S_TAN: return kern<T, FnTan<T>, 1, E>(); case S_TANH: return kern<T, FnTanh<T>, 1, E>();
     default: return nullptr;
   }
@@ -343,3 +380,5 @@ EwKernel ew_pick_int(int shape, int E);
 EwKernel ew_pick_i32(int shape, int E);      // 32-bit lanes, E = 4 / 8 / 16
 EwKernel ew_pick_cmp(int shape, int cls);
 EwKernel ew_pick_idiv(int E);
+enum { RT_BIN_I = 0, RT_UN_I, RT_BIN_F, RT_UN_F, RT_BIN_D, RT_UN_D };
+EwKernel ew_pick_rt(int family, int E);      // k_ew_rt.cu

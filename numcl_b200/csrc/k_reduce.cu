@@ -41,6 +41,7 @@ static int fill_common(RedParams& p, const Nest& n, int op, int ia) {
     if (n.has_identity) { p.ident_i = n.ident_i; p.ident_f = n.ident_f; }
     else { p.ident_i = 0; p.ident_f = 0.0; }     // einsum into a fresh `zeros` output
   }
+  p.stat = n.stat; p.count = n.stat_count;
   (void)op; return NCL_OK;
 }
 
@@ -115,7 +116,8 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
   const bool dot = ib >= 0;
   const Operand& in = n.in[ia]; const Operand& out = n.out[0];
   int icls = g_dt[in.dtype].cls, ocls = g_dt[out.dtype].cls;
-  if (icls != ocls) return NCL_ERR_UNSUPPORTED;                       // e.g. integer sum into a float array: generic path
+  if (n.stat) { if (!((icls == CLS_I && ocls == CLS_F) || (icls == ocls && icls != CLS_I))) return NCL_ERR_UNSUPPORTED; }     // mean of integers is a single-float
+  else if (icls != ocls) return NCL_ERR_UNSUPPORTED;                  // e.g. integer sum into a float array: generic path
   if (g_dt[in.dtype].slot_bits < 8) return NCL_ERR_UNSUPPORTED;       // packed inputs: generic path
   if (n.fresh && !n.has_identity && op != R_ADD) return NCL_ERR_UNSUPPORTED;   // (* @1 $1) into zeros etc.: generic defines it
   RDim kd[NCL_MAX_LOOPS], rd[NCL_MAX_LOOPS]; int nk = 0, nr = 0;
@@ -170,7 +172,7 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
     // ---- few long rows ((sum a :axes 1) of a (3,N) array): one CTA per row would leave the GPU empty.  Every row is cut into
     // S pieces of L elements (L a multiple of the chunk): [rows x S x L] reduces over L into a scratch [rows x S], which then
     // reduces over S into the result; the R - S*L trailing elements of every row are accumulated last.
-    if (!dot && p.rows < 2LL * c.sm_count && R >= 65536 && (n.fresh || op == R_ADD) && nk <= 3) {
+    if (!dot && !n.stat && p.rows < 2LL * c.sm_count && R >= 65536 && (n.fresh || op == R_ADD) && nk <= 3) {
       long long S = (8LL * c.sm_count + p.rows - 1) / p.rows; if (S > R / 16384) S = R / 16384;
       const long long L = R / S / (4 * Evec) * (4 * Evec), rem = R - S * L;
       if (S >= 2 && L > 0) {
@@ -208,7 +210,7 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
     if (dot && vec && rd[0].sin2 == 1) { vec = aligned16(n.in[ib], n.in[ib].offset); for (int i = 0; i < nk && vec; i++) if (!b_vec_ok(kd[i].sin2)) vec = false; }
     // rows that do not start / end on a chunk boundary: scalar head and tail around an aligned vector body (vec = 2),
     // unless they are so short that one thread folds a whole row element by element
-    if (dot && vec && nk == 1 && kd[0].sin2 == 0 && rd[0].sin2 == 1 && R / Evec >= 512 && p.rows >= 4 && (cls == CLS_F || cls == CLS_D)) {
+    if (dot && !n.stat && vec && nk == 1 && kd[0].sin2 == 0 && rd[0].sin2 == 1 && R / Evec >= 512 && p.rows >= 4 && (cls == CLS_F || cls == CLS_D)) {
       p.vec = 1;
       const unsigned blocks4 = (unsigned)((p.rows + 3) / 4);
       red_dot_matvec_launch(cls, blocks4, c.stream, p);
@@ -262,7 +264,7 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
   for (int i = 0; i < nk - 1; i++) { p.kext[i] = kd[i].ext; p.kin[i] = kd[i].sin; p.kout[i] = kd[i].sout; p.kin2[i] = kd[i].sin2; p.rows *= kd[i].ext; }
   if (dot) { p.c_stride2 = kd[nk - 1].sin2; if (p.c_stride2 != 0 && p.c_stride2 != 1) return NCL_ERR_UNSUPPORTED; }
   // ---- few columns ((sum a :axes 0) of an (N,3) array): the whole array as one stream, reduce_fewcols_kernel ----------
-  if (!dot && nk == 1 && sR == ncols && ncols <= 128 && Evec > 1 && aligned16(in, in.offset) && R * ncols >= 32768 && R * ncols < (1LL << 40)) {
+  if (!dot && !n.stat && nk == 1 && sR == ncols && ncols <= 128 && Evec > 1 && aligned16(in, in.offset) && R * ncols >= 32768 && R * ncols < (1LL << 40)) {
     const long long Rr = (R * ncols) % Evec ? R % Evec : 0, Rm = R - Rr;      // Rm * ncols is a multiple of the chunk
     RedKernel kfn = kernel_for(cls, Evec, op, KFEWCOLS);
     if (kfn && Rm > 0) {

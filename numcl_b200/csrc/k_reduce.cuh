@@ -44,6 +44,7 @@ struct RedParams {
   const char* in; long long in_off; int lk;
   char* out; long long out_off; StoreSpec sk; int out_lk;
   int fresh; long long ident_i; double ident_f;
+  int stat; long long count;                       // fused mean / variance / stdev epilogue (store_result): 0 none, 1 / count, 3 sqrt(/ count)
   // row: rows = prod(kext), cols contiguous
   int nk; long long kext[4], kin[4], kout[4];      // kept dims (outer -> inner): extents, input strides, output strides
   long long rows, cols;
@@ -116,6 +117,31 @@ __device__ __forceinline__ T fetch_scalar(const RedParams& p, long long ia, long
 typedef void (*RedKernel)(const RedParams);
 template <class T> __device__ __forceinline__ T ident_of(const RedParams& p) {
   if constexpr (std::is_integral<T>::value) return (T)p.ident_i; else return (T)p.ident_f;
+}
+
+// The final store of a reduction.  stat == 0: through %coerce into the result's element type.  Otherwise the fused
+// epilogue of numcl:mean / variance / standard-deviation (src/5reduce.lisp:128-167), which the reference computes as
+// (numcl:/ (numcl:sum ...) count) [then numcl:sqrt]: first the rounding the SUM array's own store would have performed
+// (single-float / double-float; fixnum = wrap to 63 bits), then ONE division by the element count exactly as broadcast '/
+// performs it (float / integer: the count converted by contagion; integer / integer: the exact ratio rounded once to
+// single-float), then sqrt.  Bit-identical to the two- and three-pass composition, in one launch.
+template <class T, class V>
+__device__ __forceinline__ void store_result(const RedParams& p, long long o, V v) {
+  if (p.stat == 0) { store_scalar<V>(p.out, o, p.sk, v); return; }
+  if constexpr (std::is_same<T, float>::value) {
+    float m = __fdiv_rn(to_f32(v), __ll2float_rn(p.count));
+    if (p.stat == 3) m = __fsqrt_rn(m);
+    store_scalar<float>(p.out, o, p.sk, m);
+  } else if constexpr (std::is_same<T, double>::value) {
+    double m = __ddiv_rn(to_f64(v), __ll2double_rn(p.count));
+    if (p.stat == 3) m = __dsqrt_rn(m);
+    store_scalar<double>(p.out, o, p.sk, m);
+  } else {
+    const long long s = (long long)((unsigned long long)round_to_i64(v) << 1) >> 1;      // the fixnum sum array: 63 bits
+    float m = ratio_to_f32(s, p.count);
+    if (p.stat == 3) m = __fsqrt_rn(m);
+    store_scalar<float>(p.out, o, p.sk, m);
+  }
 }
 
 // Sum of the 16 bytes of one chunk with four dot-product instructions (8-bit element types under +): the generic path
@@ -229,7 +255,7 @@ __device__ __forceinline__ void reduce_one_row(const RedParams& p, const long lo
   pdl_wait();                                                                // nothing is written before every earlier kernel has completed
   if (live && t == 0) {
     T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, obase, p.out_lk);
-    store_scalar<T>(p.out, obase, p.sk, Red<T, OP>::f(init, a));          // r <- fn(r, partial)
+    store_result<T, T>(p, obase, Red<T, OP>::f(init, a));                  // r <- fn(r, partial)
   }
 }
 // 256 / TPR rows per CTA.  (Persistent warps walking the short rows with a grid stride were tried for TPR <= 32: no gain,
@@ -281,7 +307,7 @@ __global__ void __launch_bounds__(256) reduce_row_thread_kernel(const __grid_con
 #pragma unroll
   for (int j = 0; j < 4; j++) if (live[j]) {
     T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, ob[j], p.out_lk);
-    store_scalar<T>(p.out, ob[j], p.sk, Red<T, OP>::f(init, acc[j]));
+    store_result<T, T>(p, ob[j], Red<T, OP>::f(init, acc[j]));
   }
 }
 
@@ -339,7 +365,7 @@ __global__ void __launch_bounds__(256) dot_matvec_kernel(const __grid_constant__
     for (int k = 1; k < 8; k++) tot = Ops<T>::add(tot, sm[k][threadIdx.x]);
     const long long ob = p.out_off + (row0 + threadIdx.x) * p.kout[0];
     T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, ob, p.out_lk);
-    store_scalar<T>(p.out, ob, p.sk, Ops<T>::add(init, tot));
+    store_result<T, T>(p, ob, Ops<T>::add(init, tot));
   }
 }
 
@@ -362,7 +388,7 @@ __global__ void __launch_bounds__(256) reduce_rows_reg_kernel(const __grid_const
       for (int i = 1; i < C; i++) r = Red<T, OP>::f(r, a[(j * C + i) / E][(j * C + i) % E]);
       const long long ob = p.out_off + (row0 + j) * p.kout[0];
       T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, ob, p.out_lk);
-      store_scalar<T>(p.out, ob, p.sk, Red<T, OP>::f(init, r));
+      store_result<T, T>(p, ob, Red<T, OP>::f(init, r));
     }
   } else {                                                  // fewer than E rows left
     for (long long row = row0; row < p.rows; row++) {
@@ -370,7 +396,7 @@ __global__ void __launch_bounds__(256) reduce_rows_reg_kernel(const __grid_const
       for (int i = 1; i < C; i++) r = Red<T, OP>::f(r, load_scalar<T>(p.in, p.in_off + row * C + i, p.lk));
       const long long ob = p.out_off + row * p.kout[0];
       T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, ob, p.out_lk);
-      store_scalar<T>(p.out, ob, p.sk, Red<T, OP>::f(init, r));
+      store_result<T, T>(p, ob, Red<T, OP>::f(init, r));
     }
   }
 }
@@ -427,7 +453,7 @@ __global__ void __launch_bounds__(256) reduce_rows_staged_kernel(const __grid_co
         if (live && l == 0) {
           const long long ob = p.out_off + (r0 + row) * p.kout[0];
           T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, ob, p.out_lk);
-          store_scalar<T>(p.out, ob, p.sk, Red<T, OP>::f(init, acc));
+          store_result<T, T>(p, ob, Red<T, OP>::f(init, acc));
         }
       }
     });
@@ -529,8 +555,7 @@ __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all
     if (p.raw_partial) { *(W*)p.raw_partial = s; return; }
     W init = p.fresh ? (W)ident_of<T>(p) : (W)load_scalar<T>(p.out, p.out_off, p.out_lk);
     W r = Red<W, OP>::f(init, s);
-    if constexpr (std::is_integral<T>::value) store_scalar<long long>(p.out, p.out_off, p.sk, r);
-    else store_scalar<double>(p.out, p.out_off, p.sk, r);           // one rounding to the element type
+    store_result<T, W>(p, p.out_off, r);                            // one rounding to the element type
   }
 }
 
@@ -613,8 +638,7 @@ __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_few
     const long long o = p.out_off + (long long)j * p.kout[0];
     W init = p.fresh ? (W)ident_of<T>(p) : (W)load_scalar<T>(p.out, o, p.out_lk);
     W r = Red<W, OP>::f(init, tot);
-    if constexpr (std::is_integral<T>::value) store_scalar<long long>(p.out, o, p.sk, r);
-    else store_scalar<double>(p.out, o, p.sk, r);           // one rounding to the element type
+    store_result<T, W>(p, o, r);                            // one rounding to the element type
   }
 }
 
@@ -676,7 +700,7 @@ __global__ void __launch_bounds__(256) reduce_col_kernel(const __grid_constant__
 #pragma unroll
   for (int i = 0; i < E; i++) {
     T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, obase + i, p.out_lk);
-    store_scalar<T>(p.out, obase + i, p.sk, Red<T, OP>::f(init, acc[i]));
+    store_result<T, T>(p, obase + i, Red<T, OP>::f(init, acc[i]));
   }
 }
 template <class T, int OP, int E>
@@ -694,7 +718,7 @@ __global__ void __launch_bounds__(256) reduce_col_finish_kernel(const __grid_con
     T a = part[q * E + i];
     for (int s = 1; s < p.nseg; s++) a = Red<T, OP>::f(a, part[((long long)s * nq + q) * E + i]);
     T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, obase + i, p.out_lk);
-    store_scalar<T>(p.out, obase + i, p.sk, Red<T, OP>::f(init, a));
+    store_result<T, T>(p, obase + i, Red<T, OP>::f(init, a));
   }
 }
 

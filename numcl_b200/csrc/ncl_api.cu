@@ -22,6 +22,17 @@ int cuda_fail(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return NCL_OK;
   return set_error(NCL_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
+// ---- residency: a device mirror attached to a host base vector (what %make-array gains, src/1instantiate.lisp:81-96) ---------
+// A numcl array is an ordinary Lisp array, so the host vector stays the array; ncl_host_register gives it a device mirror that
+// SURVIVES the call.  A host-resident tensor whose `host` pointer is a registered base vector is not staged through the arena:
+// it is uploaded only when the host copy is newer (first use, or after ncl_host_dirty), so the second and every later call on
+// the same array moves nothing over PCIe.  Results are written back into the host vector at the end of the call (window
+// only), or -- NCL_RESIDENT_LAZY -- left on the device until ncl_host_fetch.
+enum { RES_IN_SYNC = 0, RES_HOST_NEWER = 1, RES_DEVICE_NEWER = 2 };
+struct Resident { void* host; size_t bytes; ncl_buf* dev; int state; unsigned flags; };
+static std::map<const void*, Resident> g_res;
+static Resident* find_resident(const void* host) { auto it = g_res.find(host); return it == g_res.end() ? nullptr : &it->second; }
+
 // ---- device buffer cache (see "buffers" below) ----
 static std::multimap<size_t, void*> g_pool;
 static size_t g_pool_bytes = 0;
@@ -65,6 +76,21 @@ void reduce_identity(int op, int dtype, long long* ident_i, double* ident_f) {
   }
 }
 
+// The sticky DOMAIN flag (ncl_fn.cuh): read back only when a kernel that can raise it has been launched since the last check.
+int check_fault() {
+  if (!g_ctx.fault_possible || g_ctx.capturing) return NCL_OK;
+  unsigned int h = 0;
+  NCL_CUDA(cudaMemcpyAsync(&h, g_ctx.fault, sizeof h, cudaMemcpyDeviceToHost, g_ctx.stream));
+  NCL_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  g_ctx.fault_possible = false;
+  if (!h) return NCL_OK;
+  NCL_CUDA(cudaMemsetAsync(g_ctx.fault, 0, sizeof h, g_ctx.stream));
+  return set_error(NCL_ERR_DOMAIN, "an earlier call left the real domain of its function:%s%s%s (the reference signals a Lisp error or returns a complex number there)",
+                   (h & 1) ? " argument outside the function's real domain (sqrt / log of a negative, asin / acos / atanh beyond 1, acosh below 1, isqrt of a negative, negative base to a fractional power);" : "",
+                   (h & 2) ? " division by zero (floor / ceiling / round / truncate / mod / rem / expt);" : "",
+                   (h & 4) ? " integer power beyond 64 bits;" : "");
+}
+
 #define LOCK std::lock_guard<std::recursive_mutex> lock__(g_mu)
 #define NEED_INIT if (!g_ctx.inited) return set_error(NCL_ERR_STATE, "ncl_init has not been called")
 
@@ -96,6 +122,9 @@ int ncl_init(int ndev, const int* devs) {
   long long consts[8] = {0, 1, 0, 0, 0, 0, 0, 0};
   NCL_CUDA(cudaMalloc(&g_ctx.consts, sizeof consts));
   NCL_CUDA(cudaMemcpy(g_ctx.consts, consts, sizeof consts, cudaMemcpyHostToDevice));
+  NCL_CUDA(cudaMalloc((void**)&g_ctx.fault, 64));
+  NCL_CUDA(cudaMemset(g_ctx.fault, 0, 64));
+  g_ctx.fault_possible = false;
   g_ctx.launches = 0; g_ctx.last_kernel = ""; g_ctx.inited = true;
   return NCL_OK;
 }
@@ -104,12 +133,15 @@ void ncl_shutdown(void) {
   LOCK;
   if (!g_ctx.inited) return;
   cudaStreamSynchronize(g_ctx.stream);
+  for (auto& kv : g_res) if (kv.second.dev) { cudaFree(kv.second.dev->ptr); delete kv.second.dev; }
+  g_res.clear();
   pool_release_all();
   if (g_ctx.scratch) cudaFree(g_ctx.scratch);
   if (g_ctx.scratch2) cudaFree(g_ctx.scratch2);
   if (g_ctx.scratch3) cudaFree(g_ctx.scratch3);
   if (g_ctx.ticket) cudaFree(g_ctx.ticket);
   if (g_ctx.consts) cudaFree(g_ctx.consts);
+  if (g_ctx.fault) cudaFree(g_ctx.fault);
   if (g_ctx.pinned) cudaFreeHost(g_ctx.pinned);
   if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
   g_ctx = Context();
@@ -134,7 +166,7 @@ void* ncl_get_stream(void) { return (void*)g_ctx.stream; }
 int ncl_sync(void) {
   LOCK; NEED_INIT;
   if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_sync inside ncl_capture_begin/end");
-  ncl_comm_join(); NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); return NCL_OK;
+  ncl_comm_join(); NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); return check_fault();
 }
 // Give every cached device block back to the driver (the cache keeps freed base vectors for re-use and would otherwise
 // only shrink when one of the library's own allocations fails): for hosts that share the GPU with another allocator.
@@ -243,7 +275,7 @@ int ncl_d2h(void* host, const ncl_buf* src, size_t off, size_t bytes) {
   ncl_comm_join();
   NCL_CUDA(cudaMemcpyAsync(host, (const char*)src->ptr + off, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
   NCL_CUDA(cudaStreamSynchronize(g_ctx.stream));
-  return NCL_OK;
+  return check_fault();
 }
 void* ncl_host_alloc_pinned(size_t bytes) {
   void* p = nullptr;
@@ -251,6 +283,44 @@ void* ncl_host_alloc_pinned(size_t bytes) {
   return p;
 }
 int ncl_host_free(void* p) { if (p) cudaFreeHost(p); return NCL_OK; }
+int ncl_host_register(void* base, size_t bytes, unsigned flags) {
+  LOCK; NEED_INIT;
+  if (!base || !bytes) return set_error(NCL_ERR_INVALID, "ncl_host_register: NULL base or zero size");
+  if (find_resident(base)) return set_error(NCL_ERR_STATE, "ncl_host_register: this base vector is registered already");
+  ncl_buf* d = ncl_alloc(bytes, 0);
+  if (!d) return NCL_ERR_NOMEM;
+  // NCL_RESIDENT_FRESH: the vector was just allocated and holds nothing yet (a result array): no first upload
+  g_res[base] = Resident{base, bytes, d, (flags & NCL_RESIDENT_FRESH) ? RES_IN_SYNC : RES_HOST_NEWER, flags};
+  return NCL_OK;
+}
+int ncl_host_unregister(void* base) {
+  LOCK;
+  auto it = g_res.find(base);
+  if (it == g_res.end()) return NCL_OK;
+  int rc = NCL_OK;
+  if (it->second.state == RES_DEVICE_NEWER && g_ctx.inited) rc = ncl_host_fetch(base);         // never lose a result
+  ncl_free(it->second.dev); g_res.erase(base);
+  return rc;
+}
+int ncl_host_dirty(void* base) {
+  LOCK;
+  Resident* r = find_resident(base);
+  if (!r) return set_error(NCL_ERR_INVALID, "ncl_host_dirty: not a registered base vector");
+  r->state = RES_HOST_NEWER; return NCL_OK;
+}
+int ncl_host_fetch(void* base) {
+  LOCK; NEED_INIT;
+  Resident* r = find_resident(base);
+  if (!r) return set_error(NCL_ERR_INVALID, "ncl_host_fetch: not a registered base vector");
+  if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_host_fetch inside ncl_capture_begin/end");
+  if (r->state != RES_DEVICE_NEWER) return NCL_OK;
+  ncl_comm_join();
+  NCL_CUDA(cudaMemcpyAsync(r->host, r->dev->ptr, r->bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+  NCL_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  g_ctx.d2h_bytes += r->bytes; r->state = RES_IN_SYNC;
+  return check_fault();
+}
+int ncl_host_state(const void* base) { Resident* r = find_resident(base); return r ? r->state : -1; }
 size_t ncl_storage_bytes(int dtype, int64_t n) {
   if (dtype < 0 || dtype >= NCL_DTYPE_COUNT) return 0;
   int64_t padded = 8 * ((n + 7) / 8); if (padded == 0) padded = 8;
@@ -272,13 +342,17 @@ static int check_tensor(const ncl_tensor* t, const char* what) {
   return NCL_OK;
 }
 
-// Host-resident tensors are staged through a device arena that lives for the call.
+// Host-resident tensors are staged through a device arena that lives for the call (or use their resident mirror).
 struct Stager {
-  struct Item { const ncl_tensor* t; char* dev; size_t bytes; bool is_out; };
+  struct Item { const ncl_tensor* t; char* dev; size_t bytes; bool is_out; Resident* res; };
   std::vector<Item> items; size_t used = 0;
   static size_t need(const ncl_tensor* t) { return (ncl_storage_bytes(t->dtype, t->elem_offset + total_elems(t)) + 255) & ~(size_t)255; }
   int plan(const ncl_tensor* ts, int n, bool is_out) {
-    for (int i = 0; i < n; i++) if (ts[i].host) { items.push_back({&ts[i], nullptr, need(&ts[i]), is_out}); used += items.back().bytes; }
+    for (int i = 0; i < n; i++) if (ts[i].host) {
+      Resident* r = find_resident(ts[i].host);
+      if (r && need(&ts[i]) > ((r->bytes + 255) & ~(size_t)255)) return set_error(NCL_ERR_INVALID, "a tensor over a registered base vector addresses %zu bytes but %zu were registered", need(&ts[i]), r->bytes);
+      items.push_back({&ts[i], r ? (char*)r->dev->ptr : nullptr, r ? 0 : need(&ts[i]), is_out, r}); used += items.back().bytes;
+    }
     return NCL_OK;
   }
   // byte window of the base vector a tensor's elements occupy: [lo, hi)
@@ -287,11 +361,18 @@ struct Stager {
     *lo = b0 / 8; *hi = (b1 + 7) / 8; *ragged = (b0 % 8) != 0 || (b1 % 8) != 0;
   }
   int upload(bool outputs_too) {
-    if (!used) return NCL_OK;
+    if (items.empty()) return NCL_OK;
     if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "host-resident tensors cannot be staged inside ncl_capture_begin/end");
-    NCL_TRY(ensure_scratch2(used));
+    if (used) NCL_TRY(ensure_scratch2(used));
     size_t off = 0;
     for (auto& it : items) {
+      if (it.res) {                                                  // resident mirror: upload only when the host copy is newer
+        if (it.res->state == RES_HOST_NEWER) {
+          NCL_CUDA(cudaMemcpyAsync(it.res->dev->ptr, it.res->host, it.res->bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+          g_ctx.h2d_bytes += it.res->bytes; it.res->state = RES_IN_SYNC;
+        }
+        continue;
+      }
       it.dev = (char*)g_ctx.scratch2 + off; off += it.bytes;
       size_t live = ncl_storage_bytes(it.t->dtype, it.t->elem_offset + total_elems(it.t));
       if (!it.is_out || outputs_too) {
@@ -313,10 +394,11 @@ struct Stager {
   int download() {
     bool any = false;
     for (auto& it : items) if (it.is_out) {
+      if (it.res && (it.res->flags & NCL_RESIDENT_LAZY)) { it.res->state = RES_DEVICE_NEWER; continue; }     // stays on the device until ncl_host_fetch
       size_t lo, hi; bool ragged; window(it.t, &lo, &hi, &ragged);
       if (hi > lo) { NCL_CUDA(cudaMemcpyAsync((char*)it.t->host + lo, it.dev + lo, hi - lo, cudaMemcpyDeviceToHost, g_ctx.stream)); any = true; g_ctx.d2h_bytes += hi - lo; }
     }
-    if (any) NCL_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    if (any) { NCL_CUDA(cudaStreamSynchronize(g_ctx.stream)); return check_fault(); }
     return NCL_OK;
   }
 };
@@ -325,7 +407,11 @@ static void operand_from(const ncl_tensor* t, Stager& st, Operand* o) {
   memset(o, 0, sizeof *o);
   o->dtype = t->dtype; o->offset = t->elem_offset;
   if (t->buf) { o->base = (char*)t->buf->ptr; o->n_storage = (int64_t)((t->buf->bytes * 8) / g_dt[t->dtype].slot_bits); }
-  else { o->base = st.dev_of(t); o->n_storage = (int64_t)((Stager::need(t) * 8) / g_dt[t->dtype].slot_bits); }
+  else {
+    o->base = st.dev_of(t);
+    Resident* r = find_resident(t->host);
+    o->n_storage = (int64_t)(((r ? r->bytes : Stager::need(t)) * 8) / g_dt[t->dtype].slot_bits);
+  }
 }
 static void rowmajor_strides(const ncl_tensor* t, int64_t* s) { int64_t acc = 1; for (int i = t->rank - 1; i >= 0; i--) { s[i] = acc; acc *= t->dims[i]; } }
 
@@ -660,6 +746,83 @@ int ncl_reduce(int op, const ncl_tensor* a, const int* axes, int n_axes, ncl_ten
     if (rc == NCL_OK) rc = run_nest(*nest);
     delete nest; return rc;
   });
+}
+
+// numcl:mean / variance / standard-deviation, src/5reduce.lisp:128-167, as ONE launch: the reduction kernels' final store
+// divides the finished sum by the element count (and takes the square root).  variance is the reference's: the mean of
+// SQUARES, no mean subtraction, computed as the dot-like reduction of the array with itself (the product of
+// each element with itself is rounded, then added -- what (numcl:sum (square array)) does in two passes).  Shapes or
+// element types the fused kernels do not take are composed from the library's own passes, exactly as the reference does.
+int ncl_reduce_stat(int stat, const ncl_tensor* a, const int* axes, int n_axes, ncl_tensor* r) {
+  LOCK; NEED_INIT;
+  NCL_TRY(check_tensor(a, "array")); NCL_TRY(check_tensor(r, "result"));
+  if (stat < NCL_STAT_MEAN || stat > NCL_STAT_STDEV) return set_error(NCL_ERR_INVALID, "ncl_reduce_stat: bad statistic %d", stat);
+  const int icls = g_dt[a->dtype].cls, ocls = g_dt[r->dtype].cls;
+  if (!((icls == CLS_I && r->dtype == NCL_F32) || (icls == CLS_F && r->dtype == NCL_F32) || (icls == CLS_D && r->dtype == NCL_F64)))
+    return set_error(NCL_ERR_INVALID, "ncl_reduce_stat: the result of a %s array is %s", g_dt[a->dtype].name, icls == CLS_D ? "double-float" : "single-float");
+  (void)ocls;
+  bool summed[NCL_MAX_RANK] = {false};
+  if (n_axes == 0) for (int k = 0; k < a->rank; k++) summed[k] = true;
+  for (int k = 0; k < n_axes; k++) { if (axes[k] < 0 || axes[k] >= a->rank) return set_error(NCL_ERR_INVALID, "bad axis %d", axes[k]); summed[axes[k]] = true; }
+  int rk = 0; int64_t count = 1;
+  for (int ax = 0; ax < a->rank; ax++) {
+    if (summed[ax]) { count *= a->dims[ax]; continue; }
+    if (rk >= r->rank || r->dims[rk] != a->dims[ax]) return set_error(NCL_ERR_SHAPE, "reduce: result shape mismatch");
+    rk++;
+  }
+  if (rk != r->rank) return set_error(NCL_ERR_SHAPE, "reduce: result rank %d, expected %d", r->rank, rk);
+  if (count == 0) return set_error(NCL_ERR_DOMAIN, "mean over zero elements: division by zero");
+  int rc = NCL_ERR_UNSUPPORTED;
+  if (a->buf && r->buf && g_dt[a->dtype].slot_bits >= 8 && a->dtype != NCL_UB64) {
+    Stager st;
+    Nest* nest = new Nest;
+    const bool sq = stat != NCL_STAT_MEAN;
+    nest->nloops = a->rank; nest->n_in = sq ? 2 : 1; nest->n_out = 1; nest->fresh = true;
+    nest->stat = stat == NCL_STAT_STDEV ? 3 : 1; nest->stat_count = count;
+    operand_from(a, st, &nest->in[0]); if (sq) operand_from(a, st, &nest->in[1]);
+    operand_from(r, st, &nest->out[0]);
+    int64_t as[NCL_MAX_RANK], rs[NCL_MAX_RANK]; rowmajor_strides(a, as); rowmajor_strides(r, rs);
+    int k = 0;
+    for (int ax = 0; ax < a->rank; ax++) {
+      nest->extent[ax] = a->dims[ax]; nest->in[0].stride[ax] = as[ax]; if (sq) nest->in[1].stride[ax] = as[ax];
+      nest->out[0].stride[ax] = summed[ax] ? 0 : rs[k++];
+    }
+    nest->has_identity = true; nest->ident_i = 0; nest->ident_f = 0.0;
+    // the transform only has to have the SHAPE the reduction families match: (+ @1 $1) / (+ @1 (* $1 $2)); the accumulator's
+    // class is the input's, the epilogue converts (k_reduce.cuh: store_result)
+    Expr& e = nest->transform[0]; e.n = 0;
+    auto node = [&](int op, int x, int y, int cls) { XNode& nd = e.node[e.n++]; memset(&nd, 0, sizeof nd); nd.op = op; nd.a = x; nd.b = y; nd.cls = cls; };
+    node(NCL_X_OUTPUT, 1, 0, icls); node(NCL_X_INPUT, 1, 0, icls);
+    if (sq) { node(NCL_X_INPUT, 2, 0, icls); node(NCL_OP_MUL, 1, 2, icls); node(NCL_OP_ADD, 0, 3, icls); }
+    else node(NCL_OP_ADD, 0, 1, icls);
+    bool runs_ok = true;                                                  // one run of adjacent summed axes (the kernels merge it)
+    { int runs = 0; for (int ax = 0; ax < a->rank; ax++) if (summed[ax] && a->dims[ax] != 1 && (ax == 0 || !summed[ax - 1])) runs++; if (runs > 1) runs_ok = false; }
+    if (runs_ok) rc = run_nest(*nest);
+    delete nest;
+  }
+  if (rc != NCL_ERR_UNSUPPORTED) return rc;
+  // ---- composition: (numcl:sqrt (numcl:/ (numcl:sum [(square a)]) count)), src/5reduce.lisp:128-167 ----
+  if (!a->buf || !r->buf) return set_error(NCL_ERR_UNSUPPORTED, "ncl_reduce_stat works on device-resident tensors");
+  ncl_tensor sqt = *a, sumt = *r, cnt; memset(&cnt, 0, sizeof cnt);
+  ncl_buf *b1 = nullptr, *b2 = nullptr, *b3 = nullptr;
+  auto cleanup = [&](int code) { if (b1) ncl_free(b1); if (b2) ncl_free(b2); if (b3) ncl_free(b3); return code; };
+  const ncl_tensor* src = a;
+  if (stat != NCL_STAT_MEAN) {                                            // (square a): fixnum for integers (any product wraps the same way modulo 2^63)
+    sqt.dtype = icls == CLS_I ? NCL_FIXNUM : a->dtype; sqt.elem_offset = 0; sqt.host = nullptr;
+    b1 = ncl_alloc(ncl_storage_bytes(sqt.dtype, total_elems(a)), 0); if (!b1) return NCL_ERR_NOMEM; sqt.buf = b1;
+    ncl_expr e; e.n = 0; x_leaf(&e, NCL_X_INPUT, 1); x_op(&e, NCL_OP_SQUARE, 0, 0);
+    rc = ncl_map(&e, a, 1, &sqt); if (rc != NCL_OK) return cleanup(rc);
+    src = &sqt;
+  }
+  sumt.dtype = icls == CLS_I ? NCL_FIXNUM : a->dtype; sumt.elem_offset = 0;
+  b2 = ncl_alloc(ncl_storage_bytes(sumt.dtype, total_elems(r)), 0); if (!b2) return cleanup(NCL_ERR_NOMEM); sumt.buf = b2;
+  rc = ncl_reduce(NCL_OP_ADD, src, axes, n_axes, &sumt, NCL_OUT_FRESH); if (rc != NCL_OK) return cleanup(rc);
+  cnt.dtype = NCL_FIXNUM; cnt.rank = 0;
+  b3 = ncl_alloc(64, 0); if (!b3) return cleanup(NCL_ERR_NOMEM); cnt.buf = b3;
+  rc = ncl_fill(&cnt, 0, count, 0.0); if (rc != NCL_OK) return cleanup(rc);
+  rc = ncl_broadcast(NCL_OP_DIV, &sumt, &cnt, r); if (rc != NCL_OK) return cleanup(rc);
+  if (stat == NCL_STAT_STDEV) { ncl_expr e; e.n = 0; x_leaf(&e, NCL_X_INPUT, 1); x_op(&e, NCL_OP_SQRT, 0, 0); ncl_tensor rin = *r; rc = ncl_map(&e, &rin, 1, r); }
+  return cleanup(rc);
 }
 
 int ncl_fill(ncl_tensor* t, int value_is_float, int64_t ival, double fval) {

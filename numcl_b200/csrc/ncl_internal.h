@@ -47,6 +47,9 @@ struct Nest {
   bool fresh = false;                   // outputs are not read: they start from zero / identity
   // for reductions through ncl_reduce with fresh=true the accumulator starts from this identity
   bool has_identity = false; int64_t ident_i = 0; double ident_f = 0;
+  // fused statistics (ncl_reduce_stat): the reduction kernels divide the finished sum by stat_count (and take the square root)
+  // in their final store; only the reduction families understand this, every other family refuses such a nest
+  int stat = 0; int64_t stat_count = 0;
 };
 
 // ---- context ------------------------------------------------------------------------------------

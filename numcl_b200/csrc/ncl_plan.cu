@@ -155,6 +155,11 @@ int run_nest(Nest& n) {
   for (int o = 0; o < n.n_out; o++) NCL_TRY(check_bounds(n.out[o], n, "output", o));
   bool empty = false;
   for (int l = 0; l < n.nloops; l++) if (n.extent[l] == 0) empty = true;
+  if (n.stat) {                                        // fused statistics: reduction kernels only (ncl_reduce_stat composes otherwise)
+    if (empty || ctx().force_generic) return NCL_ERR_UNSUPPORTED;
+    int rc = try_dot_reduce(n);
+    return rc != NCL_ERR_UNSUPPORTED ? rc : try_reduce(n);
+  }
   if (!ctx().force_generic && !empty) {
     int rc;
     if ((rc = try_dot_reduce(n)) != NCL_ERR_UNSUPPORTED) return rc;

@@ -18,10 +18,17 @@ from .einsum_spec import Double, EinsumSpecError, EinsumSpecs, Sym, einsum_norma
 
 _BINARY = {"+": "ADD", "-": "SUB", "*": "MUL", "/": "DIV", "MAX": "MAX", "MIN": "MIN",
            "=/BIT": "EQ", "/=/BIT": "NE", "<=/BIT": "LE", ">=/BIT": "GE", "</BIT": "LT", ">/BIT": "GT",
-           "LOGAND": "LOGAND", "LOGIOR": "LOGIOR", "LOGXOR": "LOGXOR"}
+           "LOGAND": "LOGAND", "LOGIOR": "LOGIOR", "LOGXOR": "LOGXOR",
+           "LOGANDC1": "LOGANDC1", "LOGANDC2": "LOGANDC2", "LOGEQV": "LOGEQV", "LOGNAND": "LOGNAND", "LOGNOR": "LOGNOR",
+           "LOGORC1": "LOGORC1", "LOGORC2": "LOGORC2", "EXPT": "EXPT"}
+# (floor number &optional (divisor 1)) ...: one argument means divisor 1 (src/4numeric.lisp:572-577)
+_DIVLIKE = {"FLOOR": "FLOOR", "CEILING": "CEILING", "ROUND": "ROUND", "TRUNCATE": "TRUNCATE", "MOD": "MOD", "REM": "REM"}
 _UNARY = {"ABS": "ABS", "%SQUARE": "SQUARE", "SQUARE": "SQUARE", "SQRT": "SQRT", "LOGNOT": "LOGNOT",
           "IDENTITY": "IDENTITY", "EXP": "EXP", "LOG": "LOG", "%LOGR": "LOG", "SIN": "SIN", "COS": "COS",
-          "TAN": "TAN", "TANH": "TANH", "SIGNUM": "SIGNUM"}
+          "TAN": "TAN", "TANH": "TANH", "SIGNUM": "SIGNUM",
+          "ASIN": "ASIN", "ACOS": "ACOS", "ATAN": "ATAN", "SINH": "SINH", "COSH": "COSH", "ASINH": "ASINH", "ACOSH": "ACOSH",
+          "ATANH": "ATANH", "%LOG2": "LOG2", "LOG2": "LOG2", "ISQRT": "ISQRT", "LOGCOUNT": "LOGCOUNT",
+          "INTEGER-LENGTH": "INTEGER_LENGTH"}
 
 
 class TransformError(NotImplementedError):
@@ -89,6 +96,10 @@ def compile_transform(form) -> _lib.Expr:
             return emit("ADD", rec(args[0]), emit("X_CONST_INT", ival=1))
         if head == "1-":
             return emit("SUB", rec(args[0]), emit("X_CONST_INT", ival=1))
+        if head in _DIVLIKE:
+            if len(args) not in (1, 2):
+                raise TransformError(f"{head} takes one or two arguments")
+            return emit(_DIVLIKE[head], rec(args[0]), rec(args[1]) if len(args) == 2 else emit("X_CONST_INT", ival=1))
         if head in _BINARY:
             if head.startswith("LOG") and len(args) != 2:
                 acc = rec(args[0])

@@ -19,7 +19,11 @@ from .einsum_spec import read_subscripts
 
 _OP = {"+": "ADD", "-": "SUB", "*": "MUL", "/": "DIV", "max": "MAX", "min": "MIN",
        "=/bit": "EQ", "/=/bit": "NE", "<=/bit": "LE", ">=/bit": "GE", "</bit": "LT", ">/bit": "GT",
-       "logand": "LOGAND", "logior": "LOGIOR", "logxor": "LOGXOR"}
+       "logand": "LOGAND", "logior": "LOGIOR", "logxor": "LOGXOR",
+       "logandc1": "LOGANDC1", "logandc2": "LOGANDC2", "logeqv": "LOGEQV", "lognand": "LOGNAND", "lognor": "LOGNOR",
+       "logorc1": "LOGORC1", "logorc2": "LOGORC2",
+       "floor": "FLOOR", "ceiling": "CEILING", "round": "ROUND", "truncate": "TRUNCATE", "mod": "MOD", "rem": "REM",
+       "expt": "EXPT"}
 
 
 def _is_scalar(x):
@@ -27,6 +31,17 @@ def _is_scalar(x):
 
 
 def _scalar_op(fn, x, y):
+    import math
+    if fn in ("floor", "ceiling", "truncate", "round") and isinstance(x, int) and isinstance(y, int):
+        from fractions import Fraction
+        q = Fraction(x, y)
+        return {"floor": math.floor, "ceiling": math.ceil, "truncate": math.trunc, "round": round}[fn](q)
+    if fn == "mod":
+        return x % y                          # sign of the divisor, like CL's mod
+    if fn == "rem":
+        return math.fmod(x, y) if isinstance(x, float) or isinstance(y, float) else int(math.fmod(x, y))
+    if fn == "expt":
+        return x ** y
     if fn == "+":
         return x + y
     if fn == "-":
@@ -222,8 +237,11 @@ def _simple_mapper(cl_fn):
     def mapper(x):
         if _is_scalar(x):
             import math
-            return {"sqrt": math.sqrt, "exp": math.exp, "log": math.log, "sin": math.sin, "cos": math.cos,
-                    "tan": math.tan, "tanh": math.tanh, "abs": abs, "square": lambda v: v * v}[cl_fn](x)
+            return {"sqrt": math.sqrt, "exp": math.exp, "log": math.log, "%logr": math.log, "%log2": math.log2, "sin": math.sin,
+                    "cos": math.cos, "tan": math.tan, "tanh": math.tanh, "abs": abs, "square": lambda v: v * v,
+                    "asin": math.asin, "acos": math.acos, "atan": math.atan, "sinh": math.sinh, "cosh": math.cosh,
+                    "asinh": math.asinh, "acosh": math.acosh, "atanh": math.atanh, "isqrt": math.isqrt,
+                    "lognot": lambda v: ~v, "signum": lambda v: (v > 0) - (v < 0)}[cl_fn](x)
         from .einsum import einsum
         t = ti.infer_type("%square" if cl_fn == "square" else cl_fn, ti.type_of_dtype(x.dtype))
         y = empty(x.shape, type=ti.upgrade(t), where=x.where)
@@ -236,3 +254,32 @@ def _simple_mapper(cl_fn):
 
 sqrt, exp, log, sin, cos, tan, tanh, abs_, square = (_simple_mapper(n) for n in
                                                      ("sqrt", "exp", "log", "sin", "cos", "tan", "tanh", "abs", "square"))
+# the rest of src/4numeric.lisp:466-519.  numcl:log is %logr (positive reals assumed), numcl:logc is CL's log, numcl:log2 is
+# %log2; logcount / integer-length have no type inferer in the reference (2typeinfer.lisp:484-497 is commented out), so the
+# mappers there produce T arrays: use map_array_into with a typed result for those two.
+asin, acos, atan, sinh, cosh, asinh, acosh, atanh, isqrt, lognot = (
+    _simple_mapper(n) for n in ("asin", "acos", "atan", "sinh", "cosh", "asinh", "acosh", "atanh", "isqrt", "lognot"))
+logc = _simple_mapper("log")
+log = _simple_mapper("%logr")
+log2 = _simple_mapper("%log2")
+
+
+def _binary(name):
+    def f(x, y):
+        return broadcast(name, x, y)
+    f.__name__ = name
+    return f
+
+
+def _divlike(name):
+    def f(number, divisor=1):
+        """(numcl:NAME number &optional (divisor 1)) = (broadcast 'NAME number divisor), src/4numeric.lisp:572-577"""
+        return broadcast(name, number, divisor)
+    f.__name__ = name
+    return f
+
+
+floor, ceiling, round_, truncate, mod, rem = (_divlike(n) for n in ("floor", "ceiling", "round", "truncate", "mod", "rem"))
+expt = _binary("expt")
+logandc1, logandc2, logeqv, lognand, lognor, logorc1, logorc2 = (
+    _binary(n) for n in ("logandc1", "logandc2", "logeqv", "lognand", "lognor", "logorc1", "logorc2"))

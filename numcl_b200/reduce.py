@@ -99,9 +99,45 @@ def _count(array, axes):
     return n
 
 
-def mean(array, axes=None):
-    """numcl:mean = (numcl:/ (numcl:sum array :axes axes) (array-dimension* array axes)), :128-133."""
+def _stat(stat: int, array: NArray, axes):
+    """One fused launch (ncl_reduce_stat) when the array is device resident; None when the composition has to run
+    (host arrays, packed / ub64 element types, and full reductions of integer arrays, whose result in the reference is
+    an exact Lisp rational, not a float)."""
+    if not isinstance(array, NArray) or array.where != "device" or array.dtype.slot_bits < 8 or array.dtype.name == "ub64":
+        return None
+    ax = _axes(array, axes)
+    is_int = array.dtype.name not in ("f32", "f64")
+    if not ax or (is_int and len(ax) == array.rank) or array.size == 0:
+        return None
+    kept = [array.shape[d] for d in range(array.rank) if d not in ax]
+    r = empty(kept, type="f64" if array.dtype.name == "f64" else "f32")
+    ta, tr = array.tensor(), r.tensor()
+    axc = (C.c_int * len(ax))(*ax)
+    _lib.check(_lib.lib().ncl_reduce_stat(stat, C.byref(ta), axc, len(ax), C.byref(tr)))
+    return ensure_singleton(r)
+
+
+def mean_composed(array, axes=None):
+    """numcl:mean = (numcl:/ (numcl:sum array :axes axes) (array-dimension* array axes)), :128-133, pass by pass."""
     return div(sum(array, axes=axes), _count(array, axes))
+
+
+def variance_composed(array, axes=None):
+    return div(sum(square(array), axes=axes), _count(array, axes))
+
+
+def standard_deviation_composed(array, axes=None):
+    v = variance_composed(array, axes=axes)
+    if isinstance(v, NArray):
+        return sqrt(v)
+    import math
+    return math.sqrt(v)
+
+
+def mean(array, axes=None):
+    """numcl:mean, :128-133; fused into the sum kernel's final store (bit-identical to the composition)."""
+    r = _stat(_lib.STAT_MEAN, array, axes)
+    return mean_composed(array, axes) if r is None else r
 
 
 avg = mean
@@ -110,18 +146,17 @@ avg = mean
 def variance(array, axes=None):
     """numcl:variance as the reference defines it (:134-139): the mean of SQUARES, no mean
     subtraction (replicate, do not fix)."""
-    return div(sum(square(array), axes=axes), _count(array, axes))
+    r = _stat(_lib.STAT_VARIANCE, array, axes)
+    return variance_composed(array, axes) if r is None else r
 
 
 var = variance
 
 
 def standard_deviation(array, axes=None):
-    v = variance(array, axes=axes)
-    if isinstance(v, NArray):
-        return sqrt(v)
-    import math
-    return math.sqrt(v)
+    """numcl:standard-deviation, :140-146 = (numcl:sqrt variance)."""
+    r = _stat(_lib.STAT_STDEV, array, axes)
+    return standard_deviation_composed(array, axes) if r is None else r
 
 
 stdev = standard_deviation

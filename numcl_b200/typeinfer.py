@@ -254,6 +254,106 @@ _INFERERS.update({
 })
 
 
+# ---- the rest of the scalar-function surface (src/2typeinfer.lisp:255-454,606-660) -----------------------------------
+def _f32(v):
+    import numpy as np
+    return float(np.float32(v))
+
+
+def _divlike(kind):
+    """floor / ceiling / round / truncate inferers (:396-454): (integer ,@(interval-KIND l1 h1 l2 h2)).  interval-divlike
+    (src/1type.lisp:238-281) evaluates the function on the four corners with the divisor converted by (float y), i.e. in
+    single-float; a divisor type that contains or touches zero, or any open bound, gives an unbounded integer -> a T array."""
+    fn = {"floor": math.floor, "ceiling": math.ceil, "truncate": math.trunc,
+          "round": lambda q: int(round(q))}[kind]                      # Python's round is half-even like CL's
+
+    def infer(x, y=("integer", 1, 1)):
+        if None in (x[1], x[2], y[1], y[2]) or y[1] <= 0 <= y[2]:
+            raise TypeInferenceError(f"({kind} x y): the quotient's bounds are open: (integer * *) upgrades to T (general array)")
+        corners = []
+        for a in (x[1], x[2]):
+            for b in (y[1], y[2]):
+                q = _f32(_f32(a) / _f32(b)) if (x[0] == "integer") else a / b
+                corners.append(fn(q))
+        lo, hi = min(corners), max(corners)
+        return ("integer", max(lo, MOST_NEGATIVE_FIXNUM), min(hi, MOST_POSITIVE_FIXNUM))
+    return infer
+
+
+def _interval_intersection(l1, h1, l2, h2):
+    lo = l2 if l1 is None else l1 if l2 is None else max(l1, l2)
+    hi = h2 if h1 is None else h1 if h2 is None else min(h1, h2)
+    if lo is not None and hi is not None and lo > hi:
+        raise TypeInferenceError("empty interval: the reference infers the type NIL")
+    return lo, hi
+
+
+def _infer_mod(x, y):                     # (set-type-inferer 'mod 'intersection-to-float-type), :456 -- replicated, not fixed
+    return infer_rational_arithmetic_result(_interval_intersection, [x, y])
+
+
+def _infer_rem(x, y):                     # :459-481: x ^ (y v -y); the two pieces of the union are taken as their hull
+    m = None if (y[1] is None or y[2] is None) else max(abs(y[1]), abs(y[2]))
+    hull = (y[0], None if m is None else -m, m)
+    return infer_rational_arithmetic_result(_interval_intersection, [x, hull])
+
+
+COMPLEX_WHEN_UNPROVEN = {}
+
+
+def _real_when(name, pred, why):
+    """Functions that leave the reals outside a domain.  When the argument's TYPE is not provably inside the domain the
+    reference infers (complex <float>) and stores #C(x 0.0) for every in-domain element.  The CUDA backend has no complex
+    element types: it keeps the real float type (the real parts are the same numbers) and the kernels raise NCL_ERR_DOMAIN
+    if any ELEMENT is outside the domain -- exactly the elements whose imaginary part would be non-zero.
+    `reference_infers_complex(name, type)` tells the two cases apart."""
+    COMPLEX_WHEN_UNPROVEN[name] = (pred, why)
+
+    def infer(t):
+        return (float_substitution(t, int_result=DEFAULT_FLOAT), None, None)
+    return infer
+
+
+def reference_infers_complex(name: str, t) -> bool:
+    name = name.lower().split(":")[-1]
+    return name in COMPLEX_WHEN_UNPROVEN and not COMPLEX_WHEN_UNPROVEN[name][0](t)
+
+
+def _infer_isqrt(t):                      # (floor (sqrt x)), :644
+    if t[1] is None or t[1] < 0 or t[2] is None:
+        raise TypeInferenceError("(isqrt x): open upper bound: (integer * *) upgrades to T")
+    return ("integer", math.isqrt(int(t[1])), math.isqrt(int(t[2])))
+
+
+def _infer_expt(base, power):             # (exp (* (log base) power)), :255
+    head = float_contagion((float_substitution(base, DEFAULT_FLOAT), None, None), power)
+    return (float_substitution((head, None, None), DEFAULT_FLOAT) if head == "integer" else head, None, None)
+
+
+_nonneg = lambda t: t[1] is not None and t[1] >= 0                                  # noqa: E731
+_INFERERS.update({
+    "floor": _divlike("floor"), "ceiling": _divlike("ceiling"), "round": _divlike("round"), "truncate": _divlike("truncate"),
+    "mod": _infer_mod, "rem": _infer_rem, "expt": _infer_expt, "isqrt": _infer_isqrt,
+    # sqrt = (exp (/ (log x) 2)) and log (numcl:logc) leave the reals unless the type is provably non-negative (:196-214, 642);
+    # numcl:log (%logr) and %log2 ignore that on purpose (:216-240, 257-283)
+    "sqrt": _real_when("sqrt", _nonneg, "(sqrt x) of a type that may be negative"),
+    "log": _real_when("log", _nonneg, "(log x) of a type that may be negative"),
+    "%log2": _irrational, "log2": _irrational,
+    "asin": _real_when("asin", lambda t: t[1] is not None and t[2] is not None and -1 < t[1] and t[2] < 1, "(asin x) unless -1 < x < 1"),
+    "acos": _real_when("acos", lambda t: t[1] is not None and t[2] is not None and -1 < t[1] and t[2] < 1, "(acos x) unless -1 < x < 1"),
+    "atan": _irrational, "sinh": _irrational, "cosh": _irrational,
+    "asinh": _real_when("asinh", _nonneg, "(asinh x) = (log (+ x (sqrt (+ 1 (* x x))))) of a type that may be negative"),
+    "acosh": _real_when("acosh", lambda t: t[1] is not None and t[1] >= 1, "(acosh x) unless x >= 1"),
+    "atanh": _real_when("atanh", lambda t: t[1] is not None and t[2] is not None and t[1] >= -1 and t[2] <= 1, "(atanh x) unless -1 <= x <= 1"),
+    "logandc1": lambda x, y: _bitwise("logand")(_bitwise("lognot")(x), y),
+    "logandc2": lambda x, y: _bitwise("logand")(x, _bitwise("lognot")(y)),
+    "logorc1": lambda x, y: _bitwise("logior")(_bitwise("lognot")(x), y),
+    "logorc2": lambda x, y: _bitwise("logior")(x, _bitwise("lognot")(y)),
+    "lognand": lambda x, y: _bitwise("lognot")(_bitwise("logand")(x, y)),
+    "lognor": lambda x, y: _bitwise("lognot")(_bitwise("logior")(x, y)),
+})
+
+
 def infer_type(name: str, *types) -> tuple:
     """infer-type, src/2typeinfer.lisp:40-45."""
     name = name.lower().split(":")[-1]

@@ -138,6 +138,9 @@ static int cmp_val(val a, val b) {
 enum {
   F_ADD, F_SUB, F_MUL, F_DIV, F_MAX, F_MIN, F_EQ, F_NE, F_LE, F_GE, F_LT, F_GT,
   F_LOGAND, F_LOGIOR, F_LOGXOR,
+  F_LOGANDC1, F_LOGANDC2, F_LOGEQV, F_LOGNAND, F_LOGNOR, F_LOGORC1, F_LOGORC2,
+  F_FLOOR, F_CEILING, F_ROUND, F_TRUNCATE, F_MOD, F_REM, F_EXPT,
+  F_ASIN, F_ACOS, F_ATAN, F_SINH, F_COSH, F_ASINH, F_ACOSH, F_ATANH, F_LOG2, F_ISQRT, F_LOGCOUNT, F_INTEGER_LENGTH,
   F_NEG, F_ABS, F_SQUARE, F_SQRT, F_LOGNOT, F_IDENTITY, F_EXP, F_LOG, F_SIN, F_COS, F_TAN, F_TANH,
   F_SIGNUM, F_ONEPLUS, F_ONEMINUS, F_COUNT
 };
@@ -151,6 +154,16 @@ static const struct { const char* name; int f; int arity; } FN[] = {
   {"LOGNOT", F_LOGNOT, 1}, {"IDENTITY", F_IDENTITY, 1}, {"EXP", F_EXP, 1}, {"LOG", F_LOG, 1},
   {"%LOGR", F_LOG, 1}, {"SIN", F_SIN, 1}, {"COS", F_COS, 1}, {"TAN", F_TAN, 1}, {"TANH", F_TANH, 1},
   {"SIGNUM", F_SIGNUM, 1}, {"1+", F_ONEPLUS, 1}, {"1-", F_ONEMINUS, 1},
+  /* src/4numeric.lisp:592-599 */
+  {"LOGANDC1", F_LOGANDC1, 2}, {"LOGANDC2", F_LOGANDC2, 2}, {"LOGEQV", F_LOGEQV, 2}, {"LOGNAND", F_LOGNAND, 2},
+  {"LOGNOR", F_LOGNOR, 2}, {"LOGORC1", F_LOGORC1, 2}, {"LOGORC2", F_LOGORC2, 2},
+  /* :568-581 (first value: the quotient; mod / rem: the remainder) and :533 */
+  {"FLOOR", F_FLOOR, 2}, {"CEILING", F_CEILING, 2}, {"ROUND", F_ROUND, 2}, {"TRUNCATE", F_TRUNCATE, 2},
+  {"MOD", F_MOD, 2}, {"REM", F_REM, 2}, {"EXPT", F_EXPT, 2},
+  /* :466-519 */
+  {"ASIN", F_ASIN, 1}, {"ACOS", F_ACOS, 1}, {"ATAN", F_ATAN, 1}, {"SINH", F_SINH, 1}, {"COSH", F_COSH, 1},
+  {"ASINH", F_ASINH, 1}, {"ACOSH", F_ACOSH, 1}, {"ATANH", F_ATANH, 1}, {"%LOG2", F_LOG2, 1}, {"LOG2", F_LOG2, 1},
+  {"ISQRT", F_ISQRT, 1}, {"LOGCOUNT", F_LOGCOUNT, 1}, {"INTEGER-LENGTH", F_INTEGER_LENGTH, 1},
 };
 static int fn_lookup(const char* name) {
   for (size_t i = 0; i < sizeof FN / sizeof FN[0]; i++) if (!strcmp(FN[i].name, name)) return FN[i].f;
@@ -159,10 +172,90 @@ static int fn_lookup(const char* name) {
 
 static int g_trap;  /* set when SBCL would have signalled (division-by-zero etc.) */
 
+/* ---- the rounding family (floor ceiling round truncate mod rem), CLHS 12.2 / SBCL src/code/numbers.lisp -------------
+ * rationals: exact.  floats: SBCL's definitions -- (truncate x y) = (%unary-truncate (/ x y)) with remainder
+ * (- x (* q y)), each op rounded on its own; floor / ceiling / round adjust the truncated quotient by the sign of the
+ * remainder; (round x 1) is the one-argument round (ties to even). */
+static i128 floor_div128(i128 n, i128 d) { i128 q = n / d, r = n % d; if (r != 0 && ((r < 0) != (d < 0))) q -= 1; return q; }
+static val rational_divide(int f, val a, val b, int want_rem) {
+  if (b.i == 0) { g_trap = 1; return v_int(0); }
+  i128 n = a.i * b.den, d = a.den * b.i;                    /* a / b = n / d */
+  if (d < 0) { n = -n; d = -d; }
+  i128 q;
+  switch (f) {
+    case F_FLOOR: case F_MOD: q = floor_div128(n, d); break;
+    case F_CEILING: q = -floor_div128(-n, d); break;
+    case F_TRUNCATE: case F_REM: q = n / d; break;
+    default: {                                              /* round: nearest, ties to even */
+      q = floor_div128(n, d); i128 r = n - q * d, twice = 2 * r;
+      if (twice > d || (twice == d && (q & 1))) q += 1;
+    }
+  }
+  if (!want_rem) return v_int(q);
+  return v_ratio(a.i * b.den - q * b.i * a.den, a.den * b.den);   /* a - q*b */
+}
+#define FLOAT_DIVIDE(T, NAME, TRUNCF, FABSF)                                                              \
+  static i128 NAME(int f, T x, T y, T* rem_out) {                                                         \
+    T q = x / y; T tq = TRUNCF(q);                                                                        \
+    if (!isfinite((double)tq)) { g_trap = 1; *rem_out = 0; return 0; }                                    \
+    i128 tru = (i128)tq; T prod = (T)tru * y; T rem = x - prod;                                           \
+    switch (f) {                                                                                          \
+      case F_FLOOR: case F_MOD: if (rem != 0 && (y < 0 ? x > 0 : x < 0)) { tru -= 1; rem = rem + y; } break; \
+      case F_CEILING: if (rem != 0 && (y < 0 ? x < 0 : x > 0)) { tru += 1; rem = rem - y; } break;        \
+      case F_ROUND:                                                                                       \
+        if (rem != 0) { T thresh = FABSF(y) / (T)2;                                                       \
+          if (rem > thresh || (rem == thresh && (tru & 1))) { if (y < 0) { tru -= 1; rem = rem + y; } else { tru += 1; rem = rem - y; } } \
+          else if (rem < -thresh || (rem == -thresh && (tru & 1))) { if (y < 0) { tru += 1; rem = rem - y; } else { tru -= 1; rem = rem + y; } } } \
+        break;                                                                                            \
+      default: break; }                                                                                   \
+    *rem_out = rem; return tru; }
+FLOAT_DIVIDE(float, float_divide_f32, truncf, fabsf)
+FLOAT_DIVIDE(double, float_divide_f64, trunc, fabs)
+
+/* SBCL's intexp (src/code/irrat.lisp): repeated squaring; every product is a separate CL multiplication */
+static val apply2(int f, val a, val b);
+static i128 cl_round(val v);
+static val intexp(val base, i128 power) {
+  val total = (power & 1) ? base : v_int(1);
+  for (i128 n = power >> 1; n != 0; n >>= 1) {
+    base = apply2(F_MUL, base, base);
+    if (n & 1) total = apply2(F_MUL, base, total);
+  }
+  return total;
+}
+
 /* two-argument CL arithmetic on SBCL x86-64: each float op separately rounded */
 static val apply2(int f, val a, val b) {
   int c = contagion(a, b);
   switch (f) {
+    case F_LOGANDC1: return v_int(~a.i & b.i);
+    case F_LOGANDC2: return v_int(a.i & ~b.i);
+    case F_LOGEQV: return v_int(~(a.i ^ b.i));
+    case F_LOGNAND: return v_int(~(a.i & b.i));
+    case F_LOGNOR: return v_int(~(a.i | b.i));
+    case F_LOGORC1: return v_int(~a.i | b.i);
+    case F_LOGORC2: return v_int(a.i | ~b.i);
+    case F_FLOOR: case F_CEILING: case F_ROUND: case F_TRUNCATE: case F_MOD: case F_REM: {
+      const int want_rem = f == F_MOD || f == F_REM;
+      const int df = f == F_REM ? F_TRUNCATE : f;
+      if (c == V_INT) return rational_divide(df, a, b, want_rem);
+      if (f == F_ROUND && b.k == V_INT && b.i == 1) return v_int(cl_round(a));          /* (round x 1) = (round x) */
+      if (c == V_F32) { float r; i128 q = float_divide_f32(df, as_f32(a), as_f32(b), &r); return want_rem ? v_f32(r) : v_int(q); }
+      double r; i128 q = float_divide_f64(df, as_f64(a), as_f64(b), &r); return want_rem ? v_f64(r) : v_int(q);
+    }
+    case F_EXPT:
+      if (b.k == V_INT) {                                                                 /* integer power: intexp */
+        if (b.i == 0) return a.k == V_F32 ? v_f32(1.0f) : a.k == V_F64 ? v_f64(1.0) : v_int(1);
+        if (b.i > 0) { if (a.k <= V_RATIO && bits128((u128)iabs128(a.i)) * b.i > 120) { g_trap = 1; return v_int(0); } return intexp(a, b.i); }
+        if (a.k <= V_RATIO && a.i == 0) { g_trap = 1; return v_int(0); }
+        if (a.k <= V_RATIO && bits128((u128)iabs128(a.i)) * (-b.i) > 120) { g_trap = 1; return v_int(0); }
+        return apply2(F_DIV, v_int(1), intexp(a, -b.i));
+      } else {                                                                            /* real-expt: pow in double-float */
+        double x = as_f64(a), y = as_f64(b);
+        if (x < 0 && y != rint(y)) { g_trap = 1; return v_int(0); }                       /* complex result */
+        double r = pow(x, y);
+        return (a.k == V_F64 || b.k == V_F64) ? v_f64(r) : v_f32((float)r);
+      }
     case F_ADD: case F_SUB: case F_MUL:
       if (c == V_INT) {
         i128 n, d = a.den * b.den;
@@ -210,8 +303,31 @@ static val apply1(int f, val a) {
       if (a.k <= V_RATIO) return v_int(a.i > 0 ? 1 : a.i < 0 ? -1 : 0);
       if (a.k == V_F32) return v_f32(a.f > 0 ? 1.0f : a.f < 0 ? -1.0f : a.f);
       return v_f64(a.d > 0 ? 1.0 : a.d < 0 ? -1.0 : a.d);
+    case F_ISQRT: {
+      if (a.k != V_INT || a.i < 0) { g_trap = 1; return v_int(0); }
+      u128 u = (u128)a.i, r = (u128)sqrtl((long double)a.i);
+      while (r * r > u) r--;
+      while ((r + 1) * (r + 1) <= u) r++;
+      return v_int((i128)r);
+    }
+    case F_LOGCOUNT: { if (a.k != V_INT) { g_trap = 1; return v_int(0); } u128 u = (u128)(a.i < 0 ? ~a.i : a.i); int c = 0; while (u) { c += (int)(u & 1); u >>= 1; } return v_int(c); }
+    case F_INTEGER_LENGTH: { if (a.k != V_INT) { g_trap = 1; return v_int(0); } return v_int(bits128((u128)(a.i < 0 ? ~a.i : a.i))); }
+    case F_ASIN: case F_ACOS: case F_ATAN: case F_SINH: case F_COSH: case F_ASINH: case F_ACOSH: case F_ATANH: case F_LOG2: {
+      /* outside the real domain CL returns a complex number: trapped */
+      double xd = as_f64(a);
+      if (((f == F_ASIN || f == F_ACOS || f == F_ATANH) && fabs(xd) > 1.0) || (f == F_ACOSH && xd < 1.0) || (f == F_LOG2 && xd < 0.0)) { g_trap = 1; return v_int(0); }
+      if (a.k == V_F64) {
+        double x = a.d;
+        return v_f64(f == F_ASIN ? asin(x) : f == F_ACOS ? acos(x) : f == F_ATAN ? atan(x) : f == F_SINH ? sinh(x) : f == F_COSH ? cosh(x)
+                     : f == F_ASINH ? asinh(x) : f == F_ACOSH ? acosh(x) : f == F_ATANH ? atanh(x) : log(x) / (double)logf(2.0f));   /* (/ (log x) (log 2)) */
+      }
+      float x = as_f32(a);
+      return v_f32(f == F_ASIN ? asinf(x) : f == F_ACOS ? acosf(x) : f == F_ATAN ? atanf(x) : f == F_SINH ? sinhf(x) : f == F_COSH ? coshf(x)
+                   : f == F_ASINH ? asinhf(x) : f == F_ACOSH ? acoshf(x) : f == F_ATANH ? atanhf(x) : logf(x) / logf(2.0f));
+    }
     /* irrational functions: rational -> single-float (float substitution, 1type.lisp:358-416) */
     case F_SQRT: case F_EXP: case F_LOG: case F_SIN: case F_COS: case F_TAN: case F_TANH: {
+      if ((f == F_SQRT || f == F_LOG) && as_f64(a) < 0.0) { g_trap = 1; return v_int(0); }      /* complex result */
       if (a.k == V_F64) {
         double x = a.d;
         return v_f64(f == F_SQRT ? sqrt(x) : f == F_EXP ? exp(x) : f == F_LOG ? log(x) : f == F_SIN ? sin(x)

@@ -164,3 +164,116 @@ def test_trim_releases_the_cache_and_the_library_keeps_working(nc):
     _lib.check(nc.lib().ncl_trim())
     y = nc.add(nc.ones((1000,), type="f32"), nc.ones((1000,), type="f32"))
     assert float(nc.sum(y)) == 2000.0
+
+
+@pytest.mark.parametrize("dt,dist,lo,hi", [("f32", 0, -3.0, 3.0), ("f64", 0, -3.0, 3.0), ("fixnum", 0, -10 ** 6, 10 ** 6), ("ub8", 0, 0, 255), ("sb16", 0, -3000, 3000),
+                                           ("f32", 1, -8, 8)])
+@pytest.mark.parametrize("shape,axes", [((64, 4096), 1), ((64, 4096), 0), ((64, 4096), None), ((33, 257), 1), ((33, 257), 0), ((7, 12, 40), (1, 2)), ((7, 12, 40), 1),
+                                        ((5, 3, 4, 6), (0, 3)), ((4000, 3), 0), ((4000, 3), 1), ((3, 70000), 1)])
+def test_fused_mean_variance_stdev_equal_the_composition(nc, oracle, dt, dist, lo, hi, shape, axes):
+    """ncl_reduce_stat (one launch: the sum kernel's final store divides by the count and takes the root) against
+    (numcl:sqrt (numcl:/ (numcl:sum (square a)) count)) run pass by pass through the same library.  Integers and exactly
+    summable floats: the same bits (the epilogue reproduces the roundings of the separate passes).  Random floats: the fused
+    and the composed sums may take different (equally valid) orders -- the usual reduction tolerance."""
+    from numcl_b200 import reduce as R
+    a = rand(oracle, shape, dt, SEED, dist, lo, hi)
+    g = to_gpu(nc, a)
+    exact = dt not in ("f32", "f64") or dist == 1
+    tol = 1e-12 if dt == "f64" else 1e-5
+    n = R._count(g, axes)
+    for fused, composed in ((R.mean, R.mean_composed), (R.variance, R.variance_composed), (R.standard_deviation, R.standard_deviation_composed)):
+        x, y = fused(g, axes=axes), composed(g, axes=axes)
+        if isinstance(y, nc.NArray):
+            assert isinstance(x, nc.NArray) and x.dtype.name == y.dtype.name and x.shape == y.shape
+            if exact:
+                assert np.array_equal(x.raw()[: x.size * x.dtype.slot_bits // 8], y.raw()[: y.size * y.dtype.slot_bits // 8]), (fused.__name__, x.numpy().reshape(-1)[:4], y.numpy().reshape(-1)[:4])
+            else:
+                xv, yv = x.numpy().astype(np.float64), y.numpy().astype(np.float64)
+                assert np.linalg.norm(xv - yv) <= tol * np.linalg.norm(yv), fused.__name__
+        else:
+            # a full reduce yields a bare number; the reference divides single-float by integer in single-float, the mirror's
+            # scalar composition in Python doubles -- compare with the single-float arithmetic
+            ft = np.float64 if dt == "f64" else np.float32
+            s = ft(R.sum(g if fused is R.mean else R.square(g)))
+            want = ft(s / ft(n))
+            if fused is R.standard_deviation:
+                want = np.sqrt(want)
+            if exact:
+                assert ft(x) == want, (fused.__name__, x, want)
+            else:
+                assert abs(x - want) <= tol * abs(want), (fused.__name__, x, want)
+
+
+def test_fused_statistics_are_one_launch_and_match_numpy(nc, oracle):
+    a = rand(oracle, (512, 2048), "f32", SEED, 1, -8, 8)           # exact data: sums are order independent
+    g = to_gpu(nc, a)
+    v = a.values().astype(np.float64)
+    L = nc.lib()
+    n0 = L.ncl_launch_count()
+    m = nc.mean(g, axes=1)
+    assert L.ncl_launch_count() - n0 == 1
+    assert np.array_equal(m.numpy(), (v.sum(axis=1).astype(np.float32) / np.float32(2048)))
+    n0 = L.ncl_launch_count()
+    s = nc.stdev(g, axes=1)
+    assert L.ncl_launch_count() - n0 == 1
+    want = np.sqrt(((v * v).sum(axis=1).astype(np.float32) / np.float32(2048)).astype(np.float32))
+    assert np.array_equal(s.numpy(), want)
+    i = rand(oracle, (300, 77), "ub8", SEED, 0, 0, 255)
+    mi = nc.mean(to_gpu(nc, i), axes=0)
+    assert mi.dtype.name == "f32" and np.array_equal(mi.numpy(), (i.values().sum(axis=0) / 300.0).astype(np.float32))
+
+
+def test_resident_host_arrays_upload_once(nc, oracle):
+    """ncl_host_register: the device mirror outlives the call; a warm call moves ZERO input bytes over PCIe"""
+    a = rand(oracle, (256, 1024), "f32", SEED, 1, -8, 8)
+    b = rand(oracle, (1024,), "f32", SEED + 1, 1, -8, 8)
+    ha = nc.asarray(a.values(), type="f32", where="host").make_resident()
+    hb = nc.asarray(b.values(), type="f32", where="host").make_resident()
+    want = refsem.arith(oracle, "+", [a, b])
+    h0, d0 = _lib.transfer_stats()
+    r1 = nc.add(ha, hb)                                             # cold: both inputs cross once
+    h1, d1 = _lib.transfer_stats()
+    assert h1 - h0 == ha.nbytes + hb.nbytes and d1 - d0 == r1.nbytes
+    assert_bit_exact(r1, want)
+    r2 = nc.add(ha, hb)                                             # warm: nothing goes up
+    h2, d2 = _lib.transfer_stats()
+    assert h2 - h1 == 0 and d2 - d1 == r2.nbytes
+    assert_bit_exact(r2, want)
+    s = nc.sum(ha, axes=1)                                          # another op on the same resident array: still no upload
+    assert _lib.transfer_stats()[0] == h2
+    assert_bit_exact(s, refsem.reduce_array(oracle, "+", a, (1,)))
+    # the host writes into the array: the next use uploads it again (and sees the new contents)
+    a2 = rand(oracle, (256, 1024), "f32", SEED + 9, 1, -8, 8)
+    ha.set_raw(a2.storage)                                          # marks it dirty
+    h3 = _lib.transfer_stats()[0]
+    r3 = nc.add(ha, hb)
+    assert _lib.transfer_stats()[0] - h3 == ha.nbytes
+    assert_bit_exact(r3, refsem.arith(oracle, "+", [a2, b]))
+
+
+def test_lazy_resident_results_stay_on_the_device_until_fetched(nc, oracle):
+    a = rand(oracle, (128, 512), "f32", SEED, 1, -8, 8)
+    ha = nc.asarray(a.values(), type="f32", where="host").make_resident()
+    out = nc.NArray((128, 512), "f32", where="host")
+    out._host[:] = 0xEE
+    out.make_resident(lazy=True, fresh=True)
+    tmp = nc.NArray((128,), "f32", where="host").make_resident(lazy=True, fresh=True)
+    h0, d0 = _lib.transfer_stats()
+    nc.map_array_into(out, "+", ha, ha)                             # out = a + a, left on the device
+    L = nc.lib()
+    assert L.ncl_host_state(out._host.ctypes.data) == 2 and bytes(out._host[:4]) == b"\xee" * 4
+    t_out, t_tmp = out.tensor(), tmp.tensor()
+    ax = (C.c_int * 1)(1)
+    _lib.check(L.ncl_reduce(_lib.OPS["ADD"], C.byref(t_out), ax, 1, C.byref(t_tmp), _lib.OUT_FRESH))     # consumes the device-side result
+    h1, d1 = _lib.transfer_stats()
+    assert h1 - h0 == ha.nbytes and d1 - d0 == 0                     # one upload of a, nothing came back yet
+    two = refsem.arith(oracle, "+", [a, a])
+    assert_bit_exact(tmp, refsem.reduce_array(oracle, "+", two, (1,)))   # raw() fetches
+    assert_bit_exact(out, two)
+    assert _lib.transfer_stats()[1] - d1 == out.nbytes + tmp.nbytes
+    assert L.ncl_host_state(out._host.ctypes.data) == 0
+    # a view into a registered base vector (displaced array) is served from the same mirror
+    row = nc.NArray((512,), "f32", where="host", _storage=ha._host, offset=512)
+    h2 = _lib.transfer_stats()[0]
+    assert nc.sum(row) == float(a.values()[1].astype(np.float64).sum())
+    assert _lib.transfer_stats()[0] == h2
