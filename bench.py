@@ -404,7 +404,7 @@ def run_ours(args):
             el = tt.item()
         return el, host
 
-    job = Job(N_ROWS, N_ARRAYS)
+    job = Job(args.rows, N_ARRAYS)
     for i in range(max(args.warmup, N_ARRAYS)):
         job.step(i)
     barrier()
@@ -451,7 +451,8 @@ def run_ours(args):
             errs.append(max(abs(g.item() - part.item()) for g in gl) / abs(part.item()))        # every rank's copy of the result
         parity = {"parity_full_sum_rel_err": max(errs), "same_bits_on_every_rank": same, "parity_ok": bool(max(errs) <= 1e-6 and same),
                   "how": "float32 result of the sharded (sum a) vs torch float64 sum of the same shards, all-reduced; per array, max"}
-    value = (BYTES_ROW + BYTES_ALL) * args.steps / elapsed / 1e9
+    scale_rows = args.rows / N_ROWS
+    value = (BYTES_ROW + BYTES_ALL) * scale_rows * args.steps / elapsed / 1e9
 
     # ---- e2e: this rank's shard in pinned host memory, copies inside the timed region, through the C ABI ----------
     host = nc.NArray((job.rows, N_COLS), "f32", where="host")
@@ -478,7 +479,40 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_t = tt.item()
     e2e_value = (BYTES_ROW + BYTES_ALL) * e2e_steps / e2e_t / 1e9
-    del host
+
+    # ---- e2e, warm: the same HOST arrays carry a resident device mirror (ncl_host_register: what the Lisp glue attaches in
+    # %make-array); the calls take the host tensors themselves, the first one uploads, the timed ones move no input bytes ----
+    host.make_resident()
+    rows_host = nc.NArray((job.rows,), "f32", where="host").make_resident(fresh=True)       # written back into the host vector every call
+    th, trh = host.tensor(), rows_host.tensor()
+
+    def warm_step():
+        if world > 1:
+            _lib.check(L.ncl_reduce_all_sharded_async(_lib.OPS["ADD"], C.byref(th), C.byref(job.tt[0])))
+        else:
+            _lib.check(L.ncl_reduce(_lib.OPS["ADD"], C.byref(th), ax1, 0, C.byref(job.tt[0]), _lib.OUT_FRESH))
+        _lib.check(L.ncl_reduce(_lib.OPS["ADD"], C.byref(th), ax1, 1, C.byref(trh), _lib.OUT_FRESH))
+        if world > 1:
+            _lib.check(L.ncl_comm_join())
+        _lib.check(L.ncl_d2h(tot_h.ctypes.data, job.total[0]._buf, 0, 4))
+    warm_step()                                              # cold call: uploads the shard once
+    barrier()
+    hb0, db0 = _lib.transfer_stats()
+    warm_steps = max(3, min(args.steps, 20))
+    w0 = time.perf_counter()
+    for _ in range(warm_steps):
+        warm_step()
+    barrier()
+    warm_t = time.perf_counter() - w0
+    hb1, db1 = _lib.transfer_stats()
+    if world > 1:
+        tt = torch.tensor([warm_t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        warm_t = tt.item()
+    e2e_warm = {"value": (BYTES_ROW + BYTES_ALL) * warm_steps / warm_t / 1e9, "unit": "GB/s", "steps": warm_steps,
+                "h2d_bytes_per_step": (hb1 - hb0) // warm_steps * world, "d2h_bytes_per_step": (db1 - db0) // warm_steps * world,
+                "api": "ncl_reduce x2 on HOST tensors whose base vectors are registered (ncl_host_register); results written back to host memory every step"}
+    del host, rows_host
 
     # ---- the other configs (every rank takes part: sharded), the weak-scaling variant, the CPU baseline ------------
     others = {}
@@ -542,6 +576,7 @@ def run_ours(args):
                                        "achieved": BYTES_ALL / world / t_all / 1e9, "frac": BYTES_ALL / world / t_all / 1e9 / peak}},
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": shard_bytes * world, "d2h_bytes_per_step": (job.rows * 4 + 4) * world if world == 1 else (N_ROWS * 4 + 4 * world),
                 "steps": e2e_steps, "api": "ncl_h2d + ncl_reduce x2 + ncl_d2h (pinned host shard per rank)"},
+        "e2e_warm": e2e_warm,
         "gpu_launches": int(launches),
         "timed_region": f"{args.steps // N_ARRAYS} replays of a CUDA graph of {N_ARRAYS} steps + {args.steps % N_ARRAYS} eager steps",
         "host_enqueue_us_per_step": host_enqueue / args.steps * 1e6,
@@ -569,6 +604,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-others", action="store_true")
     ap.add_argument("--no-contractions", action="store_true", help="skip C3/C4 in `others` (bring-up)")
+    ap.add_argument("--rows", type=int, default=N_ROWS, help="rows of the global array (experiments only: the contract is 16384)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -73,10 +73,47 @@ static bool match_expr(const Expr& e, int self_out, bool fresh, Match* m) {
   return false;
 }
 
+int ew_narrow_launch(int op, bool wide, const char* a, const char* b, char* out, long long n, bool b_scalar, long long b_off, int b_lk, bool swap,
+                     bool signed8, unsigned mask16);                      // k_ew_narrow.cu
 int ew_widen_launch(int a_lk, int op, const char* a, const char* b, char* out, unsigned nchunks, int bmode, unsigned period, int btag, int swap,
                     unsigned long long mask, int shift);                 // k_ew_widen.cu
 
+static int try_elementwise_32(const Nest& n);
+
+// The engine decodes chunk and row numbers with 32-bit multiply-shift arithmetic, so one launch covers fewer than 2^31
+// elements.  Larger nests (a 2 GiB (unsigned-byte 8) array is ordinary on a 180 GB part) are cut on the host along the loop with
+// the largest output stride -- or, for one contiguous run, into runs of 2^30 elements -- and every piece takes the same fast
+// path: same kernels, same results, a few launches instead of the thread-per-element generic kernel.
 int try_elementwise(const Nest& n) {
+  if (n.n_out != 1) return NCL_ERR_UNSUPPORTED;
+  long long total = 1; int big = -1; long long bigstride = -1;
+  for (int l = 0; l < n.nloops; l++) {
+    if (n.extent[l] <= 1) continue;
+    if (n.out[0].stride[l] == 0) return try_elementwise_32(n);            // a contracted loop: not elementwise at all
+    total *= n.extent[l];
+    if (llabs(n.out[0].stride[l]) > bigstride) { bigstride = llabs(n.out[0].stride[l]); big = l; }
+  }
+  const long long LIMIT = 1LL << 30;
+  if (total <= LIMIT || big < 0) return try_elementwise_32(n);
+  // pieces of the outermost loop; a single contiguous run is cut at multiples of 2^20 elements (keeps every vector alignment)
+  const long long per_step = total / n.extent[big];
+  long long step = per_step >= LIMIT ? 1 : LIMIT / per_step;
+  if (n.out[0].stride[big] == 1 || n.out[0].stride[big] == -1) step = step >> 20 << 20;
+  if (step < 1) step = 1;
+  for (long long s0 = 0; s0 < n.extent[big]; s0 += step) {
+    Nest* x = new Nest(n);
+    x->extent[big] = n.extent[big] - s0 < step ? n.extent[big] - s0 : step;
+    x->out[0].offset += s0 * n.out[0].stride[big];
+    for (int i = 0; i < n.n_in; i++) x->in[i].offset += s0 * n.in[i].stride[big];
+    int rc = try_elementwise(*x);                                             // a piece may need cutting again along another loop
+    if (rc == NCL_ERR_UNSUPPORTED && s0 > 0) rc = launch_generic(*x);         // never hand on a half-written result
+    delete x;
+    if (rc != NCL_OK) return rc;
+  }
+  return NCL_OK;
+}
+
+static int try_elementwise_32(const Nest& n) {
   if (n.n_out != 1) return NCL_ERR_UNSUPPORTED;
   const Operand& out = n.out[0];
   for (int l = 0; l < n.nloops; l++) if (n.extent[l] > 1 && out.stride[l] == 0) return NCL_ERR_UNSUPPORTED;   // contracted loop
@@ -243,7 +280,33 @@ int try_elementwise(const Nest& n) {
     }
   }
   EwKernel kfn = nullptr;
-  if (i32) { kfn = is_cmp ? (E == 32 ? ew_pick_cmp(shape, 4) : nullptr) : ew_pick_i32(shape, E); if (!kfn) i32 = false; }
+  // comparisons into a packed bit array: the input-centric kernel (k_ew_cmppack.cu) when the rows are whole result words and
+  // every streamed operand is chunk aligned; E becomes the elements per 16-byte INPUT chunk
+  bool cmppack = false; int cmp_U = 0;
+  if (is_cmp && out_bits == 1 && m.n == 2 && !eflat && E == 32) {
+    int maxb = 0;
+    for (int k = 0; k < 2; k++) if (in0.st[1 + k] == 1) { const int b = g_dt[ops[k].dtype].slot_bits / 8; if (b > maxb) maxb = b; }
+    if (maxb >= 1) {
+      const int EI = 16 / maxb;
+      kfn = ew_pick_cmppack(i32 ? 4 : cc, EI, &cmp_U);
+      // 8- / 16-bit operands of one kind (the other may be a broadcast scalar that fits the field): SIMD-in-register compare
+      if (i32 && (maxb == 1 || maxb == 2)) {
+        bool same = true; int kind = -1;
+        for (int k = 0; k < 2 && same; k++) {
+          const int lk = dtype_load_kind(ops[k].dtype); const DtInfo& dk = g_dt[ops[k].dtype];
+          if (in0.st[1 + k] == 1) { if (dk.slot_bits != maxb * 8 || (kind >= 0 && kind != lk)) same = false; kind = lk; }
+          else if (in0.st[1 + k] != 0 || m.s[k].kind >= 2) same = false;
+        }
+        for (int k = 0; k < 2 && same; k++) if (in0.st[1 + k] == 0) {        // the scalar's every value must fit the array's fields with the same meaning
+          const DtInfo& dk = g_dt[ops[k].dtype]; const bool arr_signed = (lk_flags(kind) & 1u) != 0;
+          if (dk.is_signed ? !(arr_signed && dk.value_bits <= maxb * 8) : dk.value_bits > (arr_signed ? maxb * 8 - 1 : maxb * 8)) same = false;
+        }
+        if (same && kind >= 0) { EwKernel k2 = ew_pick_cmppack_swar(maxb * 8, &cmp_U); if (k2) kfn = k2; }
+      }
+      if (kfn && aligned(EI)) { cmppack = true; E = EI; } else kfn = nullptr;
+    }
+  }
+  if (i32 && !cmppack) { kfn = is_cmp ? (E == 32 ? ew_pick_cmp(shape, 4) : nullptr) : ew_pick_i32(shape, E); if (!kfn) i32 = false; }
   if (!kfn) {
     if (rt_family >= 0) kfn = ew_pick_rt(rt_family, E);
     else if (shape == S_IDIV) kfn = ew_pick_idiv(E);
@@ -259,7 +322,7 @@ int try_elementwise(const Nest& n) {
   // output), a row vector repeated over the outer dim (stride 0 there: numpy broadcasting), or a
   // scalar.  The nest is then walked as ONE flat run of chunks; the row-vector operands are read at
   // (chunk mod period).  This keeps warp segments full when rows are short (C5a: 256 elements).
-  if (nd == 2 && E > 1 && d[0].st[0] == d[1].ext && d[1].st[0] == 1 && d[1].ext * d[0].ext < 0x7fffffffLL) {
+  if (!cmppack && nd == 2 && E > 1 && d[0].st[0] == d[1].ext && d[1].st[0] == 1 && d[1].ext * d[0].ext < 0x7fffffffLL) {
     bool ok = true; unsigned period[3] = {0, 0, 0};
     for (int k = 0; k < m.n && ok; k++) {
       long long s_outer = d[0].st[1 + k], s_inner = d[1].st[1 + k];
@@ -278,6 +341,53 @@ int try_elementwise(const Nest& n) {
           unsigned s2 = 0; while ((1ull << s2) < period[k]) s2++;
           p.pmul[k] = (unsigned)(((1ull << (31 + s2)) + period[k] - 1) / period[k]); p.pshr[k] = s2 - 1;
         }                                                                     // period 1: ew_div(q, 0, 0) = q, so q mod 1 = 0
+      }
+    }
+  }
+  // ---- 8-bit arrays, SIMD within a register (k_ew_narrow.cu): ub8 (op) ub8 / scalar -> 8- or 16-bit result, one flat run ----
+  if (nd == 1 && !eflat && !cmppack && cc == CLS_I && out_cls == CLS_I && m.n == 2 && !is_cmp && rt_family < 0 && (out_bits == 8 || out_bits == 16) &&
+      !g_dt[out.dtype].tagged && d[0].ext % 16 == 0 && d[0].ext >= 4096 && p.period[0] == 0 && p.period[1] == 0) {
+    const int nop = (shape == S_ADD || shape == S_ADD0) ? 0 : shape == S_SUB ? 1 : (shape == S_MUL || shape == S_MUL0) ? 2 : shape == S_MAX ? 3 : shape == S_MIN ? 4
+                    : shape == S_AND ? 5 : shape == S_IOR ? 6 : shape == S_XOR ? 7 : -1;
+    const bool wide = out_bits == 16;
+    // which operand streams (stride 1, an 8-bit array) and which is the other one (the same, or a broadcast scalar)
+    int ia = -1, ib = -1;
+    for (int k = 0; k < 2; k++) if (d[0].st[1 + k] == 1 && g_dt[ops[k].dtype].slot_bits == 8 && m.s[k].kind == 0) { if (ia < 0) ia = k; else ib = k; }
+    if (ia >= 0 && ib < 0) { const int o = 1 - ia; if (d[0].st[1 + o] == 0 && m.s[o].kind == 0 && g_dt[ops[o].dtype].slot_bits <= 16) ib = o; else ia = -1; }
+    bool ok = nop >= 0 && ia >= 0 && ib >= 0 && (wide ? nop <= 2 : nop >= 3);
+    const bool b_scalar = ok && d[0].st[1 + ib] == 0;
+    const DtInfo& da = g_dt[ops[ia >= 0 ? ia : 0].dtype]; const DtInfo& db = g_dt[ops[ib >= 0 ? ib : 0].dtype];
+    bool signed8 = false;
+    if (ok && !wide) {
+      // max min and ior xor: both operands of one signedness, every value representable in the result's type
+      if (b_scalar) ok = false;                                        // (a rank-0 operand of another width: the general engine)
+      else if (da.is_signed != db.is_signed) ok = false;
+      else { signed8 = da.is_signed != 0; if (g_dt[out.dtype].is_signed != da.is_signed || da.value_bits > g_dt[out.dtype].value_bits || db.value_bits > g_dt[out.dtype].value_bits) ok = false; }
+    }
+    if (ok && wide) {
+      // unsigned bytes (a scalar: any unsigned rank-0 array whose values keep the field arithmetic inside its 16 bits:
+      // + and - up to 15 bits, * up to 8 bits so that 255 * v < 2^16); - is two's complement in the 16-bit field
+      if (da.is_signed || db.is_signed) ok = false;
+      if (ok && b_scalar && db.value_bits > (nop == 2 ? 8 : 15)) ok = false;
+      if (ok && nop == 2 && !b_scalar) ok = false;                      // array * array: the general engine
+      if (ok && nop == 1 && !g_dt[out.dtype].is_signed) ok = false;     // a difference needs a signed result
+    }
+    if (ok) {
+      const unsigned long long mk = sk.mask & 0xffffull;
+      const char* ap = ops[ia].base + ops[ia].offset;
+      char* op = out.base + out.offset * (out_bits / 8);
+      const bool swap = ia == 1;                                        // the streamed array is the SECOND argument of the function
+      if (b_scalar) {
+        if ((((uintptr_t)ap | (uintptr_t)op) & 15) == 0) {
+          int rc = ew_narrow_launch(nop, wide, ap, ops[ib].base, op, d[0].ext, true, ops[ib].offset, dtype_load_kind(ops[ib].dtype), swap, signed8, (unsigned)(mk | (mk << 16)));
+          if (rc != NCL_ERR_UNSUPPORTED) return rc;
+        }
+      } else {
+        const char* p0 = ops[0].base + ops[0].offset; const char* p1 = ops[1].base + ops[1].offset;
+        if ((((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)op) & 15) == 0) {
+          int rc = ew_narrow_launch(nop, wide, p0, p1, op, d[0].ext, false, 0, 0, false, signed8, (unsigned)(mk | (mk << 16)));
+          if (rc != NCL_ERR_UNSUPPORTED) return rc;
+        }
       }
     }
   }
@@ -325,7 +435,7 @@ int try_elementwise(const Nest& n) {
     p.epmul = (unsigned)(((1ull << (31 + s2)) + p.eper - 1) / p.eper); p.epshr = s2 - 1;
     for (int k = 0; k < m.n; k++) { p.gather[k] = gather[k]; p.gst[k] = (int)g_outer[k]; }
   }
-  int U = ew_u_host(cc != CLS_I ? 0 : i32 ? 2 : 1, E);
+  int U = cmppack ? cmp_U : ew_u_host(cc != CLS_I ? 0 : i32 ? 2 : 1, E);
   unsigned long long rows = 1; for (int i = 1; i < nd; i++) rows *= p.ext[i];
   unsigned segs = (p.ext[0] + 32 * U - 1) / (32 * U);
   unsigned long long nitems = rows * segs;
@@ -365,6 +475,6 @@ int try_elementwise(const Nest& n) {
     if (part) { Nest t = piece(1, part, 1, R - fr - 1, P - part, body); NCL_TRY(run_piece(t)); }
     if (fr) { Nest t = piece(2, fr, P, R - fr, 0, body + part); NCL_TRY(run_piece(t)); }
   }
-  note_launch(eflat ? "bcast_vec_flat" : E == 1 ? "bcast_scalar" : "bcast_vec");
+  note_launch(cmppack ? "cmp_pack" : eflat ? "bcast_vec_flat" : E == 1 ? "bcast_scalar" : "bcast_vec");
   return NCL_OK;
 }

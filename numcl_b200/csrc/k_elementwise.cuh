@@ -89,29 +89,43 @@ LIBM_FN(FnTan, tanf, tan) LIBM_FN(FnTanh, tanhf, tanh)
 // ONE kernel per (value class, E) covers a whole family; the function code is a kernel parameter and the switch on it is
 // warp-uniform.  These are HBM-bound like everything here, so the few extra instructions per element are free, and the
 // family costs 18 instantiations instead of ~150.
+// calls g(integral_constant<OP>) for the one OP of the list that equals the runtime code: taken once per work item, so that
+// inside the element loops the function is a compile-time constant (a per-element switch kept libm calls out of line:
+// sqrt ran at 0.05 of the HBM peak)
+template <int... OPS, class G> __device__ __forceinline__ void rt_switch(int op, G g) {
+  ((op == OPS ? (g(std::integral_constant<int, OPS>{}), 0) : 0), ...);
+}
 struct FnRtBinI {          // integer x integer -> integer: bitwise family, floor ceiling round truncate mod rem
   typedef long long R; static constexpr bool RT = true;
-  static __device__ __forceinline__ long long f(int op, unsigned int* flt, long long a, long long b) {
-    if (op >= NCL_OP_LOGAND && op <= NCL_OP_LOGORC2) return int_bitwise(op, a, b);
-    long long r; const long long q = int_divide(op == NCL_OP_REM ? NCL_OP_TRUNCATE : op, a, b, &r, flt);
-    return (op == NCL_OP_MOD || op == NCL_OP_REM) ? r : q;
+  template <class G> static __device__ __forceinline__ void dispatch(int op, G g) {
+    rt_switch<NCL_OP_LOGANDC1, NCL_OP_LOGANDC2, NCL_OP_LOGEQV, NCL_OP_LOGNAND, NCL_OP_LOGNOR, NCL_OP_LOGORC1, NCL_OP_LOGORC2,
+              NCL_OP_FLOOR, NCL_OP_CEILING, NCL_OP_ROUND, NCL_OP_TRUNCATE, NCL_OP_MOD, NCL_OP_REM>(op, g);
+  }
+  template <int OP> static __device__ __forceinline__ long long f(unsigned int* flt, long long a, long long b) {
+    if constexpr (OP >= NCL_OP_LOGAND && OP <= NCL_OP_LOGORC2) return int_bitwise(OP, a, b);
+    else { long long r; const long long q = int_divide(OP == NCL_OP_REM ? NCL_OP_TRUNCATE : OP, a, b, &r, flt); return (OP == NCL_OP_MOD || OP == NCL_OP_REM) ? r : q; }
   }
 };
 struct FnRtUnI {           // integer -> integer: isqrt logcount integer-length
   typedef long long R; static constexpr bool RT = true;
-  static __device__ __forceinline__ long long f(int op, unsigned int* flt, long long a) {
-    return op == NCL_OP_ISQRT ? int_isqrt(a, flt) : op == NCL_OP_LOGCOUNT ? int_logcount(a) : int_length(a);
+  template <class G> static __device__ __forceinline__ void dispatch(int op, G g) { rt_switch<NCL_OP_ISQRT, NCL_OP_LOGCOUNT, NCL_OP_INTEGER_LENGTH>(op, g); }
+  template <int OP> static __device__ __forceinline__ long long f(unsigned int* flt, long long a) {
+    if constexpr (OP == NCL_OP_ISQRT) return int_isqrt(a, flt); else if constexpr (OP == NCL_OP_LOGCOUNT) return int_logcount(a); else return int_length(a);
   }
 };
 template <class T> struct FnRtBinF {   // float x float -> float: mod rem
   typedef T R; static constexpr bool RT = true;
-  static __device__ __forceinline__ T f(int op, unsigned int* flt, T a, T b) {
-    T r; float_divide<T>(op == NCL_OP_REM ? NCL_OP_TRUNCATE : NCL_OP_MOD, a, b, &r); (void)flt; return r;
+  template <class G> static __device__ __forceinline__ void dispatch(int op, G g) { rt_switch<NCL_OP_MOD, NCL_OP_REM>(op, g); }
+  template <int OP> static __device__ __forceinline__ T f(unsigned int* flt, T a, T b) {
+    T r; float_divide<T>(OP == NCL_OP_REM ? NCL_OP_TRUNCATE : NCL_OP_MOD, a, b, &r); (void)flt; return r;
   }
 };
 template <class T> struct FnRtUnF {    // float -> float: sqrt log log2 and the inverse / hyperbolic functions, with the DOMAIN flag
   typedef T R; static constexpr bool RT = true;
-  static __device__ __forceinline__ T f(int op, unsigned int* flt, T a) { return float_unary<T>(op, a, flt); }
+  template <class G> static __device__ __forceinline__ void dispatch(int op, G g) {
+    rt_switch<NCL_OP_SQRT, NCL_OP_LOG, NCL_OP_LOG2, NCL_OP_ASIN, NCL_OP_ACOS, NCL_OP_ATAN, NCL_OP_SINH, NCL_OP_COSH, NCL_OP_ASINH, NCL_OP_ACOSH, NCL_OP_ATANH>(op, g);
+  }
+  template <int OP> static __device__ __forceinline__ T f(unsigned int* flt, T a) { return float_unary<T>(OP, a, flt); }
 };
 template <class F, class = void> struct fn_is_rt : std::false_type {};
 template <class F> struct fn_is_rt<F, std::void_t<decltype(F::RT)>> : std::true_type {};
@@ -251,6 +265,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
   const unsigned nwarps = gridDim.x * (EW_THREADS / 32);
   constexpr unsigned SEG = 32 * U;
   TI x[NIN][U][E];
+  unsigned int flt_local = 0;                       // DOMAIN faults of this thread (runtime-selected families), flushed once at the end
   bool hoisted[NIN], stepped[NIN];
 #pragma unroll
   for (int k = 0; k < NIN; k++) {
@@ -302,21 +317,34 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
       }
     }
     TO y[U][E];
+    if constexpr (fn_is_rt<F>::value) {
+      F::dispatch(p.rt_op, [&](auto OPC) {
+        constexpr int OP = decltype(OPC)::value;
 #pragma unroll
-    for (int u = 0; u < U; u++)
-#pragma unroll
-      for (int i = 0; i < E; i++) {
-        if constexpr (fn_is_rt<F>::value) {
+        for (int u = 0; u < U; u++) {
           // chunks past the end of the row were not loaded: their lanes hold junk, which must not raise the DOMAIN flag
-          if (q0 + u * 32 >= p.ext[0]) y[u][i] = (TO)0;
-          else if constexpr (NIN == 1) y[u][i] = F::f(p.rt_op, p.fault, x[0][u][i]);
-          else y[u][i] = F::f(p.rt_op, p.fault, x[0][u][i], x[1][u][i]);
-        } else if constexpr (NIN == 1) y[u][i] = F::f(x[0][u][i]);
-        else if constexpr (NIN == 2) y[u][i] = F::f(x[0][u][i], x[1][u][i]);
-        else y[u][i] = F::f(x[0][u][i], x[1][u][i], x[2][u][i]);
-      }
+          const bool valid = q0 + u * 32 < p.ext[0];
+#pragma unroll
+          for (int i = 0; i < E; i++) {
+            if (!valid) y[u][i] = (TO)0;
+            else if constexpr (NIN == 1) y[u][i] = F::template f<OP>(&flt_local, x[0][u][i]);
+            else y[u][i] = F::template f<OP>(&flt_local, x[0][u][i], x[1][u][i]);
+          }
+        }
+      });
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+          if constexpr (NIN == 1) y[u][i] = F::f(x[0][u][i]);
+          else if constexpr (NIN == 2) y[u][i] = F::f(x[0][u][i], x[1][u][i]);
+          else y[u][i] = F::f(x[0][u][i], x[1][u][i], x[2][u][i]);
+        }
+    }
     store_operand<TO, E, U>(p.base[0], rowoff[0], q0, p.ext[0], p.sk, y);
   }
+  if constexpr (fn_is_rt<F>::value) ncl_fault_flush(p.fault, flt_local);
 }
 
 typedef void (*EwKernel)(const EwParams);
@@ -380,5 +408,7 @@ EwKernel ew_pick_int(int shape, int E);
 EwKernel ew_pick_i32(int shape, int E);      // 32-bit lanes, E = 4 / 8 / 16
 EwKernel ew_pick_cmp(int shape, int cls);
 EwKernel ew_pick_idiv(int E);
+EwKernel ew_pick_cmppack(int lanes, int EI, int* U);      // k_ew_cmppack.cu
+EwKernel ew_pick_cmppack_swar(int bits, int* U);
 enum { RT_BIN_I = 0, RT_UN_I, RT_BIN_F, RT_UN_F, RT_BIN_D, RT_UN_D };
 EwKernel ew_pick_rt(int family, int E);      // k_ew_rt.cu

@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(128) generic_nest_kernel(const __grid_constant
   long long iters = 1;
   for (int l = 0; l < p.n_con; l++) { cnt[l] = 0; iters *= p.ext[p.n_kept + l]; }
   GV val[NCL_MAX_EXPR];
+  unsigned int flt_local = 0;
   for (long long it = 0; it < iters; it++) {
     for (int k = 0; k < p.n_nodes; k++) {
       const GNode& nd = p.node[k];
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(128) generic_nest_kernel(const __grid_constant
         case NCL_X_CONST_INT: val[k] = gv_i(nd.c); break;
         case NCL_X_CONST_F32: val[k] = gv_f((float)__longlong_as_double(nd.c)); break;
         case NCL_X_CONST_F64: val[k] = gv_d(__longlong_as_double(nd.c)); break;
-        default: val[k] = eval_node(nd, val, p.node, p.fault);
+        default: val[k] = eval_node(nd, val, p.node, &flt_local);
       }
     }
     acc = coerce_out(val[p.n_nodes - 1], p.node[p.n_nodes - 1].cls, p);     // (setf @k (%coerce transform type))
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(128) generic_nest_kernel(const __grid_constant
       cnt[l] = 0;
     }
   }
+  ncl_fault_flush(p.fault, flt_local);
   if (p.out_cls == CLS_F) store_scalar<float>(p.base[0], p.off[0] + (pos[0] - p.off[0]), p.st, gf(acc));
   else if (p.out_cls == CLS_D) store_scalar<double>(p.base[0], pos[0], p.st, gd(acc));
   else store_scalar<long long>(p.base[0], pos[0], p.st, acc.i);

@@ -70,11 +70,25 @@ struct RedParams {
 // element fetch of the reductions: a[i], or the product a[i] * b[i] of the einsum leaf (+ @1 (* $1 $2)) -- each product
 // rounded on its own, then added (common-lisp.lisp:226-240; no FMA contraction)
 // E > 1: raw 16-byte loads first (all of a step's loads can be issued back to back), conversion afterwards, no branch.
+// one element of the slot width that goes with (T, E) -- the kind is again two flags, no switch around the load (the broadcast
+// operand of a column-form dot product, `(i ij -> j)`: its switch-wrapped load serialised the loads of the whole step)
+template <class T, int E>
+__device__ __forceinline__ T load_one_bf(const char* base, long long idx, unsigned kf) {
+  if constexpr (std::is_same<T, float>::value) return __ldg((const float*)base + idx);
+  else if constexpr (std::is_same<T, double>::value) return __ldg((const double*)base + idx);
+  else {
+    const bool sg = (kf & 1u) != 0; const int tg = (int)((kf >> 1) & 1u);
+    if constexpr (E == 2) return (T)(__ldg((const long long*)base + idx) >> tg);
+    else if constexpr (E == 4) { const unsigned w = __ldg((const unsigned*)base + idx); return sg ? (T)(long long)(int)w : (T)(long long)w; }
+    else if constexpr (E == 8) { const unsigned short w = __ldg((const unsigned short*)base + idx); return sg ? (T)(long long)(short)w : (T)(long long)w; }
+    else { const unsigned char w = __ldg((const unsigned char*)base + idx); return sg ? (T)(long long)(signed char)w : (T)(long long)w; }
+  }
+}
 template <class T, int E> struct RawPair { uint4 a, b; T bs; };
 template <class T, int E, bool DOT>
 __device__ __forceinline__ void fetch_raw(const RedParams& p, long long ia, long long ib, bool b_contig, RawPair<T, E>& r) {
   r.a = load_raw16(p.in + ia * (16 / E));
-  if constexpr (DOT) { if (b_contig) r.b = load_raw16(p.in2 + ib * (16 / E)); else r.bs = load_scalar<T>(p.in2, ib, p.lk2); }
+  if constexpr (DOT) { if (b_contig) r.b = load_raw16(p.in2 + ib * (16 / E)); else r.bs = load_one_bf<T, E>(p.in2, ib, lk_flags(p.lk2)); }
 }
 template <class T, int E, bool DOT>
 __device__ __forceinline__ void fetch_convert(const RedParams& p, const RawPair<T, E>& r, bool b_contig, T (&v)[E]) {
@@ -146,12 +160,18 @@ __device__ __forceinline__ void store_result(const RedParams& p, long long o, V 
 
 // Sum of the 16 bytes of one chunk with four dot-product instructions (8-bit element types under +): the generic path
 // unpacks every byte into a 64-bit lane, ~5 instructions per element, and ran at 0.13 of the HBM peak.
-template <bool BYTESUM> __device__ __forceinline__ long long chunk_bytesum(const char* ptr, bool is_signed) {
+template <bool BYTESUM> __device__ __forceinline__ long long chunk_bytesum_raw(const uint4 w, bool is_signed) {
   if constexpr (BYTESUM) {
-    const uint4 w = __ldg((const uint4*)ptr);
-    if (is_signed) return (long long)__dp4a((int)w.w, 0x01010101, __dp4a((int)w.z, 0x01010101, __dp4a((int)w.y, 0x01010101, __dp4a((int)w.x, 0x01010101, 0))));
-    return (long long)__dp4a(w.w, 0x01010101u, __dp4a(w.z, 0x01010101u, __dp4a(w.y, 0x01010101u, __dp4a(w.x, 0x01010101u, 0u))));
+    // unsigned sum of the 16 bytes with four dp4a; signed bytes: every byte with its top bit set counts 256 too much.
+    // No branch: a branch around the dot products kept the loads of an unrolled step from being issued together.
+    const unsigned u = __dp4a(w.w, 0x01010101u, __dp4a(w.z, 0x01010101u, __dp4a(w.y, 0x01010101u, __dp4a(w.x, 0x01010101u, 0u))));
+    const unsigned H = 0x80808080u;
+    const int neg = __popc(w.x & H) + __popc(w.y & H) + __popc(w.z & H) + __popc(w.w & H);
+    return (long long)u - (is_signed ? 256ll * neg : 0ll);
   } else return 0;
+}
+template <bool BYTESUM> __device__ __forceinline__ long long chunk_bytesum(const char* ptr, bool is_signed) {
+  if constexpr (BYTESUM) return chunk_bytesum_raw<true>(__ldg((const uint4*)ptr), is_signed); else return 0;
 }
 template <class T, int OP, int E, bool DOT> constexpr bool use_bytesum() { return std::is_integral<T>::value && OP == R_ADD && E == 16 && !DOT; }
 
@@ -212,11 +232,11 @@ __device__ __forceinline__ void reduce_one_row(const RedParams& p, const long lo
       if constexpr (use_bytesum<T, OP, E, DOT>()) {
         const bool sg = p.lk == LK_S8;
         for (; c + 3 * TPR < nch; c += 4 * TPR) {
-          long long b[4];
+          uint4 w[4];
 #pragma unroll
-          for (int u = 0; u < 4; u++) b[u] = chunk_bytesum<true>(p.in + vbase + (c + u * TPR) * E, sg);
+          for (int u = 0; u < 4; u++) w[u] = load_raw16(p.in + vbase + (c + u * TPR) * E);
 #pragma unroll
-          for (int u = 0; u < 4; u++) acc[u] += (T)b[u];
+          for (int u = 0; u < 4; u++) acc[u] += (T)chunk_bytesum_raw<true>(w[u], sg);
         }
         for (; c < nch; c += TPR) acc[0] += (T)chunk_bytesum<true>(p.in + vbase + c * E, sg);
       } else {
@@ -260,8 +280,10 @@ __device__ __forceinline__ void reduce_one_row(const RedParams& p, const long lo
 }
 // 256 / TPR rows per CTA.  (Persistent warps walking the short rows with a grid stride were tried for TPR <= 32: no gain,
 // 0.64 -> 0.61 on rows of 512 floats.)
+// DOT: two operand streams doubled the live registers (125 -> two CTAs per SM, 0.53 of the HBM peak on `(ij ij -> i)`,
+// profiles/r02_ncu_slow_paths.md); four resident CTAs are worth a few spills outside the streaming loop
 template <class T, int OP, int E, int TPR, bool DOT>
-__global__ void __launch_bounds__(256) reduce_row_kernel(const __grid_constant__ RedParams p) {
+__global__ void __launch_bounds__(256, DOT ? 4 : 1) reduce_row_kernel(const __grid_constant__ RedParams p) {
   pdl_trigger();                                                             // the next kernel may start filling the SMs this one leaves
   reduce_one_row<T, OP, E, TPR, DOT>(p, (long long)blockIdx.x * (256 / TPR) + threadIdx.x / TPR, threadIdx.x % TPR);
 }
@@ -488,12 +510,12 @@ __global__ void __launch_bounds__(256, reduce_all_min_blocks<T, E>()) reduce_all
     long long c = tid;
     if constexpr (use_bytesum<T, OP, E, DOT>()) {
       const bool sg = p.lk == LK_S8;
-      for (; c + 3 * nthr < nch; c += 4 * nthr) {
-        long long b[4];
+      for (; c + 7 * nthr < nch; c += 8 * nthr) {                   // a byte stream needs twice the chunks in flight of a float stream
+        uint4 w[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) b[u] = chunk_bytesum<true>(p.in + p.in_off + (c + u * nthr) * E, sg);
+        for (int u = 0; u < 8; u++) w[u] = load_raw16(p.in + p.in_off + (c + u * nthr) * E);
 #pragma unroll
-        for (int u = 0; u < 4; u++) acc[u] += (T)b[u];
+        for (int u = 0; u < 8; u++) acc[u & 3] += (T)chunk_bytesum_raw<true>(w[u], sg);
       }
       for (; c < nch; c += nthr) acc[0] += (T)chunk_bytesum<true>(p.in + p.in_off + c * E, sg);
     } else {

@@ -33,6 +33,16 @@ struct Resident { void* host; size_t bytes; ncl_buf* dev; int state; unsigned fl
 static std::map<const void*, Resident> g_res;
 static Resident* find_resident(const void* host) { auto it = g_res.find(host); return it == g_res.end() ? nullptr : &it->second; }
 
+void* resident_mirror(const void* host, size_t* bytes) {
+  Resident* r = find_resident(host);
+  if (!r) return nullptr;
+  if (r->state == RES_HOST_NEWER) {
+    if (cudaMemcpyAsync(r->dev->ptr, r->host, r->bytes, cudaMemcpyHostToDevice, ctx().stream) != cudaSuccess) return nullptr;
+    ctx().h2d_bytes += r->bytes; r->state = RES_IN_SYNC;
+  }
+  if (bytes) *bytes = r->bytes;
+  return r->dev->ptr;
+}
 // ---- device buffer cache (see "buffers" below) ----
 static std::multimap<size_t, void*> g_pool;
 static size_t g_pool_bytes = 0;

@@ -23,7 +23,7 @@ static struct {
   // peer mailboxes for the fused one-element all-reduce (NVLink P2P, CUDA IPC)
   unsigned long long* mbox; unsigned long long** peers_host; unsigned long long** peers_dev; bool p2p;
   nccl_comm comm; int rank, world; void* partial;   // 8-byte device slot for the sharded full reduce
-  cudaStream_t comm_stream; cudaEvent_t ev_partial, ev_done; bool pending;
+  cudaStream_t comm_stream; cudaEvent_t ev_partial, ev_done[2]; int outstanding; unsigned long long issued;   // finalizes in flight (<= 2) / issued so far
 } g_nccl;
 
 static int nccl_load() {
@@ -76,8 +76,13 @@ template <class W>
 __global__ void mailbox_finalize_kernel(unsigned long long* const* peers, int rank, int world, char* out, long long off, StoreSpec sk, int op,
                                         long long ident_i, double ident_f) {
   __shared__ unsigned long long xch[64];
-  const unsigned long long* mb = peers[rank];
-  const unsigned long long seq = mbox_push_seq(mb, world);            // the message this rank's reduction just pushed
+  unsigned long long* mb = peers[rank];
+  // The finalizes run in order on the communication stream and count for themselves (device-resident, so the launch is
+  // identical on every graph replay): with two exchanges in flight the rank's push counter may already be one ahead.
+  __shared__ unsigned long long xseq;
+  if (threadIdx.x == 0) { xseq = ((volatile unsigned long long*)mb)[(size_t)8 * world + 1] + 1ull; ((volatile unsigned long long*)mb)[(size_t)8 * world + 1] = xseq; }
+  __syncthreads();
+  const unsigned long long seq = xseq;
   const int t = threadIdx.x;
   if (t < world) {
     unsigned long long bits = 0;
@@ -103,7 +108,7 @@ static void setup_p2p() {
   g_nccl.p2p = false;
   if (!g_nccl.allgather || g_nccl.world < 2 || g_nccl.world > 63 || getenv("NUMCL_CUDA_NO_P2P")) return;
   const int W = g_nccl.world; cudaStream_t st = ctx().stream;
-  size_t mbytes = mbox_words(W) * 8;
+  size_t mbytes = mbox_words(W) * 8;                      // 4 sequence slots x W sources x 2 words + counters
   if (cudaMalloc((void**)&g_nccl.mbox, mbytes) != cudaSuccess) return;
   cudaMemset(g_nccl.mbox, 0, mbytes);
   cudaIpcMemHandle_t mine;
@@ -159,7 +164,9 @@ int ncl_comm_init(const void* id128, int rank, int world) {
   int prio_lo = 0, prio_hi = 0; NCL_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   NCL_CUDA(cudaStreamCreateWithPriority(&g_nccl.comm_stream, cudaStreamNonBlocking, prio_hi));
   NCL_CUDA(cudaEventCreateWithFlags(&g_nccl.ev_partial, cudaEventDisableTiming));
-  NCL_CUDA(cudaEventCreateWithFlags(&g_nccl.ev_done, cudaEventDisableTiming));
+  NCL_CUDA(cudaEventCreateWithFlags(&g_nccl.ev_done[0], cudaEventDisableTiming));
+  NCL_CUDA(cudaEventCreateWithFlags(&g_nccl.ev_done[1], cudaEventDisableTiming));
+  g_nccl.outstanding = 0; g_nccl.issued = 0;
   setup_p2p();                                          // best effort: without it the NCCL path is used
   return NCL_OK;
 }
@@ -167,7 +174,7 @@ int ncl_comm_destroy(void) {
   if (g_nccl.comm) {
     cudaStreamSynchronize(ctx().stream); cudaStreamSynchronize(g_nccl.comm_stream);
     g_nccl.destroy(g_nccl.comm); g_nccl.comm = nullptr;
-    cudaStreamDestroy(g_nccl.comm_stream); cudaEventDestroy(g_nccl.ev_partial); cudaEventDestroy(g_nccl.ev_done); g_nccl.pending = false;
+    cudaStreamDestroy(g_nccl.comm_stream); cudaEventDestroy(g_nccl.ev_partial); cudaEventDestroy(g_nccl.ev_done[0]); cudaEventDestroy(g_nccl.ev_done[1]); g_nccl.outstanding = 0;
   }
   if (g_nccl.partial) { cudaFree(g_nccl.partial); g_nccl.partial = nullptr; }
   return NCL_OK;
@@ -210,11 +217,13 @@ int ncl_allreduce(int op, ncl_tensor* t) {
 // stream after it.
 int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a, ncl_tensor* r) {
   if (!ctx().inited) return set_error(NCL_ERR_STATE, "ncl_init has not been called");
-  if (!a || !r || !a->buf || !r->buf) return set_error(NCL_ERR_INVALID, "ncl_reduce_all_sharded needs device-resident tensors");
+  // the slab may be a host array with a resident device mirror (ncl_host_register): the mirror is what gets reduced
+  void* amirror = (a && !a->buf && a->host) ? resident_mirror(a->host, nullptr) : nullptr;
+  if (!a || !r || (!a->buf && !amirror) || !r->buf) return set_error(NCL_ERR_INVALID, "ncl_reduce_all_sharded needs a device-resident (or registered host) slab and a device-resident result");
   if (r->rank != 0) return set_error(NCL_ERR_SHAPE, "result of a full reduce is a rank-0 array");
   if (g_dt[a->dtype].cls != g_dt[r->dtype].cls) return set_error(NCL_ERR_UNSUPPORTED, "element classes differ");
   int nop; NCL_TRY(nccl_op(op, &nop));
-  Operand ao; memset(&ao, 0, sizeof ao); ao.base = (char*)a->buf->ptr; ao.dtype = a->dtype; ao.offset = a->elem_offset;
+  Operand ao; memset(&ao, 0, sizeof ao); ao.base = a->buf ? (char*)a->buf->ptr : (char*)amirror; ao.dtype = a->dtype; ao.offset = a->elem_offset;
   int64_t n = 1; for (int i = 0; i < a->rank; i++) n *= a->dims[i];
   int cls = g_dt[a->dtype].cls;
   Operand ro; memset(&ro, 0, sizeof ro); ro.base = (char*)r->buf->ptr; ro.dtype = r->dtype; ro.offset = r->elem_offset;
@@ -227,9 +236,10 @@ int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a, ncl_tensor* r) {
   }
   if (g_nccl.p2p) {
     // The local reduction's last block pushes the partial into every rank's mailbox over NVLink (P2P stores, no NCCL
-    // call); the one-CTA finalize collects the W messages on the communication stream.  A rank's push n + 1 is ordered
-    // after its own finalize n (two-parity mailbox, see ncl_device.cuh).
-    if (g_nccl.pending) NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done, 0));
+    // call); the one-CTA finalize collects the W messages on the communication stream.  The mailbox has FOUR sequence
+    // slots and a rank's push n is ordered after its own finalize n - 2 (see ncl_device.cuh): two exchanges may be in
+    // flight, so the compute stream never waits for the exchange it has just started -- only for the one before it.
+    if (g_nccl.outstanding >= 2) { NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done[g_nccl.issued & 1], 0)); g_nccl.outstanding = 1; }
     int rc = reduce_all_p2p(op, ao, n, ro, g_nccl.peers_dev, g_nccl.rank, g_nccl.world, 0);
     if (rc != NCL_ERR_UNSUPPORTED) {
       NCL_TRY(rc);
@@ -241,23 +251,26 @@ int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a, ncl_tensor* r) {
       else mailbox_finalize_kernel<double><<<1, 64, 0, g_nccl.comm_stream>>>(g_nccl.peers_dev, g_nccl.rank, g_nccl.world, ro.base, ro.offset, sk, op, ident_i, ident_f);
       note_side_launch("reduce_all_p2p");
       NCL_TRY(cuda_fail(cudaGetLastError(), "mailbox_finalize_kernel"));
-      NCL_CUDA(cudaEventRecord(g_nccl.ev_done, g_nccl.comm_stream));
-      g_nccl.pending = true;
+      NCL_CUDA(cudaEventRecord(g_nccl.ev_done[g_nccl.issued & 1], g_nccl.comm_stream));
+      g_nccl.issued++; g_nccl.outstanding++;
       return NCL_OK;
     }
   }
-  if (g_nccl.pending) NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done, 0));   // the slot is single-buffered
+  NCL_TRY(ncl_comm_join());                                                        // the NCCL path's partial slot is single-buffered
   NCL_TRY(reduce_all_to_partial(op, ao, n, g_nccl.partial));
   NCL_CUDA(cudaEventRecord(g_nccl.ev_partial, ctx().stream));
   NCL_CUDA(cudaStreamWaitEvent(g_nccl.comm_stream, g_nccl.ev_partial, 0));
   NCL_TRY(nccl_fail(g_nccl.allreduce(g_nccl.partial, g_nccl.partial, 1, cls == CLS_I ? 4 : 8, nop, g_nccl.comm, g_nccl.comm_stream), "ncclAllReduce"));
   NCL_TRY(finalize_partial_on(g_nccl.comm_stream, op, g_nccl.partial, cls, ro, true));
-  NCL_CUDA(cudaEventRecord(g_nccl.ev_done, g_nccl.comm_stream));
-  g_nccl.pending = true;
+  NCL_CUDA(cudaEventRecord(g_nccl.ev_done[g_nccl.issued & 1], g_nccl.comm_stream));
+  g_nccl.issued++; g_nccl.outstanding++;
   return NCL_OK;
 }
 int ncl_comm_join(void) {
-  if (g_nccl.pending) { NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done, 0)); g_nccl.pending = false; }
+  // order the compute stream after every finalize still in flight (the last one, and the one before it)
+  if (g_nccl.outstanding >= 1) NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done[(g_nccl.issued - 1) & 1], 0));
+  if (g_nccl.outstanding >= 2) NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done[g_nccl.issued & 1], 0));
+  g_nccl.outstanding = 0;
   return NCL_OK;
 }
 int ncl_reduce_all_sharded(int op, const ncl_tensor* a, ncl_tensor* r) {

@@ -437,23 +437,23 @@ __host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long 
 }
 
 // ---- peer mailboxes of the sharded full reduce (ncl_comm.cu maps every rank's mailbox into every process) --------------
-// One mailbox = [parity 2][source rank W][2 words] + [push_seq][fin_seq].  A message of sequence number n lives in parity
-// n & 1; each of its two words is {n : 32 | half of the 64-bit value : 32}, so a single 8-byte store publishes it.
-// Parity slot n & 1 is overwritten by message n + 2 only: the library orders a rank's push n + 1 after its own finalize
-// n - 1 ... and its push n + 2 after its finalize n + 1, which needs every peer's push n + 1, which that peer issued after
-// its finalize n -- so every reader of n is done before n + 2 arrives.
-__host__ __device__ inline size_t mbox_words(int world) { return (size_t)2 * world * 2 + 8; }
-__device__ __forceinline__ unsigned long long mbox_push_seq(const unsigned long long* mb, int world) { return ((const volatile unsigned long long*)mb)[(size_t)4 * world]; }
-__device__ __forceinline__ void mbox_set_push_seq(unsigned long long* mb, int world, unsigned long long seq) { ((volatile unsigned long long*)mb)[(size_t)4 * world] = seq; }
+// One mailbox = [slot 4][source rank W][2 words] + [push_seq][fin_seq].  A message of sequence number n lives in slot n & 3; each of its
+// two words is {n : 32 | half of the 64-bit value : 32}, so a single 8-byte store publishes it.  Slot n & 3 is overwritten
+// by message n + 4 only, and the library orders a rank's push n after its own finalize n - 2: a rank that pushes n + 4 has
+// finished its finalize n + 2, which needed every peer's push n + 2, which that peer issued after ITS finalize n -- so
+// every reader of n is done before n + 4 arrives, while two exchanges can be in flight per rank.
+__host__ __device__ inline size_t mbox_words(int world) { return (size_t)4 * world * 2 + 8; }
+__device__ __forceinline__ unsigned long long mbox_push_seq(const unsigned long long* mb, int world) { return ((const volatile unsigned long long*)mb)[(size_t)8 * world]; }
+__device__ __forceinline__ void mbox_set_push_seq(unsigned long long* mb, int world, unsigned long long seq) { ((volatile unsigned long long*)mb)[(size_t)8 * world] = seq; }
 __device__ __forceinline__ void mbox_send(unsigned long long* peer_mb, int world, unsigned long long seq, int from, unsigned long long bits) {
-  volatile unsigned long long* slot = peer_mb + (((size_t)(seq & 1ull) * world) + from) * 2;
+  volatile unsigned long long* slot = peer_mb + (((size_t)(seq & 3ull) * world) + from) * 2;
   const unsigned long long tag = (seq & 0xffffffffull) << 32;
   slot[0] = tag | (bits & 0xffffffffull);
   slot[1] = tag | (bits >> 32);
 }
 // spins until message `seq` from rank `from` has arrived in my mailbox; false after ~10 s (the caller traps)
 __device__ __forceinline__ bool mbox_recv(const unsigned long long* my_mb, int world, unsigned long long seq, int from, unsigned long long* bits) {
-  const unsigned long long* slot = my_mb + (((size_t)(seq & 1ull) * world) + from) * 2;
+  const unsigned long long* slot = my_mb + (((size_t)(seq & 3ull) * world) + from) * 2;
   const unsigned long long tag = seq & 0xffffffffull;
   const long long t0 = clock64();
   unsigned long long lo, hi;

@@ -18,7 +18,14 @@
 #include "ncl_device.cuh"
 
 enum { FAULT_DOMAIN = 1, FAULT_DIV0 = 2, FAULT_OVERFLOW = 4 };
-__device__ __forceinline__ void ncl_fault(unsigned int* f, unsigned int code) { if (f) atomicOr(f, code); }
+// `f` points to a THREAD-LOCAL accumulator; the kernel flushes it once, warp-aggregated, when it is done (an atomic per faulting
+// element on one global word serialised the whole kernel: sqrt over data that is half negative ran at 0.05 of the HBM peak)
+__device__ __forceinline__ void ncl_fault(unsigned int* f, unsigned int code) { *f |= code; }
+__device__ __forceinline__ void ncl_fault_flush(unsigned int* global_flag, unsigned int local) {
+  const unsigned int am = __activemask();
+  const unsigned int any = __reduce_or_sync(am, local);
+  if (any && global_flag && (threadIdx.x & 31) == (unsigned)(__ffs(am) - 1)) atomicOr(global_flag, any);
+}
 
 // sign of (a - b) for an integer a and a float b, compared exactly: -1, 0, 1; 2 when b is a NaN
 __device__ __forceinline__ int cmp_i64_f64(long long a, double b) {
@@ -122,8 +129,8 @@ template <class T> __device__ inline T float_intexp(T base, long long power) {
 }
 
 // unary functions that leave the integers / the reals; op is an ncl_op.  libm vs SBCL's libm: tolerance only (except sqrt).
-template <class T> __device__ inline T float_unary(int op, T x, unsigned int* flt);
-template <> __device__ inline float float_unary<float>(int op, float x, unsigned int* flt) {
+template <class T> __device__ __forceinline__ T float_unary(int op, T x, unsigned int* flt);
+template <> __device__ __forceinline__ float float_unary<float>(int op, float x, unsigned int* flt) {
   switch (op) {
     case NCL_OP_SQRT: if (x < 0.0f) ncl_fault(flt, FAULT_DOMAIN); return __fsqrt_rn(x);
     case NCL_OP_LOG: if (x < 0.0f) ncl_fault(flt, FAULT_DOMAIN); return logf(x);
@@ -137,7 +144,7 @@ template <> __device__ inline float float_unary<float>(int op, float x, unsigned
     default: if (fabsf(x) > 1.0f) ncl_fault(flt, FAULT_DOMAIN); return atanhf(x);
   }
 }
-template <> __device__ inline double float_unary<double>(int op, double x, unsigned int* flt) {
+template <> __device__ __forceinline__ double float_unary<double>(int op, double x, unsigned int* flt) {
   switch (op) {
     case NCL_OP_SQRT: if (x < 0.0) ncl_fault(flt, FAULT_DOMAIN); return __dsqrt_rn(x);
     case NCL_OP_LOG: if (x < 0.0) ncl_fault(flt, FAULT_DOMAIN); return log(x);

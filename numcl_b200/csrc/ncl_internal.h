@@ -117,6 +117,8 @@ inline bool op_may_fault(int op) {
     default: return false;
   }
 }
+// residency table (ncl_api.cu): device mirror of a registered host base vector (uploading it first when the host copy is newer), or nullptr
+void* resident_mirror(const void* host, size_t* bytes);
 int check_fault();                       // ncl_api.cu: reads and clears the flag; NCL_OK or NCL_ERR_DOMAIN (synchronises the stream)
 
 // ---- kernel families; each returns NCL_OK, an error, or NCL_ERR_UNSUPPORTED to fall through ------

@@ -235,7 +235,7 @@ def test_integer_vs_float_comparisons_are_exact(nc, oracle, op):
     f32 = oracle.OArr.from_values(i32.values().astype(np.float32), "f32")
     got = nc.broadcast(op, to_gpu(nc, i32), to_gpu(nc, f32))
     assert_bit_exact(got, refsem.broadcast(oracle, op, i32, f32))
-    assert nc.lib().ncl_last_kernel() == b"bcast_vec"
+    assert nc.lib().ncl_last_kernel() == b"cmp_pack"                 # the vector path (double-float lanes), not the generic kernel
     frac = oracle.OArr.from_values(np.array([0.5, -0.5, 1e30, -1e30, np.inf, -np.inf, 2.0 ** 63, -2.0 ** 63]), "f64")
     k = oracle.OArr.from_values(np.array([0, 0, 2 ** 62 - 1, -2 ** 62, 5, 5, 2 ** 62 - 1, -2 ** 62], dtype=np.int64), "fixnum")
     assert_bit_exact(nc.broadcast(op, to_gpu(nc, k), to_gpu(nc, frac)), refsem.broadcast(oracle, op, k, frac))

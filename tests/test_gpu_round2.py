@@ -277,3 +277,32 @@ def test_lazy_resident_results_stay_on_the_device_until_fetched(nc, oracle):
     h2 = _lib.transfer_stats()[0]
     assert nc.sum(row) == float(a.values()[1].astype(np.float64).sum())
     assert _lib.transfer_stats()[0] == h2
+
+
+@pytest.mark.parametrize("n", [4096, 65536 + 16, 1 << 20])
+def test_eight_bit_simd_in_register_family_bit_exact(nc, oracle, n):
+    """k_ew_narrow.cu: ub8 (op) ub8 / scalar with the result types numcl infers (ub15, sb16, ub8), against the oracle"""
+    L = nc.lib()
+    a = rand(oracle, (n,), "ub8", SEED, 0, 0, 255)
+    b = rand(oracle, (n,), "ub8", SEED + 1, 0, 0, 255)
+    sa = rand(oracle, (n,), "sb8", SEED + 2, 0, -128, 127)
+    sb = rand(oracle, (n,), "sb8", SEED + 3, 0, -128, 127)
+    ga, gb, gsa, gsb = (to_gpu(nc, x) for x in (a, b, sa, sb))
+    hits = 0
+    for fn, f in (("+", nc.add), ("-", nc.sub), ("max", nc.maximum), ("min", nc.minimum)):
+        assert_bit_exact(f(ga, gb), refsem.arith(oracle, fn, [a, b])); hits += L.ncl_last_kernel() == b"bcast_narrow"
+    for fn in ("logand", "logior", "logxor"):
+        assert_bit_exact(getattr(nc, fn)(ga, gb), refsem.broadcast(oracle, fn, a, b)); hits += L.ncl_last_kernel() == b"bcast_narrow"
+    for fn, f in (("max", nc.maximum), ("min", nc.minimum)):
+        assert_bit_exact(f(gsa, gsb), refsem.arith(oracle, fn, [sa, sb])); hits += L.ncl_last_kernel() == b"bcast_narrow"
+    for k in (3, 1, 255, 200):
+        assert_bit_exact(nc.mul(ga, k), refsem.arith(oracle, "*", [a, k])); hits += L.ncl_last_kernel() == b"bcast_narrow"
+        assert_bit_exact(nc.mul(k, ga), refsem.arith(oracle, "*", [k, a]))
+        assert_bit_exact(nc.add(ga, k), refsem.arith(oracle, "+", [a, k]))
+        assert_bit_exact(nc.sub(ga, k), refsem.arith(oracle, "-", [a, k]))
+        assert_bit_exact(nc.sub(k, ga), refsem.arith(oracle, "-", [k, a]))
+    assert hits >= 8                                         # the family is what actually ran
+    # caller-supplied narrower results wrap like %coerce: (unsigned-byte 15) keeps 15 bits, ub8 + ub8 into ub8 stays on the engine
+    for out in ("ub15", "ub16", "sb16"):
+        assert_bit_exact(nc.broadcast("+", ga, gb, type=out), oracle.broadcast("+", a, b, out))
+        assert_bit_exact(nc.broadcast("-", ga, gb, type=out), oracle.broadcast("-", a, b, out))

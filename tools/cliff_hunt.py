@@ -86,7 +86,9 @@ run("a * 2.0 (scalar)", lambda: nc.mul(a, 2.0), 2 * a.nbytes)
 run("a < b1 -> bit", lambda: nn.lt(a, b1), a.nbytes + a.nbytes // 32)
 d = R((512, 512, 512), "f64", 6); ah = R((512, 512, 512), seed=30)
 run("f32 + f64 same shape -> f64", lambda: nc.add(ah, d), ah.nbytes + 2 * d.nbytes)
-run("f64 + f64", lambda: nc.add(d, d), 3 * d.nbytes)
+d2 = R((512, 512, 512), "f64", 61)
+run("f64 + f64", lambda: nc.add(d, d2), 3 * d.nbytes)
+del d2
 del d, ah
 u = R((1024, 512, 512), "ub8", 7); u2 = R((1024, 512, 512), "ub8", 8)
 run("ub8 + ub8 -> ub15", lambda: nc.add(u, u2), u.nbytes * 4)
