@@ -85,17 +85,23 @@ __device__ __forceinline__ T load_one_bf(const char* base, long long idx, unsign
   }
 }
 template <class T, int E> struct RawPair { uint4 a, b; T bs; };
-template <class T, int E, bool DOT>
+// BC: is the second operand contiguous along the chunk?  -1 = decided at run time (a branch per fetch), 0 / 1 = compile time.
+// The streaming loops dispatch ONCE on the run-time flag and run a BC-specialised copy: with the branch inside an unrolled step
+// the loads of later chunks could not be hoisted above it and a column-form dot product kept one or two loads in flight
+// (`(i ij -> j)`: DRAM 44 % busy, long-scoreboard stalls, profiles/r02_ncu_slow_paths.md).
+template <class T, int E, bool DOT, int BC = -1>
 __device__ __forceinline__ void fetch_raw(const RedParams& p, long long ia, long long ib, bool b_contig, RawPair<T, E>& r) {
   r.a = load_raw16(p.in + ia * (16 / E));
-  if constexpr (DOT) { if (b_contig) r.b = load_raw16(p.in2 + ib * (16 / E)); else r.bs = load_one_bf<T, E>(p.in2, ib, lk_flags(p.lk2)); }
+  if constexpr (DOT) {
+    if (BC == 1 || (BC == -1 && b_contig)) r.b = load_raw16(p.in2 + ib * (16 / E)); else r.bs = load_one_bf<T, E>(p.in2, ib, lk_flags(p.lk2));
+  }
 }
-template <class T, int E, bool DOT>
+template <class T, int E, bool DOT, int BC = -1>
 __device__ __forceinline__ void fetch_convert(const RedParams& p, const RawPair<T, E>& r, bool b_contig, T (&v)[E]) {
   convert_raw16<T, E>(r.a, lk_flags(p.lk), v);
   if constexpr (DOT) {
     T w[E];
-    if (b_contig) convert_raw16<T, E>(r.b, lk_flags(p.lk2), w);
+    if (BC == 1 || (BC == -1 && b_contig)) convert_raw16<T, E>(r.b, lk_flags(p.lk2), w);
     else {
 #pragma unroll
       for (int i = 0; i < E; i++) w[i] = r.bs;
@@ -104,10 +110,10 @@ __device__ __forceinline__ void fetch_convert(const RedParams& p, const RawPair<
     for (int i = 0; i < E; i++) v[i] = Ops<T>::mul(v[i], w[i]);
   }
 }
-template <class T, int E, bool DOT>
+template <class T, int E, bool DOT, int BC = -1>
 __device__ __forceinline__ void fetch_elems(const RedParams& p, long long ia, long long ib, bool b_contig, T (&v)[E]) {
   if constexpr (E > 1) {
-    RawPair<T, E> r; fetch_raw<T, E, DOT>(p, ia, ib, b_contig, r); fetch_convert<T, E, DOT>(p, r, b_contig, v);
+    RawPair<T, E> r; fetch_raw<T, E, DOT, BC>(p, ia, ib, b_contig, r); fetch_convert<T, E, DOT, BC>(p, r, b_contig, v);
   } else {
     load_elems<T, E>(p.in, ia, p.lk, false, v);
     if constexpr (DOT) {
@@ -115,6 +121,11 @@ __device__ __forceinline__ void fetch_elems(const RedParams& p, long long ia, lo
       v[0] = Ops<T>::mul(v[0], w[0]);
     }
   }
+}
+// runs body(integral_constant<int, BC>) with BC = 1 (no second operand, or a contiguous one) or 0 (a broadcast one)
+template <bool DOT, class F> __device__ __forceinline__ void with_bc(bool b_contig, F body) {
+  if constexpr (!DOT) body(std::integral_constant<int, 1>{});
+  else { if (b_contig) body(std::integral_constant<int, 1>{}); else body(std::integral_constant<int, 0>{}); }
 }
 template <class T, int E>
 __device__ __forceinline__ void load_vec(const char* base, long long idx, int lk, T (&v)[E]) {
@@ -240,13 +251,16 @@ __device__ __forceinline__ void reduce_one_row(const RedParams& p, const long lo
         }
         for (; c < nch; c += TPR) acc[0] += (T)chunk_bytesum<true>(p.in + vbase + c * E, sg);
       } else {
-      for (; c + 3 * TPR < nch; c += 4 * TPR) {
-        T v[4][E];
-#pragma unroll
-        for (int u = 0; u < 4; u++) fetch_elems<T, E, DOT>(p, vbase + (c + u * TPR) * E, vbase2 + (c + u * TPR) * E * rs2, bc, v[u]);
-#pragma unroll
-        for (int u = 0; u < 4; u++) acc[u] = fold_elems<T, OP, E>(acc[u], v[u]);
+      // (plain macro, not a lambda: capturing the accumulators by reference cost the short-row variants half their speed)
+#define NCL_ROW_MAIN_LOOP(BC)                                                                                                   \
+      for (; c + 3 * TPR < nch; c += 4 * TPR) {                                                                                \
+        T v[4][E];                                                                                                             \
+        _Pragma("unroll") for (int u = 0; u < 4; u++)                                                                          \
+          fetch_elems<T, E, DOT, BC>(p, vbase + (c + u * TPR) * E, vbase2 + (c + u * TPR) * E * rs2, bc, v[u]);                \
+        _Pragma("unroll") for (int u = 0; u < 4; u++) acc[u] = fold_elems<T, OP, E>(acc[u], v[u]);                             \
       }
+      if constexpr (!DOT) { NCL_ROW_MAIN_LOOP(1) } else if (bc) { NCL_ROW_MAIN_LOOP(1) } else { NCL_ROW_MAIN_LOOP(0) }
+#undef NCL_ROW_MAIN_LOOP
       if constexpr (DOT) {                                  // (two operands: the batch below doubled the register count)
         for (; c < nch; c += TPR) { T v[E]; fetch_elems<T, E, DOT>(p, vbase + c * E, vbase2 + c * E * rs2, bc, v); acc[0] = fold_elems<T, OP, E>(acc[0], v); }
       } else if (c < nch) {                                 // up to three chunks left for this thread: issued together
@@ -281,9 +295,10 @@ __device__ __forceinline__ void reduce_one_row(const RedParams& p, const long lo
 // 256 / TPR rows per CTA.  (Persistent warps walking the short rows with a grid stride were tried for TPR <= 32: no gain,
 // 0.64 -> 0.61 on rows of 512 floats.)
 // DOT: two operand streams doubled the live registers (125 -> two CTAs per SM, 0.53 of the HBM peak on `(ij ij -> i)`,
-// profiles/r02_ncu_slow_paths.md); four resident CTAs are worth a few spills outside the streaming loop
+// profiles/r02_ncu_slow_paths.md); four resident CTAs are worth a few spills outside the streaming loop.
+// (0 = unspecified for the single-operand variants: with min-blocks 1 ptxas grew them from 46 to 96 registers, 0.96 -> 0.62 on ragged rows.)
 template <class T, int OP, int E, int TPR, bool DOT>
-__global__ void __launch_bounds__(256, DOT ? 4 : 1) reduce_row_kernel(const __grid_constant__ RedParams p) {
+__global__ void __launch_bounds__(256, DOT ? 4 : 0) reduce_row_kernel(const __grid_constant__ RedParams p) {
   pdl_trigger();                                                             // the next kernel may start filling the SMs this one leaves
   reduce_one_row<T, OP, E, TPR, DOT>(p, (long long)blockIdx.x * (256 / TPR) + threadIdx.x / TPR, threadIdx.x % TPR);
 }
@@ -686,15 +701,16 @@ __global__ void __launch_bounds__(256) reduce_col_kernel(const __grid_constant__
   // (8 rows in flight for 16-byte chunks was tried after ncu showed the kernel latency-bound at 49 % of DRAM bandwidth: worse everywhere,
   // 0.96 -> 0.73 on (1024,512,512) axis 1 and 0.57 -> 0.25 on 8192^2 fixnum -- more rows per thread means more DRAM pages open at once)
   constexpr int UR = E == 1 ? 16 : 4;
-  for (; r + UR - 1 < r1; r += UR) {
-    T v[UR][E];
-#pragma unroll
-    for (int u = 0; u < UR; u++) fetch_elems<T, E, DOT>(p, ibase + (r + u) * p.r_stride, ibase2 + (r + u) * rs2, bc, v[u]);
-#pragma unroll
-    for (int u = 0; u < UR; u++)
-#pragma unroll
-      for (int i = 0; i < E; i++) acc[i] = Red<T, OP>::f(acc[i], v[u][i]);
+#define NCL_COL_MAIN_LOOP(BC)                                                                                                   \
+  for (; r + UR - 1 < r1; r += UR) {                                                                                            \
+    T v[UR][E];                                                                                                                 \
+    _Pragma("unroll") for (int u = 0; u < UR; u++)                                                                              \
+      fetch_elems<T, E, DOT, BC>(p, ibase + (r + u) * p.r_stride, ibase2 + (r + u) * rs2, bc, v[u]);                            \
+    _Pragma("unroll") for (int u = 0; u < UR; u++)                                                                              \
+      _Pragma("unroll") for (int i = 0; i < E; i++) acc[i] = Red<T, OP>::f(acc[i], v[u][i]);                                    \
   }
+  if constexpr (!DOT) { NCL_COL_MAIN_LOOP(1) } else if (bc) { NCL_COL_MAIN_LOOP(1) } else { NCL_COL_MAIN_LOOP(0) }
+#undef NCL_COL_MAIN_LOOP
   if constexpr (DOT) {
     for (; r < r1; r++) {
       T v[E]; fetch_elems<T, E, DOT>(p, ibase + r * p.r_stride, ibase2 + r * rs2, bc, v);
@@ -738,7 +754,15 @@ __global__ void __launch_bounds__(256) reduce_col_finish_kernel(const __grid_con
 #pragma unroll
   for (int i = 0; i < E; i++) {
     T a = part[q * E + i];
-    for (int s = 1; s < p.nseg; s++) a = Red<T, OP>::f(a, part[((long long)s * nq + q) * E + i]);
+    int s = 1;
+    for (; s + 7 < p.nseg; s += 8) {                        // eight segment partials in flight, folded in segment order
+      T t[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) t[k] = part[((long long)(s + k) * nq + q) * E + i];
+#pragma unroll
+      for (int k = 0; k < 8; k++) a = Red<T, OP>::f(a, t[k]);
+    }
+    for (; s < p.nseg; s++) a = Red<T, OP>::f(a, part[((long long)s * nq + q) * E + i]);
     T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, obase + i, p.out_lk);
     store_result<T, T>(p, obase + i, Red<T, OP>::f(init, a));
   }

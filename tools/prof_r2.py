@@ -29,6 +29,8 @@ elif case == "dot_cols":
     a = R((32768, 8192), seed=9); b = R((32768, 8192), seed=10); f = lambda: nc.einsum("ij ij -> j", a, b)
 elif case == "vecmat":
     a = R((32768, 8192), seed=9); b = R((32768,), seed=15); f = lambda: nc.einsum("i ij -> j", b, a)
+elif case == "col_fixnum":
+    a = R((8192, 8192), "fixnum", 9); f = lambda: nc.sum(a, axes=0)
 elif case == "sum_u8_all":
     a = R((1024, 512, 512), "ub8", 7); f = lambda: nc.sum(a)
 elif case == "transpose_thin":
