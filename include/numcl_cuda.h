@@ -199,6 +199,11 @@ int  ncl_trim(void);
  * staging of host-resident tensors, the residency table below): lets a caller verify that a warm
  * call moved nothing over PCIe. */
 void ncl_transfer_stats(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* Calls on pinned host-resident arrays are cut into panels of their outermost kept loop: panel p is uploaded while
+ * panel p-1 is computed and panel p-2 travels back (PCIe is full duplex, the copy engines run beside the SMs).  Number of
+ * calls that ran that way and the panels they were cut into, since ncl_init.  NUMCL_NO_PIPELINE=1 disables it,
+ * NUMCL_PANEL_MB sets the panel size (default 32). */
+void ncl_pipeline_stats(int64_t* calls, int64_t* panels);
 /* Number of kernels the library has launched since ncl_init (bench.py's gpu_launches). */
 int64_t ncl_launch_count(void);
 /* Name of the kernel family the last compute call dispatched to ("bcast_vec", "bcast_vec_flat", "bcast_widen",

@@ -37,7 +37,7 @@ EXPORTS = [
     "ncl_einsum", "ncl_broadcast", "ncl_fold", "ncl_map", "ncl_reduce", "ncl_convert",
     "ncl_comm_unique_id", "ncl_comm_init", "ncl_comm_destroy", "ncl_allreduce", "ncl_reduce_all_sharded",
     "ncl_reduce_all_sharded_async", "ncl_comm_join",
-    "ncl_trim", "ncl_transfer_stats", "ncl_capture_begin", "ncl_capture_end", "ncl_graph_launch", "ncl_graph_kernels",
+    "ncl_trim", "ncl_transfer_stats", "ncl_pipeline_stats", "ncl_capture_begin", "ncl_capture_end", "ncl_graph_launch", "ncl_graph_kernels",
     "ncl_graph_free", "ncl_fill_random_at", "ncl_reduce_stat",
     "ncl_host_register", "ncl_host_unregister", "ncl_host_dirty", "ncl_host_fetch", "ncl_host_state",
 ]
@@ -134,6 +134,8 @@ def load():
     L.ncl_fill_random_at.argtypes = [C.POINTER(Tensor), C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_double]
     L.ncl_transfer_stats.restype = None
     L.ncl_transfer_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.ncl_pipeline_stats.restype = None
+    L.ncl_pipeline_stats.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ncl_capture_end.argtypes = [C.POINTER(C.c_void_p)]
     L.ncl_graph_launch.argtypes = [C.c_void_p]
     L.ncl_graph_kernels.restype = C.c_int64
@@ -227,3 +229,9 @@ def transfer_stats():
     h, d = C.c_uint64(), C.c_uint64()
     lib().ncl_transfer_stats(C.byref(h), C.byref(d))
     return h.value, d.value
+
+
+def pipeline_stats():
+    c, p = C.c_int64(), C.c_int64()
+    lib().ncl_pipeline_stats(C.byref(c), C.byref(p))
+    return c.value, p.value

@@ -59,6 +59,16 @@ static void pool_release_all() {
   g_pool.clear(); g_pool_bytes = 0;
 }
 
+// pinned host blocks (ncl_host_alloc_pinned below)
+static std::multimap<size_t, void*> g_hpool;                 // free blocks by size
+static std::map<const void*, size_t> g_hsize;                // every live or cached block -> its size
+static size_t g_hpool_bytes = 0;
+static size_t hpool_cap() { static size_t v = (size_t)-1; if (v == (size_t)-1) { const char* e = getenv("NUMCL_PINNED_POOL_MB"); v = (size_t)(e ? atol(e) : 4096) << 20; } return v; }
+static void hpool_release_all() {
+  for (auto& kv : g_hpool) { g_hsize.erase(kv.second); cudaFreeHost(kv.second); }
+  g_hpool.clear(); g_hpool_bytes = 0;
+}
+
 static int grow(void** p, size_t* have, size_t want) {
   if (*have >= want) return NCL_OK;
   if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "a scratch arena must grow (%zu bytes) inside ncl_capture_begin/end: run the sequence once before capturing it", want);
@@ -145,7 +155,7 @@ void ncl_shutdown(void) {
   cudaStreamSynchronize(g_ctx.stream);
   for (auto& kv : g_res) if (kv.second.dev) { cudaFree(kv.second.dev->ptr); delete kv.second.dev; }
   g_res.clear();
-  pool_release_all();
+  pool_release_all(); hpool_release_all();
   if (g_ctx.scratch) cudaFree(g_ctx.scratch);
   if (g_ctx.scratch2) cudaFree(g_ctx.scratch2);
   if (g_ctx.scratch3) cudaFree(g_ctx.scratch3);
@@ -154,6 +164,10 @@ void ncl_shutdown(void) {
   if (g_ctx.fault) cudaFree(g_ctx.fault);
   if (g_ctx.pinned) cudaFreeHost(g_ctx.pinned);
   if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
+  if (g_ctx.copy_in) cudaStreamDestroy(g_ctx.copy_in);
+  if (g_ctx.copy_out) cudaStreamDestroy(g_ctx.copy_out);
+  for (int k = 0; k < g_ctx.n_events; k++) cudaEventDestroy(g_ctx.events[k]);
+  free(g_ctx.events);
   g_ctx = Context();
 }
 
@@ -180,7 +194,8 @@ int ncl_sync(void) {
 }
 // Give every cached device block back to the driver (the cache keeps freed base vectors for re-use and would otherwise
 // only shrink when one of the library's own allocations fails): for hosts that share the GPU with another allocator.
-int ncl_trim(void) { LOCK; NEED_INIT; if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_trim inside a capture"); pool_release_all(); return NCL_OK; }
+int ncl_trim(void) { LOCK; NEED_INIT; if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "ncl_trim inside a capture"); pool_release_all(); hpool_release_all(); return NCL_OK; }
+void ncl_pipeline_stats(int64_t* calls, int64_t* panels) { if (calls) *calls = g_ctx.pipelined_calls; if (panels) *panels = g_ctx.pipelined_panels; }
 void ncl_transfer_stats(uint64_t* h2d_bytes, uint64_t* d2h_bytes) { if (h2d_bytes) *h2d_bytes = g_ctx.h2d_bytes; if (d2h_bytes) *d2h_bytes = g_ctx.d2h_bytes; }
 
 // ---- CUDA graphs: a launch-bound sequence of calls recorded once, replayed with ONE launch ---------------------------------
@@ -287,12 +302,33 @@ int ncl_d2h(void* host, const ncl_buf* src, size_t off, size_t bytes) {
   NCL_CUDA(cudaStreamSynchronize(g_ctx.stream));
   return check_fault();
 }
+// Pinned host vectors are what %make-array hands out on the :cuda backend, once per RESULT of every numcl call -- and
+// cudaMallocHost / cudaFreeHost cost about 0.4 ms per MiB (a 64 MiB result: 25 ms, ten times its PCIe time).  Freed blocks
+// are therefore kept in a size-bucketed cache like the device blocks (ncl_alloc); NUMCL_PINNED_POOL_MB caps what it may
+// hold (default 4096), ncl_trim gives it back.
 void* ncl_host_alloc_pinned(size_t bytes) {
+  LOCK;
+  const size_t sz = pool_round(bytes);
+  auto it = g_hpool.find(sz);
+  if (it != g_hpool.end()) { void* p = it->second; g_hpool.erase(it); g_hpool_bytes -= sz; return p; }
   void* p = nullptr;
-  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_error(NCL_ERR_NOMEM, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+  cudaError_t e = cudaMallocHost(&p, sz);
+  if (e != cudaSuccess && !g_hpool.empty()) { cudaGetLastError(); hpool_release_all(); e = cudaMallocHost(&p, sz); }
+  if (e != cudaSuccess) { cudaGetLastError(); set_error(NCL_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", sz, cudaGetErrorString(e)); return nullptr; }
+  g_hsize[p] = sz;
   return p;
 }
-int ncl_host_free(void* p) { if (p) cudaFreeHost(p); return NCL_OK; }
+int ncl_host_free(void* p) {
+  LOCK;
+  if (!p) return NCL_OK;
+  auto it = g_hsize.find(p);
+  if (it == g_hsize.end()) { cudaFreeHost(p); return NCL_OK; }
+  const size_t sz = it->second;
+  // a copy into or out of the block may still be in flight on the library's streams only if the caller freed it before the
+  // call returned, which the ABI forbids; the block can be handed out again at once
+  if (g_ctx.inited && pool_enabled() && g_hpool_bytes + sz <= hpool_cap()) { g_hpool.emplace(sz, p); g_hpool_bytes += sz; return NCL_OK; }
+  g_hsize.erase(it); cudaFreeHost(p); return NCL_OK;
+}
 int ncl_host_register(void* base, size_t bytes, unsigned flags) {
   LOCK; NEED_INIT;
   if (!base || !bytes) return set_error(NCL_ERR_INVALID, "ncl_host_register: NULL base or zero size");
@@ -370,11 +406,22 @@ struct Stager {
     const size_t bits = (size_t)g_dt[t->dtype].slot_bits, b0 = (size_t)t->elem_offset * bits, b1 = ((size_t)t->elem_offset + (size_t)total_elems(t)) * bits;
     *lo = b0 / 8; *hi = (b1 + 7) / 8; *ragged = (b0 % 8) != 0 || (b1 % 8) != 0;
   }
-  int upload(bool outputs_too) {
-    if (items.empty()) return NCL_OK;
+  bool prepared = false, uploaded = false, downloaded = false, outputs_too = false;
+  // arena addresses are fixed before anything is copied, so that the nest can be built first and the copies can then be
+  // issued either all at once (upload) or panel by panel under the kernels (try_pipeline)
+  int prepare(bool outputs_too_) {
+    outputs_too = outputs_too_;
+    if (prepared || items.empty()) { prepared = true; return NCL_OK; }
     if (g_ctx.capturing) return set_error(NCL_ERR_STATE, "host-resident tensors cannot be staged inside ncl_capture_begin/end");
     if (used) NCL_TRY(ensure_scratch2(used));
     size_t off = 0;
+    for (auto& it : items) if (!it.res) { it.dev = (char*)g_ctx.scratch2 + off; off += it.bytes; }
+    prepared = true; return NCL_OK;
+  }
+  int upload() {
+    if (uploaded) return NCL_OK;
+    uploaded = true;
+    if (items.empty()) return NCL_OK;
     for (auto& it : items) {
       if (it.res) {                                                  // resident mirror: upload only when the host copy is newer
         if (it.res->state == RES_HOST_NEWER) {
@@ -383,7 +430,6 @@ struct Stager {
         }
         continue;
       }
-      it.dev = (char*)g_ctx.scratch2 + off; off += it.bytes;
       size_t live = ncl_storage_bytes(it.t->dtype, it.t->elem_offset + total_elems(it.t));
       if (!it.is_out || outputs_too) {
         NCL_CUDA(cudaMemcpyAsync(it.dev, it.t->host, live, cudaMemcpyHostToDevice, g_ctx.stream));
@@ -398,10 +444,22 @@ struct Stager {
     }
     return NCL_OK;
   }
+  int try_pipeline(Nest& nest);
+  // the nest is built; copy what it reads, run it -- in panels of its outermost kept loop when that pays (try_pipeline)
+  int run(Nest& nest) {
+    if (!uploaded) {
+      int rc = try_pipeline(nest);
+      if (rc != NCL_ERR_UNSUPPORTED) return rc;
+      NCL_TRY(upload());
+    }
+    return run_nest(nest);
+  }
   char* dev_of(const ncl_tensor* t) { for (auto& it : items) if (it.t == t) return it.dev; return nullptr; }
+  int index_of(const ncl_tensor* t) { for (size_t i = 0; i < items.size(); i++) if (items[i].t == t) return (int)i; return -1; }
   // Only the bytes of the tensor's own window travel back: the arena in front of a displaced view (elem_offset > 0) and the
   // padding behind it were never initialised when the output was not uploaded, and must not overwrite the host base vector.
   int download() {
+    if (downloaded) return NCL_OK;
     bool any = false;
     for (auto& it : items) if (it.is_out) {
       if (it.res && (it.res->flags & NCL_RESIDENT_LAZY)) { it.res->state = RES_DEVICE_NEWER; continue; }     // stays on the device until ncl_host_fetch
@@ -415,15 +473,167 @@ struct Stager {
 
 static void operand_from(const ncl_tensor* t, Stager& st, Operand* o) {
   memset(o, 0, sizeof *o);
-  o->dtype = t->dtype; o->offset = t->elem_offset;
+  o->dtype = t->dtype; o->offset = t->elem_offset; o->stage_item = -1;
   if (t->buf) { o->base = (char*)t->buf->ptr; o->n_storage = (int64_t)((t->buf->bytes * 8) / g_dt[t->dtype].slot_bits); }
   else {
-    o->base = st.dev_of(t);
+    o->base = st.dev_of(t); o->stage_item = st.index_of(t);
     Resident* r = find_resident(t->host);
     o->n_storage = (int64_t)(((r ? r->bytes : Stager::need(t)) * 8) / g_dt[t->dtype].slot_bits);
   }
 }
 static void rowmajor_strides(const ncl_tensor* t, int64_t* s) { int64_t acc = 1; for (int i = t->rank - 1; i >= 0; i--) { s[i] = acc; acc *= t->dims[i]; } }
+
+// ---- panel pipeline of host-resident tensors ----------------------------------------------------------------------------
+// A call on host arrays used to be three phases in a row on one stream: copy in, kernels, copy out.  PCIe is full duplex and
+// the copy engines run beside the SMs, so the nest is cut into PANELS of its outermost kept loop -- rows of an elementwise
+// result or of a row-wise reduction, row panels of A and C in a matrix product, batches of a batched product: panel p goes up
+// on one copy stream while panel p-1 is computed and panel p-2 travels back on another.  Operands that do not move with the
+// loop (the row vector of C1, B of a matrix product) go up once, first.  Conditions: pinned host memory (pageable copies block
+// the host), byte-addressable element types, the loop is kept by every output (panels write disjoint elements) and is the
+// slowest-varying axis of every staged array (a panel is one contiguous byte range).  Everything else takes the plain path.
+static size_t panel_target_bytes() { static size_t v = 0; if (!v) { const char* e = getenv("NUMCL_PANEL_MB"); long mb = e ? atol(e) : 32; if (mb < 1) mb = 1; v = (size_t)mb << 20; } return v; }
+static bool pipeline_enabled() { static int on = -1; if (on < 0) { const char* e = getenv("NUMCL_NO_PIPELINE"); on = (e && atoi(e)) ? 0 : 1; } return on == 1; }
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+static int pipeline_event(int i, cudaEvent_t* ev) {
+  if (i >= g_ctx.n_events) {
+    int want = (i + 64) & ~63;
+    cudaEvent_t* ne = (cudaEvent_t*)realloc(g_ctx.events, (size_t)want * sizeof(cudaEvent_t));
+    if (!ne) return set_error(NCL_ERR_NOMEM, "event pool");
+    g_ctx.events = ne;
+    for (int k = g_ctx.n_events; k < want; k++) NCL_CUDA(cudaEventCreateWithFlags(&g_ctx.events[k], cudaEventDisableTiming));
+    g_ctx.n_events = want;
+  }
+  *ev = g_ctx.events[i]; return NCL_OK;
+}
+
+int Stager::try_pipeline(Nest& nest) {
+  if (items.empty() || !prepared || !pipeline_enabled() || g_ctx.capturing || g_ctx.force_generic || nest.nloops < 1) return NCL_ERR_UNSUPPORTED;
+  struct Mov { Operand* op; Item* it; bool is_out; int64_t span; size_t sb; bool up, down; };
+  Mov mv[2 * NCL_MAX_OPERANDS]; int nm = 0;
+  Operand* all[2 * NCL_MAX_OPERANDS]; int na = 0;
+  std::vector<char> seen(items.size(), 0);
+  for (int k = 0; k < nest.n_in + nest.n_out; k++) {
+    const bool is_out = k >= nest.n_in;
+    Operand* op = is_out ? &nest.out[k - nest.n_in] : &nest.in[k];
+    all[na++] = op;
+    if (op->stage_item < 0) continue;
+    if (op->stage_item >= (int)items.size() || seen[op->stage_item]) return NCL_ERR_UNSUPPORTED;
+    seen[op->stage_item] = 1;
+    Item* it = &items[op->stage_item];
+    if (it->is_out != is_out || g_dt[op->dtype].slot_bits < 8) return NCL_ERR_UNSUPPORTED;
+    bool up = it->res ? it->res->state == RES_HOST_NEWER && (!is_out || outputs_too) : (!is_out || outputs_too);
+    bool down = is_out && !(it->res && (it->res->flags & NCL_RESIDENT_LAZY));
+    mv[nm++] = Mov{op, it, is_out, 0, (size_t)g_dt[op->dtype].slot_bits / 8, up, down};
+  }
+  for (char c : seen) if (!c) return NCL_ERR_UNSUPPORTED;
+  // the loop to cut
+  int L = -1;
+  for (int l = 0; l < nest.nloops && L < 0; l++) {
+    if (nest.extent[l] < 2) continue;
+    bool ok = true;
+    for (int o = 0; o < nest.n_out && ok; o++) if (nest.out[o].stride[l] == 0) ok = false;
+    for (int m = 0; m < nm && ok; m++) {
+      const Operand& X = *mv[m].op; const int64_t s = X.stride[l];
+      if (s == 0) continue;                                        // an input that does not move with the loop: uploaded whole
+      if (s < 0) { ok = false; break; }
+      int64_t span = 0;
+      for (int k = 0; k < nest.nloops; k++) if (k != l) { if (X.stride[k] < 0) ok = false; span += (nest.extent[k] - 1) * X.stride[k]; }
+      if (span >= s) ok = false;
+      mv[m].span = span;
+    }
+    if (ok) L = l;
+  }
+  if (L < 0) return NCL_ERR_UNSUPPORTED;
+  for (int k = 0; k < nest.nloops; k++) if (nest.extent[k] <= 0) return NCL_ERR_UNSUPPORTED;
+  const int64_t E = nest.extent[L];
+  size_t row_bytes = 0, moved = 0, out_bytes = 0;
+  for (int m = 0; m < nm; m++) {
+    const int64_t s = mv[m].op->stride[L];
+    const size_t whole = s ? (size_t)s * mv[m].sb * (size_t)E : (size_t)(mv[m].span + 1) * mv[m].sb;
+    if (mv[m].up) { moved += whole; if (s) row_bytes += (size_t)s * mv[m].sb; }
+    if (mv[m].down) { moved += whole; out_bytes += whole; row_bytes += (size_t)s * mv[m].sb; }
+    if ((mv[m].up || mv[m].down) && !is_pinned(mv[m].it->t->host)) return NCL_ERR_UNSUPPORTED;
+  }
+  if (moved < ((size_t)8 << 20) || row_bytes == 0) return NCL_ERR_UNSUPPORTED;
+  // an output written back while an input that overlaps it on the host is still being read: not worth reasoning about
+  for (int a = 0; a < nm; a++) if (mv[a].down) for (int b = 0; b < nm; b++) if (!mv[b].is_out) {
+    size_t alo, ahi, blo, bhi; bool rg; window(mv[a].it->t, &alo, &ahi, &rg); window(mv[b].it->t, &blo, &bhi, &rg);
+    const char* A = (const char*)mv[a].it->t->host; const char* B = (const char*)mv[b].it->t->host;
+    if (A + alo < B + bhi && B + blo < A + ahi) return NCL_ERR_UNSUPPORTED;
+  }
+  bool contraction = false;
+  for (int l = 0; l < nest.nloops; l++) if (nest.extent[l] > 1) { bool red = true; for (int o = 0; o < nest.n_out; o++) if (nest.out[o].stride[l] != 0) red = false; if (red) contraction = true; }
+  // panel size: NUMCL_PANEL_MB (32 MiB: a copy of that size runs at the link rate and its fixed cost is below 1 %), but at least
+  // eight panels for arrays of a few tens of MiB; a contraction with a stationary operand re-reads it per panel, so it gets four
+  size_t target = panel_target_bytes();
+  if (moved / 8 < target) target = moved / 8 > ((size_t)4 << 20) ? moved / 8 : ((size_t)4 << 20);
+  bool stationary = false;                                         // e.g. B of (ij jk -> ik): re-packed / re-read by every panel product
+  for (int k = 0; k < nest.n_in; k++) if (nest.in[k].stride[L] == 0) stationary = true;
+  int64_t rows = contraction && stationary ? (E + 3) / 4 : (int64_t)(target / row_bytes);
+  if (rows < 1) rows = 1;
+  if ((E + rows - 1) / rows > 256) rows = (E + 255) / 256;
+  if (rows >= 256) rows &= ~(int64_t)255; else if (rows >= 8) rows &= ~(int64_t)7;
+  const int np = (int)((E + rows - 1) / rows);
+  if (np < 2) return NCL_ERR_UNSUPPORTED;
+
+  if (!g_ctx.copy_in) { NCL_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_in, cudaStreamNonBlocking)); NCL_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_out, cudaStreamNonBlocking)); }
+  const bool pipe_out = out_bytes >= ((size_t)1 << 20);           // small results travel back in one piece at the end (download)
+  cudaEvent_t ev;
+  NCL_TRY(pipeline_event(0, &ev));
+  NCL_CUDA(cudaEventRecord(ev, g_ctx.stream));                    // the arena / the mirrors may still be read by earlier kernels
+  NCL_CUDA(cudaStreamWaitEvent(g_ctx.copy_in, ev, 0));
+  if (pipe_out) NCL_CUDA(cudaStreamWaitEvent(g_ctx.copy_out, ev, 0));
+  uploaded = true;
+  auto full_hi = [&](const Mov& m) { return m.it->res ? m.it->res->bytes : ncl_storage_bytes(m.it->t->dtype, m.it->t->elem_offset + total_elems(m.it->t)); };
+  auto dev_base = [&](const Mov& m) { return m.it->res ? (char*)m.it->res->dev->ptr : m.it->dev; };
+  for (int m = 0; m < nm; m++) if (mv[m].up && mv[m].op->stride[L] == 0) {          // stationary operands, whole
+    const size_t n = full_hi(mv[m]);
+    NCL_CUDA(cudaMemcpyAsync(dev_base(mv[m]), mv[m].it->t->host, n, cudaMemcpyHostToDevice, g_ctx.copy_in)); g_ctx.h2d_bytes += n;
+  }
+  int rc = NCL_OK;
+  for (int p = 0; p < np && rc == NCL_OK; p++) {
+    const int64_t r0 = (int64_t)p * rows, r1 = r0 + rows < E ? r0 + rows : E;
+    for (int m = 0; m < nm; m++) if (mv[m].up && mv[m].op->stride[L] != 0) {
+      const Operand& X = *mv[m].op;
+      // the first panel also carries what lies in front of the window, the last what lies behind it (padding, the rest of a mirror)
+      const size_t lo = p == 0 ? 0 : (size_t)(X.offset + r0 * X.stride[L]) * mv[m].sb;
+      const size_t hi = p == np - 1 ? full_hi(mv[m]) : (size_t)(X.offset + r1 * X.stride[L]) * mv[m].sb;
+      if (hi > lo) { NCL_CUDA(cudaMemcpyAsync(dev_base(mv[m]) + lo, (const char*)mv[m].it->t->host + lo, hi - lo, cudaMemcpyHostToDevice, g_ctx.copy_in)); g_ctx.h2d_bytes += hi - lo; }
+    }
+    NCL_TRY(pipeline_event(1 + 2 * p, &ev));
+    NCL_CUDA(cudaEventRecord(ev, g_ctx.copy_in));
+    NCL_CUDA(cudaStreamWaitEvent(g_ctx.stream, ev, 0));
+    Nest* sub = new Nest(nest);
+    sub->extent[L] = r1 - r0;
+    for (int k = 0; k < sub->n_in; k++) sub->in[k].offset += r0 * sub->in[k].stride[L];
+    for (int k = 0; k < sub->n_out; k++) sub->out[k].offset += r0 * sub->out[k].stride[L];
+    rc = run_nest(*sub);
+    delete sub;
+    if (rc != NCL_OK || !pipe_out) continue;
+    NCL_TRY(pipeline_event(2 + 2 * p, &ev));
+    NCL_CUDA(cudaEventRecord(ev, g_ctx.stream));
+    NCL_CUDA(cudaStreamWaitEvent(g_ctx.copy_out, ev, 0));
+    for (int m = 0; m < nm; m++) if (mv[m].down) {
+      const Operand& X = *mv[m].op;
+      const size_t lo = (size_t)(X.offset + r0 * X.stride[L]) * mv[m].sb, hi = (size_t)(X.offset + (r1 - 1) * X.stride[L] + mv[m].span + 1) * mv[m].sb;
+      NCL_CUDA(cudaMemcpyAsync((char*)mv[m].it->t->host + lo, dev_base(mv[m]) + lo, hi - lo, cudaMemcpyDeviceToHost, g_ctx.copy_out)); g_ctx.d2h_bytes += hi - lo;
+    }
+  }
+  for (int m = 0; m < nm; m++) if (mv[m].it->res && mv[m].up) mv[m].it->res->state = RES_IN_SYNC;
+  g_ctx.pipelined_calls++; g_ctx.pipelined_panels += np;
+  if (rc != NCL_OK) { cudaStreamSynchronize(g_ctx.copy_in); cudaStreamSynchronize(g_ctx.copy_out); return rc; }
+  if (pipe_out) {
+    for (int m = 0; m < nm; m++) if (mv[m].is_out && !mv[m].down && mv[m].it->res) mv[m].it->res->state = RES_DEVICE_NEWER;
+    downloaded = true;
+    NCL_CUDA(cudaStreamSynchronize(g_ctx.copy_out));
+    return check_fault();
+  }
+  return NCL_OK;                                                   // download() brings the (small) results back and synchronises
+}
 
 // ---- einsum: shape-resolver + plan-broadcast + nest construction -----------------------------------
 static int64_t normalize_index(int64_t index, int64_t dim) {            // src/3einsum.lisp:274-278
@@ -598,8 +808,8 @@ static int broadcast_nest(const ncl_tensor* args, int n_args, ncl_tensor* r, Sta
 
 template <class F> static int with_staging(const ncl_tensor* in, int n_in, ncl_tensor* out, int n_out, bool upload_outputs, F body) {
   Stager st;
-  st.plan(in, n_in, false); st.plan(out, n_out, true);
-  NCL_TRY(st.upload(upload_outputs));
+  NCL_TRY(st.plan(in, n_in, false)); NCL_TRY(st.plan(out, n_out, true));
+  NCL_TRY(st.prepare(upload_outputs));
   NCL_TRY(body(st));
   return st.download();
 }
@@ -627,12 +837,13 @@ int ncl_einsum(const ncl_einsum_desc* desc, const ncl_tensor* in, int n_in, ncl_
           for (int k2 = k + 1; k2 < desc->out_rank[o]; k2++) if (desc->out_spec[o][k] >= 0 && desc->out_spec[o][k] == desc->out_spec[o][k2]) sparse = true;
       }
       if (sparse) {
+        rc = st.upload();                                          // boundary bytes of packed windows first, then the zeros
         for (int o = 0; o < desc->n_out && rc == NCL_OK; o++)
           rc = fill_const(nest->out[o].base, out[o].dtype, out[o].elem_offset, total_elems(&out[o]), false, 0, 0.0);
         nest->fresh = false;
       }
     }
-    if (rc == NCL_OK) rc = run_nest(*nest);
+    if (rc == NCL_OK) rc = st.run(*nest);
     delete nest; return rc;
   });
 }
@@ -659,7 +870,7 @@ int ncl_fold(int op, int use_identity, const ncl_tensor* args, int n, ncl_tensor
       int out_dt = r->dtype;
       rc = type_expr(&e, in_dt, n, &out_dt, 1, 0, &nest->transform[0]);
     }
-    if (rc == NCL_OK) rc = run_nest(*nest);
+    if (rc == NCL_OK) rc = st.run(*nest);
     delete nest; return rc;
   });
 }
@@ -686,7 +897,7 @@ int ncl_map(const ncl_expr* fn, const ncl_tensor* args, int n, ncl_tensor* r) {
     int out_dt = r->dtype;
     if (rc == NCL_OK) rc = type_expr(fn, in_dt, n, &out_dt, 1, 0, &nest->transform[0]);
     if (rc == NCL_OK && expr_reads_output(nest->transform[0])) rc = set_error(NCL_ERR_INVALID, "map function may not read @");
-    if (rc == NCL_OK) rc = run_nest(*nest);
+    if (rc == NCL_OK) rc = st.run(*nest);
     delete nest; return rc;
   });
 }
@@ -753,7 +964,7 @@ int ncl_reduce(int op, const ncl_tensor* a, const int* axes, int n_axes, ncl_ten
     ncl_expr e; e.n = 0; x_leaf(&e, NCL_X_OUTPUT, 1); x_leaf(&e, NCL_X_INPUT, 1); x_op(&e, op, 0, 1);   // (funcall fn r a)
     int in_dt = a->dtype, out_dt = r->dtype;
     int rc = type_expr(&e, &in_dt, 1, &out_dt, 1, 0, &nest->transform[0]);
-    if (rc == NCL_OK) rc = run_nest(*nest);
+    if (rc == NCL_OK) rc = st.run(*nest);
     delete nest; return rc;
   });
 }

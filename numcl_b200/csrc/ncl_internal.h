@@ -35,6 +35,7 @@ struct Operand {
   int64_t offset = 0;              // element offset of the nest origin
   int64_t stride[NCL_MAX_LOOPS];   // elements, per loop
   int64_t n_storage = 0;           // elements addressable in the base vector (bounds check)
+  int     stage_item = -1;         // host-resident tensor: index of its staging item (ncl_api.cu: Stager), else -1
 };
 
 struct Nest {
@@ -74,6 +75,10 @@ struct Context {
   unsigned int* fault = nullptr;        // sticky DOMAIN flag written by kernels (ncl_fn.cuh); checked at sync points when fault_possible
   bool fault_possible = false;
   void* pinned = nullptr; size_t pinned_bytes = 0;
+  // panel pipeline of host-resident tensors (ncl_api.cu: Stager::try_pipeline): copy streams and a grow-only event pool
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t* events = nullptr; int n_events = 0;
+  int64_t pipelined_calls = 0, pipelined_panels = 0;
 };
 Context& ctx();
 int  set_error(int code, const char* fmt, ...);
