@@ -77,6 +77,8 @@ typedef enum {
   NCL_SB64,
   NCL_F32,       /* single-float                     */
   NCL_F64,       /* double-float                     */
+  NCL_C64,       /* (complex single-float): 8-byte slots, real part first (src/1type.lisp:341-344: only float complexes exist) */
+  NCL_C128,      /* (complex double-float): 16-byte slots */
   NCL_DTYPE_COUNT
 } ncl_dtype;
 
@@ -104,6 +106,10 @@ typedef enum {
   NCL_OP_ASIN, NCL_OP_ACOS, NCL_OP_ATAN, NCL_OP_SINH, NCL_OP_COSH, NCL_OP_ASINH, NCL_OP_ACOSH, NCL_OP_ATANH,
   NCL_OP_LOG2,                                   /* %log2 = (log x 2), src/4numeric.lisp:514-516 */
   NCL_OP_ISQRT, NCL_OP_LOGCOUNT, NCL_OP_INTEGER_LENGTH,   /* integers only, exact */
+  /* complex numbers (src/4numeric.lisp:486-489; vdot conjugates its first argument, src/4linear-algebra2.lisp:54-59).
+   * Complex operands are accepted by + - * / and by neg abs square identity conjugate realpart imagpart; every other
+   * function of a complex value returns NCL_ERR_UNSUPPORTED. */
+  NCL_OP_CONJUGATE, NCL_OP_REALPART, NCL_OP_IMAGPART,
   /* leaves of an expression */
   NCL_X_INPUT = 64,  /* $a : element of input  number a (1-based)  */
   NCL_X_OUTPUT,      /* @a : element of output number a (1-based)  */

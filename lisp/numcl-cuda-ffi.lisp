@@ -33,7 +33,7 @@
 
 (cffi:defcenum ncl-dtype
   :bit :ub2 :ub4 :ub7 :ub8 :ub15 :ub16 :ub31 :ub32 :ub62 :ub63 :ub64
-  :sb8 :sb16 :sb32 :fixnum :sb64 :f32 :f64)
+  :sb8 :sb16 :sb32 :fixnum :sb64 :f32 :f64 :c64 :c128)
 
 (cffi:defcenum ncl-op
   (:add 0) :sub :mul :div :max :min :eq :ne :le :ge :lt :gt :logand :logior :logxor
@@ -41,6 +41,7 @@
   :floor :ceiling :round :truncate :mod :rem :expt
   (:neg 32) :abs :square :sqrt :lognot :identity :exp :log :sin :cos :tan :tanh :signum
   :asin :acos :atan :sinh :cosh :asinh :acosh :atanh :log2 :isqrt :logcount :integer-length
+  :conjugate :realpart :imagpart
   (:x-input 64) :x-output :x-const-int :x-const-f32 :x-const-f64)
 
 (defparameter *binary-ops*
@@ -57,7 +58,8 @@ compiler, cuda-broadcast and cuda-fold, so that the three dispatch points cannot
   '((abs . :abs) (%square . :square) (sqrt . :sqrt) (lognot . :lognot) (identity . :identity) (exp . :exp)
     (log . :log) (%logr . :log) (sin . :sin) (cos . :cos) (tan . :tan) (tanh . :tanh) (signum . :signum)
     (asin . :asin) (acos . :acos) (atan . :atan) (sinh . :sinh) (cosh . :cosh) (asinh . :asinh) (acosh . :acosh)
-    (atanh . :atanh) (%log2 . :log2) (isqrt . :isqrt) (logcount . :logcount) (integer-length . :integer-length))
+    (atanh . :atanh) (%log2 . :log2) (isqrt . :isqrt) (logcount . :logcount) (integer-length . :integer-length)
+    (conjugate . :conjugate) (realpart . :realpart) (imagpart . :imagpart))
   "The functions of define-simple-mapper (src/4numeric.lisp:466-519) -> ncl_op.")
 
 (defun binary-op (name)
@@ -149,6 +151,8 @@ backend would have signalled DIVISION-BY-ZERO or stored a complex number.  Repor
 packed bits, tagged fixnums, ...: nothing is converted on the way to the device)."
   (cond ((csubtypep element-type 'single-float) :f32)
         ((csubtypep element-type 'double-float) :f64)
+        ((csubtypep element-type '(complex single-float)) :c64)     ; pairs (real, imaginary): SBCL's own layout
+        ((csubtypep element-type '(complex double-float)) :c128)
         ((csubtypep element-type 'bit) :bit)
         ((csubtypep element-type '(unsigned-byte 2)) :ub2)
         ((csubtypep element-type '(unsigned-byte 4)) :ub4)

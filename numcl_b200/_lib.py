@@ -25,7 +25,7 @@ OPS = dict(ADD=0, SUB=1, MUL=2, DIV=3, MAX=4, MIN=5, EQ=6, NE=7, LE=8, GE=9, LT=
            NEG=32, ABS=33, SQUARE=34, SQRT=35, LOGNOT=36, IDENTITY=37, EXP=38, LOG=39, SIN=40, COS=41,
            TAN=42, TANH=43, SIGNUM=44,
            ASIN=45, ACOS=46, ATAN=47, SINH=48, COSH=49, ASINH=50, ACOSH=51, ATANH=52, LOG2=53, ISQRT=54, LOGCOUNT=55,
-           INTEGER_LENGTH=56,
+           INTEGER_LENGTH=56, CONJUGATE=57, REALPART=58, IMAGPART=59,
            X_INPUT=64, X_OUTPUT=65, X_CONST_INT=66, X_CONST_F32=67, X_CONST_F64=68)
 
 # every symbol include/numcl_cuda.h declares (tests/test_abi.py checks the .so exports them all)

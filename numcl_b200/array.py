@@ -199,6 +199,10 @@ def infer_asarray_type(values: np.ndarray) -> str:
         return "f32"
     if values.dtype == np.float64:
         return "f64"
+    if values.dtype == np.complex64:
+        return "c64"
+    if values.dtype == np.complex128:
+        return "c128"
     if values.dtype.kind in "iub":
         if values.size == 0:
             return "bit"
@@ -210,8 +214,10 @@ def asarray(values, type=None, where="device") -> NArray:
     if isinstance(values, NArray):
         return values
     v = np.asarray(values)
-    if v.dtype == np.float64 and not isinstance(values, np.ndarray) and type is None:
+    if v.dtype == np.float64 and not isinstance(values, (np.ndarray, np.generic)) and type is None:
         v = v.astype(np.float32)           # Lisp reads 1.0 as a single-float
+    if v.dtype == np.complex128 and not isinstance(values, (np.ndarray, np.generic)) and type is None:
+        v = v.astype(np.complex64)         # ... and #C(1.0 2.0) as a (complex single-float)
     if type is None:
         type = infer_asarray_type(v)
     a = NArray(v.shape, type, where=where)

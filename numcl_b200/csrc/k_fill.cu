@@ -149,6 +149,10 @@ static int launch_fill(FillParams& p) {
 }
 
 int fill_const(void* base, int dtype, int64_t offset, int64_t n, bool is_float, int64_t iv, double fv) {
+  if (cls_complex(g_dt[dtype].cls)) {                              // zeros of a complex type are zero words; other constants: ncl_fill builds a nest
+    if ((is_float && fv != 0.0) || (!is_float && iv != 0)) return set_error(NCL_ERR_UNSUPPORTED, "fill_const: non-zero complex constant");
+    return dtype == NCL_C64 ? fill_const(base, NCL_F64, offset, n, true, 0, 0.0) : fill_const(base, NCL_F64, 2 * offset, 2 * n, true, 0, 0.0);
+  }
   FillParams p; memset(&p, 0, sizeof p);
   p.base = (char*)base; p.offset = offset; p.n = n; p.st = dtype_store_spec(dtype);
   p.slot_bits = g_dt[dtype].slot_bits; p.cls = g_dt[dtype].cls;

@@ -32,6 +32,12 @@ __device__ __forceinline__ GV gv_f(float v) { GV g; g.i = __float_as_int(v); g.j
 __device__ __forceinline__ GV gv_d(double v) { GV g; g.i = __double_as_longlong(v); g.j = 0; return g; }
 __device__ __forceinline__ float gf(GV g) { return __int_as_float((int)g.i); }
 __device__ __forceinline__ double gd(GV g) { return __longlong_as_double(g.i); }
+// complex numbers: i = real part, j = imaginary part (float or double bits by class)
+__device__ __forceinline__ GV gv_cf(float re, float im) { GV g; g.i = __float_as_int(re); g.j = __float_as_int(im); return g; }
+__device__ __forceinline__ GV gv_cd(double re, double im) { GV g; g.i = __double_as_longlong(re); g.j = __double_as_longlong(im); return g; }
+__device__ __forceinline__ float gfi(GV g) { return __int_as_float((int)g.j); }
+__device__ __forceinline__ double gdi(GV g) { return __longlong_as_double(g.j); }
+__device__ __forceinline__ bool is_cx(int cls) { return cls == CLS_CF || cls == CLS_CD; }
 
 __device__ inline double ratio_to_f64(long long n, long long d) {
   // exact operands -> one correctly rounded division when both fit 53 bits; beyond that the
@@ -70,6 +76,16 @@ __device__ __forceinline__ GV gv_convert(GV g, int from, int to) {
 }
 // %coerce into the output's logical value (what a later @k read sees)
 __device__ inline GV coerce_out(GV v, int cls, const GenericParams& p) {
+  if (p.out_cls == CLS_CF) {                                           // (coerce x '(complex single-float))
+    if (cls == CLS_CF) return v;
+    if (cls == CLS_CD) return gv_cf(__double2float_rn(gd(v)), __double2float_rn(gdi(v)));
+    return gv_cf(gv_to_f32(v, cls), 0.0f);
+  }
+  if (p.out_cls == CLS_CD) {
+    if (cls == CLS_CD) return v;
+    if (cls == CLS_CF) return gv_cd((double)gf(v), (double)gfi(v));
+    return gv_cd(gv_to_f64(v, cls), 0.0);
+  }
   if (p.out_cls == CLS_F) return gv_f(gv_to_f32(v, cls));
   if (p.out_cls == CLS_D) return gv_d(gv_to_f64(v, cls));
   long long x = gv_round(v, cls);
@@ -80,11 +96,58 @@ __device__ inline GV coerce_out(GV v, int cls, const GenericParams& p) {
   return gv_i(x);
 }
 
+
+// ---- complex arithmetic as SBCL's number dispatch does it (src/code/numbers.lisp [SBCL, unverified]): every float operation
+// rounded on its own; complex o complex: + - componentwise, * = (ac - bd, ad + bc), / = Smith's scaling by the larger part of
+// the divisor; real o complex touches only the parts the real takes part in ((+ x #C(a b)) = #C((+ x a) b), (* x #C(a b)) =
+// #C((* x a) (* x b)), (/ #C(a b) x) = #C((/ a x) (/ b x))); real / complex goes through the general quotient.
+template <class T> struct CxOps;
+template <> struct CxOps<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); } static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); } static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <> struct CxOps<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); } static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); } static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+template <class T> __device__ inline void cx_binary(int op, bool acx, T ar, T ai, bool bcx, T br, T bi, T* rr, T* ri) {
+  typedef CxOps<T> O;
+  switch (op) {
+    case NCL_OP_ADD: *rr = O::add(ar, br); *ri = acx && bcx ? O::add(ai, bi) : (acx ? ai : bi); return;
+    case NCL_OP_SUB: *rr = O::sub(ar, br); *ri = acx && bcx ? O::sub(ai, bi) : (acx ? ai : -bi); return;
+    case NCL_OP_MUL:
+      if (acx && bcx) { *rr = O::sub(O::mul(ar, br), O::mul(ai, bi)); *ri = O::add(O::mul(ar, bi), O::mul(ai, br)); }
+      else if (acx) { *rr = O::mul(ar, br); *ri = O::mul(ai, br); }
+      else { *rr = O::mul(ar, br); *ri = O::mul(ar, bi); }
+      return;
+    default:                                                          // NCL_OP_DIV
+      if (!bcx) { *rr = O::div(ar, br); *ri = O::div(ai, br); return; }
+      if (!acx) ai = (T)0;
+      if (fabs((double)br) > fabs((double)bi)) {
+        const T r = O::div(bi, br), dn = O::add(br, O::mul(r, bi));
+        *rr = O::div(O::add(ar, O::mul(ai, r)), dn); *ri = O::div(O::sub(ai, O::mul(ar, r)), dn);
+      } else {
+        const T r = O::div(br, bi), dn = O::add(bi, O::mul(r, br));
+        *rr = O::div(O::add(O::mul(ar, r), ai), dn); *ri = O::div(O::sub(O::mul(ai, r), ar), dn);
+      }
+  }
+}
+
 __device__ inline GV eval_node(const GNode& nd, const GV* val, const GNode* nodes, unsigned int* flt) {
   int op = nd.op;
   if (op < NCL_OP_BINARY_END) {
     int ca = nodes[nd.a].cls, cb = nodes[nd.b].cls;
     GV a = val[nd.a], b = val[nd.b];
+    if (is_cx(ca) || is_cx(cb)) {                                        // the host typer admits + - * / only
+      const bool acx = is_cx(ca), bcx = is_cx(cb);
+      if (nd.cls == CLS_CD) {
+        const double ar = acx ? (ca == CLS_CD ? gd(a) : (double)gf(a)) : gv_to_f64(a, ca), ai = acx ? (ca == CLS_CD ? gdi(a) : (double)gfi(a)) : 0.0;
+        const double br = bcx ? (cb == CLS_CD ? gd(b) : (double)gf(b)) : gv_to_f64(b, cb), bi = bcx ? (cb == CLS_CD ? gdi(b) : (double)gfi(b)) : 0.0;
+        double rr, ri; cx_binary<double>(op, acx, ar, ai, bcx, br, bi, &rr, &ri); return gv_cd(rr, ri);
+      }
+      const float ar = acx ? gf(a) : gv_to_f32(a, ca), ai = acx ? gfi(a) : 0.0f, br = bcx ? gf(b) : gv_to_f32(b, cb), bi = bcx ? gfi(b) : 0.0f;
+      float rr, ri; cx_binary<float>(op, acx, ar, ai, bcx, br, bi, &rr, &ri); return gv_cf(rr, ri);
+    }
     // comparisons between an integer and a float are exact in Common Lisp (CLHS 12.1.4.1), not after contagion
     if (op >= NCL_OP_EQ && op <= NCL_OP_GT && ((ca == CLS_I) != (cb == CLS_I)) && ca != CLS_R && cb != CLS_R) {
       int c;
@@ -162,7 +225,33 @@ __device__ inline GV eval_node(const GNode& nd, const GV* val, const GNode* node
   }
   // unary
   int ca = nodes[nd.a].cls; GV a = val[nd.a];
+  if (is_cx(ca)) {
+    if (ca == CLS_CF) {
+      const float re = gf(a), im = gfi(a);
+      switch (op) {
+        case NCL_OP_NEG: return gv_cf(-re, -im);
+        case NCL_OP_CONJUGATE: return gv_cf(re, -im);
+        case NCL_OP_REALPART: return gv_f(re);
+        case NCL_OP_IMAGPART: return gv_f(im);
+        case NCL_OP_ABS: return gv_f(hypotf(re, im));                       // %hypot: tolerance only
+        case NCL_OP_SQUARE: { float rr, ri; cx_binary<float>(NCL_OP_MUL, true, re, im, true, re, im, &rr, &ri); return gv_cf(rr, ri); }
+        default: return a;
+      }
+    }
+    const double re = gd(a), im = gdi(a);
+    switch (op) {
+      case NCL_OP_NEG: return gv_cd(-re, -im);
+      case NCL_OP_CONJUGATE: return gv_cd(re, -im);
+      case NCL_OP_REALPART: return gv_d(re);
+      case NCL_OP_IMAGPART: return gv_d(im);
+      case NCL_OP_ABS: return gv_d(hypot(re, im));
+      case NCL_OP_SQUARE: { double rr, ri; cx_binary<double>(NCL_OP_MUL, true, re, im, true, re, im, &rr, &ri); return gv_cd(rr, ri); }
+      default: return a;
+    }
+  }
   switch (op) {
+    case NCL_OP_CONJUGATE: case NCL_OP_REALPART: return a;               // of a real: the number itself
+    case NCL_OP_IMAGPART: return ca == CLS_I ? gv_i(0) : ca == CLS_F ? gv_f(__fmul_rn(0.0f, gf(a))) : gv_d(__dmul_rn(0.0, gd(a)));   // (imagpart x) = (* 0 x)
     case NCL_OP_IDENTITY: return a;
     case NCL_OP_LOGNOT: return gv_i(~a.i);
     case NCL_OP_ISQRT: return gv_i(int_isqrt(a.i, flt));
@@ -193,6 +282,8 @@ __device__ inline GV eval_node(const GNode& nd, const GV* val, const GNode* node
 }
 
 __device__ inline GV load_gv(const char* base, long long idx, int lk, int cls) {
+  if (cls == CLS_CF) { const float2 v = *reinterpret_cast<const float2*>(base + idx * 8); return gv_cf(v.x, v.y); }
+  if (cls == CLS_CD) { const double2 v = *reinterpret_cast<const double2*>(base + idx * 16); return gv_cd(v.x, v.y); }
   if (cls == CLS_F) return gv_f(load_scalar<float>(base, idx, lk));
   if (cls == CLS_D) return gv_d(load_scalar<double>(base, idx, lk));
   return gv_i(load_scalar<long long>(base, idx, lk));
@@ -212,6 +303,8 @@ __global__ void __launch_bounds__(128) generic_nest_kernel(const __grid_constant
   }
   GV acc;
   if (!p.fresh) acc = load_gv(p.base[0], pos[0], p.lk[0], p.out_cls);
+  else if (p.out_cls == CLS_CF) acc = gv_cf(p.has_identity ? (float)p.ident_f : 0.0f, 0.0f);
+  else if (p.out_cls == CLS_CD) acc = gv_cd(p.has_identity ? p.ident_f : 0.0, 0.0);
   else if (p.has_identity) acc = (p.out_cls == CLS_I) ? gv_i(p.ident_i) : (p.out_cls == CLS_F) ? gv_f((float)p.ident_f) : gv_d(p.ident_f);
   else acc = (p.out_cls == CLS_I) ? gv_i(0) : (p.out_cls == CLS_F) ? gv_f(0.0f) : gv_d(0.0);
 
@@ -244,7 +337,9 @@ __global__ void __launch_bounds__(128) generic_nest_kernel(const __grid_constant
     }
   }
   ncl_fault_flush(p.fault, flt_local);
-  if (p.out_cls == CLS_F) store_scalar<float>(p.base[0], p.off[0] + (pos[0] - p.off[0]), p.st, gf(acc));
+  if (p.out_cls == CLS_CF) *reinterpret_cast<float2*>(p.base[0] + pos[0] * 8) = make_float2(gf(acc), gfi(acc));
+  else if (p.out_cls == CLS_CD) *reinterpret_cast<double2*>(p.base[0] + pos[0] * 16) = make_double2(gd(acc), gdi(acc));
+  else if (p.out_cls == CLS_F) store_scalar<float>(p.base[0], p.off[0] + (pos[0] - p.off[0]), p.st, gf(acc));
   else if (p.out_cls == CLS_D) store_scalar<double>(p.base[0], pos[0], p.st, gd(acc));
   else store_scalar<long long>(p.base[0], pos[0], p.st, acc.i);
 }

@@ -84,7 +84,7 @@ int ensure_scratch3(size_t bytes) { return grow(&g_ctx.scratch3, &g_ctx.scratch3
 void reduce_identity(int op, int dtype, long long* ident_i, double* ident_f) {
   const DtInfo& d = g_dt[dtype];
   *ident_i = op == NCL_OP_MUL ? 1 : 0; *ident_f = op == NCL_OP_MUL ? 1.0 : 0.0;
-  if (op != NCL_OP_MAX && op != NCL_OP_MIN) return;
+  if ((op != NCL_OP_MAX && op != NCL_OP_MIN) || cls_complex(d.cls)) return;      // complex numbers are not ordered: the typer refuses max / min
   const bool mx = op == NCL_OP_MAX;
   if (d.cls == CLS_F) *ident_f = mx ? -3.4028234663852886e38 : 3.4028234663852886e38;
   else if (d.cls == CLS_D) *ident_f = mx ? -1.7976931348623157e308 : 1.7976931348623157e308;
@@ -1049,11 +1049,22 @@ int ncl_reduce_stat(int stat, const ncl_tensor* a, const int* axes, int n_axes, 
 int ncl_fill(ncl_tensor* t, int value_is_float, int64_t ival, double fval) {
   LOCK; NEED_INIT; NCL_TRY(check_tensor(t, "tensor"));
   if (!t->buf) return set_error(NCL_ERR_UNSUPPORTED, "ncl_fill works on device-resident tensors");
+  if (cls_complex(g_dt[t->dtype].cls)) {                          // #C(value 0): a one-loop nest whose transform is the constant
+    Nest* nest = new Nest; Stager st;
+    nest->nloops = 1; nest->extent[0] = total_elems(t); nest->n_in = 0; nest->n_out = 1; nest->fresh = true;
+    operand_from(t, st, &nest->out[0]); nest->out[0].stride[0] = 1;
+    Expr& e = nest->transform[0]; e.n = 1; memset(&e.node[0], 0, sizeof e.node[0]);
+    e.node[0].op = value_is_float ? NCL_X_CONST_F64 : NCL_X_CONST_INT; e.node[0].cls = value_is_float ? CLS_D : CLS_I; e.node[0].ival = ival; e.node[0].fval = fval;
+    int rc = nest->extent[0] > 0 ? run_nest(*nest) : NCL_OK;
+    delete nest; return rc;
+  }
   return fill_const(t->buf->ptr, t->dtype, t->elem_offset, total_elems(t), value_is_float != 0, ival, fval);
 }
 int ncl_fill_random_at(ncl_tensor* t, uint64_t seed, uint64_t first_index, int dist, double lo, double hi) {
   LOCK; NEED_INIT; NCL_TRY(check_tensor(t, "tensor"));
   if (!t->buf) return set_error(NCL_ERR_UNSUPPORTED, "ncl_fill_random works on device-resident tensors");
+  if (cls_complex(g_dt[t->dtype].cls))                            // real and imaginary parts: the stream of a float array twice as long
+    return fill_random(t->buf->ptr, t->dtype == NCL_C64 ? NCL_F32 : NCL_F64, 2 * t->elem_offset, 2 * total_elems(t), seed, 2 * first_index, dist, lo, hi);
   return fill_random(t->buf->ptr, t->dtype, t->elem_offset, total_elems(t), seed, first_index, dist, lo, hi);
 }
 int ncl_fill_random(ncl_tensor* t, uint64_t seed, int dist, double lo, double hi) { return ncl_fill_random_at(t, seed, 0, dist, lo, hi); }

@@ -17,7 +17,8 @@
 #define NCL_MAX_ARR   9           // arrays in one nest: outputs + inputs
 
 // ---- value classes: the three machine representations a Lisp real takes inside a kernel -------
-enum NclCls { CLS_I = 0, CLS_F = 1, CLS_D = 2, CLS_R = 3 /* ratio: int/int before %coerce */ };
+enum NclCls { CLS_I = 0, CLS_F = 1, CLS_D = 2, CLS_R = 3 /* ratio: int/int before %coerce */, CLS_CF = 4 /* complex single */, CLS_CD = 5 /* complex double */ };
+inline bool cls_complex(int c) { return c == CLS_CF || c == CLS_CD; }
 
 struct DtInfo { int slot_bits, value_bits, is_signed, tagged, cls; const char* name; };
 extern const DtInfo g_dt[NCL_DTYPE_COUNT];

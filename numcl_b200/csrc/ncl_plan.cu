@@ -13,6 +13,7 @@ const DtInfo g_dt[NCL_DTYPE_COUNT] = {
   {8, 8, 1, 0, CLS_I, "sb8"},   {16, 16, 1, 0, CLS_I, "sb16"}, {32, 32, 1, 0, CLS_I, "sb32"},
   {64, 63, 1, 1, CLS_I, "fixnum"}, {64, 64, 1, 0, CLS_I, "sb64"},
   {32, 0, 1, 0, CLS_F, "f32"},  {64, 0, 1, 0, CLS_D, "f64"},
+  {64, 0, 1, 0, CLS_CF, "c64"}, {128, 0, 1, 0, CLS_CD, "c128"},
 };
 
 // ---- PDL tracker (ncl_internal.h) ----------------------------------------------------------------------------
@@ -47,6 +48,10 @@ int pdl_launch(const void* kfn, dim3 grid, dim3 block, void** args, cudaStream_t
 
 // ---- expression typing: Common Lisp contagion, decided once on the host ----------------------------
 static int contagion(int a, int b) {
+  if (cls_complex(a) || cls_complex(b)) {                       // float-contagion, src/1type.lisp:446-451: (complex <contagion of the parts>)
+    if (a == CLS_R || b == CLS_R) return CLS_R;
+    return (a == CLS_CD || b == CLS_CD || a == CLS_D || b == CLS_D) ? CLS_CD : CLS_CF;
+  }
   if (a == CLS_D || b == CLS_D) return CLS_D;
   if (a == CLS_F || b == CLS_F) return CLS_F;
   if (a == CLS_R || b == CLS_R) return CLS_R;
@@ -95,6 +100,8 @@ int type_expr(const ncl_expr* src, const int* in_dtype, int n_in, const int* out
           tainted = tainted || u64[s.b];
           int cc = contagion(ca, cb);
           if (cc == CLS_R) return set_error(NCL_ERR_UNSUPPORTED, "arithmetic on an unreduced integer ratio is outside the CUDA whitelist");
+          if (cls_complex(cc) && !(s.op == NCL_OP_ADD || s.op == NCL_OP_SUB || s.op == NCL_OP_MUL || s.op == NCL_OP_DIV))
+            return set_error(NCL_ERR_UNSUPPORTED, "function code %d of a complex number is outside the CUDA whitelist (+ - * / only)", s.op);
           if (s.op >= NCL_OP_LOGAND && s.op <= NCL_OP_LOGORC2) { if (ca != CLS_I || cb != CLS_I) return set_error(NCL_ERR_INVALID, "bitwise function on non-integers"); x.cls = CLS_I; }
           else if (s.op >= NCL_OP_EQ && s.op <= NCL_OP_GT) x.cls = CLS_I;
           else if (s.op >= NCL_OP_FLOOR && s.op <= NCL_OP_TRUNCATE) x.cls = CLS_I;           // the integer quotient
@@ -103,10 +110,19 @@ int type_expr(const ncl_expr* src, const int* in_dtype, int n_in, const int* out
           else if (s.op == NCL_OP_DIV && cc == CLS_I) x.cls = CLS_R;
           else x.cls = cc;
         } else {
+          if (cls_complex(ca) && !(s.op == NCL_OP_NEG || s.op == NCL_OP_ABS || s.op == NCL_OP_SQUARE || s.op == NCL_OP_IDENTITY ||
+                                   s.op == NCL_OP_CONJUGATE || s.op == NCL_OP_REALPART || s.op == NCL_OP_IMAGPART))
+            return set_error(NCL_ERR_UNSUPPORTED, "function code %d of a complex number is outside the CUDA whitelist", s.op);
           switch (s.op) {
+            case NCL_OP_CONJUGATE:                                   // the identity on reals
+              if (ca == CLS_R) return set_error(NCL_ERR_UNSUPPORTED, "function of an integer ratio");
+              x.cls = ca; break;
+            case NCL_OP_REALPART: case NCL_OP_IMAGPART:              // complex-part-inferer, src/2typeinfer.lisp:283-296: the part's type
+              if (ca == CLS_R) return set_error(NCL_ERR_UNSUPPORTED, "function of an integer ratio");
+              x.cls = ca == CLS_CF ? CLS_F : ca == CLS_CD ? CLS_D : ca; break;
             case NCL_OP_NEG: case NCL_OP_ABS: case NCL_OP_SQUARE: case NCL_OP_SIGNUM: case NCL_OP_IDENTITY:
               if (ca == CLS_R && s.op != NCL_OP_IDENTITY) return set_error(NCL_ERR_UNSUPPORTED, "function of an integer ratio");
-              x.cls = ca; break;
+              x.cls = (s.op == NCL_OP_ABS && cls_complex(ca)) ? (ca == CLS_CF ? CLS_F : CLS_D) : ca; break;
             case NCL_OP_LOGNOT: case NCL_OP_ISQRT: case NCL_OP_LOGCOUNT: case NCL_OP_INTEGER_LENGTH:
               if (ca != CLS_I) return set_error(NCL_ERR_INVALID, "integer function of a non-integer"); x.cls = CLS_I; break;
             case NCL_OP_SQRT: case NCL_OP_EXP: case NCL_OP_LOG: case NCL_OP_SIN: case NCL_OP_COS: case NCL_OP_TAN: case NCL_OP_TANH:
@@ -126,6 +142,8 @@ int type_expr(const ncl_expr* src, const int* in_dtype, int n_in, const int* out
       }
     }
   }
+  if (self_out >= 0 && self_out < n_out && cls_complex(dst->node[src->n - 1].cls) && !cls_complex(g_dt[out_dtype[self_out]].cls))
+    return set_error(NCL_ERR_INVALID, "a complex value cannot be stored into a %s array", g_dt[out_dtype[self_out]].name);
   if (u64[src->n - 1] && self_out >= 0 && self_out < n_out && g_dt[out_dtype[self_out]].cls != CLS_I)
     return set_error(NCL_ERR_UNSUPPORTED, "an (unsigned-byte 64) value is stored into a float array: values >= 2^63 do not fit the signed 64-bit lanes");
   return NCL_OK;
@@ -150,9 +168,50 @@ static int check_bounds(const Operand& a, const Nest& n, const char* what, int i
   return NCL_OK;
 }
 
+// ---- complex element types -------------------------------------------------------------------------------------------
+// A (complex single-float) array is pairs (real, imaginary) of floats.  Wherever every array of a nest is complex of ONE
+// precision and the transforms only add, subtract, negate or copy -- array + array, array - array, (numcl:sum a :axes ..),
+// transposes and copies -- real and imaginary parts never meet: the nest is the same nest over float arrays with one more
+// innermost loop of extent 2, and runs on the real kernel families at their speed.  Anything that multiplies, divides,
+// conjugates or mixes in a real operand or a constant (the real takes part in ONE component only) stays a complex nest and
+// runs on the generic kernel, which carries complex values.
+static bool lower_complex(Nest& n) {
+  int prec = -1;
+  for (int k = 0; k < n.n_in + n.n_out; k++) {
+    const Operand& a = k < n.n_in ? n.in[k] : n.out[k - n.n_in];
+    const int c = g_dt[a.dtype].cls;
+    if (!cls_complex(c) || (prec >= 0 && c != prec)) return false;
+    prec = c;
+  }
+  if (prec < 0 || n.nloops >= NCL_MAX_LOOPS || n.stat) return false;
+  for (int o = 0; o < n.n_out; o++)
+    for (int k = 0; k < n.transform[o].n; k++) {
+      const int op = n.transform[o].node[k].op;
+      if (!(op == NCL_X_INPUT || op == NCL_X_OUTPUT || op == NCL_OP_ADD || op == NCL_OP_SUB || op == NCL_OP_NEG || op == NCL_OP_IDENTITY)) return false;
+    }
+  if (n.has_identity && (n.ident_f != 0.0 || n.ident_i != 0)) return false;
+  const int real_dt = prec == CLS_CF ? NCL_F32 : NCL_F64, real_cls = prec == CLS_CF ? CLS_F : CLS_D;
+  const int L = n.nloops++;
+  n.extent[L] = 2;
+  for (int k = 0; k < n.n_in + n.n_out; k++) {
+    Operand& a = k < n.n_in ? n.in[k] : n.out[k - n.n_in];
+    a.dtype = real_dt; a.offset *= 2; a.n_storage *= 2;
+    for (int l = 0; l < L; l++) a.stride[l] *= 2;
+    a.stride[L] = 1;
+  }
+  for (int o = 0; o < n.n_out; o++) for (int k = 0; k < n.transform[o].n; k++) n.transform[o].node[k].cls = real_cls;
+  return true;
+}
+
 int run_nest(Nest& n) {
   for (int i = 0; i < n.n_in; i++) NCL_TRY(check_bounds(n.in[i], n, "input", i));
   for (int o = 0; o < n.n_out; o++) NCL_TRY(check_bounds(n.out[o], n, "output", o));
+  bool any_complex = false;
+  for (int k = 0; k < n.n_in + n.n_out; k++) if (cls_complex(g_dt[(k < n.n_in ? n.in[k] : n.out[k - n.n_in]).dtype].cls)) any_complex = true;
+  if (any_complex && !(!ctx().force_generic && lower_complex(n))) {
+    if (n.stat) return NCL_ERR_UNSUPPORTED;
+    return launch_generic(n);
+  }
   bool empty = false;
   for (int l = 0; l < n.nloops; l++) if (n.extent[l] == 0) empty = true;
   if (n.stat) {                                        // fused statistics: reduction kernels only (ncl_reduce_stat composes otherwise)

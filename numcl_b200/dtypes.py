@@ -23,7 +23,7 @@ class DType:
     value_bits: int     # %coerce wrap width (src/1type.lisp:673-694); 0 for floats
     signed: bool
     tagged: bool
-    kind: str           # "int" | "f32" | "f64"
+    kind: str           # "int" | "f32" | "f64" | "c64" | "c128"
 
     @property
     def lo(self):
@@ -51,11 +51,15 @@ for _i, (_n, _s, _v, _sg, _tg) in enumerate(_TABLE):
     DTYPES[_n] = DType(_n, _i, _s, _v, _sg, _tg, "int")
 DTYPES["f32"] = DType("f32", 17, 32, 0, True, False, "f32")
 DTYPES["f64"] = DType("f64", 18, 64, 0, True, False, "f64")
+# (complex single-float) / (complex double-float): pairs (real, imaginary); only float complexes exist as array element
+# types (src/1type.lisp:341-344)
+DTYPES["c64"] = DType("c64", 19, 64, 0, True, False, "c64")
+DTYPES["c128"] = DType("c128", 20, 128, 0, True, False, "c128")
 BY_CODE = {d.code: d for d in DTYPES.values()}
 
 # Lisp spellings accepted by the host mirror
 ALIASES = {
-    "single-float": "f32", "double-float": "f64", "float": "f32", "(unsigned-byte 8)": "ub8",
+    "single-float": "f32", "double-float": "f64", "float": "f32", "(complex single-float)": "c64", "(complex double-float)": "c128", "(unsigned-byte 8)": "ub8",
     "(unsigned-byte 1)": "bit", "(unsigned-byte 2)": "ub2", "(unsigned-byte 4)": "ub4",
     "(unsigned-byte 7)": "ub7", "(unsigned-byte 15)": "ub15", "(unsigned-byte 16)": "ub16",
     "(unsigned-byte 31)": "ub31", "(unsigned-byte 32)": "ub32", "(unsigned-byte 62)": "ub62",
@@ -111,6 +115,9 @@ def pack(values: np.ndarray, dt) -> np.ndarray:
     if dt.kind == "f64":
         out[: n * 8] = flat.astype(np.float64).view(np.uint8)
         return out
+    if dt.kind in ("c64", "c128"):
+        out[: n * dt.slot_bits // 8] = flat.astype(np.complex64 if dt.kind == "c64" else np.complex128).view(np.uint8)
+        return out
     if flat.dtype.kind == "f":
         flat = np.rint(flat)                    # (round x): half to even
     v = wrap(flat, dt)
@@ -139,6 +146,8 @@ def unpack(storage: np.ndarray, n: int, dt, offset: int = 0) -> np.ndarray:
         return storage[: (n + offset) * 4].view(np.float32)[offset:].copy()
     if dt.kind == "f64":
         return storage[: (n + offset) * 8].view(np.float64)[offset:].copy()
+    if dt.kind in ("c64", "c128"):
+        return storage[: (n + offset) * dt.slot_bits // 8].view(np.complex64 if dt.kind == "c64" else np.complex128)[offset:].copy()
     if dt.slot_bits < 8:
         per = 8 // dt.slot_bits
         idx = np.arange(offset, offset + n)

@@ -28,7 +28,7 @@ _UNARY = {"ABS": "ABS", "%SQUARE": "SQUARE", "SQUARE": "SQUARE", "SQRT": "SQRT",
           "TAN": "TAN", "TANH": "TANH", "SIGNUM": "SIGNUM",
           "ASIN": "ASIN", "ACOS": "ACOS", "ATAN": "ATAN", "SINH": "SINH", "COSH": "COSH", "ASINH": "ASINH", "ACOSH": "ACOSH",
           "ATANH": "ATANH", "%LOG2": "LOG2", "LOG2": "LOG2", "ISQRT": "ISQRT", "LOGCOUNT": "LOGCOUNT",
-          "INTEGER-LENGTH": "INTEGER_LENGTH"}
+          "INTEGER-LENGTH": "INTEGER_LENGTH", "CONJUGATE": "CONJUGATE", "REALPART": "REALPART", "IMAGPART": "IMAGPART"}
 
 
 class TransformError(NotImplementedError):

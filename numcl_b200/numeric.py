@@ -27,7 +27,7 @@ _OP = {"+": "ADD", "-": "SUB", "*": "MUL", "/": "DIV", "max": "MAX", "min": "MIN
 
 
 def _is_scalar(x):
-    return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, bool)
+    return isinstance(x, (int, float, complex, np.integer, np.floating, np.complexfloating)) and not isinstance(x, bool)
 
 
 def _scalar_op(fn, x, y):
@@ -62,6 +62,10 @@ def _as_array(x, like=None) -> NArray:
     if isinstance(x, NArray):
         return x
     where = like.where if like is not None else "device"
+    if isinstance(x, (complex, np.complexfloating)):
+        from .array import asarray
+        v = np.asarray(x)
+        return asarray(v.astype(np.complex64) if isinstance(x, complex) else v, where=where)
     return full((), x, type=ti.upgrade(ti.strict_type_of(x)), where=where)
 
 
@@ -241,7 +245,8 @@ def _simple_mapper(cl_fn):
                     "cos": math.cos, "tan": math.tan, "tanh": math.tanh, "abs": abs, "square": lambda v: v * v,
                     "asin": math.asin, "acos": math.acos, "atan": math.atan, "sinh": math.sinh, "cosh": math.cosh,
                     "asinh": math.asinh, "acosh": math.acosh, "atanh": math.atanh, "isqrt": math.isqrt,
-                    "lognot": lambda v: ~v, "signum": lambda v: (v > 0) - (v < 0)}[cl_fn](x)
+                    "lognot": lambda v: ~v, "signum": lambda v: (v > 0) - (v < 0),
+                    "conjugate": lambda v: v.conjugate(), "realpart": lambda v: v.real, "imagpart": lambda v: v.imag}[cl_fn](x)
         from .einsum import einsum
         t = ti.infer_type("%square" if cl_fn == "square" else cl_fn, ti.type_of_dtype(x.dtype))
         y = empty(x.shape, type=ti.upgrade(t), where=x.where)
@@ -259,6 +264,8 @@ sqrt, exp, log, sin, cos, tan, tanh, abs_, square = (_simple_mapper(n) for n in
 # mappers there produce T arrays: use map_array_into with a typed result for those two.
 asin, acos, atan, sinh, cosh, asinh, acosh, atanh, isqrt, lognot = (
     _simple_mapper(n) for n in ("asin", "acos", "atan", "sinh", "cosh", "asinh", "acosh", "atanh", "isqrt", "lognot"))
+# complex numbers, src/4numeric.lisp:486-489
+conjugate, realpart, imagpart = (_simple_mapper(n) for n in ("conjugate", "realpart", "imagpart"))
 logc = _simple_mapper("log")
 log = _simple_mapper("%logr")
 log2 = _simple_mapper("%log2")

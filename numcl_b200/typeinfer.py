@@ -23,6 +23,17 @@ MOST_NEGATIVE_FIXNUM = -(1 << 62)
 DEFAULT_FLOAT = "single-float"           # +numcl-default-float-format+, src/1constants.lisp:23-25
 
 _RANK = {"integer": 0, "single-float": 1, "double-float": 2}
+# complex element types: the head is "complex-<part>", bounds are always None.  Only (complex *-float) arrays exist
+# (src/1type.lisp:341-344); contagion works on the part types (src/1type.lisp:446-451).
+COMPLEX_PREFIX = "complex-"
+
+
+def is_complex(head) -> bool:
+    return isinstance(head, str) and head.startswith(COMPLEX_PREFIX)
+
+
+def complex_part(head) -> str:
+    return head[len(COMPLEX_PREFIX):] if is_complex(head) else head
 
 
 class TypeInferenceError(TypeError):
@@ -36,6 +47,10 @@ def type_of_dtype(dt) -> tuple:
         return ("single-float", None, None)
     if dt.kind == "f64":
         return ("double-float", None, None)
+    if dt.kind == "c64":
+        return (COMPLEX_PREFIX + "single-float", None, None)
+    if dt.kind == "c128":
+        return (COMPLEX_PREFIX + "double-float", None, None)
     return ("integer", dt.lo, dt.hi)
 
 
@@ -55,6 +70,14 @@ def strict_type_of(x) -> tuple:
         pass
     if isinstance(x, float):
         return ("single-float", x, x)    # the reader's default float format
+    if isinstance(x, complex):
+        return (COMPLEX_PREFIX + "single-float", None, None)
+    try:
+        import numpy as np
+        if isinstance(x, np.complexfloating):
+            return (COMPLEX_PREFIX + ("double-float" if x.dtype == np.complex128 else "single-float"), None, None)
+    except ImportError:  # pragma: no cover
+        pass
     raise TypeInferenceError(f"unsupported scalar {x!r}")
 
 
@@ -70,6 +93,8 @@ def upgrade(t) -> str:
         return "f32"
     if head == "double-float":
         return "f64"
+    if is_complex(head):
+        return "c128" if complex_part(head) == "double-float" else "c64"
     if head != "integer":
         raise TypeInferenceError(f"no specialized array for {t}")
     if lo is None or hi is None:
@@ -142,6 +167,10 @@ def float_substitution(t, int_result="integer"):
 
 def float_contagion(t1, t2, int_int_result="integer"):
     a, b = float_substitution(t1), float_substitution(t2)
+    if is_complex(a) or is_complex(b):                  # (complex <contagion of the parts>); an integer part becomes a float
+        pa, pb = complex_part(a), complex_part(b)
+        part = pa if _RANK[pa] >= _RANK[pb] else pb
+        return COMPLEX_PREFIX + (DEFAULT_FLOAT if part == "integer" else part)
     if a == "integer" and b == "integer":
         return float_substitution((int_int_result, None, None))
     return a if _RANK[a] >= _RANK[b] else b
@@ -160,6 +189,11 @@ def infer_rational_arithmetic_result(interval_op, types, int_int_result="integer
     prev = types[0]
     for now in types[1:]:
         head = float_contagion(prev, now, int_int_result)
+        if is_complex(head):
+            if interval_op in (interval_max, interval_min):
+                raise TypeInferenceError("max / min of complex numbers")
+            prev = (head, None, None)
+            continue
         lo, hi = interval_op(prev[1], prev[2], now[1], now[2])
         if head == "integer":
             lo = MOST_NEGATIVE_FIXNUM if lo is None else max(lo, MOST_NEGATIVE_FIXNUM)
@@ -237,6 +271,8 @@ def _infer_div(first, *rest):            # src/2typeinfer.lisp:131-139
 
 def _infer_abs(t):
     head, lo, hi = t
+    if is_complex(head):
+        return (complex_part(head), 0.0, None)
     l, h = _lo(lo), _hi(hi)
     nl = 0 if l <= 0 <= h else min(abs(l), abs(h))
     nh = max(abs(l), abs(h))
@@ -246,7 +282,12 @@ def _infer_abs(t):
     return (head, nl, nh)
 
 
+def _infer_part(t):                       # complex-part-inferer, src/2typeinfer.lisp:283-296
+    return (complex_part(t[0]), None, None) if is_complex(t[0]) else t
+
+
 _INFERERS.update({
+    "conjugate": lambda t: t, "realpart": _infer_part, "imagpart": _infer_part,
     "-": _infer_sub, "/": _infer_div, "abs": _infer_abs,
     "%square": lambda t: _INFERERS["*"](t, t), "square": lambda t: _INFERERS["*"](t, t),
     "1+": lambda t: _INFERERS["+"](("integer", 1, 1), t),

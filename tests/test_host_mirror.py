@@ -98,7 +98,7 @@ def test_survey_dtype_table():
 
 
 # ---- storage formats ----------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", list(DTYPES))
+@pytest.mark.parametrize("name", [n for n in DTYPES if DTYPES[n].kind not in ("c64", "c128")])      # the C oracle has no complex types
 def test_pack_matches_oracle_storage(oracle, name):
     rng = np.random.default_rng(7)
     d = DTYPES[name]
@@ -113,6 +113,31 @@ def test_pack_matches_oracle_storage(oracle, name):
     assert np.array_equal(mine, theirs)
     back = unpack(mine, 37, name)
     assert np.array_equal(back, v.astype(back.dtype))
+
+
+def test_pack_of_complex_types_is_interleaved_parts():
+    """(complex single-float) / (complex double-float): pairs (real, imaginary), 8 / 16 bytes per element"""
+    v = np.array([1 + 2j, -0.5 + 0.25j, 3j])
+    for name, ft, ct in (("c64", np.float32, np.complex64), ("c128", np.float64, np.complex128)):
+        raw = pack(v, name)
+        assert raw.size == storage_bytes(name, 3) == 8 * DTYPES[name].slot_bits // 8
+        assert np.array_equal(raw[: 3 * 2 * np.dtype(ft).itemsize].view(ft), np.array([1, 2, -0.5, 0.25, 0, 3], ft))
+        assert np.array_equal(unpack(raw, 3, name), v.astype(ct)) and np.array_equal(unpack(raw, 2, name, offset=1), v[1:].astype(ct))
+
+
+def test_complex_type_inference_follows_float_contagion_of_the_parts():
+    """src/1type.lisp:446-451"""
+    c, z = ti.type_of_dtype("c64"), ti.type_of_dtype("c128")
+    T = ti.type_of_dtype
+    assert ti.upgrade(ti.infer_type("+", c, T("f32"))) == "c64" and ti.upgrade(ti.infer_type("*", c, T("f64"))) == "c128"
+    assert ti.upgrade(ti.infer_type("+", c, T("ub8"))) == "c64" and ti.upgrade(ti.infer_type("/", T("fixnum"), z)) == "c128"
+    assert ti.upgrade(ti.infer_type("-", c)) == "c64" and ti.upgrade(ti.infer_type("+", c, z)) == "c128"
+    assert ti.upgrade(ti.infer_type("realpart", z)) == "f64" and ti.upgrade(ti.infer_type("imagpart", c)) == "f32"
+    assert ti.upgrade(ti.infer_type("conjugate", c)) == "c64" and ti.infer_type("realpart", T("ub8")) == T("ub8")
+    assert ti.upgrade(ti.einsum_output_types([["+", "@1", ["*", "$1", "$2"]]], [c, c], 1)[0]) == "c64"
+    assert ti.upgrade(ti.reduce_result_type("+", z)) == "c128"
+    with pytest.raises(ti.TypeInferenceError):
+        ti.infer_type("max", c, c)
 
 
 def test_pack_wraps_like_coerce(oracle):
