@@ -219,6 +219,84 @@ __global__ void __launch_bounds__(256) transpose_reg_kernel(const __grid_constan
       }
   }
 }
+
+// Strips: (N, C) <-> (C, N) with a short side of up to 128 whose rows lie back to back.  Square tiles waste the lanes that fall
+// outside a 48-wide plane (transpose (4M,48): 0.57 of the HBM peak) and the rectangular tiles of transpose_thin_kernel stop
+// at C = 16.  Here a CTA takes R consecutive positions of the long loop (R a power of two <= 256, the tile of R x C words in up
+// to 72 KB of shared memory) and ALL of the short loop: on the side where the short loop is contiguous that is ONE contiguous
+// run of R * C words, moved with fully coalesced accesses whatever C is (a thread's flat index advances by 256: its (row,
+// column) is stepped, never divided); on the other side it is C runs of R words, a thread staying on one position of the run
+// and stepping through the rows with a constant pointer increment.  The tile has an odd pitch: lanes running along either loop
+// hit 32 different banks.  Words travel global -> shared with cp.async (LDGSTS): nothing is staged in registers, every copy of
+// a thread is in flight at once at 32 registers.  (First version: 12 elements per thread behind a prologue of 64-bit
+// divisions -- ncu: 2.1 warp instructions per ELEMENT, issue slots 82 % busy, 0.45 of the peak.)
+#define STRIP_SMEM_BYTES (72 * 1024)
+template <int BYTES> __device__ __forceinline__ void cp_async_word(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
+}
+template <class WT, bool FWD, int FZ>
+__global__ void __launch_bounds__(256) transpose_strip_kernel(const __grid_constant__ TrParams p, const int C, const int pitch, const int rshift) {
+  extern __shared__ __align__(16) unsigned char strip_smem[];
+  WT* tile = reinterpret_cast<WT*>(strip_smem);
+  const int R = 1 << rshift, tid = threadIdx.x;
+  long long strip = blockIdx.x, ibase = p.in_off, obase = p.out_off;
+  if (p.nb > 0) {
+    long long b = blockIdx.x;
+    strip = b % p.tiles_o; b /= p.tiles_o;
+    for (int k = p.nb - 1; k >= 0; k--) { long long c = b % p.bext[k]; b /= p.bext[k]; ibase += c * p.bin[k]; obase += c * p.bout[k]; }
+  }
+  const long long nlong = FWD ? p.no : p.ni, n0 = strip * R;
+  const int rows = (int)(nlong - n0 < R ? nlong - n0 : R), total = rows * C;
+  auto fix = [](WT w) {
+    if constexpr (FZ == 1) return (WT)__float_as_uint(__fadd_rn(0.0f, __uint_as_float((unsigned)w)));
+    else if constexpr (FZ == 2) return (WT)__double_as_longlong(__dadd_rn(0.0, __longlong_as_double((long long)w)));
+    else return w;
+  };
+  // flat side: index tid + 256 k -> (row, column), stepped;  row side: position r2 of the run, rows c2 = cb, cb + cstep, ...
+  const int r0 = tid / C, c0 = tid - r0 * C, dr = 256 / C, dc = 256 - dr * C;
+  const int r2 = tid & (R - 1), cb = tid >> rshift, cstep = 256 >> rshift;
+  if constexpr (FWD) {
+    const WT* src = (const WT*)p.in + ibase + n0 * C + tid;
+    int r = r0, c = c0;
+#pragma unroll 4
+    for (int e = tid; e < total; e += 256) {
+      cp_async_word<sizeof(WT)>(&tile[r * pitch + c], src);
+      src += 256; r += dr; c += dc; if (c >= C) { c -= C; r++; }
+    }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (r2 < rows) {
+      WT* dst = (WT*)p.out + obase + n0 + r2 + (long long)cb * p.out_si;
+      const long long dstep = (long long)cstep * p.out_si;
+      const WT* t = tile + r2 * pitch + cb;
+#pragma unroll 4
+      for (int c2 = cb; c2 < C; c2 += cstep) { *dst = fix(*t); dst += dstep; t += cstep; }
+    }
+  } else {
+    if (r2 < rows) {
+      const WT* src = (const WT*)p.in + ibase + n0 + r2 + (long long)cb * p.in_so;
+      const long long sstep = (long long)cstep * p.in_so;
+      WT* t = tile + r2 * pitch + cb;
+#pragma unroll 4
+      for (int c2 = cb; c2 < C; c2 += cstep) { cp_async_word<sizeof(WT)>(t, src); src += sstep; t += cstep; }
+    }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    WT* dst = (WT*)p.out + obase + n0 * C + tid;
+    int r = r0, c = c0;
+#pragma unroll 4
+    for (int e = tid; e < total; e += 256) {
+      *dst = fix(tile[r * pitch + c]);
+      dst += 256; r += dr; c += dc; if (c >= C) { c -= C; r++; }
+    }
+  }
+}
+typedef void (*StripKernel)(const TrParams, int, int, int);
+template <class WT> static StripKernel strip_pick(bool fwd, int fz) {
+  if (fwd) return fz == 1 ? transpose_strip_kernel<WT, true, 1> : fz == 2 ? transpose_strip_kernel<WT, true, 2> : transpose_strip_kernel<WT, true, 0>;
+  return fz == 1 ? transpose_strip_kernel<WT, false, 1> : fz == 2 ? transpose_strip_kernel<WT, false, 2> : transpose_strip_kernel<WT, false, 0>;
+}
 typedef void (*TrKernel)(const TrParams);
 template <class V, bool FWD, int MODE> static TrKernel reg_pick(int c) {
   switch (c) {
@@ -297,6 +375,28 @@ int try_transpose(const Nest& n) {
         k<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
         note_launch("transpose_reg");
         return cuda_fail(cudaGetLastError(), "transpose_reg_kernel");
+      }
+    }
+  }
+  if (raw && (wbytes == 4 || wbytes == 8)) {
+    // strips: the short side (<= 128) lies back to back on the side where it is contiguous
+    const bool fwd = p.ni <= p.no;
+    const long long cs = fwd ? p.ni : p.no, nl = fwd ? p.no : p.ni;
+    if (cs >= 2 && cs <= 128 && nl >= 1024 && (fwd ? p.in_so == p.ni : p.out_si == p.no)) {
+      const int C = (int)cs, pitch = C | 1;
+      int rshift = 5; while (rshift < 8 && (size_t)(2 << rshift) * pitch * wbytes <= STRIP_SMEM_BYTES) rshift++;      // R = 32 .. 256
+      const size_t smem = ((size_t)(1 << rshift) * pitch * wbytes + 15) & ~(size_t)15;
+      p.tiles_i = 1; p.tiles_o = (nl + (1 << rshift) - 1) >> rshift;
+      const long long blocks = p.tiles_o * batch;
+      if (blocks > 0 && blocks <= 0x7fffffffLL) {
+        const int fz = (add_zero && icls == CLS_F) ? 1 : (add_zero && icls == CLS_D) ? 2 : 0;
+        StripKernel k = wbytes == 4 ? strip_pick<unsigned int>(fwd, fz) : strip_pick<unsigned long long>(fwd, fz);
+        static bool attr_set[2][2][3] = {};
+        bool& done = attr_set[wbytes == 8][fwd][fz];
+        if (!done) { NCL_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM_BYTES)); done = true; }
+        k<<<(unsigned)blocks, 256, smem, c.stream>>>(p, C, pitch, rshift);
+        note_launch("transpose_strip");
+        return cuda_fail(cudaGetLastError(), "transpose_strip_kernel");
       }
     }
   }

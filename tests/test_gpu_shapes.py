@@ -92,6 +92,25 @@ def test_thin_transpose_bit_exact(nc, oracle, shape, dt):
     assert_bit_exact(nc.transpose(to_gpu(nc, a)), refsem.einsum(oracle, "ij -> ji", [a]))
 
 
+# ---- strips: a short side of up to 128 whose rows lie back to back (transpose_strip_kernel) ------------------------------------
+@pytest.mark.parametrize("shape", [(4096, 9), (9, 4096), (5000, 12), (12, 5000), (3001, 16), (16, 3001), (2049, 33), (33, 2049), (20000, 48), (48, 20000),
+                                   (1500, 64), (64, 1500), (1024, 100), (100, 1024), (1025, 128), (128, 1025), (1027, 127), (127, 1027)])
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum"])
+def test_strip_transpose_bit_exact(nc, oracle, shape, dt):
+    a = rand(oracle, shape, dt, SEED + 8, 1 if dt in ("f32", "f64") else 0, -8, 8)
+    got = nc.transpose(to_gpu(nc, a))
+    assert _last(nc) == "transpose_strip", _last(nc)
+    assert_bit_exact(got, refsem.einsum(oracle, "ij -> ji", [a]))
+
+
+@pytest.mark.parametrize("spec,shape", [("bnc -> bcn", (3, 2000, 24)), ("bcn -> bnc", (3, 24, 2000)), ("anbc -> abcn", (2, 1500, 3, 10)), ("nc -> cn", (1100, 40))])
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+def test_strip_transpose_batched_and_signed_zero(nc, oracle, spec, shape, dt):
+    """batch loops in front of the plane; the default transform into a fresh output is 0 + x: -0.0 is stored as +0.0"""
+    a = rand(oracle, shape, dt, SEED + 9, 2, -1.0, 1.0)                       # set R: signed zeros, infinities, denormals
+    assert_bit_exact(nc.einsum(spec, to_gpu(nc, a)), refsem.einsum(oracle, spec, [a]))
+
+
 # ---- contractions that are really reductions (vdot, row-wise dot, matrix x vector) ---------------------------------------
 DOTS = [("i i -> ", [(70001,), (70001,)]), ("ij ij -> i", [(300, 1000), (300, 1000)]), ("ij ij -> i", [(20000, 3), (20000, 3)]),
         ("ij ij -> ", [(300, 1001), (300, 1001)]), ("ij ij -> j", [(1000, 300), (1000, 300)]), ("ij j -> i", [(300, 1000), (1000,)]),
