@@ -295,6 +295,27 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
   bool vec = (ncols % Evec == 0) && aligned16(in, in.offset) && ((sR * sb) / 8) % 16 == 0;
   for (int i = 0; i < nk - 1 && vec; i++) if (((kd[i].sin * sb) / 8) % 16) vec = false;
   if (dot && vec && p.c_stride2 == 1) { vec = aligned16(n.in[ib], n.in[ib].offset) && b_vec_ok(rd[0].sin2); for (int i = 0; i < nk - 1 && vec; i++) if (!b_vec_ok(kd[i].sin2)) vec = false; }
+  // ---- a plain matrix whose rows are not whole chunks: rows dealt into Evec alignment classes (k_reduce_rot.cu) ---------------
+  if (!vec && !dot && nk == 1 && (sb == 32 || sb == 64) && Evec > 1 && ncols >= 256 && R >= 8 * Evec && sR > 0 && ((uintptr_t)in.base % (sb / 8)) == 0) {
+    RedKernel kmain, kfin; red_col_rot_pick(cls, sb, op, &kmain, &kfin);
+    const long long nch = (ncols + 2 * Evec - 2) / Evec, bx = (nch + 255) / 256;      // chunk positions: up to Evec - 1 elements of slack on both sides
+    const long long want = persistent_blocks((const void*)kmain);
+    long long ny = (want + bx - 1) / bx; if (ny < Evec) ny = Evec;                      // CTAs along y: one resident wave
+    long long nseg = ny / Evec; const long long maxseg = R / (8 * Evec); if (nseg > maxseg) nseg = maxseg; if (nseg < 1) nseg = 1; if (nseg > 4096) nseg = 4096;
+    long long seg = (R + nseg - 1) / nseg; seg = (seg + Evec - 1) / Evec * Evec;        // whole groups of Evec rows
+    nseg = (R + seg - 1) / seg;
+    if (bx <= 0x7fffffffLL && nseg * Evec <= 65535) {
+      p.seg = seg; p.nseg = (int)nseg; p.kout[0] = kd[0].sout;
+      NCL_TRY(ensure_scratch((size_t)nseg * Evec * ncols * 8));
+      p.partial = c.scratch;
+      kmain<<<dim3((unsigned)bx, (unsigned)(nseg * Evec)), 256, 0, c.stream>>>(p);
+      note_launch("reduce_col_rot");
+      NCL_TRY(cuda_fail(cudaGetLastError(), "reduce_col_rot_kernel"));
+      kfin<<<(unsigned)((ncols + 255) / 256), 256, 0, c.stream>>>(p);
+      note_launch("reduce_col_rot");
+      return cuda_fail(cudaGetLastError(), "reduce_col_rot_finish_kernel");
+    }
+  }
   int E = vec ? Evec : 1; p.vec = vec;
   long long nq = p.rows * (ncols / E);
   // split R so that the grid is ONE resident wave of equal segments (2048 threads per SM assumed here before: two

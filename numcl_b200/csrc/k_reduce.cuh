@@ -810,3 +810,4 @@ RedKernel red_pick_int_narrow_dot(int E, int which);
 RedKernel red_staged_pick(int cls, int op);
 RedKernel red_rows_reg_pick(int cls, int slot_bits, int op, int c);
 void red_dot_matvec_launch(int cls, unsigned blocks, cudaStream_t stream, const RedParams& p);
+void red_col_rot_pick(int cls, int slot_bits, int op, RedKernel* main, RedKernel* fin);     // k_reduce_rot.cu: row pitch not a multiple of 16 bytes

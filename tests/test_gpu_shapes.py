@@ -58,6 +58,40 @@ def test_reduce_short_axes_bit_exact(nc, oracle, shape, axes, fn, dt):
     assert_bit_exact(got, want)
 
 
+# ---- column reduce of a matrix whose rows are not whole 16-byte chunks (k_reduce_rot.cu) -------------------------------------
+@pytest.mark.parametrize("shape", [(1000, 257), (4099, 301), (333, 1001), (64, 259), (2050, 8193), (129, 4097), (97, 515)])
+@pytest.mark.parametrize("fn", ["+", "max", "min", "*"])
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum", "sb32", "ub31", "sb64"])
+def test_column_reduce_with_ragged_row_pitch_bit_exact(nc, oracle, shape, fn, dt):
+    if fn == "*":
+        a = rand(oracle, shape, dt, SEED + 31, 1, 1, 1) if dt in ("f32", "f64") else rand(oracle, shape, dt, SEED + 31, 0, 1, 1)
+        v = a.values().copy(); v[::7, ::5] = 2 if shape[0] < 400 else 1; v[3::11, 1::3] = -1 if dt not in ("ub31",) else 1     # products stay exact
+        a = oracle.OArr.from_values(v, dt)
+    else:
+        a = rand(oracle, shape, dt, SEED + 31, 1 if dt in ("f32", "f64") else 0, 0 if dt == "ub31" else -8, 8)
+    want = refsem.reduce_array(oracle, fn, a, (0,))
+    got = {"+": nc.sum, "max": nc.amax, "min": nc.amin, "*": nc.prod}[fn](to_gpu(nc, a), axes=0)
+    assert _last(nc) == "reduce_col_rot", _last(nc)
+    assert_bit_exact(got, want)
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "sb32"])
+@pytest.mark.parametrize("offset", [1, 2, 3, 5])
+def test_column_reduce_of_a_misaligned_view(nc, oracle, dt, offset):
+    """a displaced view that starts in the middle of a chunk: the classes' misalignment follows the element offset"""
+    rows, cols = 700, 515
+    base = rand(oracle, (rows * cols + 8,), dt, SEED + 32, 1 if dt != "sb32" else 0, -8, 8)
+    g = to_gpu(nc, base)
+    view = nc.NArray((rows, cols), dt, _storage=g._buf, offset=offset)
+    got = nc.sum(view, axes=0)
+    assert _last(nc) == "reduce_col_rot"
+    v = base.values()[offset:offset + rows * cols].reshape(rows, cols)
+    assert np.array_equal(got.numpy(), v.sum(axis=0).astype(got.numpy().dtype))
+    m = nc.mean(view, axes=0) if dt != "sb32" else None
+    if m is not None:
+        assert np.allclose(m.numpy(), v.mean(axis=0), rtol=1e-6)
+
+
 @pytest.mark.parametrize("dt,tol", [("f32", 1e-5), ("f64", 1e-12)])
 @pytest.mark.parametrize("shape,axes", [((50000, 3), (1,)), ((50000, 3), (0,)), ((20000, 48), (1,)), ((20000, 48), (0,)), ((257, 1001), (1,)),
                                         ((257, 1001), (0,)), ((64, 100, 36), (0, 2))])
