@@ -39,6 +39,9 @@ struct EwParams {
   // (a row vector: gst 0, st 1; one value per row: gst s, st 0), the others stream as flat vectors
   unsigned eper, epmul, epshr; int gather[3]; int gst[3];
   int rt_op; unsigned int* fault;       // runtime-selected function (FnRt*: an ncl_op) and the sticky DOMAIN flag it may raise
+  // bit k: input k is a row vector whose piece is the same in EVERY item of a warp -- the host made the number of warps a
+  // multiple of the number of segments the vector spans, so item mod span = warp mod span -- and is loaded once, before the loop
+  unsigned whoist;
 };
 __device__ __forceinline__ unsigned ew_div(unsigned q, unsigned mul, unsigned shr) { return mul ? (__umulhi(q, mul) >> shr) : q; }
 
@@ -272,6 +275,26 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
     hoisted[k] = p.period[k] != 0 && (SEG % p.period[k]) == 0;        // item-invariant
     stepped[k] = p.period[k] != 0 && !hoisted[k] && (p.period[k] % SEG) == 0;   // no wrap inside an item
     if (hoisted[k]) load_operand_periodic<TI, E, U>(p.base[1 + k], p.off[1 + k], p.lk[k], (unsigned)lane, 0xffffffffu, p.period[k], p.pmul[k], p.pshr[k], x[k]);
+  }
+  // Row vectors longer than a segment (C1's 4096 floats, `outer`'s second operand): every item used to fetch its piece again
+  // -- L2 traffic as large as the output, and under a write-dominated stream the vector's lines kept being evicted (ncu on
+  // outer 16384^2: 433 MB of DRAM READS for two 64 KB inputs, 0.75 of the peak).  With the warp count a multiple of the span
+  // the piece is warp-invariant.
+  {
+    const unsigned warp0 = blockIdx.x * (EW_THREADS / 32) + (threadIdx.x >> 5);
+#pragma unroll
+    for (int k = 0; k < NIN; k++) {
+      if ((p.whoist >> k) & 1u) {
+        hoisted[k] = true;                                                         // (one flag for both kinds: nothing more is live in the loop)
+        if (p.nd == 1) {                                                           // flat mode, period a multiple of the segment
+          const unsigned s0 = warp0 * SEG, base_chunk = s0 - ew_div(s0, p.pmul[k], p.pshr[k]) * p.period[k];
+          load_operand<TI, E, U>(p.base[1 + k], p.off[1 + k] + (long long)base_chunk * E, 1, p.lk[k], (unsigned)lane, 0xffffffffu, x[k]);
+        } else {                                                                   // rows x segments, the vector moves with the segment only
+          const unsigned seg0 = warp0 - ew_div(warp0, p.seg_mul, p.seg_shr) * p.segs_per_row;
+          load_operand<TI, E, U>(p.base[1 + k], p.off[1 + k], 1, p.lk[k], seg0 * SEG + lane, p.ext[0], x[k]);
+        }
+      }
+    }
   }
   for (unsigned item = blockIdx.x * (EW_THREADS / 32) + (threadIdx.x >> 5); item < p.nitems; item += nwarps) {
     unsigned row = ew_div(item, p.seg_mul, p.seg_shr);

@@ -692,15 +692,21 @@ __global__ void __launch_bounds__(256) reduce_col_kernel(const __grid_constant__
   long long q = (long long)blockIdx.x * 256 + threadIdx.x;
   long long nq = p.rows * chunks_per_row;              // rows = prod of the outer kept dims
   if (q >= nq) return;
-  long long cc = q % chunks_per_row, orow = q / chunks_per_row;
+  // a plain matrix (no outer kept loops) needs no 64-bit division: with a reduced axis of a few rows the two divisions below were
+  // most of a thread's instructions ((sum a :axes 0) of a (3, N) array: 48 bytes of loads per thread)
+  long long cc = q, orow = 0;
+  if (p.nk > 0) { cc = q % chunks_per_row; orow = q / chunks_per_row; }
   long long ibase = p.in_off + cc * E, obase = p.out_off + cc * E, ibase2 = DOT ? p.in2_off + cc * E * p.c_stride2 : 0;
   { long long r = orow; for (int k = p.nk - 1; k >= 0; k--) { long long c = r % p.kext[k]; r /= p.kext[k]; ibase += c * p.kin[k]; obase += c * p.kout[k]; if constexpr (DOT) ibase2 += c * p.kin2[k]; } }
   const long long rs2 = DOT ? p.r_stride2 : 0; const bool bc = DOT && p.c_stride2 == 1;
   long long r0 = (long long)blockIdx.y * p.seg, r1 = r0 + p.seg; if (r1 > p.r_ext) r1 = p.r_ext;
   T acc[E];
   if (r0 >= r1) return;
-  fetch_elems<T, E, DOT>(p, ibase + r0 * p.r_stride, ibase2 + r0 * rs2, bc, acc);     // the first row seeds the accumulators
-  long long r = r0 + 1;
+  // (the first row used to seed the accumulators with a load of its own: for a reduced axis of 2 .. 8 rows that was a second
+  // memory latency in front of the batch below -- (sum a :axes 0) of a (3, N) array)
+#pragma unroll
+  for (int i = 0; i < E; i++) acc[i] = neutral<T, OP>();
+  long long r = r0;
   // rows in flight per thread: 4 x 16 bytes on the vector path; the scalar path (ragged column count) moves only one
   // element per load and needs 16 rows to keep a comparable number of bytes in flight (0.17 -> of the HBM peak with 4)
   // (8 rows in flight for 16-byte chunks was tried after ncu showed the kernel latency-bound at 49 % of DRAM bandwidth: worse everywhere,
@@ -752,7 +758,8 @@ __global__ void __launch_bounds__(256) reduce_col_finish_kernel(const __grid_con
   long long q = (long long)blockIdx.x * 256 + threadIdx.x;
   long long nq = p.rows * chunks_per_row;
   if (q >= nq) return;
-  long long cc = q % chunks_per_row, orow = q / chunks_per_row;
+  long long cc = q, orow = 0;
+  if (p.nk > 0) { cc = q % chunks_per_row; orow = q / chunks_per_row; }
   long long obase = p.out_off + cc * E;
   { long long r = orow; for (int k = p.nk - 1; k >= 0; k--) { long long c = r % p.kext[k]; r /= p.kext[k]; obase += c * p.kout[k]; } }
   const T* part = (const T*)p.partial;

@@ -35,6 +35,16 @@ elif case == "sum_u8_all":
     a = R((1024, 512, 512), "ub8", 7); f = lambda: nc.sum(a)
 elif case == "transpose_thin":
     a = R((1 << 22, 48)); f = lambda: nc.transpose(a)
+elif case == "fill":
+    f = lambda: nc.full((16384, 16384), 1.5, type="f32")
+elif case == "scale":
+    a = R((16384, 16384), seed=5); f = lambda: nc.mul(a, 2.0)
+elif case == "outer":
+    a = R((16384,), seed=5); b = R((16384,), seed=6); f = lambda: nc.outer(a, b)
+elif case == "sub_N3_N1":
+    a = R((1 << 26, 3)); w = R((1 << 26, 1), seed=3); f = lambda: nc.mul(a, w)
+elif case == "rows_reg":
+    a = R((1 << 26, 3)); f = lambda: nc.sum(a, axes=1)
 elif case == "sqrt":
     a = nc.random_array((1024, 512, 512), "f32", 3, 0, 0.0, 4.0); f = lambda: nn.sqrt(a)
 else:
