@@ -235,3 +235,62 @@ def test_matmul_with_empty_contraction(nc, oracle, dt):
     c = nc.full((256, 256), 3, type=dt)
     nc.matmul(a, b, c)
     assert np.all(c.numpy() == 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1500, 48), (48, 1500), (1027, 127), (127, 1027), (4096, 9), (9, 4096)])
+@pytest.mark.parametrize("dt,sb", [("f32", 4), ("f64", 8)])
+def test_strip_transpose_writes_only_its_output_region(nc, shape, dt, sb):
+    """the strip transpose (cp.async into a padded tile, partial last strip) behind a canary on both sides, from an input
+    that is itself a displaced window: nothing outside the output window may change"""
+    import ctypes as C
+    from numcl_b200 import _lib
+    from numcl_b200.array import NArray
+    from numcl_b200.einsum import _memoized
+    rng = np.random.default_rng(12)
+    A = rng.integers(-8, 9, shape).astype(np.float32 if dt == "f32" else np.float64)
+    n = A.size
+    src = NArray((5 + n + 3,), dt)
+    buf = np.full(src.nbytes, 0xCD, dtype=np.uint8); buf[5 * sb:(5 + n) * sb] = A.view(np.uint8).reshape(-1)
+    src.set_raw(buf)
+    ts = src.tensor(); ts.rank = 2; ts.dims[0], ts.dims[1] = shape; ts.elem_offset = 5
+    off, tail = 7, 29
+    store = NArray((off + n + tail,), dt)
+    store.set_raw(np.full(store.nbytes, 0xAB, dtype=np.uint8))
+    t = store.tensor(); t.rank = 2; t.dims[0], t.dims[1] = shape[1], shape[0]; t.elem_offset = off
+    _, desc = _memoized("ij -> ji")
+    tin = (_lib.Tensor * 1)(ts); tout = (_lib.Tensor * 1)(t)
+    _lib.check(_lib.lib().ncl_einsum(C.byref(desc), tin, 1, tout, 1, _lib.OUT_FRESH))
+    assert nc.lib().ncl_last_kernel() == b"transpose_strip"
+    raw = store.raw()
+    assert np.all(raw[: off * sb] == 0xAB) and np.all(raw[(off + n) * sb: (off + n + tail) * sb] == 0xAB)
+    got = raw[off * sb: (off + n) * sb].view(A.dtype).reshape(shape[1], shape[0])
+    assert np.array_equal(got, A.T)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(700, 515), (64, 259), (2050, 1001)])
+@pytest.mark.parametrize("dt,sb", [("f32", 4), ("f64", 8)])
+def test_column_reduce_of_ragged_rows_writes_only_its_output_region(nc, shape, dt, sb):
+    """k_reduce_rot.cu reads whole aligned chunks (a few elements of the neighbouring rows travel along) but must store
+    nothing outside the result's window"""
+    import ctypes as C
+    from numcl_b200 import _lib
+    from numcl_b200.array import NArray
+    rng = np.random.default_rng(13)
+    A = rng.integers(-8, 9, shape).astype(np.float32 if dt == "f32" else np.float64)
+    a = nc.asarray(A, type=dt)
+    off, tail, ncols = 3, 21, shape[1]
+    store = NArray((off + ncols + tail,), dt)
+    store.set_raw(np.full(store.nbytes, 0xAB, dtype=np.uint8))
+    t = store.tensor(); t.rank = 1; t.dims[0] = ncols; t.elem_offset = off
+    ta = a.tensor(); ax = (C.c_int * 1)(0)
+    _lib.check(_lib.lib().ncl_reduce(_lib.OPS["ADD"], C.byref(ta), ax, 1, C.byref(t), _lib.OUT_FRESH))
+    assert nc.lib().ncl_last_kernel() == b"reduce_col_rot"
+    raw = store.raw()
+    assert np.all(raw[: off * sb] == 0xAB) and np.all(raw[(off + ncols) * sb: (off + ncols + tail) * sb] == 0xAB)
+    assert np.array_equal(raw[off * sb: (off + ncols) * sb].view(A.dtype), A.sum(axis=0))
+    # accumulate into the same window: r <- r + column sums
+    _lib.check(_lib.lib().ncl_reduce(_lib.OPS["ADD"], C.byref(ta), ax, 1, C.byref(t), 0))
+    raw = store.raw()
+    assert np.all(raw[: off * sb] == 0xAB) and np.array_equal(raw[off * sb: (off + ncols) * sb].view(A.dtype), 2 * A.sum(axis=0))
