@@ -84,6 +84,10 @@ run("sqrt (map)", lambda: nn.sqrt(a), 2 * a.nbytes)
 run("exp (map)", lambda: nn.exp(a), 2 * a.nbytes)
 run("a * 2.0 (scalar)", lambda: nc.mul(a, 2.0), 2 * a.nbytes)
 run("a < b1 -> bit", lambda: nn.lt(a, b1), a.nbytes + a.nbytes // 32)
+a2 = R((1024, 512, 512), seed=77)
+run("a < a2 same shape -> bit", lambda: nn.lt(a, a2), 2 * a.nbytes + a.nbytes // 32)
+del a2
+run("a < 0.5 (scalar) -> bit", lambda: nn.lt(a, 0.5), a.nbytes + a.nbytes // 32)
 d = R((512, 512, 512), "f64", 6); ah = R((512, 512, 512), seed=30)
 run("f32 + f64 same shape -> f64", lambda: nc.add(ah, d), ah.nbytes + 2 * d.nbytes)
 d2 = R((512, 512, 512), "f64", 61)
