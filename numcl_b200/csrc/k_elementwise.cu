@@ -478,8 +478,19 @@ static int try_elementwise_32(const Nest& n) {
     }
     if (mask) { blocks = blocks / need * need; p.whoist = mask; }
   }
-  kfn<<<(unsigned)blocks, EW_THREADS, 0, c.stream>>>(p);
-  NCL_TRY(cuda_fail(cudaGetLastError(), "ew_kernel"));
+  const char* kname = cmppack ? "cmp_pack" : eflat ? "bcast_vec_flat" : E == 1 ? "bcast_scalar" : "bcast_vec";
+  {
+    // programmatic dependent launch (ncl_internal.h): ew_kernel reads its first item while the previous kernel drains and
+    // writes nothing before griddepcontrol.wait, provided nothing it reads is written by a kernel that may still be in flight.
+    // The packed-comparison kernels do not take part.
+    PdlRange reads[3]; int nr = 0;
+    for (int k = 0; k < m.n; k++) if (m.s[k].kind < 2) reads[nr++] = pdl_range(ops[k]);
+    const bool early = !cmppack && pdl_eligible(reads, nr);
+    void* args[1] = {(void*)&p};
+    NCL_TRY(pdl_launch((const void*)kfn, dim3((unsigned)blocks), dim3(EW_THREADS), args, c.stream, early));
+    note_launch(kname);
+    if (!cmppack) { PdlRange w = pdl_range(out); pdl_commit(early, &w, 1); }
+  }
   if (eflat && eflat_tail) {
     // fewer than E trailing elements: the end of the last partial row, then whole rows, as two tiny nests
     const long long P = eflat_P, R = eflat_R, fr = eflat_tail / P, part = eflat_tail - fr * P, body = P * R - eflat_tail;
@@ -500,6 +511,6 @@ static int try_elementwise_32(const Nest& n) {
     if (part) { Nest t = piece(1, part, 1, R - fr - 1, P - part, body); NCL_TRY(run_piece(t)); }
     if (fr) { Nest t = piece(2, fr, P, R - fr, 0, body + part); NCL_TRY(run_piece(t)); }
   }
-  note_launch(cmppack ? "cmp_pack" : eflat ? "bcast_vec_flat" : E == 1 ? "bcast_scalar" : "bcast_vec");
+  c.last_kernel = kname;                                  // (the tail pieces above launched kernels of their own)
   return NCL_OK;
 }

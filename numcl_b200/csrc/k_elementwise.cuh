@@ -269,6 +269,10 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
   constexpr unsigned SEG = 32 * U;
   TI x[NIN][U][E];
   unsigned int flt_local = 0;                       // DOMAIN faults of this thread (runtime-selected families), flushed once at the end
+  // programmatic dependent launch (ncl_internal.h: PdlTracker): the next kernel of the stream may start while this one drains;
+  // this one reads its first item while its predecessor drains and writes nothing before griddepcontrol.wait
+  pdl_trigger();
+  bool waited = false;
   bool hoisted[NIN], stepped[NIN];
 #pragma unroll
   for (int k = 0; k < NIN; k++) {
@@ -365,6 +369,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
           else y[u][i] = F::f(x[0][u][i], x[1][u][i], x[2][u][i]);
         }
     }
+    if (!waited) { pdl_wait(); waited = true; }
     store_operand<TO, E, U>(p.base[0], rowoff[0], q0, p.ext[0], p.sk, y);
   }
   if constexpr (fn_is_rt<F>::value) ncl_fault_flush(p.fault, flt_local);
