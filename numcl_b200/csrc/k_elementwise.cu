@@ -76,7 +76,7 @@ static bool match_expr(const Expr& e, int self_out, bool fresh, Match* m) {
 int ew_narrow_launch(int op, bool wide, const char* a, const char* b, char* out, long long n, bool b_scalar, long long b_off, int b_lk, bool swap,
                      bool signed8, unsigned mask16);                      // k_ew_narrow.cu
 int ew_widen_launch(int a_lk, int op, const char* a, const char* b, char* out, unsigned nchunks, int bmode, unsigned period, int btag, int swap,
-                    unsigned long long mask, int shift);                 // k_ew_widen.cu
+                    unsigned long long mask, int shift, const Operand* oa, const Operand* ob, const Operand* oout);   // k_ew_widen.cu
 
 static int try_elementwise_32(const Nest& n);
 
@@ -409,7 +409,8 @@ static int try_elementwise_32(const Nest& n) {
         const char* ap = ops[ia].base + (ops[ia].offset * g_dt[ops[ia].dtype].slot_bits) / 8;
         const char* bp = ops[ib].base + ops[ib].offset * 8;
         char* op = out.base + out.offset * 8;
-        int rc = ew_widen_launch(la, wop, ap, bp, op, (unsigned)(d[0].ext / 2), bmode, p.period[ib], lb == LK_T64 ? 1 : 0, ia == 1 ? 1 : 0, sk.mask, sk.shift);
+        int rc = ew_widen_launch(la, wop, ap, bp, op, (unsigned)(d[0].ext / 2), bmode, p.period[ib], lb == LK_T64 ? 1 : 0, ia == 1 ? 1 : 0, sk.mask, sk.shift,
+                                 &ops[ia], &ops[ib], &out);
         if (rc != NCL_ERR_UNSUPPORTED) return rc;
       }
     }

@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(256) ew_widen_kernel(const __grid_constant__ W
   const unsigned nwarps = gridDim.x * 8, warp0 = blockIdx.x * 8 + (threadIdx.x >> 5);
   const unsigned nitems = (p.nchunks + SEG - 1) / SEG;
   long long y[U][2];
+  pdl_trigger();                                            // programmatic dependent launch: see ew_kernel
+  bool waited = false;
   if (p.bmode == WB_HOISTED) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(256) ew_widen_kernel(const __grid_constant__ W
       for (int u = 0; u < U; u++) if (q0 + 32 * u < p.nchunks) wide_load(p.b + (size_t)(b0 + 32 * u) * 16, p.btag, y[u][0], y[u][1]);
     }
     char* op = p.out + (size_t)q0 * 16;
+    if (!waited) { pdl_wait(); waited = true; }
 #pragma unroll
     for (int u = 0; u < U; u++) if (q0 + 32 * u < p.nchunks) {
       long long r0 = p.swap ? widen_op<OP>(y[u][0], x[u][0]) : widen_op<OP>(x[u][0], y[u][0]);
@@ -115,7 +118,7 @@ template <int BITS, bool SGN> static WidenKernel pick_op(int op) {
 
 // a_lk: LK_U8 .. LK_S32 of the narrow operand.  Returns NCL_ERR_UNSUPPORTED when the kinds are not covered.
 int ew_widen_launch(int a_lk, int op, const char* a, const char* b, char* out, unsigned nchunks, int bmode, unsigned period, int btag, int swap,
-                    unsigned long long mask, int shift) {
+                    unsigned long long mask, int shift, const Operand* oa, const Operand* ob, const Operand* oout) {
   Context& c = ctx();
   WidenKernel k = nullptr;
   switch (a_lk) {
@@ -138,7 +141,11 @@ int ew_widen_launch(int a_lk, int op, const char* a, const char* b, char* out, u
   unsigned long long cap = (unsigned long long)c.sm_count * per_sm * 8;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) return NCL_OK;
-  k<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
+  PdlRange reads[2] = {pdl_range(*oa), pdl_range(*ob)};
+  const bool early = pdl_eligible(reads, 2);
+  void* args[1] = {(void*)&p};
+  NCL_TRY(pdl_launch((const void*)k, dim3((unsigned)blocks), dim3(256), args, c.stream, early));
   note_launch("bcast_widen");
-  return cuda_fail(cudaGetLastError(), "ew_widen_kernel");
+  PdlRange w = pdl_range(*oout); pdl_commit(early, &w, 1);
+  return NCL_OK;
 }

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const __grid_constant__ 
 template <class WT, int TILE, int FZ>
 __global__ void __launch_bounds__(256) transpose_raw_kernel(const __grid_constant__ TrParams p) {
   __shared__ WT tile[TILE][TILE + 1];
+  pdl_trigger();                          // programmatic dependent launch: the tile is read while the previous kernel drains, stored after it
   long long b = blockIdx.x;
   long long ti = b % p.tiles_i; b /= p.tiles_i;
   long long to = b % p.tiles_o; b /= p.tiles_o;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) transpose_raw_kernel(const __grid_constan
 #pragma unroll
     for (int r = 0; r < TILE / ROWS; r++) tile[r * ROWS + ty][tx] = v[r];
     __syncthreads();
+    pdl_wait();
 #pragma unroll
     for (int r = 0; r < TILE / ROWS; r++) {
       WT w = tile[tx][r * ROWS + ty];
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(256) transpose_raw_kernel(const __grid_constan
 #pragma unroll
     for (int r = 0; r < TILE; r += ROWS) if (o0 + r + ty < p.no && i0 + tx < p.ni) tile[r + ty][tx] = __ldg(src + (long long)r * p.in_so);
     __syncthreads();
+    pdl_wait();
 #pragma unroll
     for (int r = 0; r < TILE; r += ROWS) if (i0 + r + ty < p.ni && o0 + tx < p.no) {
       WT w = tile[tx][r + ty];
@@ -426,14 +429,18 @@ int try_transpose(const Nest& n) {
     long long blocks = p.tiles_i * p.tiles_o * batch;
     if (blocks > 0x7fffffffLL || blocks <= 0) return NCL_ERR_UNSUPPORTED;
     int fz = (add_zero && icls == CLS_F) ? 1 : (add_zero && icls == CLS_D) ? 2 : 0;
-    unsigned g = (unsigned)blocks;
-    if (wbytes == 8) { if (fz == 2) transpose_raw_kernel<unsigned long long, 32, 2><<<g, 256, 0, c.stream>>>(p); else transpose_raw_kernel<unsigned long long, 32, 0><<<g, 256, 0, c.stream>>>(p); }
-    else if (wbytes == 4 && tile == 64) { if (fz == 1) transpose_raw_kernel<unsigned int, 64, 1><<<g, 256, 0, c.stream>>>(p); else transpose_raw_kernel<unsigned int, 64, 0><<<g, 256, 0, c.stream>>>(p); }
-    else if (wbytes == 4) { if (fz == 1) transpose_raw_kernel<unsigned int, 32, 1><<<g, 256, 0, c.stream>>>(p); else transpose_raw_kernel<unsigned int, 32, 0><<<g, 256, 0, c.stream>>>(p); }
-    else if (wbytes == 2) transpose_raw_kernel<unsigned short, 64, 0><<<g, 256, 0, c.stream>>>(p);
-    else transpose_raw_kernel<unsigned char, 64, 0><<<g, 256, 0, c.stream>>>(p);
+    TrKernel k;
+    if (wbytes == 8) k = fz == 2 ? (TrKernel)transpose_raw_kernel<unsigned long long, 32, 2> : (TrKernel)transpose_raw_kernel<unsigned long long, 32, 0>;
+    else if (wbytes == 4) k = fz == 1 ? (TrKernel)transpose_raw_kernel<unsigned int, 64, 1> : (TrKernel)transpose_raw_kernel<unsigned int, 64, 0>;
+    else if (wbytes == 2) k = (TrKernel)transpose_raw_kernel<unsigned short, 64, 0>;
+    else k = (TrKernel)transpose_raw_kernel<unsigned char, 64, 0>;
+    PdlRange rd = pdl_range(in);
+    const bool early = pdl_eligible(&rd, 1);
+    void* args[1] = {(void*)&p};
+    NCL_TRY(pdl_launch((const void*)k, dim3((unsigned)blocks), dim3(256), args, c.stream, early));
     note_launch("transpose_tile");
-    return cuda_fail(cudaGetLastError(), "transpose_raw_kernel");
+    PdlRange wr = pdl_range(out); pdl_commit(early, &wr, 1);
+    return NCL_OK;
   }
   int tile = 64;
   p.tiles_i = (p.ni + tile - 1) / tile; p.tiles_o = (p.no + tile - 1) / tile;
