@@ -9,7 +9,7 @@ python - <<PY
 import csv
 rows=list(csv.reader(open("/tmp/raw_$c.csv")))
 hdr=rows[0]; val=rows[2] if len(rows)>2 else rows[-1]
-keep=[i for i,h in enumerate(hdr) if any(s in h for s in ("Kernel Name","gpu__time_duration.sum","dram__bytes_read.sum","dram__bytes_write.sum","dram__throughput.avg.pct","launch__registers","launch__grid_size","sm__warps_active.avg.pct","smsp__issue_active.avg.pct","smsp__inst_executed.sum","l1tex__t_sector_hit_rate","lts__t_sector_hit_rate","smsp__average_warp","sm__throughput.avg.pct","launch__occupancy_limit","sm__maximum_warps","achieved_occupancy","l1tex__data_pipe","lsu","warp_issue_stalled","smsp__pcsamp","dram__cycles_active","lts__t_bytes","l1tex__t_bytes","sm__inst_executed_pipe_lsu"))]
+keep=[i for i,h in enumerate(hdr) if any(s in h for s in ("Kernel Name","gpu__time_duration.sum","dram__bytes_read.sum","dram__bytes_write.sum","dram__throughput.avg.pct","launch__registers","launch__grid_size","sm__warps_active.avg.pct","smsp__issue_active.avg.pct","smsp__inst_executed.sum","l1tex__t_sector_hit_rate","lts__t_sector_hit_rate","smsp__average_warp","sm__throughput.avg.pct","launch__occupancy_limit","sm__maximum_warps","achieved_occupancy","l1tex__data_pipe","lsu","warp_issue_stalled","smsp__pcsamp","dram__cycles_active","lts__t_bytes","l1tex__t_bytes","sm__inst_executed_pipe_lsu","tensor","tmem","dmma","pipe_fp64"))]
 with open("gpurun_out/r2_ncu_${c}_raw.txt","w") as f:
     for i in keep: f.write(f"{hdr[i]} = {val[i]}\n")
 PY

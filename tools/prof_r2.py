@@ -35,6 +35,12 @@ elif case == "sum_u8_all":
     a = R((1024, 512, 512), "ub8", 7); f = lambda: nc.sum(a)
 elif case == "transpose_thin":
     a = R((1 << 22, 48)); f = lambda: nc.transpose(a)
+elif case == "c3d":
+    a = R((8192, 8192), "f64", 8); b = R((8192, 8192), "f64", 9); f = lambda: nc.matmul(a, b)
+elif case == "c3s":
+    a = R((8192, 8192), seed=8); b = R((8192, 8192), seed=9); f = lambda: nc.matmul(a, b)
+elif case == "c4":
+    a = R((256, 512, 512), seed=6); b = R((256, 512, 512), seed=7); f = lambda: nc.einsum("bij bjk -> bik", a, b)
 elif case == "fill":
     f = lambda: nc.full((16384, 16384), 1.5, type="f32")
 elif case == "scale":
