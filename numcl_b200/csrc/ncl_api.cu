@@ -13,6 +13,7 @@ static Context g_ctx;
 static std::recursive_mutex g_mu;
 static thread_local char g_err[1024] = "";
 Context& ctx() { return g_ctx; }
+std::recursive_mutex& ncl_mutex() { return g_mu; }
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);

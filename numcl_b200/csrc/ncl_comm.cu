@@ -147,11 +147,13 @@ static void setup_p2p() {
 extern "C" {
 
 int ncl_comm_unique_id(void* id128) {
+  std::lock_guard<std::recursive_mutex> lock__(ncl_mutex());
   NCL_TRY(nccl_load());
   nccl_uid u; NCL_TRY(nccl_fail(g_nccl.get_uid(&u), "ncclGetUniqueId"));
   memcpy(id128, &u, sizeof u); return NCL_OK;
 }
 int ncl_comm_init(const void* id128, int rank, int world) {
+  std::lock_guard<std::recursive_mutex> lock__(ncl_mutex());
   if (!ctx().inited) return set_error(NCL_ERR_STATE, "ncl_init has not been called");
   NCL_TRY(nccl_load());
   if (g_nccl.comm) return NCL_OK;
@@ -171,6 +173,7 @@ int ncl_comm_init(const void* id128, int rank, int world) {
   return NCL_OK;
 }
 int ncl_comm_destroy(void) {
+  std::lock_guard<std::recursive_mutex> lock__(ncl_mutex());
   if (g_nccl.comm) {
     cudaStreamSynchronize(ctx().stream); cudaStreamSynchronize(g_nccl.comm_stream);
     g_nccl.destroy(g_nccl.comm); g_nccl.comm = nullptr;
@@ -203,6 +206,7 @@ static int nccl_op(int op, int* out) {
 }
 
 int ncl_allreduce(int op, ncl_tensor* t) {
+  std::lock_guard<std::recursive_mutex> lock__(ncl_mutex());
   if (!g_nccl.comm) return set_error(NCL_ERR_STATE, "ncl_comm_init has not been called");
   if (!t || !t->buf) return set_error(NCL_ERR_INVALID, "ncl_allreduce needs a device-resident tensor");
   int ndt, nop; NCL_TRY(nccl_dtype(t->dtype, op, &ndt)); NCL_TRY(nccl_op(op, &nop));
@@ -216,6 +220,7 @@ int ncl_allreduce(int op, ncl_tensor* t) {
 // compute stream (e.g. the axis-1 reduction of the same slab).  ncl_comm_join() orders the compute
 // stream after it.
 int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a, ncl_tensor* r) {
+  std::lock_guard<std::recursive_mutex> lock__(ncl_mutex());
   if (!ctx().inited) return set_error(NCL_ERR_STATE, "ncl_init has not been called");
   // the slab may be a host array with a resident device mirror (ncl_host_register): the mirror is what gets reduced
   void* amirror = (a && !a->buf && a->host) ? resident_mirror(a->host, nullptr) : nullptr;
@@ -267,6 +272,7 @@ int ncl_reduce_all_sharded_async(int op, const ncl_tensor* a, ncl_tensor* r) {
   return NCL_OK;
 }
 int ncl_comm_join(void) {
+  std::lock_guard<std::recursive_mutex> lock__(ncl_mutex());
   // order the compute stream after every finalize still in flight (the last one, and the one before it)
   if (g_nccl.outstanding >= 1) NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done[(g_nccl.issued - 1) & 1], 0));
   if (g_nccl.outstanding >= 2) NCL_CUDA(cudaStreamWaitEvent(ctx().stream, g_nccl.ev_done[g_nccl.issued & 1], 0));
@@ -274,6 +280,7 @@ int ncl_comm_join(void) {
   return NCL_OK;
 }
 int ncl_reduce_all_sharded(int op, const ncl_tensor* a, ncl_tensor* r) {
+  std::lock_guard<std::recursive_mutex> lock__(ncl_mutex());
   NCL_TRY(ncl_reduce_all_sharded_async(op, a, r));
   return ncl_comm_join();
 }

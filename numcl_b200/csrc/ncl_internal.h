@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include "../../include/numcl_cuda.h"
 
@@ -82,6 +83,7 @@ struct Context {
   int64_t pipelined_calls = 0, pipelined_panels = 0;
 };
 Context& ctx();
+std::recursive_mutex& ncl_mutex();          // the library's one lock (ncl_api.cu): every entry point that touches the context takes it
 int  set_error(int code, const char* fmt, ...);
 int  cuda_fail(cudaError_t e, const char* what);
 #define NCL_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
