@@ -214,9 +214,11 @@ static int try_elementwise_32(const Nest& n) {
     for (int k = 0; k < m.n; k++) { if (in0.st[1 + k] == 1) { if (!chk(ops[k], 1 + k, 1 + k)) return false; } else if (in0.st[1 + k] != 0) return false; }
     return true;
   };
-  if (E > 1 && !aligned(E) && out_bits >= 8 && nd == 1 && d[0].ext % E != 0 && d[0].ext > 4LL * E) {
+  if (E > 1 && !aligned(E) && (out_bits >= 8 || (is_cmp && out_bits == 1)) && nd == 1 && d[0].ext % E != 0 && d[0].ext > 4LL * E) {
     // One contiguous run whose length is not a multiple of the 16-byte chunk (an odd-sized array): vector body +
     // scalar tail, as two nests of one loop each.  (The all-scalar kernel ran at 0.53 of the HBM peak on 16383^2.)
+    // Packed comparison results likewise: whole 32-bit result words, then the last partial word ((numcl:< a 0.5) of an array
+    // whose size is not a multiple of 32 used to run on the generic kernel altogether).
     bool unit = d[0].st[0] == 1;
     for (int k = 0; k < m.n; k++) if (d[0].st[1 + k] != 0 && d[0].st[1 + k] != 1) unit = false;
     if (unit) {
@@ -235,9 +237,12 @@ static int try_elementwise_32(const Nest& n) {
       Nest nb = piece(body, 0);
       int rc = try_elementwise(nb);
       if (rc != NCL_OK) return rc;
+      const char* body_kernel = c.last_kernel;
       Nest nt = piece(tail, body);
       rc = try_elementwise(nt);
-      return rc == NCL_ERR_UNSUPPORTED ? launch_generic(nt) : rc;      // the body is done: never hand the whole nest on
+      if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(nt);           // the body is done: never hand the whole nest on
+      c.last_kernel = body_kernel;                                      // (ncl_last_kernel names the family that did the work)
+      return rc;
     }
   }
   // Element-granular flat mode: the output is contiguous over a (rows x P) nest whose row length P is not a multiple of
@@ -246,7 +251,9 @@ static int try_elementwise_32(const Nest& n) {
   // element, (row, col) decoded once per chunk).  Without it these nests ran element-wise, 3 lanes of a warp busy:
   // (16M,3) + (3) at 0.018 of the HBM peak.
   bool eflat = false; int gather[3] = {0, 0, 0}; long long g_outer[3] = {0, 0, 0}; long long eflat_tail = 0, eflat_P = 0, eflat_R = 0;
-  if (E > 1 && out_bits >= 8 && nd == 2 && !aligned(E) && d[0].st[0] == d[1].ext && d[1].st[0] == 1) {
+  // (packed comparison results too: `(N,3) < (3)` has rows that are not whole result words and used to run on the generic kernel,
+  // 0.05 of the HBM peak; a lane then owns one 32-bit result word = 32 consecutive flat elements)
+  if (E > 1 && (out_bits >= 8 || (is_cmp && out_bits == 1 && E == 32)) && nd == 2 && !aligned(E) && d[0].st[0] == d[1].ext && d[1].st[0] == 1) {
     const long long P = d[1].ext, R = d[0].ext, total = P * R;
     bool ok = total < 0x7fffffffLL && total >= 64LL * E && P < 0x40000000LL;
     ok = ok && (((uintptr_t)out.base + (out.offset * out_bits) / 8) % 16) == 0;

@@ -199,3 +199,33 @@ def test_comparisons_broadcast_shapes(nc, oracle, sa, sb, ta, tb, op):
     want = refsem.broadcast(oracle, op, x, y)
     assert want.dtype == "bit"
     assert_bit_exact(nc.broadcast(op, to_gpu(nc, x), to_gpu(nc, y)), want)
+
+
+@pytest.mark.parametrize("sa,sb", [((50000, 3), (3,)), ((50000, 3), (50000, 1)), ((4099, 33), (33,)), ((700, 100), ()), ((10001, 7), (10001, 7)), ((3000, 5), (1, 5))])
+@pytest.mark.parametrize("ta,tb", [("f32", "f32"), ("f64", "f32"), ("ub8", "ub8"), ("fixnum", "f32"), ("sb32", "sb32")])
+@pytest.mark.parametrize("op", ["</bit", "=/bit"])
+def test_comparisons_whose_rows_are_not_whole_result_words(nc, oracle, sa, sb, ta, tb, op):
+    """`(N,3) < (3)`: the result's rows are 3 bits long.  The element-granular flat mode walks the result as one flat run of
+    32-bit words (a lane owns a word = 32 consecutive elements, operands of another shape are gathered per element); the
+    last partial word is a tiny nest of its own"""
+    lo_hi = lambda t: (-3, 3) if t in ("f32", "f64", "fixnum", "sb32") else (0, 6)
+    x = rand(oracle, sa, ta, SEED + 42, 1, *lo_hi(ta))
+    y = rand(oracle, sb, tb, SEED + 43, 1, *lo_hi(tb))
+    want = refsem.broadcast(oracle, op, x, y)
+    got = nc.broadcast(op, to_gpu(nc, x), to_gpu(nc, y))
+    assert_bit_exact(got, want)
+    if sa[0] * sa[1] >= 64 * 32 and not (ta == "fixnum" and tb == "f32"):
+        assert _last(nc) in ("bcast_vec_flat", "bcast_vec", "cmp_pack"), _last(nc)
+
+
+@pytest.mark.parametrize("n", [33, 1000, 70001, 1 << 20 | 5])
+@pytest.mark.parametrize("ta", ["f32", "f64", "ub8", "fixnum"])
+def test_comparison_of_an_odd_sized_array_with_a_scalar(nc, oracle, n, ta):
+    """(numcl:< a 2): whole result words on the vector kernels, the last partial word on its own"""
+    x = rand(oracle, (n,), ta, SEED + 44, 1, 0 if ta == "ub8" else -3, 6 if ta == "ub8" else 3)
+    y = rand(oracle, (), ta, SEED + 45, 1, 1, 1)
+    for op in ("</bit", ">=/bit"):
+        got = nc.broadcast(op, to_gpu(nc, x), to_gpu(nc, y))
+        assert_bit_exact(got, refsem.broadcast(oracle, op, x, y))
+    y2 = rand(oracle, (n,), ta, SEED + 46, 1, 0 if ta == "ub8" else -3, 6 if ta == "ub8" else 3)
+    assert_bit_exact(nc.broadcast("=/bit", to_gpu(nc, x), to_gpu(nc, y2)), refsem.broadcast(oracle, "=/bit", x, y2))

@@ -43,6 +43,7 @@ def R(shape, dt="f32", seed=1):
 
 a = R((1 << 26, 3)); v = R((3,), seed=2); w = R((1 << 26, 1), seed=3)
 run("(64M,3) + (3,)", lambda: nc.add(a, v), 2 * a.nbytes)
+run("(64M,3) < (3,) -> bit", lambda: nn.lt(a, v), a.nbytes + a.nbytes // 32)
 run("(64M,3) * (64M,1)", lambda: nc.mul(a, w), 2 * a.nbytes + w.nbytes)
 run("sum (64M,3) axis 1", lambda: nc.sum(a, axes=1), a.nbytes * 4 // 3)
 run("sum (64M,3) axis 0", lambda: nc.sum(a, axes=0), a.nbytes)
