@@ -59,6 +59,19 @@ static bool match_expr(const Expr& e, int self_out, bool fresh, Match* m) {
       }
       if (B.op == NCL_X_INPUT && fresh) { m->shape = S_ADD0U; m->n = 1; return leaf_slot(e, root.b, self_out, &m->s[0]); }
     }
+    // (+ (* $a $b) $c) / (+ $c (* $a $b)): a map over three arrays (map-array with a fused multiply-add form): the product is
+    // rounded, then added -- the accumulate functor with the addend in the accumulator's place (float + is commutative)
+    if (root.op == NCL_OP_ADD) {
+      for (int side = 0; side < 2; side++) {
+        const int im = side ? root.b : root.a, ic = side ? root.a : root.b;
+        const XNode& M = e.node[im];
+        Slot c0;
+        if (M.op == NCL_OP_MUL && e.node[M.a].op == NCL_X_INPUT && e.node[M.b].op == NCL_X_INPUT && e.node[ic].op == NCL_X_INPUT && leaf_slot(e, ic, self_out, &c0) && c0.kind == 0) {
+          m->shape = S_ADDMUL; m->n = 3; m->s[0] = c0;
+          return leaf_slot(e, M.a, self_out, &m->s[1]) && leaf_slot(e, M.b, self_out, &m->s[2]);
+        }
+      }
+    }
     Slot a, b;
     if (leaf_slot(e, root.a, self_out, &a) && leaf_slot(e, root.b, self_out, &b)) {
       if ((a.kind == 1 || b.kind == 1) && fresh) return false;      // reads a fresh output: let the generic path define it
@@ -202,7 +215,8 @@ static int try_elementwise_32(const Nest& n) {
     if (in0.ext % e) return false;
     auto chk = [&](const Operand& o, int slot, int k) {
       int sb = g_dt[o.dtype].slot_bits;
-      if (sb < 8 && slot != 0) return false;            // packed inputs are read element-wise (E = 1)
+      if (sb == 1 && slot != 0) return e <= 32;         // packed BIT inputs: E consecutive bits from one or two words (load_bits), any offset
+      if (sb < 8 && slot != 0) return false;            // ub2 / ub4 inputs are read element-wise (E = 1)
       long long bytes = (long long)e * sb / 8; long long a = bytes >= 16 ? 16 : bytes;
       if (a <= 1) return true;
       if (((uintptr_t)o.base + (o.offset * sb) / 8) % a) return false;

@@ -203,6 +203,17 @@ __device__ __forceinline__ void load_operand(const char* base, long long elem0, 
       case LK_S32: load_op_int<T, E, U, 32, true, false>(base + e0 * 4, q0, ext0, x); break;
       case LK_W64: load_op_int<T, E, U, 64, true, false>(base + e0 * 8, q0, ext0, x); break;
       case LK_T64: load_op_int<T, E, U, 64, true, true>(base + e0 * 8, q0, ext0, x); break;
+      case LK_P1:
+        if constexpr (E <= 32) {
+          // every word of the item first (chunks past the end of the row re-read the row's first word instead of branching around the
+          // load: with a branch per chunk the four chunks' loads went out one after the other, mask * array at 0.11 of the peak)
+          unsigned raw[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) raw[u] = load_bits_raw<E>(base, (q0 + u * 32 < ext0) ? e0 + (long long)u * 32 * E : elem0);
+#pragma unroll
+          for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) bits_to_elems<T, E>(raw[u], x[u]);
+        }
+        break;
       case LK_F32: {
         const char* p = base + e0 * 4;
 #pragma unroll
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const __grid_constant__ 
       const unsigned nq0 = q0 + nwarps * SEG;
 #pragma unroll
       for (int k = 0; k < NIN; k++) {
-        if (p.period[k] == 0 && p.st[1 + k][0] == 1 && !p.gather[k]) {
+        if (p.period[k] == 0 && p.st[1 + k][0] == 1 && !p.gather[k] && lk_bits(p.lk[k]) >= 8) {      // (packed operands: 64 bytes per item, not worth a prefetch)
           const int bytes = lk_bits(p.lk[k]) >> 3;
           const char* a = p.base[1 + k] + (p.off[1 + k] + (long long)nq0 * E) * bytes;
 #pragma unroll

@@ -52,19 +52,54 @@ int try_gemm(const Nest& n) {
   p.M = nm ? (int)gm[0].ext : 1; p.N = nn ? (int)gn[0].ext : 1; p.K = (int)gk[0].ext; p.batch = nb ? (int)gb[0].ext : 1;
   if ((nm && gm[0].ext > 0x7fffffffLL) || (nn && gn[0].ext > 0x7fffffffLL) || gk[0].ext > 0x7fffffffLL || (nb && gb[0].ext > 0x7fffffffLL)) return NCL_ERR_UNSUPPORTED;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.batch <= 0) return NCL_ERR_UNSUPPORTED;   // empty loops: the generic kernel defines them
-  if (gk[0].sa != 1) return NCL_ERR_UNSUPPORTED;                        // A must be k-contiguous
-  if (nn && (gn[0].sb != 1 || gn[0].sc != 1)) return NCL_ERR_UNSUPPORTED; // B and C n-contiguous
+  if (nn && gn[0].sc != 1) return NCL_ERR_UNSUPPORTED;                  // C n-contiguous
   p.lda = nm ? gm[0].sa : 0; p.ldb = gk[0].sb; p.ldc = nm ? gm[0].sc : 0;
   p.sA = nb ? gb[0].sa : 0; p.sB = nb ? gb[0].sb : 0; p.sC = nb ? gb[0].sc : 0;
-  if (p.lda < 0 || p.ldb < 0 || p.ldc < 0 || p.sA < 0 || p.sB < 0 || p.sC < 0) return NCL_ERR_UNSUPPORTED;
   p.A = A.base + (A.offset * g_dt[A.dtype].slot_bits) / 8; p.B = B.base + (B.offset * g_dt[B.dtype].slot_bits) / 8;
   p.C = C.base + (C.offset * g_dt[C.dtype].slot_bits) / 8;
+  // Transposed operands: `(ij ik -> jk)` = A^T B (A is m-contiguous) and `(ij kj -> ik)` = A B^T (B is k-contiguous) are as common
+  // as matmul itself (normal equations, covariances, the backward products of a layer) and used to fall to the thread-per-
+  // output generic kernel -- 20.6 ms for 8192 x 256 x 256.  The operand is copied into the k- / n-contiguous layout first (one
+  // HBM-bound pass through the transpose kernels), then the same GEMM kernels run.
+  ncl_buf* tmp[2] = {nullptr, nullptr};
+  auto release = [&](int rc) { for (int i = 0; i < 2; i++) if (tmp[i]) ncl_free(tmp[i]); return rc; };
+  auto relayout = [&](const Operand& X, long long s_b, long long s_r, long long s_c, long long rows, long long cols, ncl_buf** out) -> int {
+    // X[b][r][c] with element strides (s_b, s_r, s_c) -> contiguous [batch][rows][cols]
+    const long long total = (long long)p.batch * rows * cols;
+    *out = ncl_alloc(ncl_storage_bytes(X.dtype, total), 0);
+    if (!*out) return NCL_ERR_NOMEM;
+    Nest* t = new Nest;
+    t->nloops = 3; t->extent[0] = p.batch; t->extent[1] = rows; t->extent[2] = cols;
+    t->n_in = 1; t->n_out = 1; t->fresh = true;
+    t->in[0] = X; t->in[0].stride[0] = s_b; t->in[0].stride[1] = s_r; t->in[0].stride[2] = s_c;
+    Operand& o = t->out[0]; memset(&o, 0, sizeof o);
+    o.base = (char*)ncl_buf_ptr(*out); o.dtype = X.dtype; o.offset = 0; o.n_storage = (int64_t)((ncl_buf_bytes(*out) * 8) / g_dt[X.dtype].slot_bits); o.stage_item = -1;
+    o.stride[0] = rows * cols; o.stride[1] = cols; o.stride[2] = 1;
+    Expr& x = t->transform[0]; x.n = 1; memset(&x.node[0], 0, sizeof x.node[0]); x.node[0].op = NCL_X_INPUT; x.node[0].a = 1; x.node[0].cls = g_dt[X.dtype].cls;
+    int rc = try_transpose(*t);
+    if (rc == NCL_ERR_UNSUPPORTED) rc = try_elementwise(*t);
+    if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(*t);
+    delete t; return rc;
+  };
+  if (gk[0].sa != 1) {                                                  // A must be k-contiguous
+    if (!(nm && gm[0].sa == 1) || ctx().capturing) return NCL_ERR_UNSUPPORTED;
+    int rc = relayout(A, p.sA, gm[0].sa, gk[0].sa, p.M, p.K, &tmp[0]);
+    if (rc != NCL_OK) return release(rc);
+    p.A = (const char*)ncl_buf_ptr(tmp[0]); p.lda = p.K; p.sA = nb ? (long long)p.M * p.K : 0;
+  }
+  if (nn && gn[0].sb != 1) {                                            // B must be n-contiguous
+    if (gk[0].sb != 1 || ctx().capturing) return release(NCL_ERR_UNSUPPORTED);
+    int rc = relayout(B, p.sB, gk[0].sb, gn[0].sb, p.K, p.N, &tmp[1]);
+    if (rc != NCL_OK) return release(rc);
+    p.B = (const char*)ncl_buf_ptr(tmp[1]); p.ldb = p.N; p.sB = nb ? (long long)p.K * p.N : 0;
+  }
+  if (p.lda < 0 || p.ldb < 0 || p.ldc < 0 || p.sA < 0 || p.sB < 0 || p.sC < 0) return release(NCL_ERR_UNSUPPORTED);
   p.accumulate = n.fresh ? 0 : 1;
   p.lkA = dtype_load_kind(A.dtype); p.lkB = dtype_load_kind(B.dtype); p.lkC = dtype_load_kind(C.dtype); p.skC = dtype_store_spec(C.dtype);
   int rc = NCL_ERR_UNSUPPORTED;
   long long work = (long long)p.M * p.N;
   if (ca == CLS_D && A.dtype == NCL_F64 && p.M >= 32 && p.N >= 32) rc = gemm_f64_dmma(p);
   else if (ca == CLS_F && work >= 128 * 128 && p.K >= 32) rc = gemm_f32_tf32x3(p);
-  if (rc != NCL_ERR_UNSUPPORTED) return rc;
-  return gemm_simt(p, ca);
+  if (rc != NCL_ERR_UNSUPPORTED) return release(rc);
+  return release(gemm_simt(p, ca));
 }

@@ -333,7 +333,7 @@ static int reduce_impl(const Nest& n, int op, int ia, int ib) {
   note_launch(dot ? "dot_cols" : "reduce_col");
   NCL_TRY(cuda_fail(cudaGetLastError(), "reduce_col_kernel"));
   if (p.nseg > 1) {
-    kfor(E, KCOLFIN)<<<(unsigned)bx, 256, 0, c.stream>>>(p);
+    kfor(E, KCOLFIN)<<<(unsigned)((nq * E + 255) / 256), 256, 0, c.stream>>>(p);
     note_launch(dot ? "dot_cols" : "reduce_col");
     NCL_TRY(cuda_fail(cudaGetLastError(), "reduce_col_finish_kernel"));
   }

@@ -754,30 +754,31 @@ __global__ void __launch_bounds__(256) reduce_col_kernel(const __grid_constant__
 }
 template <class T, int OP, int E>
 __global__ void __launch_bounds__(256) reduce_col_finish_kernel(const __grid_constant__ RedParams p) {
+  // ONE column per thread (not one chunk of E columns: a thread then walked E x nseg dependent loads -- (sum a :axes 0) of an
+  // 8192 x 8192 (unsigned-byte 8) array spent 300 of its 415 us here, 512 threads folding 16 x 147 partials each)
   long long chunks_per_row = p.ncols / E;
-  long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+  long long c = (long long)blockIdx.x * 256 + threadIdx.x;
   long long nq = p.rows * chunks_per_row;
-  if (q >= nq) return;
+  if (c >= nq * E) return;
+  const long long q = c / E; const int i = (int)(c - q * E);
   long long cc = q, orow = 0;
   if (p.nk > 0) { cc = q % chunks_per_row; orow = q / chunks_per_row; }
-  long long obase = p.out_off + cc * E;
-  { long long r = orow; for (int k = p.nk - 1; k >= 0; k--) { long long c = r % p.kext[k]; r /= p.kext[k]; obase += c * p.kout[k]; } }
-  const T* part = (const T*)p.partial;
+  long long obase = p.out_off + cc * E + i;
+  { long long r = orow; for (int k = p.nk - 1; k >= 0; k--) { long long c2 = r % p.kext[k]; r /= p.kext[k]; obase += c2 * p.kout[k]; } }
+  const T* part = (const T*)p.partial + c;
+  const long long pitch = nq * E;
+  T a = part[0];
+  int s = 1;
+  for (; s + 7 < p.nseg; s += 8) {                        // eight segment partials in flight, folded in segment order
+    T t[8];
 #pragma unroll
-  for (int i = 0; i < E; i++) {
-    T a = part[q * E + i];
-    int s = 1;
-    for (; s + 7 < p.nseg; s += 8) {                        // eight segment partials in flight, folded in segment order
-      T t[8];
+    for (int k = 0; k < 8; k++) t[k] = part[(long long)(s + k) * pitch];
 #pragma unroll
-      for (int k = 0; k < 8; k++) t[k] = part[((long long)(s + k) * nq + q) * E + i];
-#pragma unroll
-      for (int k = 0; k < 8; k++) a = Red<T, OP>::f(a, t[k]);
-    }
-    for (; s < p.nseg; s++) a = Red<T, OP>::f(a, part[((long long)s * nq + q) * E + i]);
-    T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, obase + i, p.out_lk);
-    store_result<T, T>(p, obase + i, Red<T, OP>::f(init, a));
+    for (int k = 0; k < 8; k++) a = Red<T, OP>::f(a, t[k]);
   }
+  for (; s < p.nseg; s++) a = Red<T, OP>::f(a, part[(long long)s * pitch]);
+  T init = p.fresh ? ident_of<T>(p) : load_scalar<T>(p.out, obase, p.out_lk);
+  store_result<T, T>(p, obase, Red<T, OP>::f(init, a));
 }
 
 // ---- kernel tables ----------------------------------------------------------------------------------------------

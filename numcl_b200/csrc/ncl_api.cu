@@ -920,6 +920,37 @@ int ncl_reduce(int op, const ncl_tensor* a, const int* axes, int n_axes, ncl_ten
   for (int ax = 0; ax < a->rank; ax++) if (!summed[ax]) { if (rk >= r->rank || r->dims[rk] != a->dims[ax]) return set_error(NCL_ERR_SHAPE, "reduce: result shape mismatch"); rk++; }
   if (rk != r->rank) return set_error(NCL_ERR_SHAPE, "reduce: result rank %d, expected %d", r->rank, rk);
   bool fresh = (flags & NCL_OUT_FRESH) != 0;
+  if (g_dt[a->dtype].slot_bits < 8 && total_elems(a) > 4096) {
+    // Packed arrays (bit: the result of every comparison; ub2 / ub4): the streaming reduction kernels read byte-addressable
+    // slots, and the generic kernel walks a reduced axis with ONE thread per result -- (numcl:sum (numcl:< a b)) over 64 M
+    // elements took 73 seconds.  Counting the ones of a whole bit array is a sum of word popcounts; everything else goes through
+    // an (unsigned-byte 8) copy, which the 8-bit reduction kernels take (dp4a sums).
+    if (a->host) {                                               // stage the packed bytes once, then the device path
+      const size_t nb = ncl_storage_bytes(a->dtype, a->elem_offset + total_elems(a));
+      ncl_buf* tb = ncl_alloc(nb, 0); if (!tb) return NCL_ERR_NOMEM;
+      int rc = ncl_h2d(tb, 0, a->host, nb);
+      ncl_tensor a2 = *a; a2.host = nullptr; a2.buf = tb;
+      if (rc == NCL_OK) rc = ncl_reduce(op, &a2, axes, n_axes, r, flags);
+      ncl_free(tb); return rc;
+    }
+    const int64_t total = total_elems(a);
+    bool all = true; for (int ax = 0; ax < a->rank; ax++) if (!summed[ax] && a->dims[ax] != 1) all = false;
+    if (a->dtype == NCL_BIT && op == NCL_OP_ADD && all && total % 32 == 0 && a->elem_offset % 32 == 0) {
+      ncl_tensor w; memset(&w, 0, sizeof w); w.buf = a->buf; w.dtype = NCL_UB32; w.rank = 1; w.dims[0] = total / 32; w.elem_offset = a->elem_offset / 32;
+      ncl_tensor cnt; memset(&cnt, 0, sizeof cnt); cnt.dtype = NCL_FIXNUM; cnt.rank = 1; cnt.dims[0] = total / 32;
+      cnt.buf = ncl_alloc(ncl_storage_bytes(NCL_FIXNUM, total / 32), 0); if (!cnt.buf) return NCL_ERR_NOMEM;
+      ncl_expr e; e.n = 0; x_leaf(&e, NCL_X_INPUT, 1); x_op(&e, NCL_OP_LOGCOUNT, 0, 0);
+      int rc = ncl_map(&e, &w, 1, &cnt);
+      const int all_axes = 0;
+      if (rc == NCL_OK) rc = ncl_reduce(NCL_OP_ADD, &cnt, &all_axes, 0, r, flags);
+      ncl_free(cnt.buf); return rc;
+    }
+    ncl_tensor b8 = *a; b8.dtype = NCL_UB8; b8.elem_offset = 0;
+    b8.buf = ncl_alloc(ncl_storage_bytes(NCL_UB8, total), 0); if (!b8.buf) return NCL_ERR_NOMEM;
+    int rc = ncl_convert(a, &b8);
+    if (rc == NCL_OK) rc = ncl_reduce(op, &b8, axes, n_axes, r, flags);
+    ncl_free(b8.buf); return rc;
+  }
   {
     // Summed axes that do not form ONE run of adjacent axes (e.g. axes (0 2) of a rank-3 array) cannot be merged into a
     // single reduced dimension, and the nest used to fall to the thread-per-output generic kernel (130 ms for
@@ -931,7 +962,7 @@ int ncl_reduce(int op, const ncl_tensor* a, const int* axes, int n_axes, ncl_ten
       if (summed[ax] && (ax == 0 || !summed[ax - 1])) { runs++; t0 = ax; }
       if (summed[ax]) t1 = ax;
     }
-    if (runs > 1 && !empty && !a->host && !r->host && a->buf && r->buf) {
+    if (runs > 1 && !empty && !a->host && a->buf) {                  // (a host-resident result is staged by the second pass)
       ncl_tensor tmp; memset(&tmp, 0, sizeof tmp);
       tmp.dtype = r->dtype; tmp.rank = 0;
       int64_t n = 1;

@@ -318,6 +318,31 @@ __device__ __forceinline__ void load_int_chunk(const char* base, long long idx, 
   }
 }
 
+// E <= 32 consecutive elements of a packed BIT array starting at element idx: one 32-bit word, or two when the run straddles a
+// word boundary (the second word then holds elements of this very run, so it lies inside the array).  Bit arrays are what
+// every numcl comparison returns; they used to be read one element per thread (mask * array: 0.03 of the HBM peak).
+template <class T, int E>
+__device__ __forceinline__ void load_bits(const char* base, long long idx, T (&v)[E]) {
+  static_assert(E <= 32, "at most one result word per chunk");
+  const unsigned* w = reinterpret_cast<const unsigned*>(base) + (idx >> 5);
+  const unsigned sh = (unsigned)idx & 31u;
+  // two loads, no branch (a branch around the second load kept the loads of an unrolled step one behind the other); when the
+  // run fits one word the second address is the first one again
+  const unsigned lo = __ldg(w), hi = __ldg(w + ((sh + E > 32) ? 1 : 0));
+  const unsigned bits = __funnelshift_r(lo, hi, sh);
+#pragma unroll
+  for (int i = 0; i < E; i++) v[i] = from_i64<T>((long long)((bits >> i) & 1u));
+}
+// the same in two steps, so that a caller can issue the loads of several chunks before the first conversion
+template <int E> __device__ __forceinline__ unsigned load_bits_raw(const char* base, long long idx) {
+  const unsigned* w = reinterpret_cast<const unsigned*>(base) + (idx >> 5);
+  const unsigned sh = (unsigned)idx & 31u;
+  return __funnelshift_r(__ldg(w), __ldg(w + ((sh + E > 32) ? 1 : 0)), sh);
+}
+template <class T, int E> __device__ __forceinline__ void bits_to_elems(unsigned bits, T (&v)[E]) {
+#pragma unroll
+  for (int i = 0; i < E; i++) v[i] = from_i64<T>((long long)((bits >> i) & 1u));
+}
 // E consecutive elements starting at element idx (innermost stride 1), or one element splat (stride 0)
 template <class T, int E>
 __device__ __forceinline__ void load_elems(const char* base, long long idx, int lk, bool contiguous, T (&v)[E]) {
@@ -340,7 +365,8 @@ __device__ __forceinline__ void load_elems(const char* base, long long idx, int 
       case LK_F32: { Chunk<E * 4> c; ld_chunk(c, base + idx * 4);
 #pragma unroll
         for (int i = 0; i < E; i++) v[i] = from_f32<T>(__uint_as_float(c.w[i])); break; }
-      default: { Chunk<E * 8> c; ld_chunk(c, base + idx * 8);       // LK_F64 (sub-byte kinds never reach the fast path)
+      case LK_P1: if constexpr (E <= 32) load_bits<T, E>(base, idx, v); break;
+      default: { Chunk<E * 8> c; ld_chunk(c, base + idx * 8);       // LK_F64 (ub2 / ub4 never reach the fast path)
 #pragma unroll
         for (int i = 0; i < E; i++) v[i] = from_f64<T>(__longlong_as_double((long long)chunk_get<64>(c, i))); break; }
     }

@@ -203,6 +203,50 @@ static bool lower_complex(Nest& n) {
   return true;
 }
 
+// ---- bit arrays ---------------------------------------------------------------------------------------------------------
+// Every numcl comparison returns a BIT array and masks are combined with logand / logior / logxor / lognot ...: on arrays of
+// one dense layout that is the same function on the 32-bit words the bits are packed in -- every bit position is independent,
+// and %coerce into (unsigned-byte 1) keeps exactly the low bit the word operation produces ((lognot 0) = -1 -> 1).  The nest
+// becomes one loop over (unsigned-byte 32) words on the elementwise engine (32 elements per lane operation instead of the
+// generic kernel's one element per thread: 0.001 of the HBM peak); fewer than 32 trailing elements stay a nest of their own.
+static int lower_bitwise(Nest& n, Nest* tail, bool* has_tail) {
+  *has_tail = false;
+  if (n.n_out != 1 || n.n_in < 1 || n.stat) return 0;
+  if (n.out[0].dtype != NCL_BIT) return 0;
+  for (int i = 0; i < n.n_in; i++) if (n.in[i].dtype != NCL_BIT) return 0;
+  const Expr& e = n.transform[0];
+  for (int k = 0; k < e.n; k++) {
+    const int op = e.node[k].op;
+    if (!(op == NCL_X_INPUT || op == NCL_OP_LOGNOT || (op >= NCL_OP_LOGAND && op <= NCL_OP_LOGORC2))) return 0;
+  }
+  // one dense row-major layout shared by every array
+  int order[NCL_MAX_LOOPS], nl = 0;
+  for (int l = 0; l < n.nloops; l++) { if (n.extent[l] == 0) return 0; if (n.extent[l] > 1) order[nl++] = l; }
+  for (int i = 1; i < nl; i++) { int k = order[i], j = i - 1; while (j >= 0 && n.out[0].stride[order[j]] < n.out[0].stride[k]) { order[j + 1] = order[j]; j--; } order[j + 1] = k; }
+  long long total = 1;
+  for (int i = nl - 1; i >= 0; i--) {
+    const int l = order[i];
+    if (n.out[0].stride[l] != total) return 0;
+    for (int k = 0; k < n.n_in; k++) if (n.in[k].stride[l] != total) return 0;
+    total *= n.extent[l];
+  }
+  if (total < 32) return 0;
+  if (n.out[0].offset % 32) return 0;
+  for (int k = 0; k < n.n_in; k++) if (n.in[k].offset % 32) return 0;
+  const long long body = total / 32 * 32, rest = total - body;
+  if (rest) {
+    *tail = n; *has_tail = true;
+    tail->nloops = 1; tail->extent[0] = rest;
+    tail->out[0].stride[0] = 1; tail->out[0].offset += body;
+    for (int k = 0; k < n.n_in; k++) { tail->in[k].stride[0] = 1; tail->in[k].offset += body; }
+  }
+  n.nloops = 1; n.extent[0] = body / 32;
+  auto words = [](Operand& a) { a.dtype = NCL_UB32; a.offset /= 32; a.n_storage /= 32; a.stride[0] = 1; };
+  words(n.out[0]);
+  for (int k = 0; k < n.n_in; k++) words(n.in[k]);
+  return 1;
+}
+
 int run_nest(Nest& n) {
   for (int i = 0; i < n.n_in; i++) NCL_TRY(check_bounds(n.in[i], n, "input", i));
   for (int o = 0; o < n.n_out; o++) NCL_TRY(check_bounds(n.out[o], n, "output", o));
@@ -214,6 +258,11 @@ int run_nest(Nest& n) {
   }
   bool empty = false;
   for (int l = 0; l < n.nloops; l++) if (n.extent[l] == 0) empty = true;
+  if (!empty && !ctx().force_generic) {
+    Nest* tail = new Nest; bool has_tail = false;
+    if (lower_bitwise(n, tail, &has_tail) && has_tail) { int rc = launch_generic(*tail); if (rc != NCL_OK) { delete tail; return rc; } }
+    delete tail;
+  }
   if (n.stat) {                                        // fused statistics: reduction kernels only (ncl_reduce_stat composes otherwise)
     if (empty || ctx().force_generic) return NCL_ERR_UNSUPPORTED;
     int rc = try_dot_reduce(n);

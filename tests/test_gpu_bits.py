@@ -1,0 +1,126 @@
+"""Bit arrays at speed: every numcl comparison returns one (src/4numeric.lisp:609-655), masks are combined with the bitwise
+functions (:584-602), counted with numcl:sum and applied with numcl:* -- none of which may fall to the one-element-per-thread
+paths.  Also: map-array over three arrays with a multiply-add form."""
+import numpy as np
+import pytest
+
+import refsem
+from test_gpu_parity import SEED, assert_bit_exact, rand, to_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _last(nc):
+    return nc.lib().ncl_last_kernel().decode()
+
+
+def bits(oracle, shape, seed):
+    return rand(oracle, shape, "bit", seed, 0, 0, 1)
+
+
+@pytest.mark.parametrize("shape", [(64,), (1000,), (4099, 33), (1 << 20 | 5,), (256, 512), (7, 32, 33)])
+@pytest.mark.parametrize("fn", ["logand", "logior", "logxor", "logeqv", "lognand", "lognor", "logandc1", "logandc2", "logorc1", "logorc2"])
+def test_bitwise_functions_of_bit_arrays_run_on_words(nc, oracle, shape, fn):
+    x, y = bits(oracle, shape, SEED + 50), bits(oracle, shape, SEED + 51)
+    want = refsem.broadcast(oracle, fn, x, y)
+    got = nc.broadcast(fn, to_gpu(nc, x), to_gpu(nc, y))
+    assert_bit_exact(got, want)
+    if int(np.prod(shape)) >= 4096:
+        assert _last(nc) != "generic_nest" or int(np.prod(shape)) % 32 != 0, _last(nc)
+
+
+@pytest.mark.parametrize("shape", [(96,), (1000,), (513, 65), (1 << 18,)])
+def test_lognot_of_a_bit_array(nc, oracle, shape):
+    """numcl infers (integer -2 -1) for (lognot bit): a (signed-byte 8) array of -1 / -2, not a bit array"""
+    x = bits(oracle, shape, SEED + 52)
+    got = nc.lognot(to_gpu(nc, x))
+    assert got.dtype.name == "sb8"
+    assert np.array_equal(got.numpy(), ~x.values())
+
+
+def test_bitwise_on_a_window_that_does_not_start_on_a_word(nc, oracle):
+    """offsets that are not multiples of 32 keep the element-wise path: same answer, neighbours untouched"""
+    base = bits(oracle, (5000,), SEED + 53)
+    g = to_gpu(nc, base)
+    a = nc.NArray((4000,), "bit", _storage=g._buf, offset=7)
+    b = to_gpu(nc, bits(oracle, (4000,), SEED + 54))
+    got = nc.broadcast("logand", a, b)
+    assert np.array_equal(got.numpy(), base.values()[7:4007] & b.numpy())
+    assert np.array_equal(g.numpy(), base.values())
+
+
+@pytest.mark.parametrize("shape,axes", [((1 << 20,), None), ((1000, 1000), None), ((1 << 16 | 3,), None), ((512, 4096), (1,)), ((512, 4096), (0,)),
+                                        ((300, 70), (1,)), ((64, 64, 64), (0, 2))])
+@pytest.mark.parametrize("where", ["device", "host"])
+def test_counting_the_ones_of_a_bit_array(nc, oracle, shape, axes, where):
+    """(numcl:sum (numcl:< a b)): word popcounts for the whole array, an (unsigned-byte 8) copy for everything else"""
+    x = bits(oracle, shape, SEED + 55)
+    g = to_gpu(nc, x) if where == "device" else nc.asarray(x.values(), type="bit", where="host")
+    got = nc.sum(g, axes=axes)
+    want = x.values().sum(axis=axes)
+    if axes is None:
+        assert got == want
+    else:
+        assert got.dtype.name == "fixnum" and np.array_equal(got.numpy(), want)
+    assert _last(nc) != "generic_nest"
+
+
+def test_amax_and_mean_of_packed_arrays(nc, oracle):
+    x = bits(oracle, (300, 1000), SEED + 56)
+    assert np.array_equal(nc.amax(to_gpu(nc, x), axes=1).numpy(), x.values().max(axis=1))
+    u4 = rand(oracle, (100, 5000), "ub4", SEED + 57, 0, 0, 15)
+    assert np.array_equal(nc.sum(to_gpu(nc, u4), axes=1).numpy(), u4.values().sum(axis=1))
+    assert nc.sum(to_gpu(nc, u4)) == u4.values().sum()
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum", "ub8"])
+@pytest.mark.parametrize("shape", [(1 << 16,), (1000, 37), (4099,)])
+def test_masking_and_conversion_of_bit_arrays(nc, oracle, dt, shape):
+    """mask * array (numcl's `where`) and astype of a bit array read E consecutive bits per chunk"""
+    m = bits(oracle, shape, SEED + 58)
+    a = rand(oracle, shape, dt, SEED + 59, 1 if dt in ("f32", "f64") else 0, 0 if dt == "ub8" else -8, 8)
+    assert_bit_exact(nc.mul(to_gpu(nc, m), to_gpu(nc, a)), refsem.arith(oracle, "*", [m, a]))
+    assert_bit_exact(nc.mul(to_gpu(nc, a), to_gpu(nc, m)), refsem.arith(oracle, "*", [a, m]))
+    c = nc.astype(to_gpu(nc, m), dt)
+    assert c.dtype.name == dt and np.array_equal(c.numpy(), m.values().astype(c.numpy().dtype))
+    if int(np.prod(shape)) >= 4096 and int(np.prod(shape)) % 32 == 0:
+        assert _last(nc) == "bcast_vec", _last(nc)
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum"])
+@pytest.mark.parametrize("form", ["(+ (* $1 $2) $3)", "(+ $3 (* $1 $2))"])
+def test_map_array_multiply_add_over_three_arrays(nc, oracle, dt, form):
+    shape = (513, 257)
+    xs = [rand(oracle, shape, dt, SEED + 60 + i, 0 if dt != "fixnum" else 0, -1.0 if dt != "fixnum" else -9, 1.0 if dt != "fixnum" else 9) for i in range(3)]
+    want = oracle.map_array(form, xs, dt)
+    got = nc.map_array(form, *[to_gpu(nc, x) for x in xs])
+    assert_bit_exact(got, want)
+    assert _last(nc) != "generic_nest", _last(nc)
+
+
+# ---- contractions with a transposed operand: A^T B, A B^T (k_gemm.cu: the operand is re-laid out, then the GEMM kernels run) -----
+@pytest.mark.parametrize("spec,sa,sb", [("ij ik -> jk", (300, 70), (300, 90)), ("ij kj -> ik", (130, 257), (64, 257)), ("ij ik -> jk", (1024, 256), (1024, 256)),
+                                        ("ji ki -> jk", (128, 512), (256, 512)), ("bij bik -> bjk", (6, 200, 48), (6, 200, 80)), ("bij bkj -> bik", (5, 128, 96), (5, 256, 96)),
+                                        ("ij ik -> jk", (4099, 33), (4099, 17))])
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum"])
+def test_contractions_with_transposed_operands(nc, oracle, spec, sa, sb, dt):
+    exact = dt == "fixnum"
+    A = rand(oracle, sa, dt, SEED + 70, 1, -4, 4)                    # integer-valued data: every order of summation is exact
+    B = rand(oracle, sb, dt, SEED + 71, 1, -4, 4)
+    want = refsem.einsum(oracle, spec, [A, B])
+    got = nc.einsum(spec, to_gpu(nc, A), to_gpu(nc, B))
+    assert_bit_exact(got, want)
+    assert _last(nc).startswith("gemm") or _last(nc).startswith("dot"), _last(nc)
+    if not exact:                                                    # random floats: within the contraction tolerance
+        A = rand(oracle, sa, dt, SEED + 72, 0, -1.0, 1.0); B = rand(oracle, sb, dt, SEED + 73, 0, -1.0, 1.0)
+        w = refsem.einsum(oracle, spec, [A, B]).values().astype(np.float64)
+        g = nc.einsum(spec, to_gpu(nc, A), to_gpu(nc, B)).numpy().astype(np.float64)
+        assert np.linalg.norm(g - w) / np.linalg.norm(w) <= (1e-5 if dt == "f32" else 1e-12)
+
+
+def test_transposed_contraction_accumulates_into_a_supplied_output(nc, oracle):
+    A = rand(oracle, (500, 64), "f64", SEED + 74, 1, -4, 4); B = rand(oracle, (500, 96), "f64", SEED + 75, 1, -4, 4)
+    C0 = rand(oracle, (64, 96), "f64", SEED + 76, 1, -4, 4)
+    g = to_gpu(nc, C0)
+    nc.einsum("ij ik -> jk", to_gpu(nc, A), to_gpu(nc, B), g)
+    assert np.array_equal(g.numpy(), C0.values() + A.values().T @ B.values())

@@ -41,6 +41,8 @@ elif case == "c3s":
     a = R((8192, 8192), seed=8); b = R((8192, 8192), seed=9); f = lambda: nc.matmul(a, b)
 elif case == "c4":
     a = R((256, 512, 512), seed=6); b = R((256, 512, 512), seed=7); f = lambda: nc.einsum("bij bjk -> bik", a, b)
+elif case == "bitmul":
+    a = R((1 << 26,)); b = R((1 << 26,), seed=2); m = nn.lt(a, b); f = lambda: nc.mul(m, a)
 elif case == "fill":
     f = lambda: nc.full((16384, 16384), 1.5, type="f32")
 elif case == "scale":
