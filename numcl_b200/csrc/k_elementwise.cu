@@ -207,16 +207,21 @@ static int try_elementwise_32(const Nest& n) {
 
   StoreSpec sk = dtype_store_spec(out.dtype);
   int out_bits = g_dt[out.dtype].slot_bits;
-  int E = out_bits >= 8 ? 128 / out_bits : 32;
-  if (out_bits < 8 && out_bits != 1) return NCL_ERR_UNSUPPORTED;           // ub2/ub4 outputs: generic path
+  // elements per chunk: 16 bytes of byte-addressable slots, or ONE 32-bit word of a packed result (32 bits, 16 ub2, 8 ub4 --
+  // numcl infers (unsigned-byte 2 / 4) for small ranges: (mod a 7), mask + mask, (arange 5))
+  int E = out_bits >= 8 ? 128 / out_bits : 32 / out_bits;
   // vector eligibility: inner extent divisible, every vectorised operand 16B-aligned at every row start
   const D& in0 = d[nd - 1];
   auto aligned = [&](int e) {
     if (in0.ext % e) return false;
     auto chk = [&](const Operand& o, int slot, int k) {
       int sb = g_dt[o.dtype].slot_bits;
-      if (sb == 1 && slot != 0) return e <= 32;         // packed BIT inputs: E consecutive bits from one or two words (load_bits), any offset
-      if (sb < 8 && slot != 0) return false;            // ub2 / ub4 inputs are read element-wise (E = 1)
+      if (sb < 8 && slot != 0) return e * sb <= 32;     // packed inputs: E consecutive fields from one or two words (load_bits_raw), any offset
+      if (sb < 8 && e * sb >= 32) {                     // packed result: every chunk is a whole, aligned 32-bit word
+        if (e * sb != 32 || ((uintptr_t)o.base % 4) || (o.offset * sb) % 32) return false;
+        for (int i = 0; i < nd - 1; i++) if ((d[i].st[k] * sb) % 32) return false;
+        return true;
+      }
       long long bytes = (long long)e * sb / 8; long long a = bytes >= 16 ? 16 : bytes;
       if (a <= 1) return true;
       if (((uintptr_t)o.base + (o.offset * sb) / 8) % a) return false;
@@ -228,7 +233,7 @@ static int try_elementwise_32(const Nest& n) {
     for (int k = 0; k < m.n; k++) { if (in0.st[1 + k] == 1) { if (!chk(ops[k], 1 + k, 1 + k)) return false; } else if (in0.st[1 + k] != 0) return false; }
     return true;
   };
-  if (E > 1 && !aligned(E) && (out_bits >= 8 || (is_cmp && out_bits == 1)) && nd == 1 && d[0].ext % E != 0 && d[0].ext > 4LL * E) {
+  if (E > 1 && !aligned(E) && nd == 1 && d[0].ext % E != 0 && d[0].ext > 4LL * E) {
     // One contiguous run whose length is not a multiple of the 16-byte chunk (an odd-sized array): vector body +
     // scalar tail, as two nests of one loop each.  (The all-scalar kernel ran at 0.53 of the HBM peak on 16383^2.)
     // Packed comparison results likewise: whole 32-bit result words, then the last partial word ((numcl:< a 0.5) of an array

@@ -214,6 +214,24 @@ __device__ __forceinline__ void load_operand(const char* base, long long elem0, 
           for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) bits_to_elems<T, E>(raw[u], x[u]);
         }
         break;
+      case LK_P2:
+        if constexpr (E <= 16) {
+          unsigned raw[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) raw[u] = load_bits_raw<E, 2>(base, (q0 + u * 32 < ext0) ? e0 + (long long)u * 32 * E : elem0);
+#pragma unroll
+          for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) bits_to_elems<T, E, 2>(raw[u], x[u]);
+        }
+        break;
+      case LK_P4:
+        if constexpr (E <= 8) {
+          unsigned raw[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) raw[u] = load_bits_raw<E, 4>(base, (q0 + u * 32 < ext0) ? e0 + (long long)u * 32 * E : elem0);
+#pragma unroll
+          for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) bits_to_elems<T, E, 4>(raw[u], x[u]);
+        }
+        break;
       case LK_F32: {
         const char* p = base + e0 * 4;
 #pragma unroll
@@ -258,6 +276,10 @@ __device__ __forceinline__ void store_operand(char* base, long long elem0, unsig
   } else {
     const long long e0 = elem0 + (long long)q0 * E;
     switch (sk.kind) {
+      case SK_P2: case SK_P4:                                   // ub2 / ub4 results: a chunk is one 32-bit word (store_elems)
+#pragma unroll
+        for (int u = 0; u < U; u++) if (q0 + u * 32 < ext0) store_elems<TO, E>(base, elem0 + (long long)(q0 + u * 32) * E, sk, y[u]);
+        break;
       case SK_8:  store_op_int<TO, E, U, 8>(base + e0, q0, ext0, sk, y); break;
       case SK_16: store_op_int<TO, E, U, 16>(base + e0 * 2, q0, ext0, sk, y); break;
       case SK_32: store_op_int<TO, E, U, 32>(base + e0 * 4, q0, ext0, sk, y); break;

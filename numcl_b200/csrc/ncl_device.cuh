@@ -333,15 +333,18 @@ __device__ __forceinline__ void load_bits(const char* base, long long idx, T (&v
 #pragma unroll
   for (int i = 0; i < E; i++) v[i] = from_i64<T>((long long)((bits >> i) & 1u));
 }
-// the same in two steps, so that a caller can issue the loads of several chunks before the first conversion
-template <int E> __device__ __forceinline__ unsigned load_bits_raw(const char* base, long long idx) {
-  const unsigned* w = reinterpret_cast<const unsigned*>(base) + (idx >> 5);
-  const unsigned sh = (unsigned)idx & 31u;
-  return __funnelshift_r(__ldg(w), __ldg(w + ((sh + E > 32) ? 1 : 0)), sh);
+// the same in two steps, so that a caller can issue the loads of several chunks before the first conversion; B = bits per
+// element (1, 2, 4: bit, ub2, ub4 arrays), E * B <= 32
+template <int E, int B = 1> __device__ __forceinline__ unsigned load_bits_raw(const char* base, long long idx) {
+  static_assert(E * B <= 32, "one word's worth of packed elements per chunk");
+  const long long bit = idx * B;
+  const unsigned* w = reinterpret_cast<const unsigned*>(base) + (bit >> 5);
+  const unsigned sh = (unsigned)bit & 31u;
+  return __funnelshift_r(__ldg(w), __ldg(w + ((sh + E * B > 32) ? 1 : 0)), sh);
 }
-template <class T, int E> __device__ __forceinline__ void bits_to_elems(unsigned bits, T (&v)[E]) {
+template <class T, int E, int B = 1> __device__ __forceinline__ void bits_to_elems(unsigned bits, T (&v)[E]) {
 #pragma unroll
-  for (int i = 0; i < E; i++) v[i] = from_i64<T>((long long)((bits >> i) & 1u));
+  for (int i = 0; i < E; i++) v[i] = from_i64<T>((long long)((bits >> (i * B)) & ((1u << B) - 1u)));
 }
 // E consecutive elements starting at element idx (innermost stride 1), or one element splat (stride 0)
 template <class T, int E>
@@ -366,6 +369,8 @@ __device__ __forceinline__ void load_elems(const char* base, long long idx, int 
 #pragma unroll
         for (int i = 0; i < E; i++) v[i] = from_f32<T>(__uint_as_float(c.w[i])); break; }
       case LK_P1: if constexpr (E <= 32) load_bits<T, E>(base, idx, v); break;
+      case LK_P2: if constexpr (E <= 16) bits_to_elems<T, E, 2>(load_bits_raw<E, 2>(base, idx), v); break;
+      case LK_P4: if constexpr (E <= 8) bits_to_elems<T, E, 4>(load_bits_raw<E, 4>(base, idx), v); break;
       default: { Chunk<E * 8> c; ld_chunk(c, base + idx * 8);       // LK_F64 (ub2 / ub4 never reach the fast path)
 #pragma unroll
         for (int i = 0; i < E; i++) v[i] = from_f64<T>(__longlong_as_double((long long)chunk_get<64>(c, i))); break; }
@@ -434,6 +439,12 @@ __device__ __forceinline__ void store_elems(char* base, long long idx, const Sto
 #pragma unroll
       for (int i = 0; i < 32; i++) w |= ((unsigned int)v[i] & 1u) << i;
       *(unsigned int*)(base + (idx >> 3)) = w;
+    } else if ((E == 16 && sk.kind == SK_P2) || (E == 8 && sk.kind == SK_P4)) {         // ub2 / ub4: E elements = one 32-bit word
+      constexpr int B = 32 / E;
+      unsigned int w = 0;
+#pragma unroll
+      for (int i = 0; i < E; i++) w |= ((unsigned int)v[i] & ((1u << B) - 1u)) << (i * B);
+      *(unsigned int*)(base + ((idx * B) >> 3)) = w;
     } else {
       if constexpr (E == 16) { Chunk<16> c;
 #pragma unroll

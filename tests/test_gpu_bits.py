@@ -124,3 +124,40 @@ def test_transposed_contraction_accumulates_into_a_supplied_output(nc, oracle):
     g = to_gpu(nc, C0)
     nc.einsum("ij ik -> jk", to_gpu(nc, A), to_gpu(nc, B), g)
     assert np.array_equal(g.numpy(), C0.values() + A.values().T @ B.values())
+
+
+# ---- (unsigned-byte 2) / (unsigned-byte 4) results and operands: one 32-bit word of packed fields per chunk ---------------------
+@pytest.mark.parametrize("n", [64, 1000, 4099, 1 << 18, (1 << 18) + 13])
+def test_small_integer_results_are_packed_words(nc, oracle, n):
+    """numcl infers the narrowest type: mask + mask and mask + 1 are (unsigned-byte 2), (mod a 7) is (unsigned-byte 4)"""
+    m1, m2 = bits(oracle, (n,), SEED + 80), bits(oracle, (n,), SEED + 81)
+    got = nc.add(to_gpu(nc, m1), to_gpu(nc, m2))
+    assert got.dtype.name == "ub2"
+    assert_bit_exact(got, refsem.arith(oracle, "+", [m1, m2]))
+    assert_bit_exact(nc.add(to_gpu(nc, m1), 1), refsem.arith(oracle, "+", [m1, 1]))
+    f = rand(oracle, (n,), "fixnum", SEED + 82, 0, -1000, 1000)
+    r = nc.mod(to_gpu(nc, f), 7)
+    assert r.dtype.name == "ub4" and np.array_equal(r.numpy(), np.mod(f.values(), 7))
+    if n >= 4096:
+        assert _last(nc) != "generic_nest", _last(nc)
+    u4 = rand(oracle, (n,), "ub4", SEED + 83, 0, 0, 7)
+    s = nc.add(to_gpu(nc, u4), r)                             # ub4 + ub4: (integer 0 13) -> ub4
+    assert_bit_exact(s, refsem.arith(oracle, "+", [u4, oracle.OArr.from_values(np.mod(f.values(), 7), "ub4")]))
+    assert_bit_exact(nc.mul(to_gpu(nc, u4), to_gpu(nc, m1)), refsem.arith(oracle, "*", [u4, m1]))
+    w = nc.astype(to_gpu(nc, u4), "f32")
+    assert np.array_equal(w.numpy(), u4.values().astype(np.float32))
+
+
+def test_packed_results_in_two_dimensions_and_views(nc, oracle):
+    a = rand(oracle, (300, 64), "ub4", SEED + 84, 0, 0, 7); b = rand(oracle, (64,), "ub4", SEED + 85, 0, 0, 7)
+    assert_bit_exact(nc.add(to_gpu(nc, a), to_gpu(nc, b)), refsem.arith(oracle, "+", [a, b]))
+    c = rand(oracle, (301, 33), "ub2", SEED + 86, 0, 0, 1)
+    assert_bit_exact(nc.add(to_gpu(nc, c), to_gpu(nc, c)), refsem.arith(oracle, "+", [c, c]))
+    # a result window that does not start on a word boundary keeps the element-wise path: neighbours untouched
+    base = nc.NArray((5000,), "ub4"); base.set_raw(np.full(base.nbytes, 0xAB, dtype=np.uint8))
+    view = nc.NArray((4000,), "ub4", _storage=base._buf, offset=3)
+    x = rand(oracle, (4000,), "ub4", SEED + 87, 0, 0, 15)
+    nc.map_array_into(view, "identity", to_gpu(nc, x))
+    got = base.numpy()
+    sentinel = np.tile(np.array([0xB, 0xA]), 2500)                          # the nibbles of 0xAB, low one first
+    assert np.array_equal(got[3:4003], x.values()) and np.array_equal(got[:3], sentinel[:3]) and np.array_equal(got[4003:], sentinel[4003:])
