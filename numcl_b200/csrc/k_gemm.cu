@@ -36,7 +36,17 @@ int try_gemm(const Nest& n) {
   if (e.node[mul.a].op != NCL_X_INPUT || e.node[mul.b].op != NCL_X_INPUT || e.node[mul.a].a == e.node[mul.b].a) return NCL_ERR_UNSUPPORTED;
   const Operand& A = n.in[e.node[mul.a].a - 1]; const Operand& B = n.in[e.node[mul.b].a - 1]; const Operand& C = n.out[0];
   int ca = g_dt[A.dtype].cls, cb = g_dt[B.dtype].cls, cc = g_dt[C.dtype].cls;
-  if (ca != cb || ca != cc) return NCL_ERR_UNSUPPORTED;               // mixed classes: the generic kernel has exact contagion
+  // Mixed classes (single-float x double-float, integer x float): Common Lisp's contagion converts the lower operand to the
+  // class of the other BEFORE the product, exactly what converting the ARRAY first does -- so one operand may be of a lower
+  // class than the result if the other already has the result's class (both lower: the product would be formed in the lower
+  // class first; that stays on the generic kernel).
+  int dtA = A.dtype, dtB = B.dtype;
+  if (ca != cc || cb != cc) {
+    if (!(cc == CLS_F || cc == CLS_D) || ca > cc || cb > cc || (ca != cc && cb != cc) || ca > CLS_D || cb > CLS_D) return NCL_ERR_UNSUPPORTED;
+    if (ca != cc) dtA = cc == CLS_F ? NCL_F32 : NCL_F64;
+    if (cb != cc) dtB = cc == CLS_F ? NCL_F32 : NCL_F64;
+    if (A.dtype == NCL_UB64 || B.dtype == NCL_UB64) return NCL_ERR_UNSUPPORTED;
+  }
   if (g_dt[A.dtype].slot_bits < 8 || g_dt[B.dtype].slot_bits < 8 || g_dt[C.dtype].slot_bits < 8) return NCL_ERR_UNSUPPORTED;
   GDim gb[NCL_MAX_LOOPS], gm[NCL_MAX_LOOPS], gn[NCL_MAX_LOOPS], gk[NCL_MAX_LOOPS]; int nb = 0, nm = 0, nn = 0, nk = 0;
   for (int l = 0; l < n.nloops; l++) {
@@ -63,17 +73,17 @@ int try_gemm(const Nest& n) {
   // HBM-bound pass through the transpose kernels), then the same GEMM kernels run.
   ncl_buf* tmp[2] = {nullptr, nullptr};
   auto release = [&](int rc) { for (int i = 0; i < 2; i++) if (tmp[i]) ncl_free(tmp[i]); return rc; };
-  auto relayout = [&](const Operand& X, long long s_b, long long s_r, long long s_c, long long rows, long long cols, ncl_buf** out) -> int {
-    // X[b][r][c] with element strides (s_b, s_r, s_c) -> contiguous [batch][rows][cols]
+  auto relayout = [&](const Operand& X, int odt, long long s_b, long long s_r, long long s_c, long long rows, long long cols, ncl_buf** out) -> int {
+    // X[b][r][c] with element strides (s_b, s_r, s_c) -> contiguous [batch][rows][cols] of element type odt
     const long long total = (long long)p.batch * rows * cols;
-    *out = ncl_alloc(ncl_storage_bytes(X.dtype, total), 0);
+    *out = ncl_alloc(ncl_storage_bytes(odt, total), 0);
     if (!*out) return NCL_ERR_NOMEM;
     Nest* t = new Nest;
     t->nloops = 3; t->extent[0] = p.batch; t->extent[1] = rows; t->extent[2] = cols;
     t->n_in = 1; t->n_out = 1; t->fresh = true;
     t->in[0] = X; t->in[0].stride[0] = s_b; t->in[0].stride[1] = s_r; t->in[0].stride[2] = s_c;
     Operand& o = t->out[0]; memset(&o, 0, sizeof o);
-    o.base = (char*)ncl_buf_ptr(*out); o.dtype = X.dtype; o.offset = 0; o.n_storage = (int64_t)((ncl_buf_bytes(*out) * 8) / g_dt[X.dtype].slot_bits); o.stage_item = -1;
+    o.base = (char*)ncl_buf_ptr(*out); o.dtype = odt; o.offset = 0; o.n_storage = (int64_t)((ncl_buf_bytes(*out) * 8) / g_dt[odt].slot_bits); o.stage_item = -1;
     o.stride[0] = rows * cols; o.stride[1] = cols; o.stride[2] = 1;
     Expr& x = t->transform[0]; x.n = 1; memset(&x.node[0], 0, sizeof x.node[0]); x.node[0].op = NCL_X_INPUT; x.node[0].a = 1; x.node[0].cls = g_dt[X.dtype].cls;
     int rc = try_transpose(*t);
@@ -81,25 +91,25 @@ int try_gemm(const Nest& n) {
     if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(*t);
     delete t; return rc;
   };
-  if (gk[0].sa != 1) {                                                  // A must be k-contiguous
-    if (!(nm && gm[0].sa == 1) || ctx().capturing) return NCL_ERR_UNSUPPORTED;
-    int rc = relayout(A, p.sA, gm[0].sa, gk[0].sa, p.M, p.K, &tmp[0]);
+  if (gk[0].sa != 1 || dtA != A.dtype) {                               // A must be k-contiguous and of the result's class
+    if ((gk[0].sa != 1 && !(nm && gm[0].sa == 1)) || ctx().capturing) return NCL_ERR_UNSUPPORTED;
+    int rc = relayout(A, dtA, p.sA, nm ? gm[0].sa : 0, gk[0].sa, p.M, p.K, &tmp[0]);
     if (rc != NCL_OK) return release(rc);
     p.A = (const char*)ncl_buf_ptr(tmp[0]); p.lda = p.K; p.sA = nb ? (long long)p.M * p.K : 0;
   }
-  if (nn && gn[0].sb != 1) {                                            // B must be n-contiguous
-    if (gk[0].sb != 1 || ctx().capturing) return release(NCL_ERR_UNSUPPORTED);
-    int rc = relayout(B, p.sB, gk[0].sb, gn[0].sb, p.K, p.N, &tmp[1]);
+  if ((nn && gn[0].sb != 1) || dtB != B.dtype) {                       // B must be n-contiguous and of the result's class
+    if ((nn && gn[0].sb != 1 && gk[0].sb != 1) || ctx().capturing) return release(NCL_ERR_UNSUPPORTED);
+    int rc = relayout(B, dtB, p.sB, gk[0].sb, nn ? gn[0].sb : 0, p.K, p.N, &tmp[1]);
     if (rc != NCL_OK) return release(rc);
     p.B = (const char*)ncl_buf_ptr(tmp[1]); p.ldb = p.N; p.sB = nb ? (long long)p.K * p.N : 0;
   }
   if (p.lda < 0 || p.ldb < 0 || p.ldc < 0 || p.sA < 0 || p.sB < 0 || p.sC < 0) return release(NCL_ERR_UNSUPPORTED);
   p.accumulate = n.fresh ? 0 : 1;
-  p.lkA = dtype_load_kind(A.dtype); p.lkB = dtype_load_kind(B.dtype); p.lkC = dtype_load_kind(C.dtype); p.skC = dtype_store_spec(C.dtype);
+  p.lkA = dtype_load_kind(dtA); p.lkB = dtype_load_kind(dtB); p.lkC = dtype_load_kind(C.dtype); p.skC = dtype_store_spec(C.dtype);
   int rc = NCL_ERR_UNSUPPORTED;
   long long work = (long long)p.M * p.N;
-  if (ca == CLS_D && A.dtype == NCL_F64 && p.M >= 32 && p.N >= 32) rc = gemm_f64_dmma(p);
-  else if (ca == CLS_F && work >= 128 * 128 && p.K >= 32) rc = gemm_f32_tf32x3(p);
+  if (cc == CLS_D && dtA == NCL_F64 && p.M >= 32 && p.N >= 32) rc = gemm_f64_dmma(p);
+  else if (cc == CLS_F && work >= 128 * 128 && p.K >= 32) rc = gemm_f32_tf32x3(p);
   if (rc != NCL_ERR_UNSUPPORTED) return release(rc);
-  return release(gemm_simt(p, ca));
+  return release(gemm_simt(p, cc));
 }

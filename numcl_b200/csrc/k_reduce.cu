@@ -74,11 +74,59 @@ static int launch_red(RedKernel kfn, dim3 grid, const RedParams& p, const Operan
   return NCL_OK;
 }
 
+// Reduced loops that do not form ONE run of neighbouring loops of the input -- `(ijk -> j)`, `(ijkl -> jl)`: the kernels merge the
+// reduced loops into one dimension and cannot, so such a nest fell to the generic kernel, where one thread walks all of
+// the reduced loops of its result element (85 ms for 256^3 single-floats).  The innermost run is reduced into a temporary
+// of the result's element type first, the rest from there: fast passes only.  Exact for integers (modular) and max / min;
+// floats round once more between the passes, within the reduction tolerance (ncl_reduce does the same for :axes (0 2)).
+static int reduce_two_pass(const Nest& n, int op) {
+  const Operand& in = n.in[0]; const Operand& out = n.out[0];
+  if (n.stat || g_dt[in.dtype].cls != g_dt[out.dtype].cls || g_dt[in.dtype].slot_bits < 8 || ctx().capturing) return NCL_ERR_UNSUPPORTED;
+  int ord[NCL_MAX_LOOPS], nl = 0;
+  for (int l = 0; l < n.nloops; l++) { if (n.extent[l] <= 0) return NCL_ERR_UNSUPPORTED; if (n.extent[l] > 1) { if (in.stride[l] <= 0) return NCL_ERR_UNSUPPORTED; ord[nl++] = l; } }
+  for (int i = 1; i < nl; i++) { int k = ord[i], j = i - 1; while (j >= 0 && in.stride[ord[j]] < in.stride[k]) { ord[j + 1] = ord[j]; j--; } ord[j + 1] = k; }
+  int runs = 0, last0 = -1;
+  for (int i = 0; i < nl; i++) { const bool red = out.stride[ord[i]] == 0; if (red && (i == 0 || out.stride[ord[i - 1]] != 0)) { runs++; last0 = i; } }
+  if (runs < 2) return NCL_ERR_UNSUPPORTED;
+  int last1 = last0; while (last1 + 1 < nl && out.stride[ord[last1 + 1]] == 0) last1++;
+  // temporary over every loop outside the innermost reduced run, row-major in the input's order
+  long long tstride[NCL_MAX_LOOPS], total = 1;
+  for (int i = nl - 1; i >= 0; i--) if (i < last0 || i > last1) { tstride[i] = total; total *= n.extent[ord[i]]; }
+  ncl_buf* tb = ncl_alloc(ncl_storage_bytes(out.dtype, total), 0);
+  if (!tb) return NCL_ERR_NOMEM;
+  Operand tmp; memset(&tmp, 0, sizeof tmp);
+  tmp.base = (char*)ncl_buf_ptr(tb); tmp.dtype = out.dtype; tmp.offset = 0; tmp.stage_item = -1;
+  tmp.n_storage = (int64_t)((ncl_buf_bytes(tb) * 8) / g_dt[out.dtype].slot_bits);
+  const int nop = op == R_ADD ? NCL_OP_ADD : op == R_MUL ? NCL_OP_MUL : op == R_MAX ? NCL_OP_MAX : NCL_OP_MIN;
+  Nest* p1 = new Nest(n);                                   // pass 1: the innermost reduced run -> tmp
+  p1->nloops = nl; p1->fresh = true; p1->has_identity = true;
+  { long long ii; double ff; reduce_identity(nop, out.dtype, &ii, &ff); p1->ident_i = ii; p1->ident_f = ff; }
+  p1->out[0] = tmp;
+  for (int i = 0; i < nl; i++) { p1->extent[i] = n.extent[ord[i]]; p1->in[0].stride[i] = in.stride[ord[i]]; p1->out[0].stride[i] = (i < last0 || i > last1) ? tstride[i] : 0; }
+  int rc = try_reduce(*p1);
+  if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(*p1);
+  delete p1;
+  if (rc == NCL_OK) {
+    Nest* p2 = new Nest(n);                                 // pass 2: the rest, from tmp into the result
+    int k = 0;
+    p2->in[0] = tmp;
+    for (int i = 0; i < nl; i++) if (i < last0 || i > last1) { p2->extent[k] = n.extent[ord[i]]; p2->in[0].stride[k] = tstride[i]; p2->out[0].stride[k] = out.stride[ord[i]]; k++; }
+    p2->nloops = k;
+    rc = try_reduce(*p2);
+    if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(*p2);
+    delete p2;
+  }
+  ncl_free(tb);
+  return rc;
+}
+
 int try_reduce(const Nest& n) {
   if (n.n_out != 1 || n.n_in != 1) return NCL_ERR_UNSUPPORTED;
   int op;
   if (!match_reduce(n.transform[0], &op)) return NCL_ERR_UNSUPPORTED;
-  return reduce_impl(n, op, 0, -1);
+  int rc = reduce_impl(n, op, 0, -1);
+  if (rc == NCL_ERR_UNSUPPORTED) rc = reduce_two_pass(n, op);
+  return rc;
 }
 
 // Contractions that are really reductions: the default transform (+ @1 (* $1 $2)) over two arrays of one element type

@@ -856,6 +856,55 @@ int ncl_fold(int op, int use_identity, const ncl_tensor* args, int n, ncl_tensor
   if (n == 1 && !use_identity) return set_error(NCL_ERR_INVALID, "ncl_fold: one argument needs the identity");
   for (int i = 0; i < n; i++) NCL_TRY(check_tensor(&args[i], "argument"));
   NCL_TRY(check_tensor(r, "result"));
+  {
+    // Three or more arrays: (numcl:+ a b c) is a chain of binary BROADCAST passes in the reference (src/4numeric.lisp:528-542),
+    // each with an intermediate array of the type inferred for it.  One fused pass over three or more arrays is not a shape the
+    // elementwise engine has (it ran on the generic kernel: 0.07 of the HBM peak); the chain is: every step at stream speed,
+    // the intermediates in the class of the partial result (fixnum / single-float / double-float -- what the reference's own
+    // intermediates hold, exactly), the last step stored through %coerce into the result.
+    bool dev = r->buf != nullptr && !g_ctx.capturing && !g_ctx.force_generic;
+    for (int i = 0; i < n && dev; i++) if (!args[i].buf || cls_complex(g_dt[args[i].dtype].cls) || args[i].dtype == NCL_UB64) dev = false;
+    if (n >= 3 && dev && !cls_complex(g_dt[r->dtype].cls)) {
+      auto join = [&](int a, int b) { int c = a > b ? a : b; if (op == NCL_OP_DIV && c == CLS_I) c = CLS_F; return c; };    // int / int is a single-float
+      auto tdtype = [](int cls) { return cls == CLS_D ? NCL_F64 : cls == CLS_F ? NCL_F32 : NCL_FIXNUM; };
+      // shape of a partial result: the broadcast of the arguments folded so far (right-aligned, src/4numeric.lisp:174-199)
+      auto bshape = [&](ncl_tensor* t, const ncl_tensor* x) {
+        const int rk = t->rank > x->rank ? t->rank : x->rank;
+        int64_t d[NCL_MAX_RANK];
+        for (int k = 0; k < rk; k++) {
+          const int it = t->rank - rk + k, ix = x->rank - rk + k;
+          const int64_t a = it >= 0 ? t->dims[it] : 1, b = ix >= 0 ? x->dims[ix] : 1;
+          d[k] = a == 1 ? b : a;
+        }
+        t->rank = rk; for (int k = 0; k < rk; k++) t->dims[k] = d[k];
+      };
+      ncl_tensor acc; memset(&acc, 0, sizeof acc);
+      acc.rank = args[0].rank; for (int k = 0; k < acc.rank; k++) acc.dims[k] = args[0].dims[k];
+      bshape(&acc, &args[1]);
+      ncl_buf* held = nullptr;
+      int cls = join(g_dt[args[0].dtype].cls, g_dt[args[1].dtype].cls), rc = NCL_OK;
+      acc.dtype = tdtype(cls);
+      held = ncl_alloc(ncl_storage_bytes(acc.dtype, total_elems(&acc)), 0); if (!held) return NCL_ERR_NOMEM;
+      acc.buf = held;
+      rc = ncl_fold(op, use_identity, args, 2, &acc);
+      for (int i = 2; i < n && rc == NCL_OK; i++) {
+        ncl_tensor pair[2] = {acc, args[i]};
+        if (i == n - 1) { rc = ncl_fold(op, 0, pair, 2, r); break; }
+        const int c2 = join(cls, g_dt[args[i].dtype].cls);
+        ncl_tensor nxt = acc; bshape(&nxt, &args[i]);
+        bool same_shape = nxt.rank == acc.rank; for (int k = 0; k < nxt.rank && same_shape; k++) if (nxt.dims[k] != acc.dims[k]) same_shape = false;
+        if (c2 == cls && same_shape) rc = ncl_fold(op, 0, pair, 2, &acc);   // in place: an element is read and written by the same thread
+        else {
+          nxt.dtype = tdtype(c2);
+          nxt.buf = ncl_alloc(ncl_storage_bytes(nxt.dtype, total_elems(&nxt)), 0); if (!nxt.buf) { rc = NCL_ERR_NOMEM; break; }
+          rc = ncl_fold(op, 0, pair, 2, &nxt);
+          ncl_free(held); held = nxt.buf; acc = nxt; cls = c2;
+        }
+      }
+      ncl_free(held);
+      return rc;
+    }
+  }
   return with_staging(args, n, r, 1, false, [&](Stager& st) {
     Nest* nest = new Nest;
     int rc = broadcast_nest(args, n, r, st, nest);

@@ -161,3 +161,50 @@ def test_packed_results_in_two_dimensions_and_views(nc, oracle):
     got = base.numpy()
     sentinel = np.tile(np.array([0xB, 0xA]), 2500)                          # the nibbles of 0xAB, low one first
     assert np.array_equal(got[3:4003], x.values()) and np.array_equal(got[:3], sentinel[:3]) and np.array_equal(got[4003:], sentinel[4003:])
+
+
+# ---- n-ary folds and reductions over non-adjacent axes through einsum -----------------------------------------------------------
+@pytest.mark.parametrize("fn,op", [("add", "+"), ("mul", "*"), ("sub", "-"), ("div", "/"), ("maximum", "max"), ("minimum", "min")])
+@pytest.mark.parametrize("dts", [("f32", "f32", "f32"), ("f32", "f64", "f32"), ("ub8", "ub8", "ub8"), ("fixnum", "f32", "ub8"), ("f64", "f64", "f64", "f64")])
+@pytest.mark.parametrize("shapes", [((300, 70), (300, 70), (300, 70), (300, 70)), ((300, 1), (1, 70), (70,), (300, 70)), ((4099,), (), (4099,), ())])
+def test_folds_over_three_and_four_arrays(nc, oracle, fn, op, dts, shapes):
+    """(numcl:+ a b c): the reference's chain of binary passes with typed intermediates"""
+    if op in ("max", "min") and len(set(dts)) > 1 and "fixnum" in dts:
+        pytest.skip("max / min of mixed integer / float arrays return the original object in CL: single-pass path")
+    xs = []
+    for i, dt in enumerate(dts):
+        lo, hi = ((1, 9) if dt in ("ub8", "fixnum") else (1.0, 9.0)) if op == "/" else ((0, 9) if dt == "ub8" else (-9, 9))
+        xs.append(rand(oracle, shapes[i], dt, SEED + 90 + i, 1, lo, hi))
+    want = refsem.arith(oracle, op, xs)
+    got = getattr(nc, fn)(*[to_gpu(nc, x) for x in xs])
+    assert_bit_exact(got, want)
+    if int(np.prod(want.shape)) >= 4096:
+        assert _last(nc) != "generic_nest", _last(nc)
+
+
+@pytest.mark.parametrize("spec,shape", [("ijk -> j", (40, 50, 60)), ("ijkl -> jl", (12, 30, 14, 40)), ("ijkl -> k", (12, 30, 14, 40)), ("ijk -> j", (256, 64, 256))])
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum", "ub8"])
+def test_einsum_reductions_over_non_adjacent_axes(nc, oracle, spec, shape, dt):
+    a = rand(oracle, shape, dt, SEED + 95, 1, 0 if dt == "ub8" else -8, 8)
+    assert_bit_exact(nc.einsum(spec, to_gpu(nc, a)), refsem.einsum(oracle, spec, [a]))
+    assert _last(nc) != "generic_nest", _last(nc)
+    b = rand(oracle, shape, dt, SEED + 96, 1, 0 if dt == "ub8" else -8, 8)
+    ax = tuple(i for i, ch in enumerate(spec.split(" -> ")[0]) if ch not in spec.split(" -> ")[1])
+    assert_bit_exact(nc.amax(to_gpu(nc, b), axes=ax), refsem.reduce_array(oracle, "max", b, ax))
+
+
+@pytest.mark.parametrize("spec,sa,sb", [("ij jk -> ik", (200, 96), (96, 300)), ("ij ik -> jk", (256, 128), (256, 256)), ("bij bjk -> bik", (4, 128, 64), (4, 64, 256))])
+@pytest.mark.parametrize("da,db", [("f32", "f64"), ("f64", "f32"), ("fixnum", "f32"), ("f64", "ub8"), ("ub8", "f32")])
+def test_contractions_of_mixed_element_classes(nc, oracle, spec, sa, sb, da, db):
+    """single-float x double-float, integer x float: contagion converts the lower operand before the product, which is what
+    converting the array first does; the result has the higher class"""
+    A = rand(oracle, sa, da, SEED + 97, 1, 0 if da == "ub8" else -4, 4); B = rand(oracle, sb, db, SEED + 98, 1, 0 if db == "ub8" else -4, 4)
+    want = refsem.einsum(oracle, spec, [A, B])
+    got = nc.einsum(spec, to_gpu(nc, A), to_gpu(nc, B))
+    assert_bit_exact(got, want)                                      # integer-valued data: exact in any order
+    assert _last(nc).startswith("gemm"), _last(nc)
+    if "fixnum" not in (da, db) and "ub8" not in (da, db):
+        A = rand(oracle, sa, da, SEED + 99, 0, -1.0, 1.0); B = rand(oracle, sb, db, SEED + 100, 0, -1.0, 1.0)
+        w = refsem.einsum(oracle, spec, [A, B]).values().astype(np.float64)
+        g = nc.einsum(spec, to_gpu(nc, A), to_gpu(nc, B)).numpy().astype(np.float64)
+        assert np.linalg.norm(g - w) / np.linalg.norm(w) <= 1e-12
