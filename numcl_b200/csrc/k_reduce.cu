@@ -134,6 +134,22 @@ int try_reduce(const Nest& n) {
 // dots `(ij ij -> i)`, matrix x vector `(ij j -> i)`, vector x matrix `(i ij -> j)`.  Every element of the larger input is
 // used once, so they are HBM-bound streams and run on the reduction kernels with the product formed on load.
 int try_dot_reduce(const Nest& n) {
+  if (n.n_in == 1 && n.n_out == 1 && n.transform[0].n == 5) {
+    // (+ @1 (* $1 $1)): the sum of squares / squared norm of ONE array, `(i -> (+ @1 (* $1 $1)) -> )`.  The same array is both
+    // operands of the dot-like reduction (it used to fall to the generic kernel: one thread for the whole norm).
+    const Expr& e1 = n.transform[0];
+    const XNode& root = e1.node[4];
+    if (root.op == NCL_OP_ADD && e1.node[root.a].op == NCL_X_OUTPUT && e1.node[root.b].op == NCL_OP_MUL) {
+      const XNode& mul = e1.node[root.b];
+      if (e1.node[mul.a].op == NCL_X_INPUT && e1.node[mul.b].op == NCL_X_INPUT && e1.node[mul.a].a == 1 && e1.node[mul.b].a == 1) {
+        Nest* t = new Nest(n);
+        t->n_in = 2; t->in[1] = n.in[0];
+        t->transform[0].node[mul.b].a = 2;
+        int rc = try_dot_reduce(*t);
+        delete t; return rc;
+      }
+    }
+  }
   if (n.n_in != 2 || n.n_out != 1) return NCL_ERR_UNSUPPORTED;
   const Expr& e = n.transform[0];
   if (e.n != 5) return NCL_ERR_UNSUPPORTED;

@@ -247,6 +247,75 @@ static int lower_bitwise(Nest& n, Nest* tail, bool* has_tail) {
   return 1;
 }
 
+// ---- composite transforms -----------------------------------------------------------------------------------------------
+// (map-array '(sqrt (+ (* $1 $1) (* $2 $2))) a b), (einsum '(i -> (* 2.0 (+ $1 $2)) -> i) ...): the elementwise engine has
+// one-function shapes, so a transform of several functions ran on the generic kernel (an interpreter per element: 0.05 of the
+// HBM peak).  It is evaluated node by node instead, every node one pass of the engine into a temporary of the node's own
+// class (raw 64-bit words / single-float / double-float: what the interpreter holds in a register, so the bits are the same),
+// the root straight into the result through %coerce.  Four passes at stream speed beat one pass at a twentieth of it.
+static int run_composite_map(Nest& n) {
+  if (n.n_out != 1 || n.stat || ctx().capturing) return NCL_ERR_UNSUPPORTED;
+  const Expr& e = n.transform[0];
+  int nops = 0;
+  for (int k = 0; k < e.n; k++) {
+    const XNode& x = e.node[k];
+    if (x.op == NCL_X_OUTPUT || x.cls == CLS_R || x.cls > CLS_D) return NCL_ERR_UNSUPPORTED;
+    if (x.op < NCL_X_INPUT) nops++;
+  }
+  if (nops < 2) return NCL_ERR_UNSUPPORTED;
+  long long total = 1;
+  for (int l = 0; l < n.nloops; l++) { if (n.extent[l] <= 0 || n.out[0].stride[l] == 0) { if (n.extent[l] != 1) return NCL_ERR_UNSUPPORTED; } total *= n.extent[l] > 0 ? n.extent[l] : 1; }
+  if (total < 65536) return NCL_ERR_UNSUPPORTED;             // small arrays: one launch of the interpreter is cheaper than several passes
+  for (int k = 0; k < n.n_in; k++) { const int c = g_dt[n.in[k].dtype].cls; if (c > CLS_D || n.in[k].dtype == NCL_UB64) return NCL_ERR_UNSUPPORTED; }
+  // dense row-major layout of the temporaries over the nest's loops, in the order of the result's strides
+  int ord[NCL_MAX_LOOPS], nl = 0; long long tstr[NCL_MAX_LOOPS];
+  for (int l = 0; l < n.nloops; l++) { tstr[l] = 0; if (n.extent[l] > 1) ord[nl++] = l; }
+  for (int i = 1; i < nl; i++) { int k = ord[i], j = i - 1; while (j >= 0 && llabs(n.out[0].stride[ord[j]]) < llabs(n.out[0].stride[k])) { ord[j + 1] = ord[j]; j--; } ord[j + 1] = k; }
+  { long long acc = 1; for (int i = nl - 1; i >= 0; i--) { tstr[ord[i]] = acc; acc *= n.extent[ord[i]]; } }
+  auto tdtype = [](int cls) { return cls == CLS_D ? NCL_F64 : cls == CLS_F ? NCL_F32 : NCL_SB64; };
+  ncl_buf* buf[NCL_MAX_EXPR]; Operand val[NCL_MAX_EXPR]; int kind[NCL_MAX_EXPR];     // kind: 0 not materialised, 1 array operand
+  for (int k = 0; k < e.n; k++) { buf[k] = nullptr; kind[k] = 0; }
+  auto release = [&](int rc) { for (int k = 0; k < e.n; k++) if (buf[k]) ncl_free(buf[k]); return rc; };
+  auto scalar = [&](int k, bool is_float, long long iv, double fv, int cls) -> int {      // a constant as a rank-0 array
+    buf[k] = ncl_alloc(64, 0); if (!buf[k]) return NCL_ERR_NOMEM;
+    Operand& o = val[k]; memset(&o, 0, sizeof o); o.base = (char*)ncl_buf_ptr(buf[k]); o.dtype = tdtype(cls); o.n_storage = 8; o.stage_item = -1;
+    kind[k] = 1;
+    return fill_const(o.base, o.dtype, 0, 1, is_float, iv, fv);
+  };
+  int rc = NCL_OK;
+  for (int k = 0; k < e.n && rc == NCL_OK; k++) {
+    const XNode& x = e.node[k];
+    if (x.op == NCL_X_INPUT) { val[k] = n.in[x.a - 1]; kind[k] = 1; continue; }
+    if (x.op == NCL_X_CONST_INT) { rc = scalar(k, false, x.ival, 0.0, CLS_I); continue; }
+    if (x.op == NCL_X_CONST_F32) { rc = scalar(k, true, 0, (double)(float)x.fval, CLS_F); continue; }
+    if (x.op == NCL_X_CONST_F64) { rc = scalar(k, true, 0, x.fval, CLS_D); continue; }
+    const bool binary = x.op < NCL_OP_BINARY_END, root = k == e.n - 1;
+    Nest* t = new Nest;
+    t->nloops = n.nloops; for (int l = 0; l < n.nloops; l++) t->extent[l] = n.extent[l];
+    t->n_in = binary ? 2 : 1; t->n_out = 1; t->fresh = true;
+    t->in[0] = val[x.a]; if (binary) t->in[1] = val[x.b];
+    if (root) t->out[0] = n.out[0];
+    else {
+      buf[k] = ncl_alloc(ncl_storage_bytes(tdtype(x.cls), total), 0);
+      if (!buf[k]) { delete t; rc = NCL_ERR_NOMEM; break; }
+      Operand& o = val[k]; memset(&o, 0, sizeof o); o.base = (char*)ncl_buf_ptr(buf[k]); o.dtype = tdtype(x.cls); o.stage_item = -1;
+      o.n_storage = (int64_t)((ncl_buf_bytes(buf[k]) * 8) / g_dt[o.dtype].slot_bits);
+      for (int l = 0; l < n.nloops; l++) o.stride[l] = tstr[l];
+      kind[k] = 1; t->out[0] = o;
+    }
+    Expr& te = t->transform[0]; te.n = 0;
+    auto leaf = [&](int src, int slot) { XNode& nd = te.node[te.n++]; memset(&nd, 0, sizeof nd); nd.op = NCL_X_INPUT; nd.a = slot; nd.cls = e.node[src].cls; };
+    leaf(x.a, 1); if (binary) leaf(x.b, 2);
+    { XNode& nd = te.node[te.n++]; nd = x; nd.a = 0; nd.b = binary ? 1 : 0; }
+    if (op_may_fault(x.op)) ctx().fault_possible = true;
+    rc = try_elementwise(*t);
+    if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(*t);
+    delete t;
+    // operands that are no longer needed could be freed here; they are a few arrays and go back to the cache below
+  }
+  return release(rc);
+}
+
 int run_nest(Nest& n) {
   for (int i = 0; i < n.n_in; i++) NCL_TRY(check_bounds(n.in[i], n, "input", i));
   for (int o = 0; o < n.n_out; o++) NCL_TRY(check_bounds(n.out[o], n, "output", o));
@@ -275,6 +344,7 @@ int run_nest(Nest& n) {
     if ((rc = try_reduce(n)) != NCL_ERR_UNSUPPORTED) return rc;
     if ((rc = try_transpose(n)) != NCL_ERR_UNSUPPORTED) return rc;
     if ((rc = try_elementwise(n)) != NCL_ERR_UNSUPPORTED) return rc;
+    if ((rc = run_composite_map(n)) != NCL_ERR_UNSUPPORTED) return rc;
   }
   return launch_generic(n);
 }

@@ -208,3 +208,47 @@ def test_contractions_of_mixed_element_classes(nc, oracle, spec, sa, sb, da, db)
         w = refsem.einsum(oracle, spec, [A, B]).values().astype(np.float64)
         g = nc.einsum(spec, to_gpu(nc, A), to_gpu(nc, B)).numpy().astype(np.float64)
         assert np.linalg.norm(g - w) / np.linalg.norm(w) <= 1e-12
+
+
+# ---- composite transforms: node-by-node passes of the engine instead of the per-element interpreter -------------------------------
+@pytest.mark.parametrize("form", ["(sqrt (+ (* $1 $1) (* $2 $2)))", "(* 2.0 (+ $1 $2))", "(+ (* $1 $2) (* $1 $1) $2)", "(max (abs $1) (abs $2))",
+                                  "(- (* $1 $1) (/ $2 3.0d0))", "(* (+ $1 1) (- $2 1))", "(+ (square $1) (abs (- $2)))"])
+@pytest.mark.parametrize("dts", [("f32", "f32"), ("f64", "f64"), ("f32", "f64"), ("fixnum", "fixnum"), ("ub8", "f32")])
+def test_composite_transforms_match_the_interpreter(nc, oracle, form, dts):
+    if "sqrt" in form and "fixnum" in dts:
+        pytest.skip("sqrt of integers goes through single-float substitution: tolerance only")
+    shape = (300, 257)
+    xs = [rand(oracle, shape, dt, SEED + 110 + i, 1, 0 if dt == "ub8" else -6, 6) for i, dt in enumerate(dts)]
+    gs = [to_gpu(nc, x) for x in xs]
+    got = nc.map_array(form, *gs)
+    assert _last(nc) != "generic_nest", (_last(nc), form)
+    L = nc.lib(); L.ncl_force_generic(1)
+    try:
+        ref = nc.map_array(form, *gs)                            # the interpreter: one kernel, every node rounded in its own class
+        assert _last(nc) == "generic_nest"
+    finally:
+        L.ncl_force_generic(0)
+    assert got.dtype.name == ref.dtype.name and np.array_equal(got.raw(), ref.raw())
+    if "sqrt" not in form and "3.0d0" not in form:
+        want = oracle.map_array(form, xs, got.dtype.name)
+        assert_bit_exact(got, want)
+
+
+def test_composite_transform_in_an_einsum_with_broadcasting(nc, oracle):
+    a = rand(oracle, (400, 300), "f32", SEED + 120, 1, -6, 6); v = rand(oracle, (300,), "f32", SEED + 121, 1, -6, 6)
+    spec = "ij j -> (* $2 (+ $1 1.0)) -> ij"
+    got = nc.einsum(spec, to_gpu(nc, a), to_gpu(nc, v))
+    assert _last(nc) != "generic_nest"
+    assert np.array_equal(got.numpy(), (v.values() * (a.values() + np.float32(1.0))).astype(np.float32))
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum"])
+def test_sum_of_squares_of_one_array(nc, oracle, dt):
+    """(einsum '(i -> (+ @1 (* $1 $1)) -> )): the squared norm; the same array is both operands of the dot-like reduction"""
+    x = rand(oracle, (1 << 18,), dt, SEED + 122, 1, -4, 4)
+    got = nc.einsum("i -> (+ @1 (* $1 $1)) -> ", to_gpu(nc, x))
+    assert _last(nc).startswith("dot_"), _last(nc)
+    assert got == (x.values().astype(np.float64) ** 2).sum()
+    m = rand(oracle, (300, 1000), dt, SEED + 123, 1, -4, 4)
+    rows = nc.einsum("ij -> (+ @1 (* $1 $1)) -> i", to_gpu(nc, m))
+    assert np.array_equal(rows.numpy().astype(np.float64), (m.values().astype(np.float64) ** 2).sum(axis=1))
