@@ -34,7 +34,22 @@ int try_gemm(const Nest& n) {
   if (root.op != NCL_OP_ADD || e.node[root.a].op != NCL_X_OUTPUT || e.node[root.b].op != NCL_OP_MUL) return NCL_ERR_UNSUPPORTED;
   const XNode& mul = e.node[root.b];
   if (e.node[mul.a].op != NCL_X_INPUT || e.node[mul.b].op != NCL_X_INPUT || e.node[mul.a].a == e.node[mul.b].a) return NCL_ERR_UNSUPPORTED;
-  const Operand& A = n.in[e.node[mul.a].a - 1]; const Operand& B = n.in[e.node[mul.b].a - 1]; const Operand& C = n.out[0];
+  const Operand& C = n.out[0];
+  // C[m][n] with n contiguous is what the kernels write.  When the result is m-contiguous instead -- `(ij jk -> ki)` -- the
+  // operands swap roles: C^T = B^T A^T is the same product with the loops private to B as rows.
+  bool swap_roles = false;
+  {
+    long long best_a = 0, best_b = 0;                                    // smallest result stride among the loops private to A / to B
+    for (int l = 0; l < n.nloops; l++) {
+      if (n.extent[l] == 1 || C.stride[l] == 0) continue;
+      const bool a = n.in[e.node[mul.a].a - 1].stride[l] != 0, b = n.in[e.node[mul.b].a - 1].stride[l] != 0;
+      const long long sc = llabs(C.stride[l]);
+      if (a && !b && (best_a == 0 || sc < best_a)) best_a = sc;
+      if (!a && b && (best_b == 0 || sc < best_b)) best_b = sc;
+    }
+    swap_roles = best_a == 1 && best_b != 1 && best_b != 0;
+  }
+  const Operand& A = n.in[(swap_roles ? e.node[mul.b].a : e.node[mul.a].a) - 1]; const Operand& B = n.in[(swap_roles ? e.node[mul.a].a : e.node[mul.b].a) - 1];
   int ca = g_dt[A.dtype].cls, cb = g_dt[B.dtype].cls, cc = g_dt[C.dtype].cls;
   // Mixed classes (single-float x double-float, integer x float): Common Lisp's contagion converts the lower operand to the
   // class of the other BEFORE the product, exactly what converting the ARRAY first does -- so one operand may be of a lower

@@ -316,6 +316,75 @@ static int run_composite_map(Nest& n) {
   return release(rc);
 }
 
+// ---- contractions of two arrays of different element types --------------------------------------------------------------
+// (vdot a b) with a single-float and a double-float vector, (inner ub8-array fixnum-array), matrix x vector of mixed types:
+// the dot-like reduction kernels and the GEMMs want both operands in ONE element type, and the generic kernel walks the
+// contracted loops with one thread per result -- a full dot product of mixed types was a single thread.  Common Lisp's
+// contagion converts the lower operand to the other's class before the product, which is what converting the ARRAY does; so
+// the lower operand is copied into the other's type first (one elementwise pass) when the result has that class.  Integers of
+// different widths are both brought to fixnum (values that fit 62 bits only).
+static int materialize_as(const Nest& n, const Operand& X, int odt, Operand* out, ncl_buf** buf) {
+  int ord[NCL_MAX_LOOPS], nl = 0; long long total = 1;
+  for (int l = 0; l < n.nloops; l++) if (n.extent[l] > 1 && X.stride[l] != 0) { if (X.stride[l] < 0) return NCL_ERR_UNSUPPORTED; ord[nl++] = l; total *= n.extent[l]; }
+  for (int i = 1; i < nl; i++) { int k = ord[i], j = i - 1; while (j >= 0 && X.stride[ord[j]] < X.stride[k]) { ord[j + 1] = ord[j]; j--; } ord[j + 1] = k; }
+  *buf = ncl_alloc(ncl_storage_bytes(odt, total), 0);
+  if (!*buf) return NCL_ERR_NOMEM;
+  Operand o; memset(&o, 0, sizeof o);
+  o.base = (char*)ncl_buf_ptr(*buf); o.dtype = odt; o.stage_item = -1; o.n_storage = (int64_t)((ncl_buf_bytes(*buf) * 8) / g_dt[odt].slot_bits);
+  { long long acc = 1; for (int i = nl - 1; i >= 0; i--) { o.stride[ord[i]] = acc; acc *= n.extent[ord[i]]; } }
+  Nest* t = new Nest;
+  t->nloops = nl; t->n_in = 1; t->n_out = 1; t->fresh = true;
+  t->in[0] = X; t->out[0] = o;
+  for (int i = 0; i < nl; i++) { t->extent[i] = n.extent[ord[i]]; t->in[0].stride[i] = X.stride[ord[i]]; t->out[0].stride[i] = o.stride[ord[i]]; }
+  for (int i = nl; i < NCL_MAX_LOOPS; i++) { t->in[0].stride[i] = 0; t->out[0].stride[i] = 0; }
+  if (nl == 0) { t->nloops = 1; t->extent[0] = 1; }
+  Expr& x = t->transform[0]; x.n = 1; memset(&x.node[0], 0, sizeof x.node[0]); x.node[0].op = NCL_X_INPUT; x.node[0].a = 1; x.node[0].cls = g_dt[X.dtype].cls;
+  int rc = try_elementwise(*t);
+  if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(*t);
+  delete t;
+  *out = o;
+  return rc;
+}
+static int harmonize_contraction(Nest& n, ncl_buf** tmp) {
+  tmp[0] = tmp[1] = nullptr;
+  if (n.n_in != 2 || n.n_out != 1 || n.stat || ctx().capturing) return NCL_OK;
+  const Expr& e = n.transform[0];
+  if (e.n != 5) return NCL_OK;
+  const XNode& root = e.node[4];
+  if (root.op != NCL_OP_ADD || e.node[root.a].op != NCL_X_OUTPUT || e.node[root.b].op != NCL_OP_MUL) return NCL_OK;
+  const XNode& mul = e.node[root.b];
+  if (e.node[mul.a].op != NCL_X_INPUT || e.node[mul.b].op != NCL_X_INPUT || e.node[mul.a].a == e.node[mul.b].a) return NCL_OK;
+  if (n.in[0].dtype == n.in[1].dtype) return NCL_OK;
+  bool contracted = false;
+  for (int l = 0; l < n.nloops; l++) if (n.extent[l] > 1 && n.out[0].stride[l] == 0) contracted = true;
+  if (!contracted) return NCL_OK;
+  const int c0 = g_dt[n.in[0].dtype].cls, c1 = g_dt[n.in[1].dtype].cls, cc = g_dt[n.out[0].dtype].cls;
+  if (c0 > CLS_D || c1 > CLS_D || cc > CLS_D) return NCL_OK;
+  int want[2] = {n.in[0].dtype, n.in[1].dtype};
+  if (c0 != c1) {
+    const int hi = c0 > c1 ? 0 : 1;
+    if (cc != g_dt[n.in[hi].dtype].cls || !(n.in[hi].dtype == NCL_F32 || n.in[hi].dtype == NCL_F64) || n.in[1 - hi].dtype == NCL_UB64) return NCL_OK;
+    want[1 - hi] = n.in[hi].dtype;
+  } else if (c0 == CLS_I && cc == CLS_I) {
+    for (int k = 0; k < 2; k++) {
+      const DtInfo& d = g_dt[n.in[k].dtype];
+      if (n.in[k].dtype == NCL_FIXNUM) continue;
+      if (d.value_bits > (d.is_signed ? 63 : 62)) return NCL_OK;       // sb64 / ub63 / ub64 values need not fit a fixnum
+      want[k] = NCL_FIXNUM;
+    }
+  } else return NCL_OK;
+  for (int k = 0; k < 2; k++) if (want[k] != n.in[k].dtype) {
+    Operand o; int rc = materialize_as(n, n.in[k], want[k], &o, &tmp[k]);
+    if (rc != NCL_OK) return rc;
+    n.in[k] = o;
+  }
+  // the typed transform: both products now have the operands' common class
+  Expr& te = n.transform[0];
+  const int pc = g_dt[n.in[0].dtype].cls;
+  te.node[mul.a].cls = pc; te.node[mul.b].cls = pc; te.node[root.b].cls = pc;
+  return NCL_OK;
+}
+
 int run_nest(Nest& n) {
   for (int i = 0; i < n.n_in; i++) NCL_TRY(check_bounds(n.in[i], n, "input", i));
   for (int o = 0; o < n.n_out; o++) NCL_TRY(check_bounds(n.out[o], n, "output", o));
@@ -338,13 +407,17 @@ int run_nest(Nest& n) {
     return rc != NCL_ERR_UNSUPPORTED ? rc : try_reduce(n);
   }
   if (!ctx().force_generic && !empty) {
-    int rc;
-    if ((rc = try_dot_reduce(n)) != NCL_ERR_UNSUPPORTED) return rc;
-    if ((rc = try_gemm(n)) != NCL_ERR_UNSUPPORTED) return rc;
-    if ((rc = try_reduce(n)) != NCL_ERR_UNSUPPORTED) return rc;
-    if ((rc = try_transpose(n)) != NCL_ERR_UNSUPPORTED) return rc;
-    if ((rc = try_elementwise(n)) != NCL_ERR_UNSUPPORTED) return rc;
-    if ((rc = run_composite_map(n)) != NCL_ERR_UNSUPPORTED) return rc;
+    ncl_buf* tmp[2];
+    int rc = harmonize_contraction(n, tmp);
+    auto done = [&](int code) { for (int k = 0; k < 2; k++) if (tmp[k]) ncl_free(tmp[k]); return code; };
+    if (rc != NCL_OK) return done(rc);
+    if ((rc = try_dot_reduce(n)) != NCL_ERR_UNSUPPORTED) return done(rc);
+    if ((rc = try_gemm(n)) != NCL_ERR_UNSUPPORTED) return done(rc);
+    if ((rc = try_reduce(n)) != NCL_ERR_UNSUPPORTED) return done(rc);
+    if ((rc = try_transpose(n)) != NCL_ERR_UNSUPPORTED) return done(rc);
+    if ((rc = try_elementwise(n)) != NCL_ERR_UNSUPPORTED) return done(rc);
+    if ((rc = run_composite_map(n)) != NCL_ERR_UNSUPPORTED) return done(rc);
+    return done(launch_generic(n));
   }
   return launch_generic(n);
 }

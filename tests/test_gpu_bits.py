@@ -252,3 +252,30 @@ def test_sum_of_squares_of_one_array(nc, oracle, dt):
     m = rand(oracle, (300, 1000), dt, SEED + 123, 1, -4, 4)
     rows = nc.einsum("ij -> (+ @1 (* $1 $1)) -> i", to_gpu(nc, m))
     assert np.array_equal(rows.numpy().astype(np.float64), (m.values().astype(np.float64) ** 2).sum(axis=1))
+
+
+@pytest.mark.parametrize("spec,sa,sb", [("i i -> ", (70001,), (70001,)), ("ij ij -> i", (300, 1000), (300, 1000)), ("ij j -> i", (300, 1000), (1000,)),
+                                        ("i ij -> j", (999,), (999, 301)), ("ij ij -> ", (257, 513), (257, 513))])
+@pytest.mark.parametrize("da,db", [("f32", "f64"), ("f64", "f32"), ("ub8", "fixnum"), ("fixnum", "f32"), ("sb16", "ub8"), ("f64", "ub8")])
+def test_dot_like_contractions_of_mixed_element_types(nc, oracle, spec, sa, sb, da, db):
+    """a full dot product of a single-float and a double-float vector used to be ONE thread of the generic kernel"""
+    lo = lambda t: 0 if t == "ub8" else -4
+    A = rand(oracle, sa, da, SEED + 130, 1, lo(da), 4); B = rand(oracle, sb, db, SEED + 131, 1, lo(db), 4)
+    want = refsem.einsum(oracle, spec, [A, B])
+    got = nc.einsum(spec, to_gpu(nc, A), to_gpu(nc, B))
+    assert _last(nc).startswith("dot_") or _last(nc).startswith("gemm"), _last(nc)
+    if want.shape == ():
+        assert got == want.values().reshape(-1)[0]
+    else:
+        assert_bit_exact(got, want)
+
+
+@pytest.mark.parametrize("spec,sa,sb", [("ij jk -> ki", (300, 70), (70, 90)), ("ij jk -> ki", (256, 128), (128, 256)), ("bij bjk -> bki", (4, 128, 64), (4, 64, 256)),
+                                        ("ij ik -> kj", (256, 128), (256, 64))])
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum"])
+def test_contraction_with_a_transposed_result(nc, oracle, spec, sa, sb, dt):
+    """C^T = B^T A^T: the operands swap roles when the result is contiguous along the loops of the first operand"""
+    A = rand(oracle, sa, dt, SEED + 140, 1, -4, 4); B = rand(oracle, sb, dt, SEED + 141, 1, -4, 4)
+    got = nc.einsum(spec, to_gpu(nc, A), to_gpu(nc, B))
+    assert_bit_exact(got, refsem.einsum(oracle, spec, [A, B]))
+    assert _last(nc).startswith("gemm"), _last(nc)

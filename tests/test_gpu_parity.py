@@ -471,8 +471,9 @@ def test_integer_matmul_bit_exact(nc, oracle, ta, tb):
     got = nc.matmul(to_gpu(nc, A), to_gpu(nc, B))
     assert want.dtype == "fixnum"
     assert_bit_exact(got, want)
-    # packed sub-byte operands stay on the generic reference-ordered kernel
-    assert nc.lib().ncl_last_kernel() == (b"generic_nest" if "ub4" in (ta, tb) else b"gemm_int_simt")
+    # operands of different integer types (a packed sub-byte one included) are brought to fixnum first (ncl_plan.cu:
+    # harmonize_contraction), then the integer GEMM runs
+    assert nc.lib().ncl_last_kernel() == b"gemm_int_simt"
 
 
 def test_integer_matmul_wraps_like_coerce(nc, oracle):
