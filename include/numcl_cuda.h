@@ -214,7 +214,7 @@ void ncl_pipeline_stats(int64_t* calls, int64_t* panels);
 int64_t ncl_launch_count(void);
 /* Name of the kernel family the last compute call dispatched to ("bcast_vec", "bcast_vec_flat", "bcast_widen",
  * "reduce_row_block", "reduce_rows_reg", "reduce_fewcols", "reduce_all", "reduce_col", "dot_all", "dot_rows",
- * "dot_matvec", "transpose_tile", "transpose_reg", "gemm_f64_dmma", "gemm_tf32x3_tcgen05", "generic_nest", ...). */
+ * "dot_matvec", "transpose_tile", "transpose_reg", "gemm_f64_dmma", "gemm_tf32x3_tcgen05", "generic_nest", "map_reduce", ...). */
 const char* ncl_last_kernel(void);
 /* Force the generic (thread-per-output, reference-ordered) nest kernel: test hook. */
 int  ncl_force_generic(int on);

@@ -316,6 +316,108 @@ static int run_composite_map(Nest& n) {
   return release(rc);
 }
 
+// ---- reductions of a FUNCTION of the arrays ------------------------------------------------------------------------------
+// `(ij -> (+ @1 (abs $1)) -> )` (the L1 norm), `(max @1 (abs $1))` (the infinity norm), `(+ @1 (abs (- $1 $2)))` (an L1
+// distance), and plain sums whose result has another class than the array (a single-float array summed into a double-float
+// scalar): reduction kernels fold ARRAYS of the result's class, so these nests ran on the generic kernel, where ONE thread
+// walks all reduced loops of its result element -- 19 .. 36 SECONDS for a 4096 x 4096 array.  Three fast steps instead:
+//   1. the function of the inputs, evaluated over the whole iteration space into a temporary (elementwise engine / composite
+//      passes) -- only when some input spans every loop, so that the temporary is no larger than that input;
+//   2. the temporary folded over the reduced loops into a small temporary of its own class (reduction kernels);
+//   3. result <- (op result partial) over the kept loops: accumulation into a supplied result, the start value of a fresh
+//      one and the final %coerce are exactly the nest's own.
+static int run_map_reduce(Nest& n) {
+  if (n.n_out != 1 || n.stat || ctx().capturing) return NCL_ERR_UNSUPPORTED;
+  const Expr& e = n.transform[0];
+  const XNode& root = e.node[e.n - 1];
+  if (!(root.op == NCL_OP_ADD || root.op == NCL_OP_MUL || root.op == NCL_OP_MAX || root.op == NCL_OP_MIN)) return NCL_ERR_UNSUPPORTED;
+  int sub = -1;
+  if (e.node[root.a].op == NCL_X_OUTPUT && e.node[root.a].a == 1) sub = root.b;
+  else if (e.node[root.b].op == NCL_X_OUTPUT && e.node[root.b].a == 1 && (root.op == NCL_OP_ADD || root.op == NCL_OP_MUL)) sub = root.a;
+  if (sub < 0) return NCL_ERR_UNSUPPORTED;
+  // nodes of the subtree, remapped; it may not read the result
+  int map[NCL_MAX_EXPR]; bool used[NCL_MAX_EXPR];
+  for (int k = 0; k < e.n; k++) { used[k] = false; map[k] = -1; }
+  used[sub] = true;
+  for (int k = sub; k >= 0; k--) if (used[k]) {
+    const XNode& x = e.node[k];
+    if (x.op == NCL_X_OUTPUT || x.cls == CLS_R || x.cls > CLS_D) return NCL_ERR_UNSUPPORTED;
+    if (x.op < NCL_X_INPUT) { used[x.a] = true; if (x.op < NCL_OP_BINARY_END) used[x.b] = true; }
+  }
+  const int csub = e.node[sub].cls, cc = g_dt[n.out[0].dtype].cls;
+  if (cc > CLS_D) return NCL_ERR_UNSUPPORTED;
+  bool contracted = false; long long total = 1;
+  for (int l = 0; l < n.nloops; l++) { if (n.extent[l] <= 0) return NCL_ERR_UNSUPPORTED; if (n.extent[l] > 1 && n.out[0].stride[l] == 0) contracted = true; total *= n.extent[l]; }
+  if (!contracted || total < 65536 || total > (1LL << 32)) return NCL_ERR_UNSUPPORTED;
+  int span = -1;                                             // an input that moves with every loop
+  for (int k = 0; k < n.n_in && span < 0; k++) {
+    bool all = true; for (int l = 0; l < n.nloops; l++) if (n.extent[l] > 1 && n.in[k].stride[l] <= 0) all = false;
+    if (all && g_dt[n.in[k].dtype].cls <= CLS_D && n.in[k].dtype != NCL_UB64) span = k;
+  }
+  if (span < 0) return NCL_ERR_UNSUPPORTED;
+  for (int k = 0; k < n.n_in; k++) if (g_dt[n.in[k].dtype].cls > CLS_D || n.in[k].dtype == NCL_UB64) return NCL_ERR_UNSUPPORTED;
+  auto tdtype = [](int cls) { return cls == CLS_D ? NCL_F64 : cls == CLS_F ? NCL_F32 : NCL_SB64; };
+  // class of the temporaries: the higher of the function's and the result's.  (+ @1 $1) into a double-float result converts
+  // every single-float element before it is added (contagion), i.e. the sum runs in double-float
+  const int ct = csub > cc ? csub : cc;
+  const int tdt = tdtype(ct);
+  if ((double)total * (g_dt[tdt].slot_bits / 8) > 8.0 * 1073741824.0) return NCL_ERR_UNSUPPORTED;
+  // loop order of the spanning input; dense strides of the big temporary (all loops) and the small one (kept loops)
+  int ord[NCL_MAX_LOOPS], nl = 0; long long tstr[NCL_MAX_LOOPS], ustr[NCL_MAX_LOOPS], kept_total = 1;
+  for (int l = 0; l < n.nloops; l++) { tstr[l] = 0; ustr[l] = 0; if (n.extent[l] > 1) ord[nl++] = l; }
+  for (int i = 1; i < nl; i++) { int k = ord[i], j = i - 1; while (j >= 0 && n.in[span].stride[ord[j]] < n.in[span].stride[k]) { ord[j + 1] = ord[j]; j--; } ord[j + 1] = k; }
+  { long long acc = 1, ua = 1; for (int i = nl - 1; i >= 0; i--) { const int l = ord[i]; tstr[l] = acc; acc *= n.extent[l]; if (n.out[0].stride[l] != 0) { ustr[l] = ua; ua *= n.extent[l]; } } kept_total = ua; }
+  ncl_buf* tb = ncl_alloc(ncl_storage_bytes(tdt, total), 0);
+  ncl_buf* ub = ncl_alloc(ncl_storage_bytes(tdt, kept_total), 0);
+  auto release = [&](int rc) { if (tb) ncl_free(tb); if (ub) ncl_free(ub); return rc; };
+  if (!tb || !ub) return release(NCL_ERR_NOMEM);
+  auto operand = [&](ncl_buf* b, const long long* str) { Operand o; memset(&o, 0, sizeof o); o.base = (char*)ncl_buf_ptr(b); o.dtype = tdt; o.stage_item = -1;
+    o.n_storage = (int64_t)((ncl_buf_bytes(b) * 8) / g_dt[tdt].slot_bits); for (int l = 0; l < n.nloops; l++) o.stride[l] = str[l]; return o; };
+  const Operand T = operand(tb, tstr), U = operand(ub, ustr);
+  // 1. the function of the inputs over the whole iteration space
+  int rc;
+  {
+    Nest* m = new Nest(n);
+    m->out[0] = T; m->fresh = true; m->has_identity = false;
+    Expr& me = m->transform[0]; me.n = 0;
+    for (int k = 0; k <= sub; k++) if (used[k]) { map[k] = me.n; XNode x = e.node[k]; if (x.op < NCL_X_INPUT) { x.a = map[x.a]; if (x.op < NCL_OP_BINARY_END) x.b = map[x.b]; } me.node[me.n++] = x; }
+    for (int k = 0; k < me.n; k++) if (op_may_fault(me.node[k].op)) ctx().fault_possible = true;
+    rc = try_elementwise(*m);
+    if (rc == NCL_ERR_UNSUPPORTED) rc = run_composite_map(*m);
+    if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(*m);
+    delete m;
+  }
+  if (rc != NCL_OK) return release(rc);
+  // 2. the temporary folded over the reduced loops
+  {
+    Nest* r = new Nest(n);
+    r->n_in = 1; r->in[0] = T; r->out[0] = U; r->fresh = true; r->has_identity = true;
+    { long long ii; double ff; reduce_identity(root.op, tdt, &ii, &ff); r->ident_i = ii; r->ident_f = ff; }
+    Expr& re = r->transform[0]; re.n = 3;
+    for (int k = 0; k < 3; k++) { memset(&re.node[k], 0, sizeof re.node[k]); re.node[k].cls = ct; }
+    re.node[0].op = NCL_X_OUTPUT; re.node[0].a = 1; re.node[1].op = NCL_X_INPUT; re.node[1].a = 1; re.node[2].op = root.op; re.node[2].a = 0; re.node[2].b = 1;
+    rc = try_reduce(*r);
+    if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(*r);
+    delete r;
+  }
+  if (rc != NCL_OK) return release(rc);
+  // 3. result <- (op result partial) over the kept loops
+  {
+    Nest* c = new Nest(n);
+    c->n_in = 1; c->in[0] = U;
+    for (int l = 0; l < n.nloops; l++) if (n.out[0].stride[l] == 0) c->extent[l] = 1;      // the reduced loops are gone
+    ncl_expr src; src.n = 3;
+    for (int k = 0; k < 3; k++) memset(&src.node[k], 0, sizeof src.node[k]);
+    src.node[0].op = NCL_X_OUTPUT; src.node[0].a = 1; src.node[1].op = NCL_X_INPUT; src.node[1].a = 1; src.node[2].op = root.op; src.node[2].a = 0; src.node[2].b = 1;
+    int in_dt = tdt, out_dt = n.out[0].dtype;
+    rc = type_expr(&src, &in_dt, 1, &out_dt, 1, 0, &c->transform[0]);
+    if (rc == NCL_OK) { rc = try_elementwise(*c); if (rc == NCL_ERR_UNSUPPORTED) rc = launch_generic(*c); }
+    delete c;
+  }
+  if (rc == NCL_OK) ctx().last_kernel = "map_reduce";       // (ncl_last_kernel names the family: the last launch may be the tiny combine)
+  return release(rc);
+}
+
 // ---- contractions of two arrays of different element types --------------------------------------------------------------
 // (vdot a b) with a single-float and a double-float vector, (inner ub8-array fixnum-array), matrix x vector of mixed types:
 // the dot-like reduction kernels and the GEMMs want both operands in ONE element type, and the generic kernel walks the
@@ -417,6 +519,7 @@ int run_nest(Nest& n) {
     if ((rc = try_transpose(n)) != NCL_ERR_UNSUPPORTED) return done(rc);
     if ((rc = try_elementwise(n)) != NCL_ERR_UNSUPPORTED) return done(rc);
     if ((rc = run_composite_map(n)) != NCL_ERR_UNSUPPORTED) return done(rc);
+    if ((rc = run_map_reduce(n)) != NCL_ERR_UNSUPPORTED) return done(rc);
     return done(launch_generic(n));
   }
   return launch_generic(n);

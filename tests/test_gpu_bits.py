@@ -279,3 +279,35 @@ def test_contraction_with_a_transposed_result(nc, oracle, spec, sa, sb, dt):
     got = nc.einsum(spec, to_gpu(nc, A), to_gpu(nc, B))
     assert_bit_exact(got, refsem.einsum(oracle, spec, [A, B]))
     assert _last(nc).startswith("gemm"), _last(nc)
+
+
+# ---- reductions of a function of the arrays, and sums into a result of another class (ncl_plan.cu: run_map_reduce) ---------------
+@pytest.mark.parametrize("spec,nin", [("ij -> (+ @1 (abs $1)) -> ", 1), ("ij -> (max @1 (abs $1)) -> ", 1), ("ij ij -> (+ @1 (abs (- $1 $2))) -> ", 2),
+                                      ("ij -> (+ @1 (abs $1)) -> i", 1), ("ij -> (max @1 (* $1 $1)) -> j", 1), ("ij ij -> (+ @1 (* (+ $1 $2) $2)) -> i", 2),
+                                      ("ij -> (min @1 (- $1)) -> ", 1)])
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum"])
+def test_reductions_of_a_function_of_the_arrays(nc, oracle, spec, nin, dt):
+    """norms and distances written as einsum transforms: one thread of the generic kernel used to walk the whole array"""
+    xs = [rand(oracle, (300, 1000), dt, SEED + 150 + i, 1, -6, 6) for i in range(nin)]
+    want = refsem.einsum(oracle, spec, xs)
+    got = nc.einsum(spec, *[to_gpu(nc, x) for x in xs])
+    assert _last(nc) == "map_reduce", _last(nc)
+    if want.shape == ():
+        assert got == want.values().reshape(-1)[0]
+    else:
+        assert_bit_exact(got, want)
+
+
+def test_sum_into_a_result_of_another_class(nc, oracle):
+    """a single-float array summed into a supplied double-float scalar: every element is converted before it is added, so the
+    sum runs in double-float; an (unsigned-byte 8) array into a single-float vector; accumulation into what the result held"""
+    a = rand(oracle, (300, 1000), "f32", SEED + 160, 0, -1.0, 1.0)
+    out = nc.asarray(np.array(2.5), type="f64")
+    nc.einsum("ij -> ", to_gpu(nc, a), out)
+    truth = 2.5 + a.values().astype(np.float64).sum()
+    assert abs(out.item() - truth) <= 1e-12 * max(1.0, abs(truth)) * 300
+    assert _last(nc) == "map_reduce"
+    u = rand(oracle, (300, 1000), "ub8", SEED + 161, 0, 0, 9)
+    rows = nc.zeros((300,), type="f32")
+    nc.einsum("ij -> i", to_gpu(nc, u), rows)
+    assert np.array_equal(rows.numpy(), u.values().sum(axis=1).astype(np.float32))
