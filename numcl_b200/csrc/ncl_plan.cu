@@ -354,8 +354,13 @@ static int run_map_reduce(Nest& n) {
     bool all = true; for (int l = 0; l < n.nloops; l++) if (n.extent[l] > 1 && n.in[k].stride[l] <= 0) all = false;
     if (all && g_dt[n.in[k].dtype].cls <= CLS_D && n.in[k].dtype != NCL_UB64) span = k;
   }
-  if (span < 0) return NCL_ERR_UNSUPPORTED;
   for (int k = 0; k < n.n_in; k++) if (g_dt[n.in[k].dtype].cls > CLS_D || n.in[k].dtype == NCL_UB64) return NCL_ERR_UNSUPPORTED;
+  // no input spans every loop (`(i j -> )`, the sum of an outer product): the temporary is larger than any input, so it is
+  // only built when it is small (<= 1 GiB) and the results are few; the loops then keep the nest's own order
+  if (span < 0) {
+    long long results = 1; for (int l = 0; l < n.nloops; l++) if (n.out[0].stride[l] != 0) results *= n.extent[l];
+    if ((double)total * 8.0 > 1073741824.0 || results >= 4096) return NCL_ERR_UNSUPPORTED;     // many results: the generic kernel has a thread for each
+  }
   auto tdtype = [](int cls) { return cls == CLS_D ? NCL_F64 : cls == CLS_F ? NCL_F32 : NCL_SB64; };
   // class of the temporaries: the higher of the function's and the result's.  (+ @1 $1) into a double-float result converts
   // every single-float element before it is added (contagion), i.e. the sum runs in double-float
@@ -365,7 +370,8 @@ static int run_map_reduce(Nest& n) {
   // loop order of the spanning input; dense strides of the big temporary (all loops) and the small one (kept loops)
   int ord[NCL_MAX_LOOPS], nl = 0; long long tstr[NCL_MAX_LOOPS], ustr[NCL_MAX_LOOPS], kept_total = 1;
   for (int l = 0; l < n.nloops; l++) { tstr[l] = 0; ustr[l] = 0; if (n.extent[l] > 1) ord[nl++] = l; }
-  for (int i = 1; i < nl; i++) { int k = ord[i], j = i - 1; while (j >= 0 && n.in[span].stride[ord[j]] < n.in[span].stride[k]) { ord[j + 1] = ord[j]; j--; } ord[j + 1] = k; }
+  if (span >= 0)
+    for (int i = 1; i < nl; i++) { int k = ord[i], j = i - 1; while (j >= 0 && n.in[span].stride[ord[j]] < n.in[span].stride[k]) { ord[j + 1] = ord[j]; j--; } ord[j + 1] = k; }
   { long long acc = 1, ua = 1; for (int i = nl - 1; i >= 0; i--) { const int l = ord[i]; tstr[l] = acc; acc *= n.extent[l]; if (n.out[0].stride[l] != 0) { ustr[l] = ua; ua *= n.extent[l]; } } kept_total = ua; }
   ncl_buf* tb = ncl_alloc(ncl_storage_bytes(tdt, total), 0);
   ncl_buf* ub = ncl_alloc(ncl_storage_bytes(tdt, kept_total), 0);

@@ -311,3 +311,12 @@ def test_sum_into_a_result_of_another_class(nc, oracle):
     rows = nc.zeros((300,), type="f32")
     nc.einsum("ij -> i", to_gpu(nc, u), rows)
     assert np.array_equal(rows.numpy(), u.values().sum(axis=1).astype(np.float32))
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "fixnum"])
+def test_sum_of_an_outer_product(nc, oracle, dt):
+    """(einsum '(i j -> ) a b): no input spans both loops; the (small) iteration space is materialised, then folded"""
+    a = rand(oracle, (700,), dt, SEED + 170, 1, -4, 4); b = rand(oracle, (900,), dt, SEED + 171, 1, -4, 4)
+    got = nc.einsum("i j -> ", to_gpu(nc, a), to_gpu(nc, b))
+    assert _last(nc) == "map_reduce", _last(nc)
+    assert got == a.values().astype(np.float64).sum() * b.values().astype(np.float64).sum()
